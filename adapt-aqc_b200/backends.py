@@ -1,0 +1,281 @@
+"""B200 backends behind ADAPT-AQC's backend interface.
+
+``B200SVBackend`` is the drop-in for ``AerSVBackend`` (adaptaqc/backends/aer_sv_backend.py:19-59):
+same four methods, same argument (the compiler object), same return types, same errors.  When
+the reference package is importable the class *subclasses* ``AerSVBackend`` so that the
+``isinstance`` gates in the reference (adaptaqc/utils/utilityfunctions.py:122-130,
+approximate_compiler.py:112-113) take the statevector code paths; otherwise it derives from a
+local copy of the 4-method ABC (adaptaqc/backends/aqc_backend.py:14-29).
+
+``backend.simulator`` is an AerSimulator-shaped facade (``run(circuit).result().get_statevector()``)
+because the reference calls it directly, bypassing the backend, once per candidate pair
+(adaptaqc/utils/circuit_operations/circuit_operations_running.py:58-63).
+
+Everything is evaluated on the GPU through libb200aqc.so; there is no CPU path.
+"""
+import abc
+import weakref
+
+import numpy as np
+
+from . import gates as G
+from .sv_engine import SLOT_BASE, SLOT_WORK, SVCostEvaluator, SVEngine
+
+try:  # the reference (needs qiskit + qiskit-aer) is not installable in the build image
+    from adaptaqc.backends.aer_sv_backend import AerSVBackend as _SVBase  # pragma: no cover
+    HAVE_REFERENCE = True
+except Exception:  # noqa: BLE001
+    HAVE_REFERENCE = False
+
+    class AQCBackend(abc.ABC):
+        """Mirror of adaptaqc/backends/aqc_backend.py:14-29."""
+
+        @abc.abstractmethod
+        def evaluate_global_cost(self, compiler):
+            pass
+
+        @abc.abstractmethod
+        def evaluate_local_cost(self, compiler):
+            pass
+
+        @abc.abstractmethod
+        def evaluate_circuit(self, compiler):
+            pass
+
+        @abc.abstractmethod
+        def measure_qubit_expectation_values(self, compiler):
+            pass
+
+    _SVBase = AQCBackend
+
+
+class DeviceStatevector:
+    """What ``result.get_statevector()`` returns: a handle on an HBM-resident state.
+
+    Supports what the reference touches on Aer's Statevector (aer_sv_backend.py:29,52,56;
+    entanglement_measures.py:333-340): ``sv[0]``, ``len(sv)``, ``.num_qubits``,
+    ``.probabilities([i])``, ``.data`` / ``np.asarray(sv)`` (downloads; small n only), plus
+    ``partial_trace(a, b)`` served by the all-pairs RDM kernel.
+    """
+
+    def __init__(self, owner, version):
+        self._owner = owner
+        self._version = version
+        self.num_qubits = owner._engine.num_qubits
+        self._expz = None
+        self._rdm = {}
+
+    def _engine(self):
+        if self._owner._state_version != self._version:
+            raise RuntimeError("this DeviceStatevector has been overwritten by a later evaluation")
+        return self._owner._engine
+
+    def __len__(self):
+        return 1 << self.num_qubits
+
+    def __getitem__(self, index):
+        if isinstance(index, (int, np.integer)):
+            return self._engine().amp(SLOT_WORK, int(index) % len(self))
+        return self.data[index]
+
+    @property
+    def data(self):
+        if self.num_qubits > 30:
+            raise MemoryError("refusing to download a >16 GiB statevector to the host")
+        return self._engine().download(SLOT_WORK)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.data
+        return a if dtype is None else a.astype(dtype)
+
+    def expectation_z(self):
+        if self._expz is None:
+            self._expz = self._engine().expz(SLOT_WORK)
+        return self._expz
+
+    def probabilities(self, qargs=None):
+        if qargs is None or len(qargs) != 1:
+            raise NotImplementedError("only single-qubit marginals are served on the device")
+        z, norm = self.expectation_z()
+        zq = z[qargs[0]]
+        return np.array([0.5 * (norm + zq), 0.5 * (norm - zq)])
+
+    def pair_rdms(self, pairs):
+        """4x4 RDMs for all `pairs` ((a,b) tuples); computed in one batched device call."""
+        need = [p for p in {tuple(sorted(p)) for p in pairs} if p not in self._rdm]
+        if need:
+            rho = self._engine().pair_rdm(SLOT_WORK, need)
+            for p, r in zip(need, rho):
+                self._rdm[p] = r
+        return [self._rdm[tuple(sorted(p))] for p in pairs]
+
+    def partial_trace(self, a, b):
+        """entanglement_measures.py:325-340 (lower qubit = least significant index)."""
+        if self.num_qubits == 2:
+            sv = self.data
+            return np.outer(sv, sv.conj())
+        hint = self._owner._pair_hint
+        if hint and tuple(sorted((a, b))) in hint and tuple(sorted((a, b))) not in self._rdm:
+            self.pair_rdms(list(hint))
+        return self.pair_rdms([(a, b)])[0]
+
+
+class _Result:
+    def __init__(self, sv):
+        self._sv = sv
+
+    def get_statevector(self, *_a, **_k):
+        return self._sv
+
+    def get_counts(self, *_a, **_k):
+        raise NotImplementedError("B200SVBackend is an exact-amplitude backend; no sampling")
+
+
+class _Job:
+    def __init__(self, sv):
+        self._sv = sv
+
+    def result(self):
+        return _Result(self._sv)
+
+
+class B200StatevectorSimulator:
+    """``Aer.get_backend('statevector_simulator')``-shaped facade (aer_sv_backend.py:20,42-47)."""
+
+    name = "b200_statevector_simulator"
+
+    def __init__(self, backend):
+        self._backend = weakref.ref(backend)
+
+    def run(self, circuit, **_options):
+        return _Job(self._backend()._simulate(circuit))
+
+
+class B200SVBackend(_SVBase):
+    def __init__(self, device=0, simulator=None):
+        self.device = device
+        self._engine = None
+        self._evaluator = None
+        self._state_version = 0
+        self._last_run_key = None
+        self._last_run_sv = None
+        self._pair_hint = None
+        self._compiler_ref = None
+        self.simulator = simulator if simulator is not None else B200StatevectorSimulator(self)
+
+    # checkpointing pickles the whole compiler, backend included (adapt_compiler.py:484-497)
+    def __getstate__(self):
+        return {"device": self.device}
+
+    def __setstate__(self, state):
+        self.__init__(device=state.get("device", 0))
+
+    # ---- engine management ----
+    def _get_engine(self, num_qubits):
+        if self._engine is None or self._engine.num_qubits != num_qubits:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = SVEngine(num_qubits, device=self.device, n_slots=4)
+            self._evaluator = SVCostEvaluator(self._engine)
+            self._state_version += 1
+            self._last_run_key = None
+        return self._engine
+
+    def _prefix_key(self, compiler):
+        lhs = compiler.lhs_gate_count
+        ref = self._compiler_ref() if self._compiler_ref is not None else None
+        if ref is not compiler:
+            self._compiler_ref = weakref.ref(compiler)
+            self._prefix_serial = getattr(self, "_prefix_serial", 0) + 1
+        return (self._prefix_serial, lhs)
+
+    def reset_cache(self):
+        """Forget every cached state (call after editing the target part of full_circuit)."""
+        self._compiler_ref = None
+        if self._evaluator is not None:
+            self._evaluator.base_key = None
+            self._evaluator.invalidate()
+        self._last_run_key = None
+
+    def _simulate(self, circuit, pair_hint=None):
+        """Full circuit from |0..0> into slot WORK (facade path, no caching assumptions except an
+        identical-circuit shortcut: the reference re-runs the same circuit once per pair)."""
+        eng = self._get_engine(circuit.num_qubits)
+        window = G.canonical_window(circuit)
+        key = tuple(window)
+        if self._last_run_key is not None and key == self._last_run_key and self._last_run_sv is not None \
+                and self._last_run_sv._version == self._state_version:
+            return self._last_run_sv
+        eng.run(SLOT_WORK, -1, G.GateStream.from_window(window))
+        self._state_version += 1
+        sv = DeviceStatevector(self, self._state_version)
+        self._last_run_key, self._last_run_sv = key, sv
+        return sv
+
+    def _prepare(self, compiler):
+        circuit = compiler.full_circuit
+        eng = self._get_engine(circuit.num_qubits)
+        lhs = compiler.lhs_gate_count
+        key = self._prefix_key(compiler)
+        ev = self._evaluator
+        if ev.base_key != key:
+            ev.set_base(key, G.GateStream.from_circuit(circuit, 0, lhs))
+        return eng, ev, G.canonical_window(circuit, lhs, None)
+
+    # ---- the four backend methods ----
+    def evaluate_global_cost(self, compiler):
+        if compiler.soften_global_cost:
+            raise NotImplementedError(
+                "soften_global_cost is currently only implemented for AerMPSBackend"
+            )
+        _, ev, window = self._prepare(compiler)
+        self._state_version += 1  # slot WORK may be overwritten
+        amp = ev.amp0(window)
+        return 1 - (np.absolute(amp)) ** 2
+
+    def evaluate_local_cost(self, compiler):
+        e_vals = self.measure_qubit_expectation_values(compiler)
+        return 0.5 * (1 - np.mean(e_vals))
+
+    def evaluate_circuit(self, compiler):
+        eng, ev, window = self._prepare(compiler)
+        eng.run(SLOT_WORK, SLOT_BASE, G.GateStream.from_window(window))
+        self._state_version += 1
+        sv = DeviceStatevector(self, self._state_version)
+        self._last_run_key, self._last_run_sv = None, sv
+        return sv
+
+    def measure_qubit_expectation_values(self, compiler):
+        sv = self.evaluate_circuit(compiler)
+        z, _ = sv.expectation_z()
+        return [float(v) for v in z]
+
+    # ---- batched extensions (used by B200CostMinimiser / the compiler hooks) ----
+    def set_pair_hint(self, pairs):
+        """Tell the facade which pairs will be asked for, so the first ``partial_trace`` call
+        computes all of them in one batched launch sequence."""
+        self._pair_hint = {tuple(sorted(p)) for p in pairs} if pairs else None
+
+    def shift_costs(self, compiler, gate_index, candidates):
+        """Global cost for each (gate_name, angle) in `candidates` placed at full_circuit index
+        `gate_index`: one inner-product launch for all of them (K6)."""
+        if compiler.soften_global_cost:
+            raise NotImplementedError(
+                "soften_global_cost is currently only implemented for AerMPSBackend"
+            )
+        _, ev, window = self._prepare(compiler)
+        k = gate_index - compiler.lhs_gate_count
+        mats = [G.one_qubit_matrix(name, theta) for name, theta in candidates]
+        amps = ev.shift_amplitudes(window, k, mats)
+        return [1 - (np.absolute(a)) ** 2 for a in amps]
+
+    def overlap_between_circuits(self, circuit1, circuit2):
+        """|<psi1|psi2>|^2 on the device (replaces the pure-python qiskit simulation in
+        calculate_overlap_between_circuits, circuit_operations_full_circuit.py:413-438)."""
+        eng = self._get_engine(circuit1.num_qubits)
+        from .sv_engine import SLOT_L, SLOT_R
+        eng.run(SLOT_L, -1, G.GateStream.from_circuit(circuit1))
+        eng.run(SLOT_R, -1, G.GateStream.from_circuit(circuit2))
+        if self._evaluator is not None:
+            self._evaluator.lr_valid = False
+        return np.absolute(eng.inner(SLOT_L, SLOT_R, -1)) ** 2

@@ -1,0 +1,541 @@
+// api.cu -- C-ABI entry points of libb200aqc.so (statevector path).  See include/b200aqc.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b200aqc.h"
+#include "ctx.h"
+#include "sv_kernels.cuh"
+#include "sv_plan.h"
+
+using namespace b200;
+
+namespace b200 {
+thread_local std::string g_last_error;
+int set_error(const std::string& msg) {
+    g_last_error = msg;
+    return -1;
+}
+}  // namespace b200
+
+namespace {
+
+int ensure_scratch(b200_ctx* ctx) {
+    if (ctx->d_partial) return 0;
+    CUDA_TRY(cudaMalloc(&ctx->d_partial, PARTIAL_DOUBLES * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&ctx->d_out, OUT_DOUBLES * sizeof(double)));
+    CUDA_TRY(cudaMallocHost(&ctx->h_out, OUT_DOUBLES * sizeof(double)));
+    return 0;
+}
+
+int check_slot(b200_ctx* ctx, int slot) {
+    if (!ctx) return set_error("null context");
+    if (ctx->nq <= 0) return set_error("statevector not allocated (call b200_sv_alloc)");
+    if (slot < 0 || slot >= (int)ctx->slots.size() || !ctx->slots[slot])
+        return set_error("invalid statevector slot " + std::to_string(slot));
+    return 0;
+}
+
+// grows a device buffer to hold `bytes`
+int reserve_dev(void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    const size_t want = std::max(bytes * 2, (size_t)1 << 16);
+    CUDA_TRY(cudaMalloc(p, want));
+    *cap = want;
+    return 0;
+}
+
+int reserve_host(void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return 0;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *cap = 0;
+    const size_t want = std::max(bytes * 2, (size_t)1 << 16);
+    CUDA_TRY(cudaMallocHost(p, want));
+    *cap = want;
+    return 0;
+}
+
+struct Timer {
+    b200_ctx* ctx;
+    explicit Timer(b200_ctx* c) : ctx(c) {
+        if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream);
+    }
+    void stop() {
+        if (ctx->timing) {
+            cudaEventRecord(ctx->ev1, ctx->stream);
+            ctx->timing_pending = true;
+        }
+    }
+};
+
+// Upload the plan (rounds, ops, mat2 table) in one pinned staging copy.
+int upload_plan(b200_ctx* ctx, const Plan& plan, const DevRound** d_rounds, const DevOp** d_ops,
+                const double** d_mat2) {
+    const size_t b_rounds = plan.rounds.size() * sizeof(DevRound);
+    const size_t b_ops = plan.ops.size() * sizeof(DevOp);
+    const size_t b_mat2 = plan.mat2.size() * sizeof(double);
+    auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t o_ops = up16(b_rounds), o_mat2 = o_ops + up16(b_ops), total = o_mat2 + up16(b_mat2) + 16;
+    // The staging buffer may still be in flight from the previous call on this stream.
+    if (ctx->plan_in_flight) { CUDA_TRY(cudaEventSynchronize(ctx->ev_plan)); ctx->plan_in_flight = false; }
+    if (reserve_host(&ctx->h_plan, &ctx->h_plan_cap, total)) return -1;
+    if (ctx->d_plan_cap < total) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // old buffer may be in use by a running kernel
+        if (reserve_dev(&ctx->d_plan, &ctx->d_plan_cap, total)) return -1;
+    }
+    char* h = (char*)ctx->h_plan;
+    if (b_rounds) std::memcpy(h, plan.rounds.data(), b_rounds);
+    if (b_ops) std::memcpy(h + o_ops, plan.ops.data(), b_ops);
+    if (b_mat2) std::memcpy(h + o_mat2, plan.mat2.data(), b_mat2);
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_plan, h, total, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev_plan, ctx->stream));
+    ctx->plan_in_flight = true;
+    *d_rounds = (const DevRound*)ctx->d_plan;
+    *d_ops = (const DevOp*)((char*)ctx->d_plan + o_ops);
+    *d_mat2 = (const double*)((char*)ctx->d_plan + o_mat2);
+    return 0;
+}
+
+int run_plan(b200_ctx* ctx, int dst_slot, int src_slot, const Plan& plan) {
+    const int n = ctx->nq;
+    const uint64_t dim = 1ull << n;
+    double2* dst = (double2*)ctx->slots[dst_slot];
+    const double2* src = src_slot >= 0 ? (const double2*)ctx->slots[src_slot] : nullptr;
+    Timer tm(ctx);
+
+    if (plan.small) {
+        const DevRound* d_rounds; const DevOp* d_ops; const double* d_mat2;
+        if (upload_plan(ctx, plan, &d_rounds, &d_ops, &d_mat2)) return -1;
+        const size_t smem = dim * sizeof(double2);
+        sv_small_kernel<<<1, 256, smem, ctx->stream>>>(src, dst, n, d_ops, (int)plan.ops.size(), d_mat2,
+                                                        src == nullptr ? 1 : 0);
+        CUDA_TRY(cudaGetLastError());
+        ctx->counters[0] += 1; ctx->counters[1] += 1;
+        ctx->counters[2] += plan.n_gates_in; ctx->counters[3] += 32 * dim;
+        tm.stop();
+        return 0;
+    }
+
+    if (src == nullptr) {
+        sv_init_zero_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(dst, dim);
+        CUDA_TRY(cudaGetLastError());
+        ctx->counters[0] += 1;
+        src = dst;
+    }
+    if (plan.sweeps.empty()) {
+        if (src != dst)
+            CUDA_TRY(cudaMemcpyAsync(dst, src, dim * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
+        tm.stop();
+        return 0;
+    }
+    const DevRound* d_rounds; const DevOp* d_ops; const double* d_mat2;
+    if (upload_plan(ctx, plan, &d_rounds, &d_ops, &d_mat2)) return -1;
+    const uint32_t ntiles = (uint32_t)(dim >> TILE_BITS);
+    for (const DevSweep& sw : plan.sweeps) {
+        const int nr = sw.round_end - sw.round_begin;
+        const size_t smem = nr > 1 ? ((size_t)1 << TILE_BITS) * sizeof(double2) : 0;
+        const int per_sm = nr > 1 ? ctx->sweep_occ_smem : ctx->sweep_occ_nosmem;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * per_sm * ctx->grid_mult);
+        sv_sweep_kernel<REG_BITS><<<grid, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, d_rounds, d_ops,
+                                                                               d_mat2, ntiles);
+        CUDA_TRY(cudaGetLastError());
+        src = dst;
+        ctx->counters[0] += 1; ctx->counters[1] += 1; ctx->counters[3] += 32 * dim;
+    }
+    ctx->counters[2] += plan.n_gates_in;
+    tm.stop();
+    return 0;
+}
+
+int make_plan(int nq, const b200_gate* gates, int n_gates, const double* mats, int n_mats, bool inverse,
+              Plan& plan) {
+    if (n_gates < 0 || (n_gates > 0 && !gates)) return set_error("null gate array");
+    std::vector<COp> ops;
+    const std::string err = canonicalize(nq, gates, n_gates, mats, n_mats, inverse, ops);
+    if (!err.empty()) return set_error(err);
+    fuse_single_qubit_runs(ops);
+    build_plan(nq, ops, plan);
+    plan.n_gates_in = n_gates;
+    return 0;
+}
+
+int sv_run_impl(b200_ctx* ctx, int dst_slot, int src_slot, const b200_gate* gates, int n_gates,
+                const double* mats, int n_mats, bool inverse) {
+    if (check_slot(ctx, dst_slot)) return -1;
+    if (src_slot >= 0 && check_slot(ctx, src_slot)) return -1;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Plan plan;
+    if (make_plan(ctx->nq, gates, n_gates, mats, n_mats, inverse, plan)) return -1;
+    return run_plan(ctx, dst_slot, src_slot, plan);
+}
+
+// copy `count` doubles of d_out to the caller (sync)
+int fetch_out(b200_ctx* ctx, double* out, int count) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_out, ctx->d_out, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(out, ctx->h_out, count * sizeof(double));
+    return 0;
+}
+
+int red_grid(b200_ctx* ctx, uint64_t work_items) {
+    const uint64_t want = (work_items + RED_THREADS - 1) / RED_THREADS;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)ctx->num_sms * 8));
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_abi_version(void) { return B200AQC_ABI_VERSION; }
+
+const char* b200_last_error(void) { return g_last_error.c_str(); }
+
+int b200_device_count(int* count) {
+    if (!count) return set_error("null pointer");
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int b200_ctx_create(int device, b200_ctx** out) {
+    if (!out) return set_error("null pointer");
+    *out = nullptr;
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count)
+        return set_error("device " + std::to_string(device) + " not present (" + std::to_string(count) + " visible)");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_error(std::string("libb200aqc is built for sm_100a only; device is ") + prop.name + " (sm_" +
+                         std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    b200_ctx* ctx = new b200_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&ctx->ev0));
+    CUDA_TRY(cudaEventCreate(&ctx->ev1));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_plan, cudaEventDisableTiming));
+    const size_t tile_bytes = ((size_t)1 << TILE_BITS) * sizeof(double2);
+    CUDA_TRY(cudaFuncSetAttribute(sv_sweep_kernel<REG_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tile_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(sv_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(((size_t)1 << SMALL_MAX_QUBITS) * sizeof(double2))));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sweep_occ_smem, sv_sweep_kernel<REG_BITS>,
+                                                           SWEEP_THREADS, tile_bytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sweep_occ_nosmem, sv_sweep_kernel<REG_BITS>,
+                                                           SWEEP_THREADS, 0));
+    if (ctx->sweep_occ_smem < 1 || ctx->sweep_occ_nosmem < 1) { delete ctx; return set_error("sweep kernel does not fit on an SM"); }
+    if (const char* e = std::getenv("B200AQC_GRID_MULT")) ctx->grid_mult = std::max(1, std::atoi(e));
+    if (ensure_scratch(ctx)) { delete ctx; return -1; }
+    *out = ctx;
+    return 0;
+}
+
+int b200_ctx_destroy(b200_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (size_t i = 0; i < ctx->slots.size(); ++i)
+        if (ctx->slots[i] && ctx->owned[i]) cudaFree(ctx->slots[i]);
+    if (ctx->d_partial) cudaFree(ctx->d_partial);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->d_plan) cudaFree(ctx->d_plan);
+    if (ctx->h_plan) cudaFreeHost(ctx->h_plan);
+    b200_mps_release(ctx);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev_plan);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+int b200_ctx_sync(b200_ctx* ctx) {
+    if (!ctx) return set_error("null context");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200_ctx_counters(b200_ctx* ctx, uint64_t out[4]) {
+    if (!ctx || !out) return set_error("null pointer");
+    for (int k = 0; k < 4; ++k) out[k] = ctx->counters[k];
+    return 0;
+}
+
+int b200_ctx_set_timing(b200_ctx* ctx, int enable) {
+    if (!ctx) return set_error("null context");
+    ctx->timing = enable != 0;
+    ctx->timing_pending = false;
+    return 0;
+}
+
+int b200_ctx_last_ms(b200_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return set_error("null pointer");
+    if (!ctx->timing || !ctx->timing_pending) return set_error("no timed call pending (b200_ctx_set_timing)");
+    CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+    float f = 0;
+    CUDA_TRY(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+    *ms = f;
+    return 0;
+}
+
+int b200_sv_alloc(b200_ctx* ctx, int num_qubits, int n_slots) {
+    if (!ctx) return set_error("null context");
+    if (num_qubits < 1 || num_qubits > 40) return set_error("num_qubits out of range [1,40]");
+    if (n_slots < 1 || n_slots > 64) return set_error("n_slots out of range [1,64]");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < ctx->slots.size(); ++i)
+        if (ctx->slots[i] && ctx->owned[i]) cudaFree(ctx->slots[i]);
+    ctx->slots.assign(n_slots, nullptr);
+    ctx->owned.assign(n_slots, 0);
+    ctx->nq = 0;
+    const size_t bytes = ((size_t)1 << num_qubits) * sizeof(double2);
+    for (int i = 0; i < n_slots; ++i) {
+        cudaError_t e = cudaMalloc(&ctx->slots[i], bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int j = 0; j < i; ++j) { cudaFree(ctx->slots[j]); ctx->slots[j] = nullptr; }
+            return set_error("cudaMalloc of " + std::to_string(bytes) + " bytes for slot " + std::to_string(i) +
+                             " failed: " + cudaGetErrorString(e));
+        }
+        ctx->owned[i] = 1;
+    }
+    ctx->nq = num_qubits;
+    return 0;
+}
+
+int b200_sv_attach(b200_ctx* ctx, int slot, void* device_ptr) {
+    if (!ctx) return set_error("null context");
+    if (ctx->nq <= 0) return set_error("statevector not allocated (call b200_sv_alloc)");
+    if (slot < 0 || slot >= (int)ctx->slots.size()) return set_error("invalid slot");
+    if (!device_ptr || ((uintptr_t)device_ptr & 15)) return set_error("device pointer must be 16-byte aligned");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->slots[slot] && ctx->owned[slot]) cudaFree(ctx->slots[slot]);
+    ctx->slots[slot] = device_ptr;
+    ctx->owned[slot] = 0;
+    return 0;
+}
+
+int b200_sv_device_ptr(b200_ctx* ctx, int slot, void** out) {
+    if (check_slot(ctx, slot)) return -1;
+    *out = ctx->slots[slot];
+    return 0;
+}
+
+int b200_sv_num_qubits(b200_ctx* ctx, int* out) {
+    if (!ctx || !out) return set_error("null pointer");
+    *out = ctx->nq;
+    return 0;
+}
+
+int b200_sv_init_zero(b200_ctx* ctx, int slot) {
+    if (check_slot(ctx, slot)) return -1;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t dim = 1ull << ctx->nq;
+    const int grid = (int)std::min<uint64_t>((dim + 255) / 256, (uint64_t)ctx->num_sms * 8);
+    sv_init_zero_kernel<<<grid, 256, 0, ctx->stream>>>((double2*)ctx->slots[slot], dim);
+    CUDA_TRY(cudaGetLastError());
+    ctx->counters[0] += 1;
+    return 0;
+}
+
+int b200_sv_copy(b200_ctx* ctx, int dst_slot, int src_slot) {
+    if (check_slot(ctx, dst_slot) || check_slot(ctx, src_slot)) return -1;
+    if (dst_slot == src_slot) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(ctx->slots[dst_slot], ctx->slots[src_slot], ((size_t)1 << ctx->nq) * sizeof(double2),
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
+int b200_sv_run(b200_ctx* ctx, int dst_slot, int src_slot, const b200_gate* gates, int n_gates,
+                const double* mats, int n_mats) {
+    return sv_run_impl(ctx, dst_slot, src_slot, gates, n_gates, mats, n_mats, false);
+}
+
+int b200_sv_run_inverse(b200_ctx* ctx, int dst_slot, int src_slot, const b200_gate* gates, int n_gates,
+                        const double* mats, int n_mats) {
+    return sv_run_impl(ctx, dst_slot, src_slot, gates, n_gates, mats, n_mats, true);
+}
+
+int b200_sv_amp(b200_ctx* ctx, int slot, uint64_t index, double out[2]) {
+    if (check_slot(ctx, slot)) return -1;
+    if (index >> ctx->nq) return set_error("amplitude index out of range");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_out, (const double2*)ctx->slots[slot] + index, sizeof(double2),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    out[0] = ctx->h_out[0];
+    out[1] = ctx->h_out[1];
+    return 0;
+}
+
+int b200_sv_expz(b200_ctx* ctx, int slot, double* out) {
+    if (check_slot(ctx, slot)) return -1;
+    if (!out) return set_error("null pointer");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int n = ctx->nq;
+    const double2* psi = (const double2*)ctx->slots[slot];
+    Timer tm(ctx);
+    if (n <= SMALL_MAX_QUBITS) {
+        sv_expz_small_kernel<<<1, 64, 0, ctx->stream>>>(psi, n, ctx->d_out);
+        CUDA_TRY(cudaGetLastError());
+        ctx->counters[0] += 1;
+    } else {
+        const int tb = std::min(n - 3, 17), kb = n - tb;
+        const int nblocks = 1 << (tb - 8);
+        sv_expz_kernel<<<nblocks, RED_THREADS, 0, ctx->stream>>>(psi, tb, kb, ctx->d_partial);
+        CUDA_TRY(cudaGetLastError());
+        sv_expz_final_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, nblocks, n, tb, ctx->d_out);
+        CUDA_TRY(cudaGetLastError());
+        ctx->counters[0] += 2;
+    }
+    ctx->counters[3] += 16ull << n;
+    tm.stop();
+    return fetch_out(ctx, out, n + 1);
+}
+
+int b200_sv_pair_rdm(b200_ctx* ctx, int slot, const int32_t* pairs, int n_pairs, double* out) {
+    if (check_slot(ctx, slot)) return -1;
+    if (n_pairs < 0 || (n_pairs > 0 && (!pairs || !out))) return set_error("null pointer");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int n = ctx->nq;
+    const double2* psi = (const double2*)ctx->slots[slot];
+    for (int p = 0; p < n_pairs; ++p) {
+        const int a = pairs[2 * p], b = pairs[2 * p + 1];
+        if (a < 0 || b < 0 || a >= n || b >= n || a == b)
+            return set_error("pair " + std::to_string(p) + ": qubits out of range");
+    }
+    // Cover the requested pairs with qubit triples (three pair-RDMs per read pass).
+    std::vector<char> want(n * n, 0), have(n * n, 0);
+    std::vector<double> acc((size_t)n * n * 16, 0.0);  // indexed [lo*n+hi][16]
+    for (int p = 0; p < n_pairs; ++p) {
+        const int lo = std::min(pairs[2 * p], pairs[2 * p + 1]), hi = std::max(pairs[2 * p], pairs[2 * p + 1]);
+        want[lo * n + hi] = 1;
+    }
+    Timer tm(ctx);
+    std::vector<double> host;
+    for (int lo = 0; lo < n; ++lo)
+        for (int hi = lo + 1; hi < n; ++hi) {
+            if (!want[lo * n + hi] || have[lo * n + hi]) continue;
+            int best = -1, best_gain = -1;
+            if (n >= 3) {
+                for (int c = 0; c < n; ++c) {
+                    if (c == lo || c == hi) continue;
+                    auto need = [&](int u, int v) { const int l = std::min(u, v), h = std::max(u, v); return want[l * n + h] && !have[l * n + h] ? 1 : 0; };
+                    const int gain = need(lo, c) + need(hi, c);
+                    if (gain > best_gain) { best_gain = gain; best = c; }
+                }
+            }
+            if (best < 0 || best_gain == 0) {
+                const int grid = red_grid(ctx, 1ull << (n - 2));
+                sv_rdm2_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>(psi, n, lo, hi, ctx->d_partial);
+                CUDA_TRY(cudaGetLastError());
+                reduce_partials_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, grid, 16, ctx->d_out);
+                CUDA_TRY(cudaGetLastError());
+                ctx->counters[0] += 2; ctx->counters[3] += 16ull << n;
+                double r[16];
+                if (fetch_out(ctx, r, 16)) return -1;
+                std::memcpy(&acc[(size_t)(lo * n + hi) * 16], r, sizeof r);
+                have[lo * n + hi] = 1;
+            } else {
+                int q[3] = {lo, hi, best};
+                std::sort(q, q + 3);
+                const int grid = red_grid(ctx, 1ull << (n - 3));
+                sv_rdm3_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>(psi, n, q[0], q[1], q[2], ctx->d_partial);
+                CUDA_TRY(cudaGetLastError());
+                reduce_partials_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, grid, RDM3_WIDTH, ctx->d_out);
+                CUDA_TRY(cudaGetLastError());
+                ctx->counters[0] += 2; ctx->counters[3] += 16ull << n;
+                double r[RDM3_WIDTH];
+                if (fetch_out(ctx, r, RDM3_WIDTH)) return -1;
+                const int pl[3][2] = {{q[0], q[1]}, {q[0], q[2]}, {q[1], q[2]}};
+                for (int t = 0; t < 3; ++t) {
+                    std::memcpy(&acc[(size_t)(pl[t][0] * n + pl[t][1]) * 16], r + 16 * t, 16 * sizeof(double));
+                    have[pl[t][0] * n + pl[t][1]] = 1;
+                }
+            }
+        }
+    tm.stop();
+    // expand the packed Hermitian accumulators into row-major 4x4 complex
+    static const int off_r[6] = {1, 2, 3, 2, 3, 3}, off_c[6] = {0, 0, 0, 1, 1, 2};
+    for (int p = 0; p < n_pairs; ++p) {
+        const int lo = std::min(pairs[2 * p], pairs[2 * p + 1]), hi = std::max(pairs[2 * p], pairs[2 * p + 1]);
+        const double* a = &acc[(size_t)(lo * n + hi) * 16];
+        double* o = out + (size_t)p * 32;
+        for (int k = 0; k < 32; ++k) o[k] = 0.0;
+        for (int d = 0; d < 4; ++d) o[2 * (5 * d)] = a[d];
+        for (int k = 0; k < 6; ++k) {
+            const int r = off_r[k], c = off_c[k];
+            o[2 * (4 * r + c)] = a[4 + 2 * k];
+            o[2 * (4 * r + c) + 1] = a[5 + 2 * k];
+            o[2 * (4 * c + r)] = a[4 + 2 * k];
+            o[2 * (4 * c + r) + 1] = -a[5 + 2 * k];
+        }
+    }
+    return 0;
+}
+
+int b200_sv_inner(b200_ctx* ctx, int l_slot, int r_slot, int q, double out[8]) {
+    if (check_slot(ctx, l_slot) || check_slot(ctx, r_slot)) return -1;
+    if (q >= ctx->nq) return set_error("qubit out of range");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int n = ctx->nq;
+    Timer tm(ctx);
+    const int grid = red_grid(ctx, q < 0 ? (1ull << n) : (1ull << (n - 1)));
+    sv_inner_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>((const double2*)ctx->slots[l_slot],
+                                                           (const double2*)ctx->slots[r_slot], n, q, ctx->d_partial);
+    CUDA_TRY(cudaGetLastError());
+    reduce_partials_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, grid, INNER_WIDTH, ctx->d_out);
+    CUDA_TRY(cudaGetLastError());
+    ctx->counters[0] += 2; ctx->counters[3] += 32ull << n;
+    tm.stop();
+    return fetch_out(ctx, out, 8);
+}
+
+int b200_sv_download(b200_ctx* ctx, int slot, uint64_t offset, uint64_t count, double* host) {
+    if (check_slot(ctx, slot)) return -1;
+    if (offset + count > (1ull << ctx->nq)) return set_error("download range out of bounds");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(host, (const double2*)ctx->slots[slot] + offset, count * sizeof(double2),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200_sv_upload(b200_ctx* ctx, int slot, uint64_t offset, uint64_t count, const double* host) {
+    if (check_slot(ctx, slot)) return -1;
+    if (offset + count > (1ull << ctx->nq)) return set_error("upload range out of bounds");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpyAsync((double2*)ctx->slots[slot] + offset, host, count * sizeof(double2),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200_sv_plan_stats(int num_qubits, const b200_gate* gates, int n_gates, const double* mats, int n_mats,
+                       int32_t out[4]) {
+    if (!out) return set_error("null pointer");
+    if (num_qubits < 1 || num_qubits > 40) return set_error("num_qubits out of range [1,40]");
+    Plan plan;
+    if (make_plan(num_qubits, gates, n_gates, mats, n_mats, false, plan)) return -1;
+    out[0] = plan.small ? 1 : (int32_t)plan.sweeps.size();
+    out[1] = plan.small ? 1 : (int32_t)plan.rounds.size();
+    out[2] = (int32_t)plan.ops.size();
+    out[3] = plan.small ? 1 : 0;
+    return 0;
+}
+
+}  // extern "C"

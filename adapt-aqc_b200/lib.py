@@ -1,0 +1,83 @@
+"""ctypes binding of libb200aqc.so (C-ABI declared in include/b200aqc.h).
+
+There is deliberately no fallback: if the shared library is missing, or a call returns an
+error, an exception is raised.  Every cost evaluation runs on the GPU or not at all.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200aqc.so")
+
+# Every symbol include/b200aqc.h declares (checked by tests/test_abi.py).
+SYMBOLS = [
+    "b200_abi_version", "b200_last_error", "b200_device_count", "b200_ctx_create",
+    "b200_ctx_destroy", "b200_ctx_sync", "b200_ctx_counters", "b200_ctx_last_ms",
+    "b200_ctx_set_timing", "b200_sv_alloc", "b200_sv_attach", "b200_sv_device_ptr",
+    "b200_sv_num_qubits", "b200_sv_init_zero", "b200_sv_copy", "b200_sv_run",
+    "b200_sv_run_inverse", "b200_sv_amp", "b200_sv_expz", "b200_sv_pair_rdm", "b200_sv_inner",
+    "b200_sv_download", "b200_sv_upload", "b200_sv_plan_stats",
+]
+
+
+class B200Error(RuntimeError):
+    """Raised for every non-zero return code of the C-ABI."""
+
+
+_lib = None
+
+
+def load():
+    """Load libb200aqc.so; raises B200Error if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cu64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.b200_abi_version.restype = ci
+    L.b200_last_error.restype = ctypes.c_char_p
+    L.b200_device_count.argtypes = [ctypes.POINTER(ci)]
+    L.b200_ctx_create.argtypes = [ci, ctypes.POINTER(vp)]
+    L.b200_ctx_destroy.argtypes = [vp]
+    L.b200_ctx_sync.argtypes = [vp]
+    L.b200_ctx_counters.argtypes = [vp, ctypes.POINTER(cu64)]
+    L.b200_ctx_last_ms.argtypes = [vp, dp]
+    L.b200_ctx_set_timing.argtypes = [vp, ci]
+    L.b200_sv_alloc.argtypes = [vp, ci, ci]
+    L.b200_sv_attach.argtypes = [vp, ci, vp]
+    L.b200_sv_device_ptr.argtypes = [vp, ci, ctypes.POINTER(vp)]
+    L.b200_sv_num_qubits.argtypes = [vp, ctypes.POINTER(ci)]
+    L.b200_sv_init_zero.argtypes = [vp, ci]
+    L.b200_sv_copy.argtypes = [vp, ci, ci]
+    L.b200_sv_run.argtypes = [vp, ci, ci, vp, ci, vp, ci]
+    L.b200_sv_run_inverse.argtypes = [vp, ci, ci, vp, ci, vp, ci]
+    L.b200_sv_amp.argtypes = [vp, ci, cu64, dp]
+    L.b200_sv_expz.argtypes = [vp, ci, dp]
+    L.b200_sv_pair_rdm.argtypes = [vp, ci, vp, ci, dp]
+    L.b200_sv_inner.argtypes = [vp, ci, ci, ci, dp]
+    L.b200_sv_download.argtypes = [vp, ci, cu64, cu64, vp]
+    L.b200_sv_upload.argtypes = [vp, ci, cu64, cu64, vp]
+    L.b200_sv_plan_stats.argtypes = [ci, vp, ci, vp, ci, ctypes.POINTER(ctypes.c_int32)]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if name not in ("b200_last_error", "b200_abi_version"):
+            fn.restype = ci
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise B200Error(load().b200_last_error().decode("utf-8", "replace"))
+
+
+def dptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))

@@ -1,0 +1,129 @@
+/*
+ * b200aqc.h -- C-ABI of libb200aqc.so, the B200 (sm_100a) simulation library behind
+ * ADAPT-AQC's backend interface.
+ *
+ * The reference (qiskit-community/adapt-aqc) is pure Python; its simulator "FFI" is the set
+ * of Python calls it makes into qiskit-aer / aqc_research.  Every entry point below replaces
+ * one of those call sites (cited as file:line under /root/reference).  INTEGRATION.md shows
+ * the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; b200_last_error() gives the text
+ *     (thread-local).  The Python host raises on any non-zero return: there is no CPU
+ *     fallback.
+ *   - opaque context handle; one context = one GPU + one CUDA stream; not thread-safe per ctx.
+ *   - caller-owned host buffers; complex numbers are interleaved (re, im) doubles.
+ *   - little-endian qubit order: basis index i = sum_q bit_q << q (qubit 0 = LSB), as
+ *     qiskit/Aer (adaptaqc/utils/utilityfunctions.py:145-149,220).
+ *   - a statevector context owns `n_slots` device buffers of 2^n complex128 ("slots");
+ *     slot ids are small integers chosen by the caller (work state, cached target state
+ *     U|0>, bra/ket halves of the Rotosolve evaluation ...).
+ */
+#ifndef B200AQC_H
+#define B200AQC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200AQC_ABI_VERSION 1
+
+/* Gate record, 40 bytes.  Gate names are those that reach the simulator after
+ * unroll_to_basis_gates (adaptaqc/utils/circuit_operations/circuit_operations_basic.py:204-205,
+ * circuit_operations_full_circuit.py:318-326): u3 cx cz rx ry rz x y z h (+ u1 u2 id from the
+ * DEFAULT_GATES unroll of the starting circuit), plus dense fall-backs for custom ansatz gates. */
+typedef struct {
+    int32_t op;   /* B200_OP_*                                             */
+    int32_t q0;   /* qubit (1q gates); control (cx); first qubit (2q)      */
+    int32_t q1;   /* target (cx); second qubit (2q); -1 for 1q gates       */
+    int32_t aux;  /* MAT1/MAT2: offset (in doubles) into the `mats` array  */
+    double p[3];  /* rx/ry/rz: theta; u1: lambda; u2: phi,lambda; u3: theta,phi,lambda */
+} b200_gate;
+
+enum {
+    B200_OP_ID = 0, B200_OP_X = 1, B200_OP_Y = 2, B200_OP_Z = 3, B200_OP_H = 4,
+    B200_OP_RX = 5, B200_OP_RY = 6, B200_OP_RZ = 7,
+    B200_OP_U1 = 8, B200_OP_U2 = 9, B200_OP_U3 = 10,
+    B200_OP_CX = 11, B200_OP_CZ = 12,
+    B200_OP_MAT1 = 13, /* dense 2x2, row-major, 8 doubles at mats[aux]                        */
+    B200_OP_MAT2 = 14, /* dense 4x4, row-major, index = bit(q0) + 2*bit(q1), 32 doubles       */
+    B200_OP_S = 15, B200_OP_SDG = 16, B200_OP_T = 17, B200_OP_TDG = 18, B200_OP_SX = 19,
+    B200_OP_SWAP = 20
+};
+
+typedef struct b200_ctx b200_ctx;
+
+/* ---- library / context ------------------------------------------------------------------ */
+int b200_abi_version(void);
+const char *b200_last_error(void);
+int b200_device_count(int *count);
+/* Replaces `Aer.get_backend("statevector_simulator")` / `AerSimulator(method=...)` object
+ * creation (adaptaqc/backends/aer_sv_backend.py:20, aer_mps_backend.py:37-42). */
+int b200_ctx_create(int device, b200_ctx **out);
+int b200_ctx_destroy(b200_ctx *ctx);
+int b200_ctx_sync(b200_ctx *ctx);
+/* Device-side counters since ctx creation: [0] kernels launched, [1] sweeps, [2] gates applied,
+ * [3] bytes of algorithmic statevector traffic (32*2^n per sweep, 16*2^n per read-only pass). */
+int b200_ctx_counters(b200_ctx *ctx, uint64_t out[4]);
+/* CUDA-event time (ms) of the kernels launched by the most recent b200_sv_* / b200_mps_* call. */
+int b200_ctx_last_ms(b200_ctx *ctx, double *ms);
+int b200_ctx_set_timing(b200_ctx *ctx, int enable);
+
+/* ---- statevector path ------------------------------------------------------------------- */
+/* (Re)allocate `n_slots` device statevectors of `num_qubits` qubits. */
+int b200_sv_alloc(b200_ctx *ctx, int num_qubits, int n_slots);
+/* Use caller-provided device memory (e.g. a torch CUDA tensor's data_ptr()) for one slot. */
+int b200_sv_attach(b200_ctx *ctx, int slot, void *device_ptr);
+int b200_sv_device_ptr(b200_ctx *ctx, int slot, void **out);
+int b200_sv_num_qubits(b200_ctx *ctx, int *out);
+
+/* slot <- |0...0> */
+int b200_sv_init_zero(b200_ctx *ctx, int slot);
+/* dst <- src (device copy) */
+int b200_sv_copy(b200_ctx *ctx, int dst_slot, int src_slot);
+
+/* dst <- G_{n-1} ... G_1 G_0 src.  src_slot = -1 means |0...0>.  dst may equal src.
+ * This is the replacement for `simulator.run(full_circuit).result().get_statevector()`
+ * (adaptaqc/backends/aer_sv_backend.py:42-47; circuit_operations_running.py:58-63): the gate
+ * stream is planned into fused sweeps on the host and executed by the sm_100a gate kernels;
+ * the state stays resident in HBM.  `mats` may be NULL when no MAT1/MAT2 op is present. */
+int b200_sv_run(b200_ctx *ctx, int dst_slot, int src_slot, const b200_gate *gates, int n_gates,
+                const double *mats, int n_mats);
+/* Same, applying the inverse circuit (gates reversed, each inverted): dst <- G_0^+ ... G_{n-1}^+ src */
+int b200_sv_run_inverse(b200_ctx *ctx, int dst_slot, int src_slot, const b200_gate *gates,
+                        int n_gates, const double *mats, int n_mats);
+
+/* out = amplitude <index|psi>  -> `sv[0]` in 1-|sv[0]|^2 (aer_sv_backend.py:29). */
+int b200_sv_amp(b200_ctx *ctx, int slot, uint64_t index, double out[2]);
+/* out[q] = <Z_q> for every qubit in one pass; out[n] = <psi|psi>.  Replaces the n separate
+ * `sv.probabilities([i])` passes (aer_sv_backend.py:49-59). */
+int b200_sv_expz(b200_ctx *ctx, int slot, double *out /* n+1 */);
+/* out[p] = 4x4 reduced density matrix (row-major, 32 doubles) of pairs[2p], pairs[2p+1]; the
+ * lower-numbered qubit of the pair is the least-significant matrix index, as
+ * qiskit.quantum_info.partial_trace returns it (adaptaqc/utils/entanglement_measures.py:325-340).
+ * All pairs from a few read passes instead of one re-simulation + host trace per pair
+ * (adaptaqc/compilers/adapt/adapt_compiler.py:964-975). */
+int b200_sv_pair_rdm(b200_ctx *ctx, int slot, const int32_t *pairs, int n_pairs, double *out);
+/* out = 2x2 complex M[i][j] = sum_rest conj(L[i,rest]) R[j,rest] for qubit q (row-major,
+ * 8 doubles).  <L|G_q|R> = sum_ij G[i][j] M[i][j] then gives the cost for ANY 1-qubit gate G
+ * on q, i.e. all Rotosolve / Rotoselect shift evaluations of one gate
+ * (adaptaqc/utils/cost_minimiser.py:318-368) from one launch.  q = -1: out[0..1] = <L|R>. */
+int b200_sv_inner(b200_ctx *ctx, int l_slot, int r_slot, int q, double out[8]);
+
+/* Host <-> device transfer of `count` amplitudes starting at `offset` (tests, small n, target
+ * upload).  Replaces the Statevector object's `.data`. */
+int b200_sv_download(b200_ctx *ctx, int slot, uint64_t offset, uint64_t count, double *host);
+int b200_sv_upload(b200_ctx *ctx, int slot, uint64_t offset, uint64_t count, const double *host);
+
+/* Planner introspection (no GPU needed): how many sweeps / rounds / fused ops the gate stream
+ * compiles to for an n-qubit state.  out = {sweeps, rounds, ops, small_path}. */
+int b200_sv_plan_stats(int num_qubits, const b200_gate *gates, int n_gates, const double *mats,
+                       int n_mats, int32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AQC_H */
