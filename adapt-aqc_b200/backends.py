@@ -114,7 +114,7 @@ class DeviceStatevector:
         if self.num_qubits == 2:
             sv = self.data
             return np.outer(sv, sv.conj())
-        hint = self._owner._pair_hint
+        hint = self._owner._current_pair_hint()
         if hint and tuple(sorted((a, b))) in hint and tuple(sorted((a, b))) not in self._rdm:
             self.pair_rdms(list(hint))
         return self.pair_rdms([(a, b)])[0]
@@ -152,6 +152,8 @@ class B200StatevectorSimulator:
 
 
 class B200SVBackend(_SVBase):
+    kind = "sv"  # what isinstance(backend, AerSVBackend) decides in the reference
+
     def __init__(self, device=0, simulator=None):
         self.device = device
         self._engine = None
@@ -249,6 +251,13 @@ class B200SVBackend(_SVBase):
         sv = self.evaluate_circuit(compiler)
         z, _ = sv.expectation_z()
         return [float(v) for v in z]
+
+    def _current_pair_hint(self):
+        if self._pair_hint:
+            return self._pair_hint
+        comp = self._compiler_ref() if self._compiler_ref is not None else None
+        cmap = getattr(comp, "coupling_map", None)
+        return {tuple(sorted(p)) for p in cmap} if cmap else None
 
     # ---- batched extensions (used by B200CostMinimiser / the compiler hooks) ----
     def set_pair_hint(self, pairs):

@@ -1,0 +1,150 @@
+"""Shared test helpers: random circuits, the benchmark circuit families, emulator driver."""
+import ctypes
+
+import numpy as np
+
+from adapt_aqc_b200.circuit import Circuit, Gate
+from adapt_aqc_b200.gates import GateStream
+
+
+def random_unitary(dim, rng):
+    a = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+    q, r = np.linalg.qr(a)
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+def random_gates(n, ng, rng, allow_mat=True):
+    """[(name, qubits, params)] over every opcode the C-ABI knows."""
+    names1 = ["x", "y", "z", "h", "s", "sdg", "t", "tdg", "sx", "rx", "ry", "rz", "u1", "u2", "u3", "id"]
+    names2 = ["cx", "cz", "swap"]
+    if allow_mat:
+        names1.append("mat1")
+        names2.append("mat2")
+    npar = {"rx": 1, "ry": 1, "rz": 1, "u1": 1, "u2": 2, "u3": 3}
+    out = []
+    for _ in range(ng):
+        if n < 2 or rng.random() < 0.55:
+            nm = names1[rng.integers(len(names1))]
+            q = [int(rng.integers(n))]
+            if nm == "mat1":
+                out.append((nm, q, random_unitary(2, rng)))
+            else:
+                out.append((nm, q, list(rng.uniform(-np.pi, np.pi, npar.get(nm, 0)))))
+        else:
+            nm = names2[rng.integers(len(names2))]
+            q = [int(x) for x in rng.choice(n, 2, replace=False)]
+            out.append((nm, q, random_unitary(4, rng) if nm == "mat2" else []))
+    return out
+
+
+def circuit_from_gates(n, gates):
+    c = Circuit(n)
+    for name, qubits, params in gates:
+        if name in ("mat1", "mat2"):
+            c.unitary(params, qubits)
+        else:
+            c.append(Gate(name, params), qubits)
+    return c
+
+
+def brickwork(n, depth, seed):
+    """SURVEY 8d C3/C5 target: layer l acts on pairs (i,i+1), i = l mod 2; brick = u3 on both
+    qubits then cx(i,i+1); angles uniform(-pi,pi) drawn in (layer, pair, qubit, param) order."""
+    rng = np.random.default_rng(seed)
+    c = Circuit(n)
+    for layer in range(depth):
+        for i in range(layer % 2, n - 1, 2):
+            for q in (i, i + 1):
+                t, p, l = rng.uniform(-np.pi, np.pi, 3)
+                c.u3(t, p, l, q)
+            c.cx(i, i + 1)
+    return c, rng
+
+
+def brickwall_pairs(n, layers):
+    """Pair order of AdaptConfig(method='brickwall') (adapt_compiler.py:803-825)."""
+    pairs = []
+    for _ in range(layers):
+        if not pairs or n == 2:
+            pairs.append((0, 1))
+            continue
+        prev = pairs[-1]
+        nxt = (prev[0] + 2, prev[1] + 2)
+        n_odd = n % 2
+        if nxt == (n, n + 1):
+            nxt = (1 - n_odd, 2 - n_odd)
+        elif nxt == (n - 1, n):
+            nxt = (0 + n_odd, 1 + n_odd)
+        pairs.append(nxt)
+    return pairs
+
+
+def thin_ansatz(n, layers, rng):
+    """`layers` thinly-dressed-CNOT layers (rz rz cx rz rz, basic.py:135-189) in brickwall order."""
+    c = Circuit(n)
+    for (a, b) in brickwall_pairs(n, layers):
+        th = rng.uniform(-np.pi, np.pi, 4)
+        c.rz(th[0], a, label="rz"); c.rz(th[1], b, label="rz")
+        c.cx(a, b)
+        c.rz(th[2], a, label="rz"); c.rz(th[3], b, label="rz")
+    return c
+
+
+def emu_run(emu, n, gates, psi0=None, inverse=False):
+    gs = gates if isinstance(gates, GateStream) else GateStream.from_gates(gates)
+    st = np.zeros(1 << n, dtype=np.complex128) if psi0 is None else np.array(psi0, dtype=np.complex128)
+    stats = (ctypes.c_int32 * 4)()
+    rc = emu.emu_sv_run(n, st.view(np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                        1 if psi0 is None else 0, gs.rec_ptr(), len(gs), gs.mats_ptr(), len(gs.mats),
+                        int(inverse), stats)
+    assert rc == 0, emu.emu_last_error()
+    return st, tuple(stats)
+
+
+class FakeEngine:
+    """CPU stand-in for SVEngine used by the `not gpu` host-logic tests: gate application goes
+    through the product planner + kernel thread bodies (tests/emu), read-outs through the oracle.
+    It exists only to exercise the evaluator / backend / compile-loop logic without a GPU."""
+
+    def __init__(self, emu, num_qubits, n_slots=4):
+        self.emu = emu
+        self.num_qubits = num_qubits
+        self.slots = [np.zeros(1 << num_qubits, dtype=np.complex128) for _ in range(n_slots)]
+        self.runs = 0
+        self.inners = 0
+
+    def close(self):
+        pass
+
+    def run(self, dst, src, stream, inverse=False):
+        psi0 = None if src < 0 else self.slots[src]
+        self.slots[dst], _ = emu_run(self.emu, self.num_qubits, stream, psi0=psi0, inverse=inverse)
+        self.runs += 1
+
+    def amp(self, slot, index=0):
+        return complex(self.slots[slot][index])
+
+    def expz(self, slot):
+        from oracle import sv_oracle as orc
+        psi = self.slots[slot]
+        return np.array(orc.measure_qubit_expectation_values(psi)), float(np.vdot(psi, psi).real)
+
+    def pair_rdm(self, slot, pairs):
+        from oracle import sv_oracle as orc
+        return np.array([orc.partial_trace(self.slots[slot], a, b) for a, b in pairs]).reshape(-1, 4, 4)
+
+    def inner(self, l_slot, r_slot, q=-1):
+        self.inners += 1
+        L, R = self.slots[l_slot], self.slots[r_slot]
+        if q < 0:
+            return complex(np.vdot(L, R))
+        n = self.num_qubits
+        Lt = np.moveaxis(L.reshape([2] * n), n - 1 - q, 0).reshape(2, -1)
+        Rt = np.moveaxis(R.reshape([2] * n), n - 1 - q, 0).reshape(2, -1)
+        return Lt.conj() @ Rt.T
+
+    def download(self, slot, offset=0, count=None):
+        return self.slots[slot][offset:None if count is None else offset + count].copy()
+
+    def upload(self, slot, host, offset=0):
+        self.slots[slot][offset:offset + len(host)] = host

@@ -1,0 +1,93 @@
+"""Planner + kernel thread bodies, run on the CPU (tests/emu), against the oracle.
+
+This is the `not gpu` safety net for the sm_100a sweep kernel: the *same* __host__ __device__
+functions the CUDA kernel calls are executed thread by thread on the host, driven by the same
+planner, and compared with the oracle on seeded random circuits."""
+import numpy as np
+import pytest
+
+from adapt_aqc_b200.gates import GateStream
+from adapt_aqc_b200.sv_engine import plan_stats
+from oracle import sv_oracle as orc
+from oracle.oracle_backends import circuit_to_gates
+
+from helpers import brickwork, emu_run, random_gates, thin_ansatz
+
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 10, 11, 12, 13, 15])
+def test_random_circuits_all_opcodes(emu, n):
+    rng = np.random.default_rng(1000 + n)
+    for trial in range(3):
+        gates = random_gates(n, int(rng.integers(1, 150)), rng)
+        ref = orc.evaluate_circuit(n, gates)
+        got, stats = emu_run(emu, n, gates)
+        np.testing.assert_allclose(got, ref, atol=TOL)
+        assert stats[3] == (1 if n <= 11 else 0)
+
+
+@pytest.mark.parametrize("n", [3, 11, 12, 14])
+def test_inverse_round_trip(emu, n):
+    rng = np.random.default_rng(2000 + n)
+    gates = random_gates(n, 80, rng)
+    psi, _ = emu_run(emu, n, gates)
+    back, _ = emu_run(emu, n, gates, psi0=psi, inverse=True)
+    e0 = np.zeros(1 << n, dtype=np.complex128); e0[0] = 1
+    np.testing.assert_allclose(back, e0, atol=TOL)
+
+
+def test_empty_and_identity_streams(emu):
+    for n in (2, 12):
+        got, _ = emu_run(emu, n, [])
+        assert got[0] == 1 and np.count_nonzero(got) == 1
+        got, _ = emu_run(emu, n, [("id", [0], []), ("id", [n - 1], [])])
+        assert got[0] == 1 and np.count_nonzero(got) == 1
+
+
+def test_brickwork_plus_ansatz_matches_oracle(emu):
+    n = 16
+    target, rng = brickwork(n, 4, seed=1234)
+    ansatz = thin_ansatz(n, 8, rng)
+    gates = circuit_to_gates(target) + circuit_to_gates(ansatz)
+    ref = orc.evaluate_circuit(n, gates)
+    got, stats = emu_run(emu, n, gates)
+    np.testing.assert_allclose(got, ref, atol=TOL)
+    # fused sweeps: far fewer passes over the state than gates
+    assert stats[0] <= len(gates) // 6
+
+
+def test_low_qubit_mixing_gets_load_and_store_rounds(emu):
+    """A mixing gate on a lane qubit (< 5) can be neither in the first nor in the last round."""
+    n = 13
+    gates = [("h", [0], []), ("cx", [0, 1], []), ("ry", [3], [0.4])]
+    ref = orc.evaluate_circuit(n, gates)
+    got, stats = emu_run(emu, n, gates)
+    np.testing.assert_allclose(got, ref, atol=TOL)
+    assert stats[0] == 1 and stats[1] == 3
+
+
+def test_diagonal_and_control_qubits_do_not_need_tile_slots(emu):
+    """rz / cz / cx-controls on 12 different high qubits still fit one sweep: only mixing targets
+    occupy tile slots."""
+    n = 20
+    gates = [("h", [19], [])]
+    for q in range(5, 19):
+        gates += [("rz", [q], [0.1 * q]), ("cz", [q, 19], [])]
+    gates += [("cx", [7, 19], []), ("cx", [12, 19], [])]
+    gs = GateStream.from_gates(gates)
+    assert plan_stats(n, gs)[0] == 1
+    ref = orc.evaluate_circuit(n, gates)
+    got, _ = emu_run(emu, n, gates)
+    np.testing.assert_allclose(got, ref, atol=TOL)
+
+
+def test_plan_for_c3_workload_is_a_few_sweeps():
+    """BASELINE config C3: 28-qubit depth-8 brickwork target, 16 thinly dressed layers."""
+    n = 28
+    target, rng = brickwork(n, 8, seed=1234)
+    ansatz = thin_ansatz(n, 16, rng)
+    t_stats = plan_stats(n, GateStream.from_circuit(target))
+    a_stats = plan_stats(n, GateStream.from_circuit(ansatz))
+    assert t_stats[0] <= 24, t_stats
+    assert a_stats[0] <= 3, a_stats
