@@ -77,6 +77,48 @@ struct Timer {
     }
 };
 
+// Brackets one kernel launch: counts it and, in profile mode, records an event pair around it.
+struct KScope {
+    b200_ctx* c;
+    int cls;
+    cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get_ev(b200_ctx* c) {
+        if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    KScope(b200_ctx* ctx, int k) : c(ctx), cls(k) {
+        c->counters[0] += 1;
+        if (c->profiling) {
+            a = get_ev(c); b = get_ev(c);
+            cudaEventRecord(a, c->stream);
+        }
+    }
+    ~KScope() {
+        if (a) {
+            cudaEventRecord(b, c->stream);
+            c->prof_recs.push_back({cls, a, b});
+        }
+    }
+};
+
+// Folds finished event pairs into the per-class accumulators (synchronises the stream).
+int prof_drain(b200_ctx* ctx) {
+    if (ctx->prof_recs.empty()) return 0;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (auto& r : ctx->prof_recs) {
+        float f = 0;
+        CUDA_TRY(cudaEventElapsedTime(&f, r.a, r.b));
+        ctx->prof_ms[r.cls] += f;
+        ctx->prof_n[r.cls] += 1;
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof_recs.clear();
+    return 0;
+}
+
 // Upload the plan (rounds, ops, mat2 table) in one pinned staging copy.
 int upload_plan(b200_ctx* ctx, const Plan& plan, const DevRound** d_rounds, const DevOp** d_ops,
                 const double** d_mat2) {
@@ -97,6 +139,7 @@ int upload_plan(b200_ctx* ctx, const Plan& plan, const DevRound** d_rounds, cons
     if (b_ops) std::memcpy(h + o_ops, plan.ops.data(), b_ops);
     if (b_mat2) std::memcpy(h + o_mat2, plan.mat2.data(), b_mat2);
     CUDA_TRY(cudaMemcpyAsync(ctx->d_plan, h, total, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->counters[4] += total;
     CUDA_TRY(cudaEventRecord(ctx->ev_plan, ctx->stream));
     ctx->plan_in_flight = true;
     *d_rounds = (const DevRound*)ctx->d_plan;
@@ -116,24 +159,31 @@ int run_plan(b200_ctx* ctx, int dst_slot, int src_slot, const Plan& plan) {
         const DevRound* d_rounds; const DevOp* d_ops; const double* d_mat2;
         if (upload_plan(ctx, plan, &d_rounds, &d_ops, &d_mat2)) return -1;
         const size_t smem = dim * sizeof(double2);
-        sv_small_kernel<<<1, 256, smem, ctx->stream>>>(src, dst, n, d_ops, (int)plan.ops.size(), d_mat2,
-                                                        src == nullptr ? 1 : 0);
+        {
+            KScope ks(ctx, B200_PROF_SMALL);
+            sv_small_kernel<<<1, 256, smem, ctx->stream>>>(src, dst, n, d_ops, (int)plan.ops.size(), d_mat2,
+                                                            src == nullptr ? 1 : 0);
+        }
         CUDA_TRY(cudaGetLastError());
-        ctx->counters[0] += 1; ctx->counters[1] += 1;
+        ctx->counters[1] += 1;
         ctx->counters[2] += plan.n_gates_in; ctx->counters[3] += 32 * dim;
         tm.stop();
         return 0;
     }
 
     if (src == nullptr) {
-        sv_init_zero_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(dst, dim);
+        {
+            KScope ks(ctx, B200_PROF_FILL);
+            sv_init_zero_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(dst, dim);
+        }
         CUDA_TRY(cudaGetLastError());
-        ctx->counters[0] += 1;
         src = dst;
     }
     if (plan.sweeps.empty()) {
-        if (src != dst)
+        if (src != dst) {
+            KScope ks(ctx, B200_PROF_FILL);
             CUDA_TRY(cudaMemcpyAsync(dst, src, dim * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         tm.stop();
         return 0;
     }
@@ -145,11 +195,14 @@ int run_plan(b200_ctx* ctx, int dst_slot, int src_slot, const Plan& plan) {
         const size_t smem = nr > 1 ? ((size_t)1 << TILE_BITS) * sizeof(double2) : 0;
         const int per_sm = nr > 1 ? ctx->sweep_occ_smem : ctx->sweep_occ_nosmem;
         const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * per_sm * ctx->grid_mult);
-        sv_sweep_kernel<REG_BITS><<<grid, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, d_rounds, d_ops,
-                                                                               d_mat2, ntiles);
+        {
+            KScope ks(ctx, B200_PROF_SWEEP);
+            sv_sweep_kernel<REG_BITS><<<grid, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, d_rounds, d_ops,
+                                                                                   d_mat2, ntiles);
+        }
         CUDA_TRY(cudaGetLastError());
         src = dst;
-        ctx->counters[0] += 1; ctx->counters[1] += 1; ctx->counters[3] += 32 * dim;
+        ctx->counters[1] += 1; ctx->counters[3] += 32 * dim;
     }
     ctx->counters[2] += plan.n_gates_in;
     tm.stop();
@@ -175,6 +228,7 @@ int sv_run_impl(b200_ctx* ctx, int dst_slot, int src_slot, const b200_gate* gate
     CUDA_TRY(cudaSetDevice(ctx->device));
     Plan plan;
     if (make_plan(ctx->nq, gates, n_gates, mats, n_mats, inverse, plan)) return -1;
+    ctx->counters[6] += 1;
     return run_plan(ctx, dst_slot, src_slot, plan);
 }
 
@@ -183,6 +237,7 @@ int fetch_out(b200_ctx* ctx, double* out, int count) {
     CUDA_TRY(cudaMemcpyAsync(ctx->h_out, ctx->d_out, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     std::memcpy(out, ctx->h_out, count * sizeof(double));
+    ctx->counters[5] += count * sizeof(double);
     return 0;
 }
 
@@ -225,6 +280,8 @@ int b200_ctx_create(int device, b200_ctx** out) {
     CUDA_TRY(cudaEventCreate(&ctx->ev0));
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_plan, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreate(&ctx->ev_mark[0]));
+    CUDA_TRY(cudaEventCreate(&ctx->ev_mark[1]));
     const size_t tile_bytes = ((size_t)1 << TILE_BITS) * sizeof(double2);
     CUDA_TRY(cudaFuncSetAttribute(sv_sweep_kernel<REG_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tile_bytes));
@@ -256,6 +313,10 @@ int b200_ctx_destroy(b200_ctx* ctx) {
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_plan);
+    cudaEventDestroy(ctx->ev_mark[0]);
+    cudaEventDestroy(ctx->ev_mark[1]);
+    for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -267,9 +328,41 @@ int b200_ctx_sync(b200_ctx* ctx) {
     return 0;
 }
 
-int b200_ctx_counters(b200_ctx* ctx, uint64_t out[4]) {
+int b200_ctx_counters(b200_ctx* ctx, uint64_t out[8]) {
     if (!ctx || !out) return set_error("null pointer");
-    for (int k = 0; k < 4; ++k) out[k] = ctx->counters[k];
+    for (int k = 0; k < 8; ++k) out[k] = ctx->counters[k];
+    return 0;
+}
+
+int b200_ctx_mark(b200_ctx* ctx, int which) {
+    if (!ctx) return set_error("null context");
+    if (which < 0 || which > 1) return set_error("mark index must be 0 or 1");
+    CUDA_TRY(cudaEventRecord(ctx->ev_mark[which], ctx->stream));
+    return 0;
+}
+
+int b200_ctx_elapsed_ms(b200_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return set_error("null pointer");
+    CUDA_TRY(cudaEventSynchronize(ctx->ev_mark[1]));
+    float f = 0;
+    CUDA_TRY(cudaEventElapsedTime(&f, ctx->ev_mark[0], ctx->ev_mark[1]));
+    *ms = f;
+    return 0;
+}
+
+int b200_ctx_profile(b200_ctx* ctx, int enable) {
+    if (!ctx) return set_error("null context");
+    if (prof_drain(ctx)) return -1;
+    ctx->profiling = enable != 0;
+    if (enable)
+        for (int k = 0; k < B200_PROF_CLASSES; ++k) { ctx->prof_ms[k] = 0; ctx->prof_n[k] = 0; }
+    return 0;
+}
+
+int b200_ctx_profile_read(b200_ctx* ctx, double ms[B200_PROF_CLASSES], uint64_t launches[B200_PROF_CLASSES]) {
+    if (!ctx || !ms || !launches) return set_error("null pointer");
+    if (prof_drain(ctx)) return -1;
+    for (int k = 0; k < B200_PROF_CLASSES; ++k) { ms[k] = ctx->prof_ms[k]; launches[k] = ctx->prof_n[k]; }
     return 0;
 }
 
@@ -345,9 +438,11 @@ int b200_sv_init_zero(b200_ctx* ctx, int slot) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     const uint64_t dim = 1ull << ctx->nq;
     const int grid = (int)std::min<uint64_t>((dim + 255) / 256, (uint64_t)ctx->num_sms * 8);
-    sv_init_zero_kernel<<<grid, 256, 0, ctx->stream>>>((double2*)ctx->slots[slot], dim);
+    {
+        KScope ks(ctx, B200_PROF_FILL);
+        sv_init_zero_kernel<<<grid, 256, 0, ctx->stream>>>((double2*)ctx->slots[slot], dim);
+    }
     CUDA_TRY(cudaGetLastError());
-    ctx->counters[0] += 1;
     return 0;
 }
 
@@ -355,6 +450,7 @@ int b200_sv_copy(b200_ctx* ctx, int dst_slot, int src_slot) {
     if (check_slot(ctx, dst_slot) || check_slot(ctx, src_slot)) return -1;
     if (dst_slot == src_slot) return 0;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    KScope ks(ctx, B200_PROF_FILL);
     CUDA_TRY(cudaMemcpyAsync(ctx->slots[dst_slot], ctx->slots[src_slot], ((size_t)1 << ctx->nq) * sizeof(double2),
                              cudaMemcpyDeviceToDevice, ctx->stream));
     return 0;
@@ -379,6 +475,8 @@ int b200_sv_amp(b200_ctx* ctx, int slot, uint64_t index, double out[2]) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     out[0] = ctx->h_out[0];
     out[1] = ctx->h_out[1];
+    ctx->counters[5] += sizeof(double2);
+    ctx->counters[6] += 1;
     return 0;
 }
 
@@ -390,19 +488,27 @@ int b200_sv_expz(b200_ctx* ctx, int slot, double* out) {
     const double2* psi = (const double2*)ctx->slots[slot];
     Timer tm(ctx);
     if (n <= SMALL_MAX_QUBITS) {
-        sv_expz_small_kernel<<<1, 64, 0, ctx->stream>>>(psi, n, ctx->d_out);
+        {
+            KScope ks(ctx, B200_PROF_EXPZ);
+            sv_expz_small_kernel<<<1, 64, 0, ctx->stream>>>(psi, n, ctx->d_out);
+        }
         CUDA_TRY(cudaGetLastError());
-        ctx->counters[0] += 1;
     } else {
         const int tb = std::min(n - 3, 17), kb = n - tb;
         const int nblocks = 1 << (tb - 8);
-        sv_expz_kernel<<<nblocks, RED_THREADS, 0, ctx->stream>>>(psi, tb, kb, ctx->d_partial);
+        {
+            KScope ks(ctx, B200_PROF_EXPZ);
+            sv_expz_kernel<<<nblocks, RED_THREADS, 0, ctx->stream>>>(psi, tb, kb, ctx->d_partial);
+        }
         CUDA_TRY(cudaGetLastError());
-        sv_expz_final_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, nblocks, n, tb, ctx->d_out);
+        {
+            KScope ks(ctx, B200_PROF_REDUCE);
+            sv_expz_final_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, nblocks, n, tb, ctx->d_out);
+        }
         CUDA_TRY(cudaGetLastError());
-        ctx->counters[0] += 2;
     }
     ctx->counters[3] += 16ull << n;
+    ctx->counters[6] += 1;
     tm.stop();
     return fetch_out(ctx, out, n + 1);
 }
@@ -441,11 +547,17 @@ int b200_sv_pair_rdm(b200_ctx* ctx, int slot, const int32_t* pairs, int n_pairs,
             }
             if (best < 0 || best_gain == 0) {
                 const int grid = red_grid(ctx, 1ull << (n - 2));
-                sv_rdm2_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>(psi, n, lo, hi, ctx->d_partial);
+                {
+                    KScope ks(ctx, B200_PROF_RDM);
+                    sv_rdm2_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>(psi, n, lo, hi, ctx->d_partial);
+                }
                 CUDA_TRY(cudaGetLastError());
-                reduce_partials_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, grid, 16, ctx->d_out);
+                {
+                    KScope ks(ctx, B200_PROF_REDUCE);
+                    reduce_partials_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, grid, 16, ctx->d_out);
+                }
                 CUDA_TRY(cudaGetLastError());
-                ctx->counters[0] += 2; ctx->counters[3] += 16ull << n;
+                ctx->counters[3] += 16ull << n;
                 double r[16];
                 if (fetch_out(ctx, r, 16)) return -1;
                 std::memcpy(&acc[(size_t)(lo * n + hi) * 16], r, sizeof r);
@@ -454,11 +566,17 @@ int b200_sv_pair_rdm(b200_ctx* ctx, int slot, const int32_t* pairs, int n_pairs,
                 int q[3] = {lo, hi, best};
                 std::sort(q, q + 3);
                 const int grid = red_grid(ctx, 1ull << (n - 3));
-                sv_rdm3_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>(psi, n, q[0], q[1], q[2], ctx->d_partial);
+                {
+                    KScope ks(ctx, B200_PROF_RDM);
+                    sv_rdm3_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>(psi, n, q[0], q[1], q[2], ctx->d_partial);
+                }
                 CUDA_TRY(cudaGetLastError());
-                reduce_partials_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, grid, RDM3_WIDTH, ctx->d_out);
+                {
+                    KScope ks(ctx, B200_PROF_REDUCE);
+                    reduce_partials_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, grid, RDM3_WIDTH, ctx->d_out);
+                }
                 CUDA_TRY(cudaGetLastError());
-                ctx->counters[0] += 2; ctx->counters[3] += 16ull << n;
+                ctx->counters[3] += 16ull << n;
                 double r[RDM3_WIDTH];
                 if (fetch_out(ctx, r, RDM3_WIDTH)) return -1;
                 const int pl[3][2] = {{q[0], q[1]}, {q[0], q[2]}, {q[1], q[2]}};
@@ -495,12 +613,19 @@ int b200_sv_inner(b200_ctx* ctx, int l_slot, int r_slot, int q, double out[8]) {
     const int n = ctx->nq;
     Timer tm(ctx);
     const int grid = red_grid(ctx, q < 0 ? (1ull << n) : (1ull << (n - 1)));
-    sv_inner_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>((const double2*)ctx->slots[l_slot],
-                                                           (const double2*)ctx->slots[r_slot], n, q, ctx->d_partial);
+    {
+        KScope ks(ctx, B200_PROF_INNER);
+        sv_inner_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>((const double2*)ctx->slots[l_slot],
+                                                               (const double2*)ctx->slots[r_slot], n, q, ctx->d_partial);
+    }
     CUDA_TRY(cudaGetLastError());
-    reduce_partials_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, grid, INNER_WIDTH, ctx->d_out);
+    {
+        KScope ks(ctx, B200_PROF_REDUCE);
+        reduce_partials_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, grid, INNER_WIDTH, ctx->d_out);
+    }
     CUDA_TRY(cudaGetLastError());
-    ctx->counters[0] += 2; ctx->counters[3] += 32ull << n;
+    ctx->counters[3] += 32ull << n;
+    ctx->counters[6] += 1;
     tm.stop();
     return fetch_out(ctx, out, 8);
 }
@@ -512,6 +637,7 @@ int b200_sv_download(b200_ctx* ctx, int slot, uint64_t offset, uint64_t count, d
     CUDA_TRY(cudaMemcpyAsync(host, (const double2*)ctx->slots[slot] + offset, count * sizeof(double2),
                              cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->counters[5] += count * sizeof(double2);
     return 0;
 }
 
@@ -522,6 +648,7 @@ int b200_sv_upload(b200_ctx* ctx, int slot, uint64_t offset, uint64_t count, con
     CUDA_TRY(cudaMemcpyAsync((double2*)ctx->slots[slot] + offset, host, count * sizeof(double2),
                              cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->counters[4] += count * sizeof(double2);
     return 0;
 }
 

@@ -6,6 +6,8 @@
 #include <string>
 #include <vector>
 
+#include "b200aqc.h"
+
 namespace b200 {
 extern thread_local std::string g_last_error;
 int set_error(const std::string& msg);
@@ -52,7 +54,18 @@ struct b200_ctx {
     int sweep_occ_smem = 1, sweep_occ_nosmem = 1;
     int grid_mult = 1;
 
-    uint64_t counters[4] = {0, 0, 0, 0};
+    uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    // bench marks (b200_ctx_mark / b200_ctx_elapsed_ms)
+    cudaEvent_t ev_mark[2] = {nullptr, nullptr};
+
+    // per-kernel-class profile (b200_ctx_profile*): event pairs around every launch
+    bool profiling = false;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[B200_PROF_CLASSES] = {0};
+    uint64_t prof_n[B200_PROF_CLASSES] = {0};
 
     b200::MpsState* mps = nullptr;
 };

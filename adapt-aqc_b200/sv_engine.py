@@ -116,9 +116,31 @@ class SVEngine:
         check(self._lib.b200_ctx_sync(self._ctx))
 
     def counters(self):
-        out = (ctypes.c_uint64 * 4)()
+        out = (ctypes.c_uint64 * 8)()
         check(self._lib.b200_ctx_counters(self._ctx, out))
-        return {"launches": out[0], "sweeps": out[1], "gates": out[2], "bytes": out[3]}
+        return {"launches": out[0], "sweeps": out[1], "gates": out[2], "bytes": out[3],
+                "h2d_bytes": out[4], "d2h_bytes": out[5], "calls": out[6]}
+
+    def mark(self, which):
+        """Record bench event 0 (start) / 1 (stop) on the context's stream."""
+        check(self._lib.b200_ctx_mark(self._ctx, int(which)))
+
+    def elapsed_ms(self):
+        ms = ctypes.c_double()
+        check(self._lib.b200_ctx_elapsed_ms(self._ctx, ctypes.byref(ms)))
+        return ms.value
+
+    PROF_CLASSES = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps")
+
+    def profile(self, enable=True):
+        check(self._lib.b200_ctx_profile(self._ctx, 1 if enable else 0))
+
+    def profile_read(self):
+        """{class: (total_ms, launches)} of the kernels launched since profile(True)."""
+        ms = (ctypes.c_double * 8)()
+        cnt = (ctypes.c_uint64 * 8)()
+        check(self._lib.b200_ctx_profile_read(self._ctx, ms, cnt))
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(self.PROF_CLASSES)}
 
     def set_timing(self, enable=True):
         check(self._lib.b200_ctx_set_timing(self._ctx, 1 if enable else 0))

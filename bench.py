@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- cost evaluations / second of the ADAPT-AQC hot path on B200 (BASELINE.json metric).
+
+Workload: 28-qubit brickwork target (depth 8, seed 1234) + 16 thinly
+dressed CNOT layers in brickwall order.  One STEP = the evaluation stream the reference optimiser
+issues for one layer: Rotoselect over the newest layer (4 rotations x 7 costs,
+cost_minimiser.py:318-342) followed by one Rotosolve cycle over all 64 rotations (3 costs each,
+cost_minimiser.py:344-368) = 220 cost evaluations.
+
+  value   : evals/s with everything resident in HBM, batched front end (B200CostMinimiser: one
+            transfer-matrix launch serves all shift values of a gate).
+  e2e     : evals/s through the reference-facing interface -- the unmodified CostMinimiser asking
+            backend.evaluate_global_cost(compiler) for ONE scalar per call; the circuit lives on
+            the host, every call ships gate records / plans to the device and reads the
+            amplitude back (bytes counted by the library).
+  roofline: the fused gate-sweep kernel (sv_sweep_kernel), 32 * 2^n algorithmic bytes per
+            launch, timed per launch with CUDA events on the library's stream.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, full re-simulation of
+every gate from |0..0> per evaluation, aer_sv_backend.py:37-47) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "cost_evals_per_sec"
+UNIT = "evals/s"
+
+
+def build_workload(n, depth, layers, seed=1234):
+    from helpers import brickwork, thin_ansatz
+    target, rng = brickwork(n, depth, seed)
+    ansatz = thin_ansatz(n, layers, rng)
+    return target, ansatz
+
+
+def make_compiler(target, ansatz, backend, batched):
+    from adapt_aqc_b200.compiler import AdaptCompiler
+    from adapt_aqc_b200.minimiser import B200CostMinimiser
+    comp = AdaptCompiler(target, backend=backend, minimiser_cls=B200CostMinimiser if batched else None)
+    comp.full_circuit.data.extend(ansatz.copy().data)
+    return comp
+
+
+def one_step(comp, n_layer_gates=5):
+    """Rotoselect over the newest layer, then one Rotosolve cycle over the whole ansatz."""
+    lo, hi = comp.variational_circuit_range()
+    comp.minimizer._reduce_cost(True, (hi - n_layer_gates, hi))
+    comp.minimizer._reduce_cost(False, (lo, hi))
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback"
+
+
+def cpu_baseline_sample(n, target, ansatz, budget_s=20.0):
+    """CPU restatement of the reference path, bounded sample: the reference re-simulates ALL G
+    gates of full_circuit from |0..0> for every evaluation; time the first k gates at full size
+    (k chosen to fit the budget) and scale to G."""
+    from oracle import sv_oracle as orc
+    from oracle.oracle_backends import circuit_to_gates
+    gates = circuit_to_gates(target) + circuit_to_gates(ansatz)
+    G = len(gates)
+    cores = orc.num_threads()
+    # calibrate on 4 gates, then size the sample
+    psi = np.zeros(1 << n, dtype=np.complex128); psi[0] = 1
+    rec, mats = orc.pack_gates(gates[:4])
+    t0 = time.perf_counter()
+    orc.lib().orc_sv_apply(n, psi.view(np.float64).ctypes.data_as(orc.ctypes.POINTER(orc.ctypes.c_double)),
+                           rec.ctypes.data, len(rec), mats.ctypes.data_as(orc.ctypes.POINTER(orc.ctypes.c_double)))
+    per_gate = (time.perf_counter() - t0) / 4
+    k = int(max(8, min(G - 4, budget_s / max(per_gate, 1e-9))))
+    rec, mats = orc.pack_gates(gates[4:4 + k])
+    t0 = time.perf_counter()
+    orc.lib().orc_sv_apply(n, psi.view(np.float64).ctypes.data_as(orc.ctypes.POINTER(orc.ctypes.c_double)),
+                           rec.ctypes.data, len(rec), mats.ctypes.data_as(orc.ctypes.POINTER(orc.ctypes.c_double)))
+    dt = time.perf_counter() - t0
+    per_gate = dt / k
+    evals_per_s = 1.0 / (per_gate * G)
+    sample = (f"{k} of the {G} gates of one full re-simulation at n={n} ({dt:.1f} s), scaled x{G}/{k}; "
+              f"per-gate sweeps, no gate fusion")
+    return {"value": evals_per_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n = args.qubits
+    target, ansatz = build_workload(n, args.depth, args.layers)
+    vals = []
+    total = args.warmup + args.steps
+    budget = max(3.0, min(20.0, 150.0 / max(1, total)))
+    base = None
+    t_all = time.perf_counter()
+    for i in range(total):
+        base = cpu_baseline_sample(n, target, ansatz, budget_s=budget)
+        if i >= args.warmup:
+            vals.append(base["value"])
+    v = float(np.mean(vals))
+    base["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * 220 / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
+        "config": workload_config(args), "cpu_baseline": base,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"C3: {args.qubits}-qubit brickwork(depth={args.depth}, seed=1234) target + {args.layers} "
+                        "thinly-dressed CNOT layers; step = Rotoselect(last layer) + Rotosolve cycle(all rotations)",
+            "qubits": args.qubits, "target_depth": args.depth, "ansatz_layers": args.layers,
+            "evals_per_step": 220 if args.layers == 16 else None,
+            "l2": "inputs larger than L2 (each statevector is 16*2^n bytes)",
+            "parallelism": f"replicas x{args.gpus}" if args.gpus > 1 else "single GPU"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--qubits", type=int, default=28)
+    ap.add_argument("--depth", type=int, default=8)
+    ap.add_argument("--layers", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import adapt_aqc_b200  # noqa: F401
+    from adapt_aqc_b200.backends import B200SVBackend
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    n = args.qubits
+    target, ansatz = build_workload(n, args.depth, args.layers)
+
+    # ---- value leg: batched front end, HBM-resident ---------------------------------------------
+    backend = B200SVBackend(device=local_rank)
+    comp = make_compiler(target, ansatz, backend, batched=True)
+    comp.evaluate_cost()                     # builds U|0> (slot BASE) and allocates the engine
+    eng = backend._engine
+    for _ in range(args.warmup):
+        one_step(comp)
+    eng.sync()
+    sampler = ClockSampler(local_rank)
+    c0 = eng.counters()
+    e0 = comp.cost_evaluation_counter
+    barrier()
+    sampler.start()
+    eng.profile(True)
+    eng.mark(0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step(comp)
+    eng.mark(1)
+    dev_ms = eng.elapsed_ms()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    prof = eng.profile_read()
+    eng.profile(False)
+    clocks = sampler.stop()
+    c1 = eng.counters()
+    evals = comp.cost_evaluation_counter - e0
+    launches = c1["launches"] - c0["launches"]
+
+    # ---- e2e leg: the reference-facing one-scalar-per-call interface ----------------------------
+    backend2 = backend            # same engine / same cached U|0>: the interface is what changes
+    comp2 = make_compiler(target, ansatz, backend2, batched=False)
+    comp2.evaluate_cost()
+    for _ in range(args.warmup):
+        one_step(comp2)
+    eng.sync()
+    d0 = eng.counters()
+    f0 = comp2.cost_evaluation_counter
+    barrier()
+    eng.mark(0)
+    for _ in range(args.steps):
+        one_step(comp2)
+    eng.mark(1)
+    e2e_ms = eng.elapsed_ms()
+    d1 = eng.counters()
+    e2e_evals = comp2.cost_evaluation_counter - f0
+
+    # ---- max over ranks ------------------------------------------------------------------------
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        cnt = torch.tensor([evals, e2e_evals, launches], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        evals, e2e_evals, launches = float(cnt[0]), float(cnt[1]), int(cnt[2])
+
+    value = evals / (dev_ms * 1e-3)
+    e2e_value = e2e_evals / (e2e_ms * 1e-3)
+
+    sweep_ms, sweep_n = prof["sweep"]
+    peak, peak_kind = measured_peak_hbm()
+    alg_bytes = 32.0 * (1 << n)
+    achieved = alg_bytes / (sweep_ms / max(1, sweep_n) * 1e-3) / 1e9 if sweep_n else None
+    roofline = {"bound": "hbm", "kernel": "sv_sweep_kernel", "achieved": achieved, "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                "traffic": None, "bytes_per_launch": alg_bytes, "launches": int(sweep_n),
+                "avg_launch_ms": sweep_ms / max(1, sweep_n),
+                "share_of_step": sweep_ms / dev_ms if world == 1 else None,
+                "other_kernels_ms": {k: round(v[0], 3) for k, v in prof.items() if k != "sweep" and v[1]}}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "complex128", "data": "synthetic", "config": workload_config(args),
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": (d1["h2d_bytes"] - d0["h2d_bytes"]) / args.steps,
+                "d2h_bytes_per_step": (d1["d2h_bytes"] - d0["d2h_bytes"]) / args.steps,
+                "ms_per_step": e2e_ms / args.steps, "evals_per_step": e2e_evals / args.steps / max(1, world)},
+        "roofline": roofline, "host_wall_ms_per_step": wall_ms / args.steps,
+        "evaluator_stats": dict(backend._evaluator.stats),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample(n, target, ansatz, budget_s=15.0)
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

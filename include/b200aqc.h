@@ -65,9 +65,31 @@ int b200_device_count(int *count);
 int b200_ctx_create(int device, b200_ctx **out);
 int b200_ctx_destroy(b200_ctx *ctx);
 int b200_ctx_sync(b200_ctx *ctx);
-/* Device-side counters since ctx creation: [0] kernels launched, [1] sweeps, [2] gates applied,
- * [3] bytes of algorithmic statevector traffic (32*2^n per sweep, 16*2^n per read-only pass). */
-int b200_ctx_counters(b200_ctx *ctx, uint64_t out[4]);
+/* Counters since ctx creation: [0] kernels launched, [1] sweeps, [2] gates applied,
+ * [3] bytes of algorithmic statevector traffic (32*2^n per sweep, 16*2^n per read-only pass),
+ * [4] host->device bytes copied, [5] device->host bytes copied, [6] C-ABI compute calls,
+ * [7] reserved. */
+int b200_ctx_counters(b200_ctx *ctx, uint64_t out[8]);
+/* Bench brackets: record CUDA event `which` (0 = start, 1 = stop) on the context's stream;
+ * elapsed_ms synchronises on the stop event and returns stop - start. */
+int b200_ctx_mark(b200_ctx *ctx, int which);
+int b200_ctx_elapsed_ms(b200_ctx *ctx, double *ms);
+/* Per-kernel-class device times: while enabled, every kernel launch is bracketed by its own CUDA
+ * event pair on the context's stream.  enable != 0 also resets the accumulators.  profile_read
+ * synchronises the stream and returns, per class, the summed milliseconds and launch count. */
+#define B200_PROF_CLASSES 8
+enum {
+    B200_PROF_SWEEP = 0,  /* sv_sweep_kernel (fused gate sweep, tiled path)  */
+    B200_PROF_SMALL = 1,  /* sv_small_kernel (n <= 11, one CTA)              */
+    B200_PROF_EXPZ = 2,   /* all-qubit <Z> pass                              */
+    B200_PROF_RDM = 3,    /* pair-RDM passes                                 */
+    B200_PROF_INNER = 4,  /* <L|.|R> transfer-matrix pass                    */
+    B200_PROF_FILL = 5,   /* |0..0> fill / device copies                     */
+    B200_PROF_REDUCE = 6, /* final fixed-order reductions                    */
+    B200_PROF_MPS = 7     /* MPS kernels                                     */
+};
+int b200_ctx_profile(b200_ctx *ctx, int enable);
+int b200_ctx_profile_read(b200_ctx *ctx, double ms[B200_PROF_CLASSES], uint64_t launches[B200_PROF_CLASSES]);
 /* CUDA-event time (ms) of the kernels launched by the most recent b200_sv_* / b200_mps_* call. */
 int b200_ctx_last_ms(b200_ctx *ctx, double *ms);
 int b200_ctx_set_timing(b200_ctx *ctx, int enable);

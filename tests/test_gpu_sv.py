@@ -1,0 +1,370 @@
+"""GPU parity tests of the statevector path: everything goes through the C-ABI of libb200aqc.so
+(ctypes, adapt_aqc_b200.lib) and is compared with the CPU oracle on the same seeded inputs.
+
+Tolerances: BASELINE north_star asks for overlap/cost within 1e-10 absolute (complex128); the
+amplitude-level checks here use 1e-12.  Pair selection must be identical."""
+import ctypes
+import pickle
+
+import numpy as np
+import pytest
+
+from adapt_aqc_b200 import lib as blib
+from adapt_aqc_b200 import measures as em
+from adapt_aqc_b200.backends import B200SVBackend
+from adapt_aqc_b200.circuit import Circuit
+from adapt_aqc_b200.compiler import (CMAP_LINEAR, AdaptCompiler, AdaptConfig, generate_coupling_map)
+from adapt_aqc_b200.gates import GateStream
+from adapt_aqc_b200.minimiser import B200CostMinimiser
+from adapt_aqc_b200.sv_engine import SLOT_BASE, SLOT_L, SLOT_R, SLOT_WORK, SVCostEvaluator, SVEngine
+from oracle import sv_oracle as orc
+from oracle.oracle_backends import OracleSVBackend, circuit_to_gates
+
+from helpers import brickwork, circuit_from_gates, random_gates, thin_ansatz
+
+pytestmark = pytest.mark.gpu
+
+AMP_TOL = 1e-12
+COST_TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def backend():
+    return B200SVBackend()
+
+
+# ---- b200_sv_run / run_inverse ------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 11, 12, 13, 14, 17, 20, 22])
+def test_run_matches_oracle_all_opcodes(n):
+    rng = np.random.default_rng(4000 + n)
+    eng = SVEngine(n, n_slots=2)
+    for trial in range(3):
+        gates = random_gates(n, int(rng.integers(1, 120)), rng)
+        ref = orc.evaluate_circuit(n, gates)
+        eng.run(0, -1, GateStream.from_gates(gates))
+        np.testing.assert_allclose(eng.download(0), ref, atol=AMP_TOL)
+    eng.close()
+
+
+@pytest.mark.parametrize("n", [4, 12, 16, 21])
+def test_run_from_slot_and_inverse_round_trip(n):
+    rng = np.random.default_rng(4100 + n)
+    eng = SVEngine(n, n_slots=3)
+    g1 = random_gates(n, 60, rng)
+    g2 = random_gates(n, 60, rng)
+    eng.run(0, -1, GateStream.from_gates(g1))
+    eng.run(1, 0, GateStream.from_gates(g2))       # out of place
+    ref1 = orc.evaluate_circuit(n, g1)
+    ref12 = orc.apply_gates(ref1, g2)
+    np.testing.assert_allclose(eng.download(0), ref1, atol=AMP_TOL)
+    np.testing.assert_allclose(eng.download(1), ref12, atol=AMP_TOL)
+    eng.run(1, 1, GateStream.from_gates(g2), inverse=True)   # in place, inverse
+    np.testing.assert_allclose(eng.download(1), ref1, atol=AMP_TOL)
+    eng.run(1, 1, GateStream.from_gates(g1), inverse=True)
+    e0 = np.zeros(1 << n, dtype=np.complex128); e0[0] = 1
+    np.testing.assert_allclose(eng.download(1), e0, atol=AMP_TOL)
+    assert abs(eng.amp(1, 0) - 1) < AMP_TOL
+    eng.close()
+
+
+def test_empty_stream_copy_upload_download():
+    n = 13
+    eng = SVEngine(n, n_slots=2)
+    eng.run(0, -1, GateStream.from_gates([]))
+    psi = eng.download(0)
+    assert psi[0] == 1 and np.count_nonzero(psi) == 1
+    rng = np.random.default_rng(1)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    eng.upload(1, v)
+    eng.run(0, 1, GateStream.from_gates([]))    # empty stream = copy
+    np.testing.assert_array_equal(eng.download(0), v)
+    np.testing.assert_array_equal(eng.download(0, 100, 50), v[100:150])
+    eng.copy(1, 0)
+    assert eng.amp(1, 77) == v[77]
+    eng.close()
+
+
+# ---- read-outs ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 5, 11, 12, 13, 16, 19, 21])
+def test_expz_matches_oracle(n):
+    rng = np.random.default_rng(4200 + n)
+    gates = random_gates(n, 60, rng)
+    ref = orc.evaluate_circuit(n, gates)
+    eng = SVEngine(n, n_slots=1)
+    eng.run(0, -1, GateStream.from_gates(gates))
+    z, norm = eng.expz(0)
+    np.testing.assert_allclose(z, orc.measure_qubit_expectation_values(ref), atol=AMP_TOL)
+    assert abs(norm - 1) < AMP_TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 6, 12, 15, 18])
+def test_pair_rdm_matches_oracle_for_every_pair(n):
+    rng = np.random.default_rng(4300 + n)
+    gates = random_gates(n, 80, rng)
+    ref = orc.evaluate_circuit(n, gates)
+    eng = SVEngine(n, n_slots=1)
+    eng.run(0, -1, GateStream.from_gates(gates))
+    pairs = [(a, b) for a in range(n) for b in range(n) if a != b]
+    if n > 8:
+        pairs = [pairs[i] for i in rng.choice(len(pairs), 40, replace=False)]
+    rho = eng.pair_rdm(0, pairs)
+    for r, (a, b) in zip(rho, pairs):
+        if n == 2:
+            lo_first = ref if a < b else ref  # 2 qubits: RDM of the whole (pure) state
+            expect = np.outer(lo_first, lo_first.conj())
+        else:
+            expect = orc.partial_trace(ref, a, b)
+        np.testing.assert_allclose(r, expect, atol=AMP_TOL)
+        assert abs(np.trace(r) - 1) < AMP_TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("n", [3, 12, 17])
+def test_inner_matches_numpy(n):
+    rng = np.random.default_rng(4400 + n)
+    eng = SVEngine(n, n_slots=2)
+    L = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    R = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    L /= np.linalg.norm(L); R /= np.linalg.norm(R)
+    eng.upload(0, L); eng.upload(1, R)
+    assert abs(eng.inner(0, 1, -1) - np.vdot(L, R)) < AMP_TOL
+    for q in sorted({0, 1, n // 2, n - 1}):
+        Lt = np.moveaxis(L.reshape([2] * n), n - 1 - q, 0).reshape(2, -1)
+        Rt = np.moveaxis(R.reshape([2] * n), n - 1 - q, 0).reshape(2, -1)
+        np.testing.assert_allclose(eng.inner(0, 1, q), Lt.conj() @ Rt.T, atol=AMP_TOL)
+    eng.close()
+
+
+# ---- error behaviour ----------------------------------------------------------------------------
+def test_errors_are_raised_not_swallowed():
+    eng = SVEngine(4, n_slots=2)
+    with pytest.raises(blib.B200Error, match="slot"):
+        eng.init_zero(5)
+    with pytest.raises(blib.B200Error, match="out of range"):
+        eng.run(0, -1, GateStream.from_gates([("h", [9], [])]))
+    with pytest.raises(blib.B200Error, match="out of range"):
+        eng.amp(0, 1 << 4)
+    with pytest.raises(blib.B200Error):
+        eng.pair_rdm(0, [(1, 1)])
+    eng.close()
+    with pytest.raises(blib.B200Error):
+        SVEngine(3, device=99)
+
+
+def test_counters_and_timing():
+    n = 16
+    eng = SVEngine(n, n_slots=1)
+    eng.set_timing(True)
+    target, _ = brickwork(n, 4, 1)
+    before = eng.counters()
+    eng.run(0, -1, GateStream.from_circuit(target))
+    ms = eng.last_ms()
+    after = eng.counters()
+    assert ms > 0
+    assert after["sweeps"] > before["sweeps"] and after["launches"] > before["launches"]
+    assert after["bytes"] - before["bytes"] == (after["sweeps"] - before["sweeps"]) * 32 * (1 << n)
+    eng.close()
+
+
+# ---- the reference's known-answer tests through the B200 backend ---------------------------------
+def test_analytic_costs_of_simple_states(backend):
+    """test/recompilers/test_approximate_compiler.py:114-150."""
+    analytic = [0, 0, 1, 1 / 2, 1 / 2, 1 / 2, 15 / 16, 1 / 2]
+    zero = Circuit(4)
+    neel = Circuit(4); neel.x([0, 2])
+    ghz = Circuit(4); ghz.h(0)
+    for i in range(3):
+        ghz.cx(0, i + 1)
+    had = Circuit(4); had.h([0, 1, 2, 3])
+    costs = []
+    for circuit in [zero, neel, ghz, had]:
+        for local in [False, True]:
+            costs.append(AdaptCompiler(circuit, backend=backend, optimise_local_cost=local).evaluate_cost())
+    np.testing.assert_allclose(costs, analytic, atol=1e-14)
+
+
+def test_sigma_z_and_ghz_kats(backend):
+    """test/utils/test_utilityfunctions.py:86-95; test_circuit_operations_running.py:48-61."""
+    qc = Circuit(3); qc.x(0); qc.h(1)
+    comp = AdaptCompiler(qc, backend=backend)
+    np.testing.assert_array_almost_equal(backend.measure_qubit_expectation_values(comp), [-1.0, 0.0, 1.0], 15)
+    ghz = Circuit(5); ghz.h(0)
+    for i in range(4):
+        ghz.cx(i, i + 1)
+    sv = backend.simulator.run(ghz).result().get_statevector()
+    expect = np.zeros(32, dtype=np.complex128); expect[0] = expect[31] = 1 / np.sqrt(2)
+    np.testing.assert_allclose(np.asarray(sv), expect, atol=1e-15)
+    assert len(sv) == 32 and sv.num_qubits == 5
+    np.testing.assert_allclose(sv.probabilities([2]), [0.5, 0.5], atol=1e-15)
+
+
+def test_soften_global_cost_raises_like_the_reference(backend):
+    """aer_sv_backend.py:24-27"""
+    qc = Circuit(2); qc.h(0)
+    comp = AdaptCompiler(qc, backend=backend, soften_global_cost=True)
+    with pytest.raises(NotImplementedError):
+        comp.evaluate_cost()
+
+
+# ---- incremental evaluator == full re-simulation ------------------------------------------------
+@pytest.mark.parametrize("n", [4, 12, 15])
+def test_evaluator_tracks_rotosolve_edits(n):
+    """Every cost the incremental evaluator serves equals the oracle's full re-simulation of the
+    edited circuit (what AerSVBackend does on each call, aer_sv_backend.py:37-47)."""
+    rng = np.random.default_rng(4500 + n)
+    target, trng = brickwork(n, 3, seed=n)
+    ansatz = thin_ansatz(n, 6, trng)
+    backend = B200SVBackend()
+    comp = AdaptCompiler(target, backend=backend)
+    comp.full_circuit.data.extend(ansatz.data)
+    oracle_comp = AdaptCompiler(target, backend=OracleSVBackend())
+    oracle_comp.full_circuit.data.extend([d for d in ansatz.copy().data])
+    rot = [i for i in range(*comp.variational_circuit_range())
+           if comp.full_circuit.data[i].operation.name in ("rx", "ry", "rz")]
+    from adapt_aqc_b200.minimiser import replace_1q_gate
+    for step in range(60):
+        idx = rot[int(rng.integers(len(rot)))] if step % 7 else rot[step % len(rot)]
+        name = ["rx", "ry", "rz"][int(rng.integers(3))]
+        theta = float(rng.uniform(-np.pi, np.pi))
+        for c in (comp, oracle_comp):
+            replace_1q_gate(c.full_circuit, idx, name, theta)
+        assert abs(comp.evaluate_cost() - oracle_comp.evaluate_cost()) < COST_TOL
+    st = backend._evaluator.stats
+    assert st["pivot_move"] + st["pivot_build"] + st["m_hits"] > 0
+
+
+def test_shift_costs_equal_individual_evaluations(backend):
+    n = 13
+    target, trng = brickwork(n, 2, seed=3)
+    ansatz = thin_ansatz(n, 4, trng)
+    comp = AdaptCompiler(target, backend=backend)
+    comp.full_circuit.data.extend(ansatz.data)
+    ocomp = AdaptCompiler(target, backend=OracleSVBackend())
+    ocomp.full_circuit.data.extend(ansatz.copy().data)
+    from adapt_aqc_b200.minimiser import replace_1q_gate
+    idx = comp.variational_circuit_range()[0] + 8
+    h = np.pi / 2
+    cands = [("rx", 0.0)] + [(g, s) for g in ("rx", "ry", "rz") for s in (h, -h)]
+    got = backend.shift_costs(comp, idx, cands)
+    for (name, theta), c in zip(cands, got):
+        replace_1q_gate(ocomp.full_circuit, idx, name, theta)
+        assert abs(c - ocomp.evaluate_cost()) < COST_TOL
+
+
+# ---- whole compile loop: identical decisions ----------------------------------------------------
+def _targets():
+    readme = Circuit(3)
+    readme.rx(1.23, 0); readme.cx(0, 1); readme.ry(2.5, 1); readme.rx(-1.6, 2); readme.ccx(2, 1, 0)
+    ghz = Circuit(5); ghz.h(0)
+    for i in range(4):
+        ghz.cx(i, i + 1)
+    rng = np.random.default_rng(11)
+    rnd4 = circuit_from_gates(4, random_gates(4, 25, rng, allow_mat=False))
+    return {"readme3": readme, "ghz5": ghz, "random4": rnd4}
+
+
+@pytest.mark.parametrize("name", ["readme3", "ghz5", "random4"])
+@pytest.mark.parametrize("batched", [False, True])
+def test_compile_makes_the_same_decisions_as_the_oracle_backend(name, batched):
+    """BASELINE north_star: identical chosen qubit pairs, ansatz structure and layer count;
+    costs within 1e-10."""
+    target = _targets()[name]
+    cfg = dict(max_layers=12)
+    ref = AdaptCompiler(target, backend=OracleSVBackend(), adapt_config=AdaptConfig(**cfg)).compile()
+    comp = AdaptCompiler(target, backend=B200SVBackend(), adapt_config=AdaptConfig(**cfg),
+                         minimiser_cls=B200CostMinimiser if batched else None)
+    got = comp.compile()
+    assert got.qubit_pair_history == ref.qubit_pair_history
+    assert got.method_history == ref.method_history
+    assert len(got.global_cost_history) == len(ref.global_cost_history)
+    np.testing.assert_allclose(got.global_cost_history, ref.global_cost_history, atol=1e-9)
+    assert [i.operation.name for i in got.circuit.data] == [i.operation.name for i in ref.circuit.data]
+    assert [i.qubits for i in got.circuit.data] == [i.qubits for i in ref.circuit.data]
+    assert abs(got.overlap - ref.overlap) < 1e-9
+    assert got.cost_evaluations == ref.cost_evaluations
+    # independent check of the answer: |<target|compiled>|^2 on the device
+    assert abs(got.exact_overlap - got.overlap) < 1e-9
+    if name != "random4":
+        assert got.overlap > 1 - 1e-2
+
+
+def test_compile_12_qubits_linear_map_matches_oracle():
+    """Tiled kernels inside the full loop (n > 11), local cost + expectation method included."""
+    n = 12
+    target, _ = brickwork(n, 2, seed=5)
+    cmap = generate_coupling_map(n, CMAP_LINEAR)
+    for kw in (dict(method="ISL"), dict(method="expectation")):
+        cfg = dict(max_layers=4, **kw)
+        ref = AdaptCompiler(target, backend=OracleSVBackend(), coupling_map=cmap,
+                            adapt_config=AdaptConfig(**cfg)).compile()
+        got = AdaptCompiler(target, backend=B200SVBackend(), coupling_map=cmap,
+                            adapt_config=AdaptConfig(**cfg)).compile()
+        assert got.qubit_pair_history == ref.qubit_pair_history
+        np.testing.assert_allclose(got.global_cost_history, ref.global_cost_history, atol=1e-9)
+
+
+def test_entanglement_measures_through_the_facade(backend):
+    """run_circuit_without_transpilation -> partial_trace -> concurrence per pair
+    (entanglement_measures.py:71-75); Bell pair gives [1,0,0]."""
+    qc = Circuit(3); qc.h(0); qc.cx(0, 1)
+    comp = AdaptCompiler(qc, backend=backend)
+    ems = comp._get_all_qubit_pair_entanglement_measures()
+    np.testing.assert_allclose(ems, [1.0, 0.0, 0.0], atol=1e-7)
+    for method in (em.EM_TOMOGRAPHY_EOF, em.EM_TOMOGRAPHY_NEGATIVITY, em.EM_TOMOGRAPHY_LOG_NEGATIVITY):
+        comp.entanglement_measure_method = method
+        o = AdaptCompiler(qc, backend=OracleSVBackend(), entanglement_measure=method)
+        np.testing.assert_allclose(comp._get_all_qubit_pair_entanglement_measures(),
+                                   o._get_all_qubit_pair_entanglement_measures(), atol=1e-9)
+
+
+def test_backend_is_picklable_for_checkpointing(tmp_path):
+    """adapt_compiler.py:484-506 pickles the whole compiler, backend included."""
+    ghz = _targets()["ghz5"]
+    comp = AdaptCompiler(ghz, backend=B200SVBackend(), adapt_config=AdaptConfig(max_layers=3))
+    comp.compile(checkpoint_every=1, checkpoint_dir=str(tmp_path))
+    with open(tmp_path / "1.pkl", "rb") as f:
+        resumed = pickle.load(f)
+    assert resumed.resume_from_layer == 2
+    resumed.adapt_config.max_layers = 12
+    res = resumed.compile()
+    ref = AdaptCompiler(ghz, backend=OracleSVBackend(), adapt_config=AdaptConfig(max_layers=12)).compile()
+    assert res.qubit_pair_history == ref.qubit_pair_history
+    assert abs(res.overlap - ref.overlap) < 1e-9
+
+
+# ---- full-size properties (BASELINE config C3: 28 qubits, 4 GiB per state) -----------------------
+def test_c3_size_properties():
+    """At 2^28 amplitudes the oracle is too slow for routine tests; check size-independent
+    properties instead: U^+ U |0> = |0>, norm preservation, <Z> of a product layer, and the
+    cost of [target | target^+] = 0."""
+    n = 28
+    target, trng = brickwork(n, 8, seed=1234)
+    eng = SVEngine(n, n_slots=2)
+    gs = GateStream.from_circuit(target)
+    eng.run(0, -1, gs)
+    z, norm = eng.expz(0)
+    assert abs(norm - 1) < 1e-10
+    assert np.all(np.abs(z) <= 1 + 1e-12)
+    eng.run(1, 0, gs, inverse=True)
+    a0 = eng.amp(1, 0)
+    assert abs(a0 - 1) < 1e-10
+    z1, norm1 = eng.expz(1)
+    np.testing.assert_allclose(z1, np.ones(n), atol=1e-10)
+    assert abs(eng.inner(0, 0, -1) - 1) < 1e-10
+    # one layer of ry(theta_q): <Z_q> = cos(theta_q) exactly
+    th = trng.uniform(-np.pi, np.pi, n)
+    eng.run(1, -1, GateStream.from_gates([("ry", [q], [th[q]]) for q in range(n)]))
+    zq, _ = eng.expz(1)
+    np.testing.assert_allclose(zq, np.cos(th), atol=1e-12)
+    # Bell pairs on (q, q+14): pair RDM is the Bell projector, others are product states
+    gates = []
+    for q in range(0, 14):
+        gates += [("h", [q], []), ("cx", [q, q + 14], [])]
+    eng.run(1, -1, GateStream.from_gates(gates))
+    rho = eng.pair_rdm(1, [(0, 14), (13, 27), (0, 1)])
+    bell = np.zeros((4, 4)); bell[0, 0] = bell[0, 3] = bell[3, 0] = bell[3, 3] = 0.5
+    np.testing.assert_allclose(rho[0], bell, atol=1e-12)
+    np.testing.assert_allclose(rho[1], bell, atol=1e-12)
+    np.testing.assert_allclose(rho[2], np.eye(4) / 4, atol=1e-12)
+    eng.close()

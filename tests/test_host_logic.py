@@ -1,0 +1,95 @@
+"""Host logic without a GPU: the incremental evaluator, the backend adapter and the compile-loop
+mirror are driven on a CPU stand-in engine (tests/helpers.FakeEngine = the product planner + the
+kernels' thread bodies executed on the host) and compared with the oracle backend, which
+re-simulates everything from |0..0> on every call like the reference does."""
+import numpy as np
+import pytest
+
+from adapt_aqc_b200.backends import B200SVBackend
+from adapt_aqc_b200.circuit import Circuit
+from adapt_aqc_b200.compiler import AdaptCompiler, AdaptConfig
+from adapt_aqc_b200.minimiser import B200CostMinimiser, replace_1q_gate
+from adapt_aqc_b200.sv_engine import SVCostEvaluator
+from oracle.oracle_backends import OracleSVBackend
+
+from helpers import FakeEngine, brickwork, circuit_from_gates, random_gates, thin_ansatz
+
+
+@pytest.fixture
+def fake_backend(emu, monkeypatch):
+    def _get_engine(self, num_qubits):
+        if self._engine is None or self._engine.num_qubits != num_qubits:
+            self._engine = FakeEngine(emu, num_qubits)
+            self._evaluator = SVCostEvaluator(self._engine)
+            self._state_version += 1
+            self._last_run_key = None
+        return self._engine
+    monkeypatch.setattr(B200SVBackend, "_get_engine", _get_engine)
+    return B200SVBackend()
+
+
+@pytest.mark.parametrize("n", [4, 12])
+def test_incremental_evaluator_equals_full_resimulation(fake_backend, n):
+    rng = np.random.default_rng(50 + n)
+    target, trng = brickwork(n, 3, seed=n)
+    ansatz = thin_ansatz(n, 5, trng)
+    comp = AdaptCompiler(target, backend=fake_backend)
+    comp.full_circuit.data.extend(ansatz.data)
+    ocomp = AdaptCompiler(target, backend=OracleSVBackend())
+    ocomp.full_circuit.data.extend(ansatz.copy().data)
+    rot = [i for i in range(*comp.variational_circuit_range())
+           if comp.full_circuit.data[i].operation.name in ("rx", "ry", "rz")]
+    for step in range(40):
+        idx = rot[int(rng.integers(len(rot)))] if step % 5 else rot[step % len(rot)]
+        name = ["rx", "ry", "rz"][int(rng.integers(3))]
+        theta = float(rng.uniform(-np.pi, np.pi))
+        for c in (comp, ocomp):
+            replace_1q_gate(c.full_circuit, idx, name, theta)
+        assert abs(comp.evaluate_cost() - ocomp.evaluate_cost()) < 1e-10
+    st = fake_backend._evaluator.stats
+    assert st["pivot_move"] > 0 and st["resim"] <= 2
+
+
+def test_structure_change_falls_back_to_resimulation(fake_backend):
+    n = 5
+    target, trng = brickwork(n, 2, seed=9)
+    comp = AdaptCompiler(target, backend=fake_backend)
+    ocomp = AdaptCompiler(target, backend=OracleSVBackend())
+    for layers in (1, 2, 3):
+        ansatz = thin_ansatz(n, layers, np.random.default_rng(layers))
+        for c in (comp, ocomp):
+            del c.full_circuit.data[c.lhs_gate_count:]
+            c.full_circuit.data.extend(ansatz.copy().data)
+        assert abs(comp.evaluate_cost() - ocomp.evaluate_cost()) < 1e-12
+        assert abs(comp.evaluate_cost() - ocomp.evaluate_cost()) < 1e-12   # unchanged circuit
+    np.testing.assert_allclose(fake_backend.measure_qubit_expectation_values(comp),
+                               ocomp.backend.measure_qubit_expectation_values(ocomp), atol=1e-12)
+
+
+@pytest.mark.parametrize("batched", [False, True])
+def test_compile_decisions_match_oracle_backend(fake_backend, batched):
+    ghz = Circuit(4); ghz.h(0)
+    for i in range(3):
+        ghz.cx(i, i + 1)
+    rng = np.random.default_rng(3)
+    rnd = circuit_from_gates(3, random_gates(3, 15, rng, allow_mat=False))
+    for target in (ghz, rnd):
+        ref = AdaptCompiler(target, backend=OracleSVBackend(), adapt_config=AdaptConfig(max_layers=6)).compile()
+        got = AdaptCompiler(target, backend=fake_backend, adapt_config=AdaptConfig(max_layers=6),
+                            minimiser_cls=B200CostMinimiser if batched else None).compile()
+        assert got.qubit_pair_history == ref.qubit_pair_history
+        np.testing.assert_allclose(got.global_cost_history, ref.global_cost_history, atol=1e-9)
+        assert got.cost_evaluations == ref.cost_evaluations
+        assert abs(got.exact_overlap - got.overlap) < 1e-9
+
+
+def test_bench_step_counts_220_evaluations(fake_backend):
+    """bench.py's step: Rotoselect over the newest layer + one Rotosolve cycle (C3 shape, small n)."""
+    import bench
+    target, ansatz = bench.build_workload(6, 2, 16)
+    for batched in (True, False):
+        comp = bench.make_compiler(target, ansatz, fake_backend, batched)
+        comp.evaluate_cost()
+        before = comp.cost_evaluation_counter
+        bench.one_step(comp)
+        assert comp.cost_evaluation_counter - before == 4 * 7 + 64 * 3
