@@ -90,6 +90,16 @@ def thin_ansatz(n, layers, rng):
     return c
 
 
+def load_golden_mps(seed):
+    """tests/golden/random_mps_seed_<seed>.npz -> QiskitMPS tuple (constants.py:17)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"random_mps_seed_{seed}.npz"))
+    n = sum(1 for k in z.files if k.startswith("g"))
+    gammas = [(z[f"g{i}"][0], z[f"g{i}"][1]) for i in range(n)]
+    lambdas = [z[f"l{i}"] for i in range(n - 1)]
+    return (gammas, lambdas)
+
+
 def emu_run(emu, n, gates, psi0=None, inverse=False):
     gs = gates if isinstance(gates, GateStream) else GateStream.from_gates(gates)
     st = np.zeros(1 << n, dtype=np.complex128) if psi0 is None else np.array(psi0, dtype=np.complex128)
