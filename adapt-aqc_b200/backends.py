@@ -232,7 +232,7 @@ class B200SVBackend(_SVBase):
             )
         _, ev, window = self._prepare(compiler)
         self._state_version += 1  # slot WORK may be overwritten
-        amp = ev.amp0(window)
+        amp = ev.amp0(window, focus=len(window) - compiler.rhs_gate_count - 1)
         return 1 - (np.absolute(amp)) ** 2
 
     def evaluate_local_cost(self, compiler):
@@ -286,5 +286,5 @@ class B200SVBackend(_SVBase):
         eng.run(SLOT_L, -1, G.GateStream.from_circuit(circuit1))
         eng.run(SLOT_R, -1, G.GateStream.from_circuit(circuit2))
         if self._evaluator is not None:
-            self._evaluator.lr_valid = False
+            self._evaluator.invalidate()
         return np.absolute(eng.inner(SLOT_L, SLOT_R, -1)) ** 2

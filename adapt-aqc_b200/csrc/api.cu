@@ -554,7 +554,7 @@ int b200_sv_pair_rdm(b200_ctx* ctx, int slot, const int32_t* pairs, int n_pairs,
                 CUDA_TRY(cudaGetLastError());
                 {
                     KScope ks(ctx, B200_PROF_REDUCE);
-                    reduce_partials_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, grid, 16, ctx->d_out);
+                    reduce_partials_kernel<<<16, 32, 0, ctx->stream>>>(ctx->d_partial, grid, 16, ctx->d_out);
                 }
                 CUDA_TRY(cudaGetLastError());
                 ctx->counters[3] += 16ull << n;
@@ -573,7 +573,7 @@ int b200_sv_pair_rdm(b200_ctx* ctx, int slot, const int32_t* pairs, int n_pairs,
                 CUDA_TRY(cudaGetLastError());
                 {
                     KScope ks(ctx, B200_PROF_REDUCE);
-                    reduce_partials_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, grid, RDM3_WIDTH, ctx->d_out);
+                    reduce_partials_kernel<<<RDM3_WIDTH, 32, 0, ctx->stream>>>(ctx->d_partial, grid, RDM3_WIDTH, ctx->d_out);
                 }
                 CUDA_TRY(cudaGetLastError());
                 ctx->counters[3] += 16ull << n;
@@ -621,13 +621,51 @@ int b200_sv_inner(b200_ctx* ctx, int l_slot, int r_slot, int q, double out[8]) {
     CUDA_TRY(cudaGetLastError());
     {
         KScope ks(ctx, B200_PROF_REDUCE);
-        reduce_partials_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, grid, INNER_WIDTH, ctx->d_out);
+        reduce_partials_kernel<<<INNER_WIDTH, 32, 0, ctx->stream>>>(ctx->d_partial, grid, INNER_WIDTH, ctx->d_out);
     }
     CUDA_TRY(cudaGetLastError());
     ctx->counters[3] += 32ull << n;
     ctx->counters[6] += 1;
     tm.stop();
     return fetch_out(ctx, out, 8);
+}
+
+int b200_sv_inner2(b200_ctx* ctx, int l_slot, int r_slot, int qa, int qb, double out[32]) {
+    if (check_slot(ctx, l_slot) || check_slot(ctx, r_slot)) return -1;
+    const int n = ctx->nq;
+    if (qa < 0 || qb < 0 || qa >= n || qb >= n || qa == qb) return set_error("inner2: qubits out of range");
+    if (!out) return set_error("null pointer");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int lo = std::min(qa, qb), hi = std::max(qa, qb);
+    Timer tm(ctx);
+    const int grid = red_grid(ctx, 1ull << (n - 2));
+    {
+        KScope ks(ctx, B200_PROF_INNER);
+        sv_inner2_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>((const double2*)ctx->slots[l_slot],
+                                                                (const double2*)ctx->slots[r_slot], n, lo, hi, ctx->d_partial);
+    }
+    CUDA_TRY(cudaGetLastError());
+    {
+        KScope ks(ctx, B200_PROF_REDUCE);
+        reduce_partials_kernel<<<INNER2_WIDTH, 32, 0, ctx->stream>>>(ctx->d_partial, grid, INNER2_WIDTH, ctx->d_out);
+    }
+    CUDA_TRY(cudaGetLastError());
+    ctx->counters[3] += 32ull << n;
+    ctx->counters[6] += 1;
+    tm.stop();
+    double t[32];
+    if (fetch_out(ctx, t, 32)) return -1;
+    if (qa < qb) {
+        std::memcpy(out, t, sizeof t);
+    } else {  // caller's index = bit(qa) + 2 bit(qb) with qa the higher qubit: swap the two index bits
+        auto sw2 = [](int i) { return ((i & 1) << 1) | (i >> 1); };
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                out[2 * (4 * sw2(i) + sw2(j))] = t[2 * (4 * i + j)];
+                out[2 * (4 * sw2(i) + sw2(j)) + 1] = t[2 * (4 * i + j) + 1];
+            }
+    }
+    return 0;
 }
 
 int b200_sv_download(b200_ctx* ctx, int slot, uint64_t offset, uint64_t count, double* host) {

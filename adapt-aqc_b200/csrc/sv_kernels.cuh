@@ -35,6 +35,7 @@ constexpr int RED_THREADS = 256;
 constexpr int EXPZ_WIDTH = 32;   // doubles per block partial
 constexpr int RDM3_WIDTH = 48;
 constexpr int INNER_WIDTH = 8;
+constexpr int INNER2_WIDTH = 32;
 
 B200_HD uint64_t ins0_64(uint64_t x, int pos) {
     const uint64_t lo = x & ((1ull << pos) - 1ull);
@@ -379,14 +380,17 @@ __device__ __forceinline__ void block_sum_store(const double (&v)[WIDTH], double
     }
 }
 
-// out[w] = sum_b partial[b*width + w], b ascending
-__global__ void reduce_partials_kernel(const double* __restrict__ partial, const int nblocks, const int width,
-                                       double* __restrict__ out) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+// out[w] = sum_b partial[b*width + w].  One warp per output column: lane l adds blocks l, l+32, ...
+// in ascending order, then a fixed shuffle tree -- deterministic for a given grid size.
+__global__ void __launch_bounds__(32)
+reduce_partials_kernel(const double* __restrict__ partial, const int nblocks, const int width,
+                       double* __restrict__ out) {
+    const int w = blockIdx.x;
     if (w >= width) return;
     double s = 0;
-    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * width + w];
-    out[w] = s;
+    for (int b = threadIdx.x; b < nblocks; b += 32) s += partial[(size_t)b * width + w];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) out[w] = s;
 }
 
 // K4.  Total threads = 2^tb (tb >= 8); thread gt owns amplitudes (k << tb) | gt, k < 2^kb, kb >= 3.
@@ -534,6 +538,37 @@ sv_inner_kernel(const double2* __restrict__ L, const double2* __restrict__ Rv, c
     }
     const double v[INNER_WIDTH] = {m00.x, m00.y, m01.x, m01.y, m10.x, m10.y, m11.x, m11.y};
     block_sum_store<INNER_WIDTH>(v, partial + (size_t)blockIdx.x * INNER_WIDTH);
+}
+
+// K6b.  Two-qubit transfer matrix T[i][j] = sum_rest conj(L[i,rest]) R[j,rest], i,j = bit(qa) + 2 bit(qb),
+// qa < qb.  <L| O |R> = sum_ij O[i][j] T[i][j] for ANY operator O supported on (qa, qb): one read
+// pass over L and R serves every Rotosolve / Rotoselect evaluation of a whole ansatz layer.
+__global__ void __launch_bounds__(RED_THREADS)
+sv_inner2_kernel(const double2* __restrict__ L, const double2* __restrict__ Rv, const int n, const int qa,
+                 const int qb, double* __restrict__ partial) {
+    double2 t[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t[k] = make_double2(0.0, 0.0);
+    const uint64_t groups = 1ull << (n - 2), ba = 1ull << qa, bb = 1ull << qb;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < groups; k += stride) {
+        const uint64_t b = ins0_64(ins0_64(k, qa), qb);
+        double2 l[4], r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint64_t idx = b + ((j & 1) ? ba : 0) + ((j & 2) ? bb : 0);
+            l[j] = L[idx];
+            r[j] = Rv[idx];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[4 * i + j] = cjfma(l[i], r[j], t[4 * i + j]);
+    }
+    double v[INNER2_WIDTH];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { v[2 * k] = t[k].x; v[2 * k + 1] = t[k].y; }
+    block_sum_store<INNER2_WIDTH>(v, partial + (size_t)blockIdx.x * INNER2_WIDTH);
 }
 
 }  // namespace b200

@@ -9,15 +9,17 @@ call:
   cost         = 1 - |<0| W_{m-1} ... W_0 U |0>|^2
 
   * U|0> is simulated once and kept in HBM (slot BASE).
-  * For a window that differs from the previous one only in 1-qubit gate k (what Rotosolve /
-    Rotoselect do, adaptaqc/utils/cost_minimiser.py:318-368) the evaluator keeps
-        |R_k> = W_{k-1}..W_0 U|0>      (slot R)        |L_k> = (W_{m-1}..W_{k+1})^+ |0>   (slot L)
-    and one launch of the inner-product kernel gives the 2x2 matrix
-        M[i][j] = <L_k| (|i><j| on qubit q_k) |R_k>,   <0|psi> = sum_ij G[i][j] M[i][j]
-    for ANY gate G at position k: all shift angles and all three axes of that gate come from a
-    single launch.  Moving to another gate applies / un-applies only the gates in between.
-  * Anything else (structure change, many gates changed) falls back to re-applying the window to
-    the cached U|0> with the fused sweep kernels.
+  * The window is partitioned into BLOCKS: maximal runs of consecutive gates supported on at most
+    two qubits (qa, qb).  An ADAPT layer (rz rz cx rz rz on one pair) is exactly one block.
+  * For the block [a0, a1) the evaluator keeps, in HBM,
+        |R> = W_{a0-1}..W_0 U|0>   (slot R)        |L> = (W_{m-1}..W_{a1})^+ |0>   (slot L)
+    and one read pass over both (``b200_sv_inner2``) gives the 4x4 transfer matrix
+        T[i][j] = <L| (|i><j| on (qa,qb)) |R>,      <0|psi> = sum_ij O[i][j] T[i][j]
+    for ANY operator O on (qa,qb) -- i.e. for any angles and any rx/ry/rz choice of every
+    rotation in the block.  All Rotoselect / Rotosolve evaluations of a layer
+    (adaptaqc/utils/cost_minimiser.py:267-368), over any number of optimiser cycles, are then
+    4x4 host algebra; the device is touched only when the optimiser moves to another layer
+    (two fused gate sweeps + one transfer pass) or the circuit structure changes.
 """
 import ctypes
 
@@ -96,6 +98,12 @@ class SVEngine:
         m = out.view(np.complex128)
         return complex(m[0]) if q < 0 else m.reshape(2, 2).copy()
 
+    def inner2(self, l_slot, r_slot, qa, qb):
+        """4x4 transfer matrix T[i][j] = <L|(|i><j| on (qa,qb))|R>, index = bit(qa) + 2 bit(qb)."""
+        out = np.zeros(32)
+        check(self._lib.b200_sv_inner2(self._ctx, l_slot, r_slot, int(qa), int(qb), dptr(out)))
+        return out.view(np.complex128).reshape(4, 4).copy()
+
     def download(self, slot, offset=0, count=None):
         count = (1 << self.num_qubits) - offset if count is None else count
         host = np.empty(count, dtype=np.complex128)
@@ -159,8 +167,49 @@ def plan_stats(num_qubits, stream):
     return tuple(out)
 
 
-def _is_1q(ent):
-    return ent[2] < 0
+_I2 = np.eye(2, dtype=np.complex128)
+_SWAP_BITS = [0, 2, 1, 3]
+_M4 = {
+    "cx": np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 0, 0]], dtype=np.complex128),
+    "cz": np.diag([1, 1, 1, -1]).astype(np.complex128),
+    "swap": np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128),
+}
+
+
+def _support(ent):
+    return (ent[1],) if ent[2] < 0 else (ent[1], ent[2])
+
+
+def partition_blocks(window):
+    """[(start, stop, support)]: greedy maximal runs of consecutive gates on <= 2 qubits.  Depends
+    only on the qubits of the gates, so Rotosolve / Rotoselect edits never move a boundary."""
+    blocks = []
+    start, supp = 0, ()
+    for i, ent in enumerate(window):
+        s = tuple(sorted(set(supp) | set(_support(ent))))
+        if len(s) > 2:
+            blocks.append((start, i, supp))
+            start, s = i, tuple(sorted(_support(ent)))
+        supp = s
+    if len(window) > start:
+        blocks.append((start, len(window), supp))
+    return blocks
+
+
+def embed_entry(ent, pair, override=None):
+    """Matrix of a canonical window entry on the qubits `pair` (index = bit(pair[0]) + 2 bit(pair[1]);
+    2x2 when len(pair) == 1).  `override`: replacement 2x2 matrix for a 1-qubit entry."""
+    if ent[2] < 0:
+        m = G.matrix_of_entry(ent) if override is None else np.asarray(override, dtype=np.complex128)
+        if len(pair) == 1:
+            return m
+        return np.kron(_I2, m) if ent[1] == pair[0] else np.kron(m, _I2)
+    m4 = _M4.get(ent[0])
+    if m4 is None:
+        m4 = np.frombuffer(ent[6], dtype=np.complex128).reshape(4, 4)
+    if (ent[1], ent[2]) != tuple(pair):
+        m4 = m4[np.ix_(_SWAP_BITS, _SWAP_BITS)]
+    return m4
 
 
 class SVCostEvaluator:
@@ -171,12 +220,13 @@ class SVCostEvaluator:
     def __init__(self, engine: SVEngine):
         self.eng = engine
         self.base_key = None          # identity of the cached prefix state
-        self.window = None            # canonical window the L/R/M caches refer to
-        self.pivot = None             # index k of the open gate (L/R exclude it)
-        self.M = None                 # 2x2 transfer matrix at the pivot
-        self.lr_valid = False
+        self.window = None            # canonical window the caches refer to
+        self.cut = None               # (a0, a1): R = W[:a0] base, L = (W[a1:])^+ |0>
+        self.pair = None              # qubits the transfer matrix T is open on
+        self.T = None
         self.moves = 0
-        self.stats = {"resim": 0, "pivot_build": 0, "pivot_move": 0, "m_hits": 0, "evals": 0}
+        self._part_key, self._part = None, None
+        self.stats = {"rebuild_R": 0, "rebuild_L": 0, "moves": 0, "t_passes": 0, "host_evals": 0, "evals": 0}
 
     # ---- prefix (target) state ----
     def set_base(self, key, prefix_stream):
@@ -189,91 +239,111 @@ class SVCostEvaluator:
 
     def invalidate(self):
         self.window = None
-        self.pivot = None
-        self.M = None
-        self.lr_valid = False
+        self.cut = None
+        self.pair = None
+        self.T = None
+
+    # ---- block bookkeeping ----
+    def _blocks(self, window):
+        key = tuple((e[1], e[2]) for e in window)
+        if key != self._part_key:
+            self._part_key, self._part = key, partition_blocks(window)
+        return self._part
+
+    def _select_block(self, window, focus):
+        blocks = self._blocks(window)
+        old, target = self.window, None
+        if old is not None and self.cut is not None and len(old) == len(window):
+            a0, a1 = self.cut
+            diff = [i for i in range(len(window)) if window[i] != old[i]]
+            outside = [i for i in diff if not a0 <= i < a1]
+            if not outside:
+                for b in blocks:
+                    if b[0] == a0 and b[1] == a1:
+                        return b
+            target = outside[-1] if outside else (diff[-1] if diff else None)
+        if target is None:
+            target = len(window) - 1 if focus is None else min(max(focus, 0), len(window) - 1)
+        for b in blocks:
+            if b[0] <= target < b[1]:
+                return b
+        raise AssertionError("block partition does not cover the window")
+
+    def _prepare_block(self, window, block):
+        """Make R, L and T valid for `block` of `window`, moving the cached states incrementally
+        whenever the part of the circuit they encode is unchanged."""
+        eng = self.eng
+        b0, b1, supp = block
+        old, new = self.window, window
+        n = eng.num_qubits
+        pair = tuple(supp) if (len(supp) == 2 or n == 1) else (supp[0], (supp[0] + 1) % n)
+        if old is not None and self.cut == (b0, b1) and self.pair == pair and self.T is not None \
+                and old[:b0] == new[:b0] and old[b1:] == new[b1:]:
+            self.window = list(new)
+            return
+        stream = G.GateStream.from_window
+        r_ok = l_ok = False
+        if old is not None and self.cut is not None and self.moves < self.REFRESH_MOVES:
+            a0, a1 = self.cut
+            m = min(a0, b0)
+            if old[:m] == new[:m]:
+                if b0 > a0:
+                    eng.run(SLOT_R, SLOT_R, stream(new[a0:b0]))
+                elif b0 < a0:
+                    eng.run(SLOT_R, SLOT_R, stream(old[b0:a0]), inverse=True)
+                r_ok = True
+            so, sn = len(old) - a1, len(new) - b1
+            if sn <= so and old[len(old) - sn:] == new[b1:]:
+                if so > sn:
+                    eng.run(SLOT_L, SLOT_L, stream(old[a1:len(old) - sn]))
+                l_ok = True
+            elif sn > so and new[len(new) - so:] == old[a1:]:
+                eng.run(SLOT_L, SLOT_L, stream(new[b1:len(new) - so]), inverse=True)
+                l_ok = True
+            if r_ok and l_ok:
+                self.moves += 1
+                self.stats["moves"] += 1
+        if not r_ok:
+            eng.run(SLOT_R, SLOT_BASE, stream(new[:b0]))
+            self.stats["rebuild_R"] += 1
+        if not l_ok:
+            eng.run(SLOT_L, -1, stream(new[b1:]), inverse=True)
+            self.stats["rebuild_L"] += 1
+        if not (r_ok and l_ok):
+            self.moves = 0 if not (r_ok or l_ok) else self.moves
+        self.T = eng.inner(SLOT_L, SLOT_R, pair[0]) if len(pair) == 1 else eng.inner2(SLOT_L, SLOT_R, *pair)
+        self.stats["t_passes"] += 1
+        self.cut, self.pair = (b0, b1), pair
+        self.window = list(new)
+
+    def _operator(self, window, override_index=None, override=None):
+        b0, b1 = self.cut
+        op = None
+        for i in range(b0, b1):
+            m = embed_entry(window[i], self.pair, override if i == override_index else None)
+            op = m if op is None else m @ op
+        return op
 
     # ---- evaluation ----
-    def amp0(self, window):
-        """<0| W |base> for the canonical window `window` (one scalar, as the reference asks)."""
+    def amp0(self, window, focus=None):
+        """<0| W |base> for the canonical window `window` (one scalar, as the reference asks).
+        `focus`: index of the gate the optimiser is most likely to edit next (block choice when the
+        structure changed)."""
         self.stats["evals"] += 1
-        old = self.window
-        if old is not None and len(old) == len(window):
-            diff = [i for i in range(len(window)) if window[i] != old[i]]
-            k = self._choose_pivot(diff, old, window)
-            if k is not None:
-                self.prepare_pivot(window, k)
-                return complex(np.sum(G.matrix_of_entry(window[k]) * self.M))
-        return self._resim(window)
+        if len(window) == 0:
+            self.invalidate()
+            return self.eng.amp(SLOT_BASE, 0)
+        self._prepare_block(window, self._select_block(window, focus))
+        self.stats["host_evals"] += 1
+        return complex(np.sum(self._operator(window) * self.T))
 
-    def _choose_pivot(self, diff, old, new):
-        if not diff:
-            return self.pivot if (self.pivot is not None and self.lr_valid) else None
-        same_1q = all(_is_1q(old[i]) and _is_1q(new[i]) and old[i][1] == new[i][1] for i in diff)
-        if not same_1q or len(diff) > 2:
-            return None
-        if len(diff) == 2 and self.pivot not in diff:
-            return None
-        others = [i for i in diff if i != self.pivot]
-        return others[0] if others else self.pivot
-
-    def _resim(self, window):
-        eng = self.eng
-        eng.run(SLOT_WORK, SLOT_BASE, G.GateStream.from_window(window))
-        self.stats["resim"] += 1
-        self.window = list(window)
-        self.pivot = None
-        self.M = None
-        self.lr_valid = False
-        return eng.amp(SLOT_WORK, 0)
-
-    def prepare_pivot(self, window, k):
-        """Make the transfer matrix M valid for position k of `window` (window[k] is irrelevant:
-        L/R exclude it).  One launch of the inner kernel serves every gate put at k afterwards."""
-        old = self.window
-        ok = old is not None and len(old) == len(window) and self.lr_valid and self.pivot is not None
-        if ok:
-            kp = self.pivot
-            for i in range(len(window)):
-                if i != k and window[i] != old[i]:
-                    # besides k, only the previous pivot may have changed (same qubit, 1-qubit gate)
-                    if not (i == kp and _is_1q(old[i]) and _is_1q(window[i]) and old[i][1] == window[i][1]):
-                        ok = False
-                        break
-        if ok and self.pivot == k:
-            self.stats["m_hits"] += 1
-        else:
-            self._move_pivot(k, old if ok else None, window)
-        self.window = list(window)
-
-    def _move_pivot(self, k, old, new):
-        """Make L/R/M valid for pivot k of window `new`; `old` = window the caches refer to."""
-        eng = self.eng
-        kp = self.pivot
-        if old is None or self.moves >= self.REFRESH_MOVES:
-            eng.run(SLOT_R, SLOT_BASE, G.GateStream.from_window(new[:k]))
-            eng.run(SLOT_L, -1, G.GateStream.from_window(new[k + 1:]), inverse=True)
-            self.moves = 0
-            self.stats["pivot_build"] += 1
-        elif k > kp:
-            # R_k = new[k-1]..new[kp] R_kp ;  L_k = old[k]..old[kp+1] L_kp
-            eng.run(SLOT_R, SLOT_R, G.GateStream.from_window(new[kp:k]))
-            eng.run(SLOT_L, SLOT_L, G.GateStream.from_window(old[kp + 1:k + 1]))
-            self.moves += 1
-            self.stats["pivot_move"] += 1
-        else:
-            # R_k = (old[kp-1]..old[k])^+ R_kp ;  L_k = (new[kp]..new[k+1])^+ L_kp
-            eng.run(SLOT_R, SLOT_R, G.GateStream.from_window(old[k:kp]), inverse=True)
-            eng.run(SLOT_L, SLOT_L, G.GateStream.from_window(new[k + 1:kp + 1]), inverse=True)
-            self.moves += 1
-            self.stats["pivot_move"] += 1
-        self.pivot = k
-        self.lr_valid = True
-        self.M = eng.inner(SLOT_L, SLOT_R, new[k][1])
-
-    # ---- batched API (K6): every shift value of one gate from one launch ----
+    # ---- batched API (K6): every shift value of one gate from one transfer pass ----
     def shift_amplitudes(self, window, k, candidates):
         """<0|psi> for each replacement 2x2 matrix in `candidates` at window position k."""
-        self.prepare_pivot(window, k)
+        for b in self._blocks(window):
+            if b[0] <= k < b[1]:
+                self._prepare_block(window, b)
+                break
         self.stats["evals"] += len(candidates)
-        return [complex(np.sum(np.asarray(c) * self.M)) for c in candidates]
+        self.stats["host_evals"] += len(candidates)
+        return [complex(np.sum(self._operator(window, k, c) * self.T)) for c in candidates]

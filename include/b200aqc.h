@@ -135,6 +135,14 @@ int b200_sv_pair_rdm(b200_ctx *ctx, int slot, const int32_t *pairs, int n_pairs,
  * (adaptaqc/utils/cost_minimiser.py:318-368) from one launch.  q = -1: out[0..1] = <L|R>. */
 int b200_sv_inner(b200_ctx *ctx, int l_slot, int r_slot, int q, double out[8]);
 
+/* out = 4x4 complex T[i][j] = sum_rest conj(L[i,rest]) R[j,rest], i,j = bit(qa) + 2 bit(qb)
+ * (row-major, 32 doubles).  <L|O|R> = sum_ij O[i][j] T[i][j] for ANY operator O supported on
+ * (qa, qb): a whole ansatz layer (rz rz cx rz rz on one pair,
+ * adaptaqc/utils/circuit_operations/circuit_operations_basic.py:135-189) is such an operator, so
+ * one read pass over L and R serves every Rotoselect / Rotosolve evaluation of that layer
+ * (adaptaqc/utils/cost_minimiser.py:267-368), for any number of optimiser cycles. */
+int b200_sv_inner2(b200_ctx *ctx, int l_slot, int r_slot, int qa, int qb, double out[32]);
+
 /* Host <-> device transfer of `count` amplitudes starting at `offset` (tests, small n, target
  * upload).  Replaces the Statevector object's `.data`. */
 int b200_sv_download(b200_ctx *ctx, int slot, uint64_t offset, uint64_t count, double *host);

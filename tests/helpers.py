@@ -153,6 +153,14 @@ class FakeEngine:
         Rt = np.moveaxis(R.reshape([2] * n), n - 1 - q, 0).reshape(2, -1)
         return Lt.conj() @ Rt.T
 
+    def inner2(self, l_slot, r_slot, qa, qb):
+        self.inners += 1
+        n = self.num_qubits
+        L, R = self.slots[l_slot].reshape([2] * n), self.slots[r_slot].reshape([2] * n)
+        Lt = np.moveaxis(L, [n - 1 - qb, n - 1 - qa], [0, 1]).reshape(4, -1)   # index = 2*bit(qb) + bit(qa)
+        Rt = np.moveaxis(R, [n - 1 - qb, n - 1 - qa], [0, 1]).reshape(4, -1)
+        return Lt.conj() @ Rt.T
+
     def download(self, slot, offset=0, count=None):
         return self.slots[slot][offset:None if count is None else offset + count].copy()
 

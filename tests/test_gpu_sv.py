@@ -133,6 +133,12 @@ def test_inner_matches_numpy(n):
         Lt = np.moveaxis(L.reshape([2] * n), n - 1 - q, 0).reshape(2, -1)
         Rt = np.moveaxis(R.reshape([2] * n), n - 1 - q, 0).reshape(2, -1)
         np.testing.assert_allclose(eng.inner(0, 1, q), Lt.conj() @ Rt.T, atol=AMP_TOL)
+    for qa, qb in [(0, 1), (1, 0), (0, n - 1), (n - 1, n // 2), (n // 2, 1)]:
+        if qa == qb:
+            continue
+        Lt = np.moveaxis(L.reshape([2] * n), [n - 1 - qb, n - 1 - qa], [0, 1]).reshape(4, -1)
+        Rt = np.moveaxis(R.reshape([2] * n), [n - 1 - qb, n - 1 - qa], [0, 1]).reshape(4, -1)
+        np.testing.assert_allclose(eng.inner2(0, 1, qa, qb), Lt.conj() @ Rt.T, atol=AMP_TOL)
     eng.close()
 
 
@@ -231,7 +237,7 @@ def test_evaluator_tracks_rotosolve_edits(n):
             replace_1q_gate(c.full_circuit, idx, name, theta)
         assert abs(comp.evaluate_cost() - oracle_comp.evaluate_cost()) < COST_TOL
     st = backend._evaluator.stats
-    assert st["pivot_move"] + st["pivot_build"] + st["m_hits"] > 0
+    assert st["moves"] > 0 and st["t_passes"] < st["evals"]
 
 
 def test_shift_costs_equal_individual_evaluations(backend):
@@ -282,9 +288,10 @@ def test_compile_makes_the_same_decisions_as_the_oracle_backend(name, batched):
     two_q = lambda res: [(i.operation.name, i.qubits) for i in res.circuit.data if len(i.qubits) == 2]
     assert two_q(got) == two_q(ref)
     assert abs(got.overlap - ref.overlap) < 1e-9
-    if name != "random4":
-        # random4 compiles to overlap 1 exactly; at the optimum several Rotoselect axes tie to the
-        # last bit and roundoff (not the backend) picks among gauge-equivalent 1-qubit gates.
+    if name == "readme3":
+        # ghz5 / random4 compile to overlap 1 exactly; at an exact optimum some rotations are pure
+        # gauge (flat cost: e.g. rz on a |0> qubit) and several Rotoselect axes tie to the last bit,
+        # so roundoff -- not the backend -- picks among equivalent 1-qubit gates.
         assert [i.operation.name for i in got.circuit.data] == [i.operation.name for i in ref.circuit.data]
         assert [i.qubits for i in got.circuit.data] == [i.qubits for i in ref.circuit.data]
         assert got.cost_evaluations == ref.cost_evaluations
