@@ -288,3 +288,26 @@ class B200SVBackend(_SVBase):
         if self._evaluator is not None:
             self._evaluator.invalidate()
         return np.absolute(eng.inner(SLOT_L, SLOT_R, -1)) ** 2
+
+
+def install():
+    """Registration hook for a real ``adaptaqc`` installation: the one reference function that
+    touches Aer's Statevector type directly (adaptaqc/utils/entanglement_measures.py:325-340) is
+    wrapped so that a DeviceStatevector answers ``partial_trace`` itself (all candidate pairs from
+    one batch of RDM passes).  A no-op when the reference package is not importable."""
+    if not HAVE_REFERENCE:
+        return False
+    import adaptaqc.utils.entanglement_measures as rem  # pragma: no cover
+
+    original = rem.partial_trace                         # pragma: no cover
+
+    def partial_trace(statevector, qubit_1, qubit_2):    # pragma: no cover
+        if isinstance(statevector, DeviceStatevector):
+            return statevector.partial_trace(qubit_1, qubit_2)
+        return original(statevector, qubit_1, qubit_2)
+
+    rem.partial_trace = partial_trace                    # pragma: no cover
+    return True                                          # pragma: no cover
+
+
+install()
