@@ -1,0 +1,424 @@
+// mps_kernels.cuh -- sm_100a kernels of the matrix-product-state path (complex128).
+//
+//   zgemm_dmma_kernel     K8/K10: complex GEMM on the FP64 tensor cores (DMMA, mma.sync.m8n8k4.f64;
+//                         tcgen05 has no f64 kind).  Generic element strides + optional conjugation
+//                         of A, so the same kernel serves the two-site contraction  (lambda Gamma
+//                         lambda)(Gamma lambda)  and every transfer-matrix step  A^H . E . B.
+//   mps_pack_*            lambda scaling + packing of site tensors into GEMM operands.
+//   mps_theta_gate_kernel applies the 4x4 gate to the contracted two-site tensor and lays the
+//                         (2 chi_l x 2 chi_r) matrix out column-major (tall orientation) for the SVD.
+//   jacobi_*              K9: one-sided (Hestenes) Jacobi SVD, complex128, round-robin ordering.
+//                         jacobi_cta_kernel does a whole SVD in one CTA (small bonds: one launch per
+//                         gate); jacobi_round_kernel is one tournament round with one CTA per
+//                         column pair (large bonds).
+//   mps_write_sites_kernel truncated U / V^H -> Gamma_i, Gamma_{i+1}, lambda_i (divides the outer
+//                         lambdas back out, as Aer does).
+//   mps_amps_kernel       batched <bitstring|psi> (one CTA per bitstring, whole chain in one launch).
+//   mps_apply1q_kernel, mps_dot_pairs_kernel, small helpers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace b200 {
+
+__device__ __forceinline__ double2 z_mul(const double2 a, const double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 z_fma(const double2 a, const double2 b, double2 c) {
+    c.x = fma(a.x, b.x, c.x); c.x = fma(-a.y, b.y, c.x);
+    c.y = fma(a.x, b.y, c.y); c.y = fma(a.y, b.x, c.y);
+    return c;
+}
+__device__ __forceinline__ double2 z_conj(const double2 a) { return make_double2(a.x, -a.y); }
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8/K10: complex GEMM on FP64 tensor cores
+// ---------------------------------------------------------------------------------------------
+// C(m,n) = rowscale[m % rs_mod] * colscale[n % cs_mod] * sum_k opA(m,k) * B(k,n)   (+ C if accumulate)
+//   opA(m,k) = A[m*sam + k*sak]  (conjugated if conj_a);   B(k,n) = B[k*sbk + n*sbn];
+//   C(m,n) at C[m*scm + n*scn].   rowscale / colscale may be null.
+struct GemmArgs {
+    const double2* A; const double2* B; double2* C;
+    int M, N, K;
+    long long sam, sak, sbk, sbn, scm, scn;
+    int conj_a, accumulate;
+    const double* rowscale; int rs_mod;
+    const double* colscale; int cs_mod;
+};
+
+constexpr int GM_TILE = 32;   // CTA tile 32 x 32, 4 warps, each warp a 16 x 16 sub-tile
+constexpr int GK_TILE = 16;
+constexpr int G_PAD = 1;
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128)
+zgemm_dmma_kernel(const GemmArgs g) {
+    __shared__ double As_re[GM_TILE][GK_TILE + G_PAD], As_im[GM_TILE][GK_TILE + G_PAD];
+    __shared__ double Bs_re[GK_TILE][GM_TILE + G_PAD], Bs_im[GK_TILE][GM_TILE + G_PAD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * GM_TILE, n0 = blockIdx.x * GM_TILE;
+    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 16;   // warp sub-tile origin inside the CTA tile
+    double cre[2][2][2], cim[2][2][2];                         // [m frag][n frag][2 columns]
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { cre[i][j][0] = cre[i][j][1] = cim[i][j][0] = cim[i][j][1] = 0.0; }
+
+    for (int k0 = 0; k0 < g.K; k0 += GK_TILE) {
+        // stage A (32 x 16) and B (16 x 32), zero-padded at the edges
+        for (int e = tid; e < GM_TILE * GK_TILE; e += 128) {
+            const int r = e / GK_TILE, c = e % GK_TILE;
+            double2 v = make_double2(0.0, 0.0);
+            if (m0 + r < g.M && k0 + c < g.K) v = g.A[(long long)(m0 + r) * g.sam + (long long)(k0 + c) * g.sak];
+            As_re[r][c] = v.x;
+            As_im[r][c] = g.conj_a ? -v.y : v.y;
+        }
+        for (int e = tid; e < GK_TILE * GM_TILE; e += 128) {
+            const int r = e / GM_TILE, c = e % GM_TILE;
+            double2 v = make_double2(0.0, 0.0);
+            if (k0 + r < g.K && n0 + c < g.N) v = g.B[(long long)(k0 + r) * g.sbk + (long long)(n0 + c) * g.sbn];
+            Bs_re[r][c] = v.x;
+            Bs_im[r][c] = v.y;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK_TILE; kk += 4) {
+            double are[2], aim[2], bre[2], bim[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                are[i] = As_re[wm + 8 * i + (lane >> 2)][kk + (lane & 3)];
+                aim[i] = As_im[wm + 8 * i + (lane >> 2)][kk + (lane & 3)];
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                bre[j] = Bs_re[kk + (lane & 3)][wn + 8 * j + (lane >> 2)];
+                bim[j] = Bs_im[kk + (lane & 3)][wn + 8 * j + (lane >> 2)];
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    dmma884(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
+                    dmma884(cre[i][j][0], cre[i][j][1], -aim[i], bim[j]);
+                    dmma884(cim[i][j][0], cim[i][j][1], are[i], bim[j]);
+                    dmma884(cim[i][j][0], cim[i][j][1], aim[i], bre[j]);
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int m = m0 + wm + 8 * i + (lane >> 2), n = n0 + wn + 8 * j + 2 * (lane & 3) + c;
+                if (m < g.M && n < g.N) {
+                    double s = 1.0;
+                    if (g.rowscale) s *= g.rowscale[m % g.rs_mod];
+                    if (g.colscale) s *= g.colscale[n % g.cs_mod];
+                    double2 v = make_double2(cre[i][j][c] * s, cim[i][j][c] * s);
+                    double2* dst = g.C + (long long)m * g.scm + (long long)n * g.scn;
+                    if (g.accumulate) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+                    *dst = v;
+                }
+            }
+}
+
+// ---------------------------------------------------------------------------------------------
+// site-tensor helpers.  Gamma_i is stored [2][chi_l][chi_r] (physical index outermost).
+// ---------------------------------------------------------------------------------------------
+// Gamma^{s'} = sum_s G[s'][s] Gamma^{s}   (G row-major 2x2 complex in gm[8])
+__global__ void mps_apply1q_kernel(double2* __restrict__ gam, const int sz, const double2 g00, const double2 g01,
+                                   const double2 g10, const double2 g11) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < sz; e += gridDim.x * blockDim.x) {
+        const double2 a = gam[e], b = gam[sz + e];
+        gam[e] = z_fma(g01, b, z_mul(g00, a));
+        gam[sz + e] = z_fma(g11, b, z_mul(g10, a));
+    }
+}
+
+// out[(s,a), b] = ll[a] * Gamma[s][a][b] * lm[b]     (ll / lm may be null = ones)
+__global__ void mps_pack_scaled_kernel(const double2* __restrict__ gam, const int chi_l, const int chi_r,
+                                       const double* __restrict__ ll, const double* __restrict__ lr,
+                                       double2* __restrict__ out) {
+    const int total = 2 * chi_l * chi_r;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int b = e % chi_r, a = (e / chi_r) % chi_l;
+        const double s = (ll ? ll[a] : 1.0) * (lr ? lr[b] : 1.0);
+        const double2 v = gam[e];
+        out[e] = make_double2(v.x * s, v.y * s);
+    }
+}
+
+// C: raw two-site tensor, row-major (2 chi_l) x (2 chi_r), rows (b, alpha), cols (b', gamma).
+// M[(p,alpha),(q,gamma)] = sum_{b,b'} U[p + 2q][b + 2b'] C[(b,alpha),(b',gamma)].
+// X = M column-major (tall == 1, leading dimension m = 2 chi_l) or X = M^H column-major
+// (tall == 0, leading dimension nn = 2 chi_r).
+struct Gate4 { double2 u[16]; };
+__global__ void mps_theta_gate_kernel(const double2* __restrict__ C, const int chi_l, const int chi_r,
+                                      const Gate4 U, const int tall, double2* __restrict__ X) {
+    const int total = chi_l * chi_r;
+    const int m = 2 * chi_l, nn = 2 * chi_r;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int gm = e % chi_r, al = e / chi_r;
+        double2 c[4];  // index b + 2 b'
+#pragma unroll
+        for (int bp = 0; bp < 2; ++bp)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+                c[b + 2 * bp] = C[(size_t)(b * chi_l + al) * nn + bp * chi_r + gm];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                double2 v = z_mul(U.u[4 * (p + 2 * q)], c[0]);
+                v = z_fma(U.u[4 * (p + 2 * q) + 1], c[1], v);
+                v = z_fma(U.u[4 * (p + 2 * q) + 2], c[2], v);
+                v = z_fma(U.u[4 * (p + 2 * q) + 3], c[3], v);
+                const int r = p * chi_l + al, cc = q * chi_r + gm;
+                if (tall) X[(size_t)cc * m + r] = v;
+                else X[(size_t)r * nn + cc] = z_conj(v);
+            }
+    }
+}
+
+__global__ void mps_set_identity_kernel(double2* __restrict__ W, const int q) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < q * q; e += gridDim.x * blockDim.x)
+        W[e] = make_double2((e / q) == (e % q) ? 1.0 : 0.0, 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9: one-sided Jacobi SVD.  X: p x q column-major (p >= q is the caller's job), W: q x q
+// column-major (starts as identity).  On exit the columns of X are orthogonal: X_in = Q S W^H.
+// ---------------------------------------------------------------------------------------------
+constexpr double JACOBI_TOL = 1e-15;
+
+// round-robin tournament on N (even) players: pair k of round r
+__device__ __forceinline__ void rr_pair(const int N, const int r, const int k, int& a, int& b) {
+    if (k == 0) { a = N - 1; b = r; }
+    else { a = (r + k) % (N - 1); b = (r - k + (N - 1)) % (N - 1); }
+    if (a > b) { const int t = a; a = b; b = t; }
+}
+
+// One Hestenes rotation of columns (ca, cb), executed by `nth` cooperating threads (thread t of
+// nth); red = reduction functor summing a double over those threads.  Returns 1 if rotated.
+template <class Reduce>
+__device__ __forceinline__ int jacobi_rotate(double2* __restrict__ X, double2* __restrict__ W, const int p,
+                                             const int q, const int ca, const int cb, const int t, const int nth,
+                                             Reduce red) {
+    double2* xa = X + (size_t)ca * p; double2* xb = X + (size_t)cb * p;
+    double al = 0, be = 0, gr = 0, gi = 0;
+    for (int i = t; i < p; i += nth) {
+        const double2 u = xa[i], v = xb[i];
+        al = fma(u.x, u.x, fma(u.y, u.y, al));
+        be = fma(v.x, v.x, fma(v.y, v.y, be));
+        gr = fma(u.x, v.x, fma(u.y, v.y, gr));      // conj(u) * v
+        gi = fma(u.x, v.y, fma(-u.y, v.x, gi));
+    }
+    al = red(al); be = red(be); gr = red(gr); gi = red(gi);
+    const double g = sqrt(gr * gr + gi * gi);
+    if (g == 0.0 || g <= JACOBI_TOL * sqrt(al * be)) return 0;
+    const double zeta = (be - al) / (2.0 * g);
+    const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+    const double2 ph = make_double2(gr / g, gi / g);   // e^{i phi}
+    const double2 sm = make_double2(-s * ph.x, s * ph.y);   // -s e^{-i phi}
+    const double2 sp = make_double2(s * ph.x, s * ph.y);    //  s e^{+i phi}
+    for (int i = t; i < p; i += nth) {
+        const double2 u = xa[i], v = xb[i];
+        double2 nu = z_mul(sm, v); nu.x = fma(c, u.x, nu.x); nu.y = fma(c, u.y, nu.y);
+        double2 nv = z_mul(sp, u); nv.x = fma(c, v.x, nv.x); nv.y = fma(c, v.y, nv.y);
+        xa[i] = nu; xb[i] = nv;
+    }
+    double2* wa = W + (size_t)ca * q; double2* wb = W + (size_t)cb * q;
+    for (int i = t; i < q; i += nth) {
+        const double2 u = wa[i], v = wb[i];
+        double2 nu = z_mul(sm, v); nu.x = fma(c, u.x, nu.x); nu.y = fma(c, u.y, nu.y);
+        double2 nv = z_mul(sp, u); nv.x = fma(c, v.x, nv.x); nv.y = fma(c, v.y, nv.y);
+        wa[i] = nu; wb[i] = nv;
+    }
+    return 1;
+}
+
+struct WarpReduce {
+    __device__ __forceinline__ double operator()(double v) const { return warp_sum_d(v); }
+};
+
+// Whole SVD in one CTA (q <= JACOBI_CTA_MAX_Q): each warp owns pairs k = warp, warp + nwarps, ...
+// of every round; rounds are separated by __syncthreads; sweeps repeat until no rotation fired.
+constexpr int JACOBI_CTA_MAX_Q = 96;
+__global__ void __launch_bounds__(1024)
+jacobi_cta_kernel(double2* __restrict__ X, double2* __restrict__ W, const int p, const int q, const int max_sweeps,
+                  int* __restrict__ sweeps_done) {
+    __shared__ int rotated;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int N = (q + 1) & ~1;
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        if (threadIdx.x == 0) rotated = 0;
+        __syncthreads();
+        for (int r = 0; r < N - 1; ++r) {
+            for (int k = warp; k < N / 2; k += nwarps) {
+                int a, b;
+                rr_pair(N, r, k, a, b);
+                if (b < q) {
+                    const int did = jacobi_rotate(X, W, p, q, a, b, lane, 32, WarpReduce());
+                    if (did && lane == 0) rotated = 1;
+                }
+            }
+            __syncthreads();
+        }
+        const int any = rotated;
+        __syncthreads();
+        if (!any) { ++sweep; break; }
+    }
+    if (threadIdx.x == 0) *sweeps_done = sweep;
+}
+
+// One tournament round, one CTA (128 threads) per column pair.
+__global__ void __launch_bounds__(128)
+jacobi_round_kernel(double2* __restrict__ X, double2* __restrict__ W, const int p, const int q, const int N,
+                    const int r, int* __restrict__ rotated) {
+    __shared__ double red_buf[4][4];
+    int a, b;
+    rr_pair(N, r, blockIdx.x, a, b);
+    if (b >= q) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int slot = 0;
+    auto red = [&](double v) -> double {
+        v = warp_sum_d(v);
+        if (lane == 0) red_buf[slot][warp] = v;
+        __syncthreads();
+        const double s = (red_buf[slot][0] + red_buf[slot][1]) + (red_buf[slot][2] + red_buf[slot][3]);
+        ++slot;
+        return s;
+    };
+    const int did = jacobi_rotate(X, W, p, q, a, b, threadIdx.x, 128, red);
+    if (did && threadIdx.x == 0) atomicOr(rotated, 1);
+}
+
+// sigma[j] = || X[:, j] ||   (one warp per column)
+__global__ void jacobi_sigma_kernel(const double2* __restrict__ X, const int p, const int q, double* __restrict__ sigma) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= q) return;
+    double s = 0;
+    for (int i = lane; i < p; i += 32) { const double2 v = X[(size_t)j * p + i]; s = fma(v.x, v.x, fma(v.y, v.y, s)); }
+    s = warp_sum_d(s);
+    if (lane == 0) sigma[j] = sqrt(s);
+}
+
+// Truncated factors -> site tensors.  perm[j] = column of X/W holding the j-th largest singular
+// value, kept[j] its (renormalised) value, sig[perm[j]] the raw norm of that column.
+//   tall:  U[(b,al), j] = X[perm_j][(b,al)] / sig      Vh[j, (b',gm)] = conj(W[perm_j][(b',gm)])
+//   wide:  U[(b,al), j] = W[perm_j][(b,al)]            Vh[j, (b',gm)] = conj(X[perm_j][(b',gm)]) / sig
+// Gamma_i[b][al][j] = U / ll[al];  Gamma_{i+1}[b'][j][gm] = Vh / lr[gm];  lambda_i[j] = kept[j].
+__global__ void mps_write_sites_kernel(const double2* __restrict__ X, const double2* __restrict__ W,
+                                       const double* __restrict__ sig, const int* __restrict__ perm,
+                                       const double* __restrict__ kept, const int chi_l, const int chi_r,
+                                       const int k, const int tall, const double* __restrict__ ll,
+                                       const double* __restrict__ lr, double2* __restrict__ g0,
+                                       double2* __restrict__ g1, double* __restrict__ lam) {
+    const int m = 2 * chi_l, nn = 2 * chi_r;
+    const int n0 = m * k, n1 = k * nn;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n0 + n1 + k; e += gridDim.x * blockDim.x) {
+        if (e < n0) {
+            const int j = e % k, r = e / k;            // r = (b, al)
+            const int col = perm[j];
+            double2 v;
+            if (tall) { v = X[(size_t)col * m + r]; const double s = 1.0 / sig[col]; v.x *= s; v.y *= s; }
+            else v = W[(size_t)col * m + r];
+            const double d = ll ? 1.0 / ll[r % chi_l] : 1.0;
+            g0[e] = make_double2(v.x * d, v.y * d);     // [b][al][j] == r * k + j
+        } else if (e < n0 + n1) {
+            const int f = e - n0;
+            const int gm = f % chi_r, j = (f / chi_r) % k, bp = f / (chi_r * k);
+            const int col = perm[j], c = bp * chi_r + gm;
+            double2 v;
+            if (tall) v = z_conj(W[(size_t)col * nn + c]);
+            else { v = z_conj(X[(size_t)col * nn + c]); const double s = 1.0 / sig[col]; v.x *= s; v.y *= s; }
+            const double d = lr ? 1.0 / lr[gm] : 1.0;
+            g1[f] = make_double2(v.x * d, v.y * d);     // [b'][j][gm]
+        } else {
+            lam[e - n0 - n1] = kept[e - n0 - n1];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// read-outs
+// ---------------------------------------------------------------------------------------------
+struct SiteTable {            // device arrays describing an MPS (built per call)
+    const double2* const* gam; // n pointers
+    const double* const* lam;  // n pointers (lam[n-1] = null)
+    const int* chi;            // chi[i] = right bond of site i; left bond = chi[i-1] (1 for i = 0)
+    int n;
+};
+
+// out[t] = <bits_t | psi>: one CTA per bitstring, the whole chain of vector-matrix products in one
+// launch; the running vector lives in shared memory (2 * maxchi double2).
+__global__ void __launch_bounds__(256)
+mps_amps_kernel(const SiteTable st, const uint64_t* __restrict__ bits, const int maxchi, double2* __restrict__ out) {
+    extern __shared__ double2 vsm[];
+    double2* cur = vsm;
+    double2* nxt = vsm + maxchi;
+    const uint64_t b = bits[blockIdx.x];
+    if (threadIdx.x == 0) cur[0] = make_double2(1.0, 0.0);
+    __syncthreads();
+    for (int i = 0; i < st.n; ++i) {
+        const int chi_l = i ? st.chi[i - 1] : 1, chi_r = st.chi[i];
+        const double2* G = st.gam[i] + (size_t)((b >> i) & 1ull) * chi_l * chi_r;
+        const double* lam = st.lam[i];
+        for (int be = threadIdx.x; be < chi_r; be += blockDim.x) {
+            double2 acc = make_double2(0.0, 0.0);
+            for (int al = 0; al < chi_l; ++al) acc = z_fma(cur[al], G[(size_t)al * chi_r + be], acc);
+            if (lam) { acc.x *= lam[be]; acc.y *= lam[be]; }
+            nxt[be] = acc;
+        }
+        __syncthreads();
+        double2* t = cur; cur = nxt; nxt = t;
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = cur[0];
+}
+
+// sum_e X[e] * Y[e] (no conjugation) -> partial per block; used for <D_i, F_{i+1}> contractions
+__global__ void __launch_bounds__(256)
+mps_dot_elem_kernel(const double2* __restrict__ X, const double2* __restrict__ Y, const int nelem,
+                    double2* __restrict__ out) {
+    __shared__ double sre[8], sim[8];
+    double re = 0, im = 0;
+    for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
+        const double2 p = z_mul(X[e], Y[e]);
+        re += p.x; im += p.y;
+    }
+    re = warp_sum_d(re); im = warp_sum_d(im);
+    if ((threadIdx.x & 31) == 0) { sre[threadIdx.x >> 5] = re; sim[threadIdx.x >> 5] = im; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sre[w]; b += sim[w]; }
+        *out = make_double2(a, b);
+    }
+}
+
+// Z = X - Y and S = X + Y elementwise
+__global__ void mps_sum_diff_kernel(const double2* X, const double2* Y, const int nelem, double2* S, double2* D) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += gridDim.x * blockDim.x) {
+        const double2 a = X[e], b = Y[e];
+        S[e] = make_double2(a.x + b.x, a.y + b.y);
+        D[e] = make_double2(a.x - b.x, a.y - b.y);
+    }
+}
+
+}  // namespace b200

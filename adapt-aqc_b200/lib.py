@@ -20,6 +20,10 @@ SYMBOLS = [
     "b200_sv_num_qubits", "b200_sv_init_zero", "b200_sv_copy", "b200_sv_run",
     "b200_sv_run_inverse", "b200_sv_amp", "b200_sv_expz", "b200_sv_pair_rdm", "b200_sv_inner", "b200_sv_inner2",
     "b200_sv_download", "b200_sv_upload", "b200_sv_plan_stats",
+    "b200_mps_create", "b200_mps_destroy", "b200_mps_set_truncation", "b200_mps_num_qubits",
+    "b200_mps_init_zero", "b200_mps_set", "b200_mps_bond_dims", "b200_mps_get", "b200_mps_copy",
+    "b200_mps_apply", "b200_mps_apply_inverse", "b200_mps_transfer", "b200_mps_amps", "b200_mps_dot",
+    "b200_mps_expz", "b200_mps_pair_rdm", "b200_mps_stats",
 ]
 
 
@@ -72,6 +76,25 @@ def load():
     L.b200_sv_download.argtypes = [vp, ci, cu64, cu64, vp]
     L.b200_sv_upload.argtypes = [vp, ci, cu64, cu64, vp]
     L.b200_sv_plan_stats.argtypes = [ci, vp, ci, vp, ci, ctypes.POINTER(ctypes.c_int32)]
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    L.b200_mps_create.argtypes = [vp, ci, ctypes.c_double, ci, ctypes.POINTER(vp)]
+    L.b200_mps_destroy.argtypes = [vp]
+    L.b200_mps_set_truncation.argtypes = [vp, ctypes.c_double, ci]
+    L.b200_mps_num_qubits.argtypes = [vp, ctypes.POINTER(ci)]
+    L.b200_mps_init_zero.argtypes = [vp]
+    L.b200_mps_set.argtypes = [vp, vp, vp, vp]
+    L.b200_mps_bond_dims.argtypes = [vp, vp]
+    L.b200_mps_get.argtypes = [vp, vp, vp]
+    L.b200_mps_copy.argtypes = [vp, vp]
+    L.b200_mps_apply.argtypes = [vp, vp, ci, vp, ci]
+    L.b200_mps_apply_inverse.argtypes = [vp, vp, ci, vp, ci]
+    L.b200_mps_transfer.argtypes = [vp, vp, vp, ci, dp]
+    L.b200_mps_amps.argtypes = [vp, vp, ci, dp]
+    L.b200_mps_dot.argtypes = [vp, vp, dp]
+    L.b200_mps_expz.argtypes = [vp, dp]
+    L.b200_mps_pair_rdm.argtypes = [vp, vp, ci, dp]
+    L.b200_mps_stats.argtypes = [vp, ctypes.POINTER(cu64)]
+    del i32p
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("b200_last_error", "b200_abi_version"):

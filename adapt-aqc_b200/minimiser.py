@@ -171,7 +171,10 @@ class B200CostMinimiser(CostMinimiser):
 
     def _batched_ok(self):
         c = self.compiler
-        return hasattr(c.backend, "shift_costs") and not c.optimise_local_cost and not c.soften_global_cost
+        if not hasattr(c.backend, "shift_costs") or c.optimise_local_cost or c.soften_global_cost:
+            return False
+        supports = getattr(c.backend, "_use_incremental", None)
+        return True if supports is None else bool(supports(c))
 
     def _shift(self, gate_index, candidates):
         costs = self.compiler.backend.shift_costs(self.compiler, gate_index, candidates)

@@ -1,0 +1,416 @@
+"""B200 MPS backend behind ADAPT-AQC's backend interface.
+
+``B200MPSBackend`` is the drop-in for ``AerMPSBackend`` (adaptaqc/backends/aer_mps_backend.py:45-93):
+same four methods + ``evaluate_hamming_weight_one_overlaps``, same argument (the compiler), same
+formulas.  ``backend.simulator`` is an ``AerSimulator(method="matrix_product_state")``-shaped facade
+(``.options.matrix_product_state_truncation_threshold`` is read by the reference at
+adaptaqc/compilers/approximate_compiler.py:223-226).  ``backend.mps_ops`` mirrors the
+``aqc_research.mps_operations`` functions the reference imports (aer_mps_backend.py:14-19,
+entanglement_measures.py:16,77, adapt_compiler.py:19,1129, gradients.py:14) with the same
+signatures, operating on device-resident states: an MPS never travels to the host unless host code
+indexes into it.
+
+Everything is evaluated on the GPU through libb200aqc.so; there is no CPU path.
+"""
+import numpy as np
+
+from . import gates as G
+from . import backends as _sv
+from .mps_engine import SLOT_BASE, SLOT_L, SLOT_R, SLOT_WORK, DeviceMPS, MPSContext, MPSEngine
+from .sv_engine import SVCostEvaluator
+
+try:  # pragma: no cover - the reference needs qiskit + qiskit-aer + aqc_research
+    from adaptaqc.backends.aer_mps_backend import AerMPSBackend as _MPSBase
+except Exception:  # noqa: BLE001
+    _MPSBase = _sv._SVBase if not _sv.HAVE_REFERENCE else object
+
+MPS_INSTRUCTIONS = ("set_matrix_product_state", "save_matrix_product_state")
+
+
+class DeviceMPSView:
+    """A *preprocessed* MPS (what ``mps_from_circuit(..., return_preprocessed=True)`` returns) that
+    lives in HBM.  List-like for host code that insists on indexing (downloads once, lazily)."""
+
+    def __init__(self, sim, handle):
+        self._sim = sim
+        self.handle = handle
+        self.num_qubits = handle.num_qubits
+        self._host = None
+        self._rdm = {}
+        self._expz = None
+        self._pair_hint = None
+
+    def __len__(self):
+        return self.num_qubits
+
+    def _materialise(self):
+        if self._host is None:
+            gammas, lambdas = self.handle.get()
+            out = []
+            for i, (a0, a1) in enumerate(gammas):
+                g = np.stack([a0, a1])
+                if i < self.num_qubits - 1:
+                    g = g * lambdas[i].reshape(1, 1, -1)
+                out.append(g)
+            self._host = out
+        return self._host
+
+    def __getitem__(self, i):
+        return self._materialise()[i]
+
+    def __iter__(self):
+        return iter(self._materialise())
+
+    def __del__(self):
+        try:
+            self._sim._recycle(self.handle)
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class _Options:
+    def __init__(self, thr, max_chi):
+        self.matrix_product_state_truncation_threshold = thr
+        self.matrix_product_state_max_bond_dimension = max_chi
+
+
+class _MPSResult:
+    def __init__(self, data):
+        self._data = data
+
+    def data(self, _experiment=0):
+        return self._data
+
+
+class _MPSJob:
+    def __init__(self, data):
+        self._data = data
+
+    def result(self):
+        return _MPSResult(self._data)
+
+
+class B200MPSSimulator:
+    """``mps_sim_with_args`` replacement (aer_mps_backend.py:27-42)."""
+
+    name = "b200_matrix_product_state"
+
+    def __init__(self, mps_truncation_threshold=1e-16, max_chi=None, mps_log_data=False, device=0):
+        self.options = _Options(mps_truncation_threshold, max_chi)
+        self.device = device
+        self._context = None
+        self._pool = {}            # num_qubits -> [DeviceMPS]
+        self._uploaded = {}        # id(host mps object) -> (host object, DeviceMPS): set_mps cache
+        self.runs = 0
+
+    def __getstate__(self):
+        return {"thr": self.options.matrix_product_state_truncation_threshold,
+                "max_chi": self.options.matrix_product_state_max_bond_dimension, "device": self.device}
+
+    def __setstate__(self, st):
+        self.__init__(st["thr"], st["max_chi"], device=st.get("device", 0))
+
+    # ---- handles ----
+    def context(self):
+        if self._context is None:
+            self._context = MPSContext(self.device)
+        return self._context
+
+    def _acquire(self, n):
+        pool = self._pool.setdefault(n, [])
+        m = pool.pop() if pool else self.context().new_mps(n)
+        m.set_truncation(self.options.matrix_product_state_truncation_threshold,
+                         self.options.matrix_product_state_max_bond_dimension)
+        return m
+
+    def _recycle(self, handle):
+        if handle is not None and handle._h.value and len(self._pool.setdefault(handle.num_qubits, [])) < 8:
+            self._pool[handle.num_qubits].append(handle)
+        elif handle is not None:
+            handle.close()
+
+    def device_copy_of(self, host_mps):
+        """Device copy of a host QiskitMPS object, cached on object identity (the target MPS sits
+        inside the set_matrix_product_state instruction and is re-used on every evaluation)."""
+        ent = self._uploaded.get(id(host_mps))
+        if ent is not None and ent[0] is host_mps:
+            return ent[1]
+        m = self.context().new_mps(len(host_mps[0]))
+        m.set(host_mps)
+        if len(self._uploaded) > 16:
+            _, old = self._uploaded.pop(next(iter(self._uploaded)))
+            old.close()
+        self._uploaded[id(host_mps)] = (host_mps, m)
+        return m
+
+    # ---- simulation ----
+    def simulate(self, circuit):
+        """Run ``[set_matrix_product_state?] gates... [save_matrix_product_state?]`` and return a
+        DeviceMPS handle owned by the caller."""
+        self.runs += 1
+        n = circuit.num_qubits
+        out = self._acquire(n)
+        data = circuit.data
+        start = 0
+        if len(data) and data[0].operation.name == "set_matrix_product_state":
+            out.copy_from(self.device_copy_of(data[0].operation.params[0]))
+            start = 1
+        else:
+            out.init_zero()
+        stop = len(data)
+        while stop > start and data[stop - 1].operation.name == "save_matrix_product_state":
+            stop -= 1
+        window = G.canonical_window(circuit, start, stop)
+        if window:
+            out.apply(G.GateStream.from_window(window))
+        return out
+
+    def run(self, circuit, **_options):
+        """Aer-shaped entry: ``sim.run(qc, shots=1).result().data(0)[label]`` gives the QiskitMPS."""
+        handle = self.simulate(circuit)
+        mps = handle.get()
+        self._recycle(handle)
+        label = "matrix_product_state"
+        for inst in circuit.data:
+            if inst.operation.name == "save_matrix_product_state":
+                label = getattr(inst.operation, "label", None) or getattr(inst.operation, "_label", None) or label
+        return _MPSJob({label: mps, "matrix_product_state": mps, "my_mps": mps})
+
+
+def mps_sim_with_args(mps_truncation_threshold=1e-16, max_chi=None, mps_log_data=False, device=0):
+    return B200MPSSimulator(mps_truncation_threshold, max_chi, mps_log_data, device)
+
+
+class MPSOps:
+    """``aqc_research.mps_operations`` with the signatures the reference uses, on device states."""
+
+    def __init__(self, default_sim):
+        self._default_sim = default_sim
+
+    # -- conversions --
+    @staticmethod
+    def check_mps(x):
+        return (isinstance(x, tuple) and len(x) == 2 and isinstance(x[0], list) and isinstance(x[1], list)
+                and len(x[0]) == len(x[1]) + 1)
+
+    @staticmethod
+    def _preprocess_mps(mps):
+        gammas, lambdas = mps
+        n = len(gammas)
+        out = []
+        for i, (a0, a1) in enumerate(gammas):
+            g = np.stack([np.asarray(a0, dtype=np.complex128), np.asarray(a1, dtype=np.complex128)])
+            if i < n - 1:
+                g = g * np.asarray(lambdas[i], dtype=np.float64).reshape(1, 1, -1)
+            out.append(g)
+        return out
+
+    def _device(self, mps, already_preprocessed, sim=None):
+        """(handle, temporary?)"""
+        sim = sim or self._default_sim
+        if isinstance(mps, DeviceMPSView):
+            return mps.handle, False
+        if isinstance(mps, DeviceMPS):
+            return mps, False
+        if self.check_mps(mps):
+            h = sim._acquire(len(mps[0]))
+            h.set(mps)
+            return h, True
+        h = sim._acquire(len(mps))
+        h.set_preprocessed(list(mps))
+        return h, True
+
+    # -- the functions --
+    def mps_from_circuit(self, qc, trunc_thr=1e-16, print_log_data=False, return_preprocessed=False, sim=None,
+                         out_state=None):
+        """Appends the save instruction to `qc` in place like aqc_research does (callers pass
+        copies, aer_mps_backend.py:77), runs the circuit on the device."""
+        if sim is None:
+            sim = self._default_sim if trunc_thr == self._default_sim.options.matrix_product_state_truncation_threshold \
+                else B200MPSSimulator(trunc_thr, device=self._default_sim.device)
+        if hasattr(qc, "save_matrix_product_state"):
+            qc.save_matrix_product_state()
+        handle = sim.simulate(qc)
+        if return_preprocessed:
+            return DeviceMPSView(sim, handle)
+        mps = handle.get()
+        sim._recycle(handle)
+        return mps
+
+    def mps_dot(self, mps1, mps2, already_preprocessed=False):
+        a, ta = self._device(mps1, already_preprocessed)
+        b, tb = self._device(mps2, already_preprocessed)
+        val = a.dot(b)
+        if ta:
+            self._default_sim._recycle(a)
+        if tb:
+            self._default_sim._recycle(b)
+        return val
+
+    def mps_expectation(self, mps, pauli, qubit, already_preprocessed=False):
+        if pauli != "Z":
+            raise NotImplementedError("only Pauli Z expectations are on the reference's hot path")
+        if isinstance(mps, DeviceMPSView):
+            if mps._expz is None:
+                mps._expz = mps.handle.expz()     # all qubits from one pair of sweeps
+            return float(mps._expz[0][qubit])
+        h, tmp = self._device(mps, already_preprocessed)
+        z, _ = h.expz()
+        if tmp:
+            self._default_sim._recycle(h)
+        return float(z[qubit])
+
+    def extract_amplitude(self, mps, bitstring, already_preprocessed=False):
+        h, tmp = self._device(mps, already_preprocessed)
+        val = complex(h.amps([int(bitstring)])[0])
+        if tmp:
+            self._default_sim._recycle(h)
+        return val
+
+    def partial_trace(self, mps, qubits, already_preprocessed=False, pair_hint=None):
+        key = tuple(sorted(int(q) for q in qubits))
+        if isinstance(mps, DeviceMPSView):
+            if key not in mps._rdm:
+                need = [key]
+                pair_hint = pair_hint or mps._pair_hint
+                if pair_hint:
+                    need = sorted({tuple(sorted(p)) for p in pair_hint} | {key})
+                    need = [p for p in need if p not in mps._rdm]
+                for p, r in zip(need, mps.handle.pair_rdm(need)):
+                    mps._rdm[p] = r
+            return mps._rdm[key]
+        h, tmp = self._device(mps, already_preprocessed)
+        rho = h.pair_rdm([key])[0]
+        if tmp:
+            self._default_sim._recycle(h)
+        return rho
+
+    def mps_to_vector(self, mps, already_preprocessed=False):
+        pp = mps if already_preprocessed else (self._preprocess_mps(mps) if self.check_mps(mps) else mps)
+        v = np.ones((1, 1), dtype=np.complex128)
+        for g in pp:
+            v = np.einsum("kx,sxy->sky", v, g).reshape(-1, g.shape[2])
+        return v[:, 0]
+
+
+class MPSCostEvaluator(SVCostEvaluator):
+    """Block transfer-matrix evaluator (sv_engine.SVCostEvaluator) on MPS slots: the base state is a
+    loaded MPS instead of a simulated prefix."""
+
+    def set_base_handle(self, key, handle):
+        if key is not None and key == self.base_key:
+            return
+        self.eng.slots[SLOT_BASE].copy_from(handle)
+        self.base_key = key
+        self.invalidate()
+
+
+class B200MPSBackend(_MPSBase):
+    kind = "mps"  # what isinstance(backend, AerMPSBackend) decides in the reference
+
+    def __init__(self, simulator=None, device=0, incremental=True):
+        self.simulator = simulator if simulator is not None else B200MPSSimulator(device=device)
+        self.mps_ops = MPSOps(self.simulator)
+        self.incremental = incremental
+        self._engine = None
+        self._evaluator = None
+
+    def __getstate__(self):
+        return {"simulator": self.simulator, "incremental": self.incremental}
+
+    def __setstate__(self, st):
+        self.__init__(simulator=st["simulator"], incremental=st.get("incremental", True))
+
+    # ---- incremental evaluation machinery ----
+    def _use_incremental(self, compiler):
+        """The transfer-matrix shortcut re-orders the contraction, which is exact only up to the
+        truncation error; use it when truncation is at roundoff level (the reference's default
+        1e-16, aer_mps_backend.py:27), otherwise reproduce the reference's contraction order."""
+        o = self.simulator.options
+        return (self.incremental and not compiler.soften_global_cost
+                and o.matrix_product_state_truncation_threshold <= 1e-12
+                and o.matrix_product_state_max_bond_dimension is None)
+
+    def _get_evaluator(self, n):
+        o = self.simulator.options
+        if self._engine is None or self._engine.num_qubits != n:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = MPSEngine(n, context=self.simulator.context(),
+                                     truncation_threshold=o.matrix_product_state_truncation_threshold,
+                                     max_bond_dimension=o.matrix_product_state_max_bond_dimension)
+            self._evaluator = MPSCostEvaluator(self._engine)
+        self._engine.set_truncation(o.matrix_product_state_truncation_threshold, o.matrix_product_state_max_bond_dimension)
+        return self._evaluator
+
+    def _base_and_window(self, compiler):
+        circuit = compiler.full_circuit
+        data = circuit.data
+        lhs = compiler.lhs_gate_count
+        if len(data) and data[0].operation.name == "set_matrix_product_state":
+            host = data[0].operation.params[0]
+            base = self.simulator.device_copy_of(host)
+            key = ("mps", id(host))
+            window = G.canonical_window(circuit, 1, None)
+        else:   # circuit target that was not converted (not produced by the reference's prepare_circuit)
+            base, key, window = None, ("zero", circuit.num_qubits), G.canonical_window(circuit, 0, None)
+        return base, key, window, lhs
+
+    def amp0(self, compiler):
+        ev = self._get_evaluator(compiler.full_circuit.num_qubits)
+        base, key, window, _ = self._base_and_window(compiler)
+        if base is not None:
+            ev.set_base_handle(key, base)
+        elif ev.base_key != key:
+            self._engine.slots[SLOT_BASE].init_zero()
+            ev.base_key = key
+            ev.invalidate()
+        return ev, window
+
+    # ---- the backend methods (aer_mps_backend.py:49-93) ----
+    def evaluate_global_cost(self, compiler):
+        if self._use_incremental(compiler):
+            ev, window = self.amp0(compiler)
+            amp = ev.amp0(window, focus=len(window) - compiler.rhs_gate_count - 1)
+            return 1 - np.absolute(amp) ** 2
+        circ_mps = self.evaluate_circuit(compiler)
+        n = compiler.full_circuit.num_qubits
+        if not compiler.soften_global_cost:
+            return 1 - np.absolute(circ_mps.handle.amps([0])[0]) ** 2
+        # <0|psi> and the n Hamming-weight-one amplitudes from one launch
+        amps = circ_mps.handle.amps([0] + [1 << i for i in range(n)])
+        global_cost = 1 - np.absolute(amps[0]) ** 2
+        previous_cost = compiler.global_cost_history[-1] if len(compiler.global_cost_history) > 0 else 1
+        alpha = abs(previous_cost - compiler.adapt_config.sufficient_cost)
+        return global_cost - alpha * sum(np.absolute(amps[1:]) ** 2)
+
+    def evaluate_local_cost(self, compiler):
+        evals = self.measure_qubit_expectation_values(compiler)
+        return 0.5 * (1 - np.mean(evals))
+
+    def evaluate_circuit(self, compiler):
+        circ = compiler.full_circuit.copy()
+        view = self.mps_ops.mps_from_circuit(circ, return_preprocessed=True, sim=self.simulator)
+        view._pair_hint = getattr(compiler, "coupling_map", None)   # all candidate pairs in one batch
+        return view
+
+    def measure_qubit_expectation_values(self, compiler):
+        mps = self.evaluate_circuit(compiler)
+        return [self.mps_ops.mps_expectation(mps, "Z", i, already_preprocessed=True)
+                for i in range(compiler.full_circuit.num_qubits)]
+
+    def evaluate_hamming_weight_one_overlaps(self, mps):
+        h, tmp = self.mps_ops._device(mps, True)
+        out = list(np.absolute(h.amps([1 << i for i in range(len(mps))])) ** 2)
+        if tmp:
+            self.simulator._recycle(h)
+        return out
+
+    # ---- batched extension (B200CostMinimiser) ----
+    def shift_costs(self, compiler, gate_index, candidates):
+        if not self._use_incremental(compiler):
+            raise NotImplementedError("batched shifts need roundoff-level truncation (see _use_incremental)")
+        ev, window = self.amp0(compiler)
+        k = gate_index - compiler.lhs_gate_count
+        mats = [G.one_qubit_matrix(name, theta) for name, theta in candidates]
+        return [1 - np.absolute(a) ** 2 for a in ev.shift_amplitudes(window, k, mats)]

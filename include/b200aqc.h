@@ -68,7 +68,7 @@ int b200_ctx_sync(b200_ctx *ctx);
 /* Counters since ctx creation: [0] kernels launched, [1] sweeps, [2] gates applied,
  * [3] bytes of algorithmic statevector traffic (32*2^n per sweep, 16*2^n per read-only pass),
  * [4] host->device bytes copied, [5] device->host bytes copied, [6] C-ABI compute calls,
- * [7] reserved. */
+ * [7] real flops issued to the FP64 tensor cores (MPS GEMMs). */
 int b200_ctx_counters(b200_ctx *ctx, uint64_t out[8]);
 /* Bench brackets: record CUDA event `which` (0 = start, 1 = stop) on the context's stream;
  * elapsed_ms synchronises on the stop event and returns stop - start. */
@@ -147,6 +147,61 @@ int b200_sv_inner2(b200_ctx *ctx, int l_slot, int r_slot, int qa, int qb, double
  * upload).  Replaces the Statevector object's `.data`. */
 int b200_sv_download(b200_ctx *ctx, int slot, uint64_t offset, uint64_t count, double *host);
 int b200_sv_upload(b200_ctx *ctx, int slot, uint64_t offset, uint64_t count, const double *host);
+
+/* ---- matrix-product-state path ------------------------------------------------------------ */
+/* A b200_mps is a Vidal-form MPS resident in HBM: Gamma_i as [2][chi_{i-1}][chi_i] complex128 and
+ * lambda_i as chi_i doubles -- the content of the reference's QiskitMPS wire format
+ * (adaptaqc/utils/constants.py:17).  Host-side layouts below: `gammas` = the n site tensors back to
+ * back, each [2][chi_l][chi_r] interleaved complex; `lambdas` = the n-1 bond vectors back to back;
+ * `bond_dims[i]` = chi_i, i < n-1 (chi_{-1} = chi_{n-1} = 1). */
+typedef struct b200_mps b200_mps;
+
+/* Replaces `AerSimulator(method="matrix_product_state", matrix_product_state_truncation_threshold,
+ * matrix_product_state_max_bond_dimension)` (adaptaqc/backends/aer_mps_backend.py:27-42).  The new
+ * MPS is |0...0>.  max_bond_dimension <= 0 means unlimited. */
+int b200_mps_create(b200_ctx *ctx, int num_qubits, double truncation_threshold, int max_bond_dimension,
+                    b200_mps **out);
+int b200_mps_destroy(b200_mps *mps);
+int b200_mps_set_truncation(b200_mps *mps, double truncation_threshold, int max_bond_dimension);
+int b200_mps_num_qubits(b200_mps *mps, int *out);
+int b200_mps_init_zero(b200_mps *mps);
+/* `set_matrix_product_state` (adaptaqc/compilers/approximate_compiler.py:196-204): loads (Gamma,
+ * lambda) verbatim. */
+int b200_mps_set(b200_mps *mps, const int32_t *bond_dims, const double *gammas, const double *lambdas);
+/* `save_matrix_product_state` as used by aqc_research.mps_from_circuit
+ * (adaptaqc/backends/aer_mps_backend.py:76-78): bond dimensions first, then the tensors. */
+int b200_mps_bond_dims(b200_mps *mps, int32_t *out /* n-1 */);
+int b200_mps_get(b200_mps *mps, double *gammas, double *lambdas);
+int b200_mps_copy(b200_mps *dst, b200_mps *src);
+/* Applies the gate stream: 1-qubit gates contract the physical index; 2-qubit gates contract the
+ * two sites (complex GEMM on FP64 tensor cores), run the on-device Jacobi SVD and truncate with
+ * Aer's rule (keep > 1e-16, cap at max bond, drop smallest while the sum of squares stays below
+ * the threshold, renormalise if anything was dropped); non-neighbours are swapped together and
+ * back.  Replaces the Aer MPS run inside mps_from_circuit (aer_mps_backend.py:78;
+ * adaptaqc/compilers/adapt/adapt_compiler.py:1129-1131). */
+int b200_mps_apply(b200_mps *mps, const b200_gate *gates, int n_gates, const double *mats, int n_mats);
+int b200_mps_apply_inverse(b200_mps *mps, const b200_gate *gates, int n_gates, const double *mats, int n_mats);
+/* out = T[i][j] = <a| (|i><j| on `qubits`) |b>: i = bra, j = ket physical index, bit(qubits[0]) +
+ * 2 bit(qubits[1]); n_open = 0 (<a|b>, 2 doubles), 1 (2x2) or 2 (4x4, 32 doubles), row-major.
+ * The MPS counterpart of b200_sv_inner / b200_sv_inner2: with |b> = prefix applied to the target
+ * and <a| = suffix applied to <0|, sum_ij O[i][j] T[i][j] is <0|psi> for ANY operator O on the open
+ * qubits, i.e. every Rotoselect / Rotosolve value of a layer (adaptaqc/utils/cost_minimiser.py:318-368)
+ * from one environment sweep instead of one Aer MPS run + mps_dot per value. */
+int b200_mps_transfer(b200_mps *a, b200_mps *b, const int32_t *qubits, int n_open, double *out);
+/* out[t] = <bitstrings[t] | psi> (little-endian integers, n <= 64), all in one launch: `mps_dot`
+ * with |0..0> (aer_mps_backend.py:54) is bitstring 0; the Hamming-weight-one overlaps are
+ * bitstrings 2^i (aer_mps_backend.py:88-93, aqc_research.extract_amplitude). */
+int b200_mps_amps(b200_mps *mps, const uint64_t *bitstrings, int count, double *out /* 2*count */);
+/* out = <a|b> (conjugate on a): aqc_research.mps_dot (adaptaqc/utils/gradients.py:77,94,110). */
+int b200_mps_dot(b200_mps *a, b200_mps *b, double out[2]);
+/* out[q] = <Z_q> for all q, out[n] = <psi|psi>: aqc_research.mps_expectation per qubit
+ * (aer_mps_backend.py:80-86), all qubits from one right + one left sweep. */
+int b200_mps_expz(b200_mps *mps, double *out /* n+1 */);
+/* 4x4 reduced density matrices, same conventions as b200_sv_pair_rdm: aqc_research.partial_trace
+ * (adaptaqc/utils/entanglement_measures.py:76-79). */
+int b200_mps_pair_rdm(b200_mps *mps, const int32_t *pairs, int n_pairs, double *out /* 32*n_pairs */);
+/* out = {SVDs run, Jacobi sweeps run, current max bond dimension, 0}. */
+int b200_mps_stats(b200_mps *mps, uint64_t out[4]);
 
 /* Planner introspection (no GPU needed): how many sweeps / rounds / fused ops the gate stream
  * compiles to for an n-qubit state.  out = {sweeps, rounds, ops, small_path}. */

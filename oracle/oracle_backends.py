@@ -123,3 +123,43 @@ class OracleSVBackend:
             [p0, p1] = sv.probabilities([i])
             expectation_values.append(p0 - p1)
         return expectation_values
+
+
+class OracleMPSBackend:
+    """Restates ``AerMPSBackend`` (adaptaqc/backends/aer_mps_backend.py:45-93) on the numpy MPS
+    oracle, including its redundancy: every evaluation re-applies all un-absorbed gates to the
+    target MPS (one SVD per 2-qubit gate) and the whole MPS is handed to host numpy."""
+
+    kind = "mps"
+
+    def __init__(self, simulator=None):
+        from . import mps_oracle as mo
+        self.mps_ops = mo
+        self.simulator = simulator if simulator is not None else mo.OracleMPSSimulator()
+
+    def evaluate_global_cost(self, compiler):
+        mo = self.mps_ops
+        circ_mps = self.evaluate_circuit(compiler)
+        global_cost = 1 - np.absolute(mo.mps_dot(circ_mps, compiler.zero_mps, already_preprocessed=True)) ** 2
+        if not compiler.soften_global_cost:
+            return global_cost
+        previous_cost = compiler.global_cost_history[-1] if len(compiler.global_cost_history) > 0 else 1
+        alpha = abs(previous_cost - compiler.adapt_config.sufficient_cost)
+        return global_cost - alpha * sum(self.evaluate_hamming_weight_one_overlaps(circ_mps))
+
+    def evaluate_local_cost(self, compiler):
+        evals = self.measure_qubit_expectation_values(compiler)
+        return 0.5 * (1 - np.mean(evals))
+
+    def evaluate_circuit(self, compiler):
+        circ = compiler.full_circuit.copy()
+        return self.mps_ops.mps_from_circuit(circ, return_preprocessed=True, sim=self.simulator)
+
+    def measure_qubit_expectation_values(self, compiler):
+        mps = self.evaluate_circuit(compiler)
+        return [self.mps_ops.mps_expectation(mps, "Z", i, already_preprocessed=True)
+                for i in range(compiler.full_circuit.num_qubits)]
+
+    def evaluate_hamming_weight_one_overlaps(self, mps):
+        return [abs(self.mps_ops.extract_amplitude(mps, 2 ** i, already_preprocessed=True)) ** 2
+                for i in range(len(mps))]

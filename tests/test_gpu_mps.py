@@ -1,0 +1,283 @@
+"""GPU parity tests of the MPS path (b200_mps_* through ctypes) against the numpy MPS oracle and
+the statevector oracle.  Tolerance: BASELINE north_star asks for overlaps/costs within 1e-8 at the
+same truncation threshold; untruncated amplitude-level checks use 1e-10."""
+import numpy as np
+import pytest
+
+from adapt_aqc_b200 import measures as em
+from adapt_aqc_b200.circuit import Circuit
+from adapt_aqc_b200.compiler import CMAP_LINEAR, AdaptCompiler, AdaptConfig, generate_coupling_map
+from adapt_aqc_b200.gates import GateStream
+from adapt_aqc_b200.minimiser import B200CostMinimiser
+from adapt_aqc_b200.mps_backend import B200MPSBackend, B200MPSSimulator, DeviceMPSView
+from adapt_aqc_b200.mps_engine import MPSContext
+from oracle import mps_oracle as mo
+from oracle import sv_oracle as orc
+from oracle.oracle_backends import OracleMPSBackend, OracleSVBackend, circuit_to_gates
+
+from helpers import circuit_from_gates, load_golden_mps, random_gates
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+COST_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = MPSContext(0)
+    yield c
+    c.close()
+
+
+def _generic_circuit(n, depth, seed, long_range=False):
+    rng = np.random.default_rng(seed)
+    c = Circuit(n)
+    for layer in range(depth):
+        for q in range(n):
+            c.u3(*rng.uniform(-np.pi, np.pi, 3), q)
+        for q in range(layer % 2, n - 1, 2):
+            c.cx(q, q + 1)
+        if long_range and n > 3:
+            a, b = rng.choice(n, 2, replace=False)
+            c.cz(int(a), int(b))
+    return c
+
+
+def _vector(mps):
+    return mo.mps_to_vector(mps)
+
+
+# ---- gate application: contraction + Jacobi SVD + truncation ------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 10])
+def test_apply_all_opcodes_matches_statevector_oracle(ctx, n):
+    rng = np.random.default_rng(7000 + n)
+    m = ctx.new_mps(n)
+    for _ in range(3):
+        gates = random_gates(n, 40, rng)
+        m.init_zero()
+        m.apply(GateStream.from_gates(gates))
+        sv = orc.evaluate_circuit(n, gates)
+        np.testing.assert_allclose(_vector(m.get()), sv, atol=TOL)
+        assert abs(m.amps([0])[0] - sv[0]) < TOL
+    m.close()
+
+
+def test_large_bond_dimension_uses_the_multi_cta_jacobi(ctx):
+    """n = 14, deep circuit: the middle bond reaches 2^7 = 128 (> JACOBI_CTA_MAX_Q / 2 columns), so the
+    per-round Jacobi kernels and 256 x 256 GEMMs are exercised; state equals the SV oracle."""
+    n = 14
+    c = _generic_circuit(n, 16, 11)
+    m = ctx.new_mps(n)
+    m.apply(GateStream.from_circuit(c))
+    assert max(m.bond_dims()) == 128
+    sv = orc.evaluate_circuit(n, circuit_to_gates(c))
+    np.testing.assert_allclose(_vector(m.get()), sv, atol=1e-9)
+    z, norm = m.expz()
+    np.testing.assert_allclose(z, orc.measure_qubit_expectation_values(sv), atol=1e-9)
+    assert abs(norm - 1) < 1e-9
+    st = m.stats()
+    assert st["svds"] > 0 and st["jacobi_sweeps"] > 0
+    m.close()
+
+
+def test_inverse_round_trip_and_long_range_gates(ctx):
+    n = 9
+    c = _generic_circuit(n, 5, 3, long_range=True)
+    gs = GateStream.from_circuit(c)
+    m = ctx.new_mps(n)
+    m.apply(gs)
+    sv = orc.evaluate_circuit(n, circuit_to_gates(c))
+    np.testing.assert_allclose(_vector(m.get()), sv, atol=TOL)
+    m.apply(gs, inverse=True)
+    assert abs(abs(m.amps([0])[0]) - 1) < 1e-9
+    m.close()
+
+
+def test_truncation_rule_matches_oracle(ctx):
+    n = 10
+    c = _generic_circuit(n, 8, 5)
+    for thr, max_chi in [(1e-6, None), (1e-16, 6), (1e-3, 8)]:
+        m = ctx.new_mps(n, thr, max_chi)
+        m.apply(GateStream.from_circuit(c))
+        ref = mo.mps_from_circuit(c.copy(), sim=mo.OracleMPSSimulator(thr, max_chi))
+        assert m.bond_dims() == [len(l) for l in ref[1]]
+        got = m.get()
+        for la, lb in zip(got[1], ref[1]):
+            np.testing.assert_allclose(la, lb, atol=1e-9)
+        assert abs(abs(mo.mps_dot(got, ref)) - abs(mo.mps_dot(ref, ref))) < 1e-8
+        m.close()
+
+
+# ---- set / get / read-outs ----------------------------------------------------------------------
+def test_golden_fixture_round_trip_and_readouts(ctx):
+    """Three of the reference's own 50-site chi=2 targets (tests/golden): set -> get is verbatim
+    (test_utilityfunctions.py:317-338), <psi|psi> = 1, <Z>, amplitudes and RDMs equal the oracle's."""
+    for seed in (1, 17, 100):
+        mps = load_golden_mps(seed)
+        m = ctx.new_mps(50)
+        m.set(mps)
+        back = m.get()
+        for (a0, a1), (b0, b1) in zip(mps[0], back[0]):
+            np.testing.assert_array_equal(a0, b0); np.testing.assert_array_equal(a1, b1)
+        for la, lb in zip(mps[1], back[1]):
+            np.testing.assert_array_equal(la, lb)
+        assert abs(m.dot(m) - 1) < 1e-12
+        pp = mo._preprocess_mps(mps)
+        z, norm = m.expz()
+        np.testing.assert_allclose(z, [mo.mps_expectation(pp, "Z", q, True) for q in range(50)], atol=1e-12)
+        assert abs(norm - 1) < 1e-12
+        bits = [0, 1, 1 << 49, (1 << 50) - 1, 0x2AAAAAAAAAAAA]
+        np.testing.assert_allclose(m.amps(bits), [mo.extract_amplitude(pp, b, True) for b in bits], atol=1e-15)
+        pairs = [(0, 1), (10, 11), (3, 30), (49, 0), (24, 25)]
+        for r, (a, b) in zip(m.pair_rdm(pairs), pairs):
+            np.testing.assert_allclose(r, mo.partial_trace(pp, [a, b], True), atol=1e-12)
+        m.close()
+
+
+@pytest.mark.parametrize("n", [2, 4, 7])
+def test_dot_transfer_and_rdm_match_oracle(ctx, n):
+    ca, cb = _generic_circuit(n, 4, 20 + n), _generic_circuit(n, 3, 40 + n)
+    a, b = ctx.new_mps(n), ctx.new_mps(n)
+    a.apply(GateStream.from_circuit(ca)); b.apply(GateStream.from_circuit(cb))
+    va = orc.evaluate_circuit(n, circuit_to_gates(ca)); vb = orc.evaluate_circuit(n, circuit_to_gates(cb))
+    assert abs(a.dot(b) - np.vdot(va, vb)) < TOL
+    for q in range(n):
+        La = np.moveaxis(va.reshape([2] * n), n - 1 - q, 0).reshape(2, -1)
+        Rb = np.moveaxis(vb.reshape([2] * n), n - 1 - q, 0).reshape(2, -1)
+        np.testing.assert_allclose(a.transfer(b, [q]), La.conj() @ Rb.T, atol=TOL)
+    for qa in range(n):
+        for qb in range(n):
+            if qa == qb:
+                continue
+            La = np.moveaxis(va.reshape([2] * n), [n - 1 - qb, n - 1 - qa], [0, 1]).reshape(4, -1)
+            Rb = np.moveaxis(vb.reshape([2] * n), [n - 1 - qb, n - 1 - qa], [0, 1]).reshape(4, -1)
+            np.testing.assert_allclose(a.transfer(b, [qa, qb]), La.conj() @ Rb.T, atol=TOL)
+    if n >= 3:
+        pairs = [(x, y) for x in range(n) for y in range(n) if x != y]
+        for r, (x, y) in zip(a.pair_rdm(pairs), pairs):
+            np.testing.assert_allclose(r, orc.partial_trace(va, x, y), atol=TOL)
+    a.close(); b.close()
+
+
+def test_errors(ctx):
+    from adapt_aqc_b200.lib import B200Error
+    m = ctx.new_mps(4)
+    with pytest.raises(B200Error):
+        m.apply(GateStream.from_gates([("cx", [0, 7], [])]))
+    with pytest.raises(B200Error):
+        m.pair_rdm([(1, 1)])
+    with pytest.raises(B200Error):
+        m.transfer(m, [0, 0])
+    m.close()
+
+
+# ---- backend level: same numbers and same decisions as the oracle-backed loop --------------------
+def _targets():
+    ghz = Circuit(4); ghz.h(0)
+    for i in range(3):
+        ghz.cx(i, i + 1)
+    return {"ghz4": ghz, "generic4": _generic_circuit(4, 3, 9), "generic6": _generic_circuit(6, 2, 10)}
+
+
+def test_mps_kats():
+    """test/utils/test_utilityfunctions.py:201-211 and the README 50-qubit example (config C2)."""
+    b = B200MPSBackend()
+    comp = AdaptCompiler(Circuit(4), backend=b)
+    np.testing.assert_allclose(b.measure_qubit_expectation_values(comp), [1, 1, 1, 1])
+    had = Circuit(4); had.h([0, 1, 2, 3])
+    comp = AdaptCompiler(had, backend=b)
+    np.testing.assert_allclose(b.measure_qubit_expectation_values(comp), [0, 0, 0, 0], atol=1e-7)
+    n = 50
+    qc = Circuit(n)
+    qc.h(0); qc.cx(0, 1); qc.h(2); qc.cx(2, 3); qc.h(list(range(4, n)))
+    comp = AdaptCompiler(qc, backend=b)
+    assert abs((1 - comp.evaluate_cost()) - 0.5 ** 48) < 1e-25
+    ems = comp._get_all_qubit_pair_entanglement_measures()
+    cm = comp.coupling_map
+    assert abs(ems[cm.index((0, 1))] - 1) < 1e-7 and abs(ems[cm.index((2, 3))] - 1) < 1e-7
+    assert max(e for p, e in zip(cm, ems) if p not in ((0, 1), (2, 3))) < 1e-7
+
+
+@pytest.mark.parametrize("name", ["ghz4", "generic4", "generic6"])
+def test_costs_and_heuristics_match_oracle_backend(name):
+    target = _targets()[name]
+    for local, soften in [(False, False), (True, False), (False, True)]:
+        got = AdaptCompiler(target, backend=B200MPSBackend(), optimise_local_cost=local, soften_global_cost=soften)
+        ref = AdaptCompiler(target, backend=OracleMPSBackend(), optimise_local_cost=local, soften_global_cost=soften)
+        got.global_cost_history = ref.global_cost_history = []
+        assert abs(got.evaluate_cost() - ref.evaluate_cost()) < COST_TOL
+    got = AdaptCompiler(target, backend=B200MPSBackend())
+    ref = AdaptCompiler(target, backend=OracleMPSBackend())
+    np.testing.assert_allclose(got.backend.measure_qubit_expectation_values(got),
+                               ref.backend.measure_qubit_expectation_values(ref), atol=COST_TOL)
+    for method in (em.EM_TOMOGRAPHY_CONCURRENCE, em.EM_TOMOGRAPHY_NEGATIVITY):
+        got.entanglement_measure_method = ref.entanglement_measure_method = method
+        np.testing.assert_allclose(got._get_all_qubit_pair_entanglement_measures(),
+                                   ref._get_all_qubit_pair_entanglement_measures(), atol=1e-7)
+    sv = AdaptCompiler(target, backend=OracleSVBackend())
+    assert abs(got.evaluate_cost() - sv.evaluate_cost()) < COST_TOL      # the reference's SV-vs-MPS bar is 1e-5
+
+
+@pytest.mark.parametrize("name", ["ghz4", "generic4"])
+@pytest.mark.parametrize("mode", ["incremental", "reference_order", "batched"])
+def test_compile_decisions_match_oracle_backend(name, mode):
+    target = _targets()[name]
+    cfg = dict(max_layers=6)
+    ref = AdaptCompiler(target, backend=OracleMPSBackend(), adapt_config=AdaptConfig(**cfg)).compile()
+    backend = B200MPSBackend(incremental=(mode != "reference_order"))
+    got = AdaptCompiler(target, backend=backend, adapt_config=AdaptConfig(**cfg),
+                        minimiser_cls=B200CostMinimiser if mode == "batched" else None).compile()
+    assert got.qubit_pair_history == ref.qubit_pair_history
+    assert got.method_history == ref.method_history
+    assert len(got.global_cost_history) == len(ref.global_cost_history)
+    np.testing.assert_allclose(got.global_cost_history, ref.global_cost_history, atol=COST_TOL)
+    two_q = lambda res: [(i.operation.name, i.qubits) for i in res.circuit.data if len(i.qubits) == 2]
+    assert two_q(got) == two_q(ref)
+
+
+def test_layer_absorption_schedule_on_device():
+    """test/recompilers/test_adapt_compiler.py:673-718."""
+    qc = _generic_circuit(4, 3, 4)
+    compiler = AdaptCompiler(qc, backend=B200MPSBackend(),
+                             adapt_config=AdaptConfig(rotosolve_frequency=4, max_layers_to_modify=3))
+    got = []
+    for i in range(9):
+        compiler._add_layer(i)
+        got.append(len(compiler.full_circuit.data) - 1)
+    assert got == [0, 0, 5, 10, 0, 0, 5, 10, 0]
+
+
+def test_general_gradient_pairs_match_oracle():
+    target = _targets()["generic4"]
+    cfg = AdaptConfig(method="general_gradient", max_layers=3)
+    got = AdaptCompiler(target, backend=B200MPSBackend(), adapt_config=cfg)
+    ref = AdaptCompiler(target, backend=OracleMPSBackend(), adapt_config=AdaptConfig(method="general_gradient", max_layers=3))
+    np.testing.assert_allclose(got._get_all_qubit_pair_gradients(), ref._get_all_qubit_pair_gradients(), atol=COST_TOL)
+    rg, rr = got.compile(), ref.compile()
+    assert rg.qubit_pair_history == rr.qubit_pair_history
+
+
+def test_golden_50_qubit_target_first_layers_match_oracle():
+    """paper/random_mps target (50 sites, chi = 2): two ADAPT layers on a linear map, decisions and
+    costs equal to the oracle-backed loop."""
+    mps = load_golden_mps(1)
+    cmap = generate_coupling_map(50, CMAP_LINEAR)
+    cfg = dict(max_layers=2)
+    got = AdaptCompiler(mps, backend=B200MPSBackend(), coupling_map=cmap, adapt_config=AdaptConfig(**cfg)).compile()
+    ref = AdaptCompiler(mps, backend=OracleMPSBackend(), coupling_map=cmap, adapt_config=AdaptConfig(**cfg)).compile()
+    assert got.qubit_pair_history == ref.qubit_pair_history
+    np.testing.assert_allclose(got.global_cost_history, ref.global_cost_history, atol=COST_TOL)
+
+
+def test_device_view_is_listlike_and_backend_pickles():
+    import pickle
+    b = B200MPSBackend(B200MPSSimulator(1e-12, 16))
+    comp = AdaptCompiler(_targets()["generic4"], backend=b)
+    view = b.evaluate_circuit(comp)
+    assert isinstance(view, DeviceMPSView) and len(view) == 4 and view[0].shape[0] == 2
+    ref = OracleMPSBackend().evaluate_circuit(AdaptCompiler(_targets()["generic4"], backend=OracleMPSBackend()))
+    assert abs(abs(mo.mps_dot(list(view), ref, True)) - 1) < 1e-9
+    b2 = pickle.loads(pickle.dumps(b))
+    assert b2.simulator.options.matrix_product_state_truncation_threshold == 1e-12
+    assert b2.simulator.options.matrix_product_state_max_bond_dimension == 16
