@@ -261,11 +261,17 @@ int apply_adjacent(b200_mps* m, int i, const cplx u4[16]) {
         CUDA_TRY(cudaGetLastError());
     } else {
         const int N = (q + 1) & ~1;
+        double* fro2 = (double*)((char*)st->flag.p + 16);
+        {
+            MScope ms(ctx);
+            jacobi_fro_kernel<<<1, 256, 0, s>>>((const double2*)st->X.p, (size_t)p * q, fro2);
+        }
+        CUDA_TRY(cudaGetLastError());
         for (; sweeps < max_sweeps; ++sweeps) {
             CUDA_TRY(cudaMemsetAsync(st->flag.p, 0, sizeof(int), s));
             for (int r = 0; r < N - 1; ++r) {
                 MScope ms(ctx);
-                jacobi_round_kernel<<<N / 2, 128, 0, s>>>((double2*)st->X.p, (double2*)st->W.p, p, q, N, r, (int*)st->flag.p);
+                jacobi_round_kernel<<<N / 2, 128, 0, s>>>((double2*)st->X.p, (double2*)st->W.p, p, q, N, r, fro2, (int*)st->flag.p);
             }
             CUDA_TRY(cudaGetLastError());
             int rotated = 0;

@@ -217,7 +217,7 @@ __device__ __forceinline__ void rr_pair(const int N, const int r, const int k, i
 template <class Reduce>
 __device__ __forceinline__ int jacobi_rotate(double2* __restrict__ X, double2* __restrict__ W, const int p,
                                              const int q, const int ca, const int cb, const int t, const int nth,
-                                             Reduce red) {
+                                             const double tiny2, Reduce red) {
     double2* xa = X + (size_t)ca * p; double2* xb = X + (size_t)cb * p;
     double al = 0, be = 0, gr = 0, gi = 0;
     for (int i = t; i < p; i += nth) {
@@ -229,7 +229,9 @@ __device__ __forceinline__ int jacobi_rotate(double2* __restrict__ X, double2* _
     }
     al = red(al); be = red(be); gr = red(gr); gi = red(gi);
     const double g = sqrt(gr * gr + gi * gi);
-    if (g == 0.0 || g <= JACOBI_TOL * sqrt(al * be)) return 0;
+    // columns below 1e-17 |X|_F are numerical zeros (Aer chops singular values <= 1e-16): rotating
+    // them against each other never converges and cannot change any kept singular triplet
+    if (g == 0.0 || g <= JACOBI_TOL * sqrt(al * be) || al <= tiny2 || be <= tiny2) return 0;
     const double zeta = (be - al) / (2.0 * g);
     const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
     const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
@@ -263,8 +265,17 @@ __global__ void __launch_bounds__(1024)
 jacobi_cta_kernel(double2* __restrict__ X, double2* __restrict__ W, const int p, const int q, const int max_sweeps,
                   int* __restrict__ sweeps_done) {
     __shared__ int rotated;
+    __shared__ double fro_w[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int N = (q + 1) & ~1;
+    double fro = 0;
+    for (size_t e = threadIdx.x; e < (size_t)p * q; e += blockDim.x) { const double2 v = X[e]; fro = fma(v.x, v.x, fma(v.y, v.y, fro)); }
+    fro = warp_sum_d(fro);
+    if (lane == 0) fro_w[warp] = fro;
+    __syncthreads();
+    fro = 0;
+    for (int w = 0; w < nwarps; ++w) fro += fro_w[w];
+    const double tiny2 = 1e-34 * fro;
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
         if (threadIdx.x == 0) rotated = 0;
@@ -274,7 +285,7 @@ jacobi_cta_kernel(double2* __restrict__ X, double2* __restrict__ W, const int p,
                 int a, b;
                 rr_pair(N, r, k, a, b);
                 if (b < q) {
-                    const int did = jacobi_rotate(X, W, p, q, a, b, lane, 32, WarpReduce());
+                    const int did = jacobi_rotate(X, W, p, q, a, b, lane, 32, tiny2, WarpReduce());
                     if (did && lane == 0) rotated = 1;
                 }
             }
@@ -290,7 +301,7 @@ jacobi_cta_kernel(double2* __restrict__ X, double2* __restrict__ W, const int p,
 // One tournament round, one CTA (128 threads) per column pair.
 __global__ void __launch_bounds__(128)
 jacobi_round_kernel(double2* __restrict__ X, double2* __restrict__ W, const int p, const int q, const int N,
-                    const int r, int* __restrict__ rotated) {
+                    const int r, const double* __restrict__ fro2, int* __restrict__ rotated) {
     __shared__ double red_buf[4][4];
     int a, b;
     rr_pair(N, r, blockIdx.x, a, b);
@@ -305,8 +316,20 @@ jacobi_round_kernel(double2* __restrict__ X, double2* __restrict__ W, const int 
         ++slot;
         return s;
     };
-    const int did = jacobi_rotate(X, W, p, q, a, b, threadIdx.x, 128, red);
+    const int did = jacobi_rotate(X, W, p, q, a, b, threadIdx.x, 128, 1e-34 * (*fro2), red);
     if (did && threadIdx.x == 0) atomicOr(rotated, 1);
+}
+
+// fro2[0] = |X|_F^2 (one CTA)
+__global__ void __launch_bounds__(256)
+jacobi_fro_kernel(const double2* __restrict__ X, const size_t nelem, double* __restrict__ fro2) {
+    __shared__ double sh[8];
+    double s = 0;
+    for (size_t e = threadIdx.x; e < nelem; e += blockDim.x) { const double2 v = X[e]; s = fma(v.x, v.x, fma(v.y, v.y, s)); }
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < 8; ++w) t += sh[w]; *fro2 = t; }
 }
 
 // sigma[j] = || X[:, j] ||   (one warp per column)
