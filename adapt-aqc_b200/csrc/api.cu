@@ -276,6 +276,7 @@ int b200_ctx_create(int device, b200_ctx** out) {
     b200_ctx* ctx = new b200_ctx();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    ctx->coop_ok = prop.cooperativeLaunch != 0 && !std::getenv("B200AQC_NO_COOP");
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&ctx->ev0));
     CUDA_TRY(cudaEventCreate(&ctx->ev1));

@@ -31,6 +31,7 @@ struct MpsState;  // mps.cu
 struct b200_ctx {
     int device = 0;
     int num_sms = 0;
+    bool coop_ok = false;  // device supports cooperative (grid-synchronised) launches
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_plan = nullptr;
     bool timing = false, timing_pending = false;

@@ -261,13 +261,36 @@ int apply_adjacent(b200_mps* m, int i, const cplx u4[16]) {
         CUDA_TRY(cudaGetLastError());
     } else {
         const int N = (q + 1) & ~1;
-        double* fro2 = (double*)((char*)st->flag.p + 16);
+        double* fro2 = (double*)((char*)st->flag.p + 32);
         {
             MScope ms(ctx);
             jacobi_fro_kernel<<<1, 256, 0, s>>>((const double2*)st->X.p, (size_t)p * q, fro2);
         }
         CUDA_TRY(cudaGetLastError());
-        for (; sweeps < max_sweeps; ++sweeps) {
+        bool coop_done = false;
+        if (ctx->coop_ok) {
+            // one cooperative launch for the whole SVD (needs all N/2 CTAs co-resident)
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_coop_kernel, 128, 0));
+            if ((long long)per_sm * ctx->num_sms >= N / 2) {
+                CUDA_TRY(cudaMemsetAsync(st->flag.p, 0, 3 * sizeof(int), s));
+                double2* Xp = (double2*)st->X.p; double2* Wp = (double2*)st->W.p;
+                int pp = p, qq = q, NN = N, ms_ = max_sweeps;
+                const double* fr = fro2; int* ctrl = (int*)st->flag.p;
+                void* args[] = {&Xp, &Wp, &pp, &qq, &NN, &ms_, &fr, &ctrl};
+                {
+                    MScope ms(ctx);
+                    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)jacobi_coop_kernel, dim3(N / 2), dim3(128), args, 0, s));
+                }
+                int done[3] = {0, 0, 0};
+                CUDA_TRY(cudaMemcpyAsync(done, st->flag.p, sizeof done, cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+                ctx->counters[5] += sizeof done;
+                sweeps = done[2];
+                coop_done = true;
+            }
+        }
+        for (; !coop_done && sweeps < max_sweeps; ++sweeps) {
             CUDA_TRY(cudaMemsetAsync(st->flag.p, 0, sizeof(int), s));
             for (int r = 0; r < N - 1; ++r) {
                 MScope ms(ctx);

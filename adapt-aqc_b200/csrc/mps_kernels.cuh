@@ -16,6 +16,7 @@
 //   mps_amps_kernel       batched <bitstring|psi> (one CTA per bitstring, whole chain in one launch).
 //   mps_apply1q_kernel, mps_dot_pairs_kernel, small helpers.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -203,7 +204,10 @@ __global__ void mps_set_identity_kernel(double2* __restrict__ W, const int q) {
 // K9: one-sided Jacobi SVD.  X: p x q column-major (p >= q is the caller's job), W: q x q
 // column-major (starts as identity).  On exit the columns of X are orthogonal: X_in = Q S W^H.
 // ---------------------------------------------------------------------------------------------
-constexpr double JACOBI_TOL = 1e-15;
+// Columns count as orthogonal when |<a|b>| <= tol |a||b| with tol = 2 sqrt(p) eps: the rounding noise
+// of a length-p complex dot product (LAPACK's zgesvj uses the same sqrt(m) eps scale).  A tighter
+// test keeps rotating noise and doubles the number of sweeps without changing any singular triplet.
+__host__ __device__ __forceinline__ double jacobi_tol(const int p) { return 4.5e-16 * sqrt((double)p); }
 
 // round-robin tournament on N (even) players: pair k of round r
 __device__ __forceinline__ void rr_pair(const int N, const int r, const int k, int& a, int& b) {
@@ -231,7 +235,7 @@ __device__ __forceinline__ int jacobi_rotate(double2* __restrict__ X, double2* _
     const double g = sqrt(gr * gr + gi * gi);
     // columns below 1e-17 |X|_F are numerical zeros (Aer chops singular values <= 1e-16): rotating
     // them against each other never converges and cannot change any kept singular triplet
-    if (g == 0.0 || g <= JACOBI_TOL * sqrt(al * be) || al <= tiny2 || be <= tiny2) return 0;
+    if (g == 0.0 || g <= jacobi_tol(p) * sqrt(al * be) || al <= tiny2 || be <= tiny2) return 0;
     const double zeta = (be - al) / (2.0 * g);
     const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
     const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
@@ -318,6 +322,48 @@ jacobi_round_kernel(double2* __restrict__ X, double2* __restrict__ W, const int 
     };
     const int did = jacobi_rotate(X, W, p, q, a, b, threadIdx.x, 128, 1e-34 * (*fro2), red);
     if (did && threadIdx.x == 0) atomicOr(rotated, 1);
+}
+
+// Whole SVD in ONE cooperative launch for large bonds: CTA k owns pair k of every tournament round,
+// rounds are separated by grid-wide barriers (the ~2 us barrier replaces a ~9 us kernel launch per
+// round: a 512-column SVD is ~5000-9000 sequential rounds).  ctrl[0..1] = per-sweep rotation flags
+// (ping-pong), ctrl[2] = sweeps done; fro2 = |X|_F^2.
+__global__ void __launch_bounds__(128)
+jacobi_coop_kernel(double2* __restrict__ X, double2* __restrict__ W, const int p, const int q, const int N,
+                   const int max_sweeps, const double* __restrict__ fro2, int* __restrict__ ctrl) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red_buf[4][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double tiny2 = 1e-34 * (*fro2);
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        int* flag = ctrl + (sweep & 1);
+        int mine = 0;
+        for (int r = 0; r < N - 1; ++r) {
+            int a, b;
+            rr_pair(N, r, blockIdx.x, a, b);
+            if (b < q) {
+                int slot = 0;
+                auto red = [&](double v) -> double {
+                    v = warp_sum_d(v);
+                    if (lane == 0) red_buf[slot][warp] = v;
+                    __syncthreads();
+                    const double s = (red_buf[slot][0] + red_buf[slot][1]) + (red_buf[slot][2] + red_buf[slot][3]);
+                    ++slot;
+                    return s;
+                };
+                mine |= jacobi_rotate(X, W, p, q, a, b, threadIdx.x, 128, tiny2, red);
+            }
+            grid.sync();
+        }
+        if (mine && threadIdx.x == 0) atomicOr(flag, 1);
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[(sweep + 1) & 1] = 0;   // next sweep's flag
+        grid.sync();
+        const int any = *((volatile int*)flag);
+        if (!any) { ++sweep; break; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[2] = sweep;
 }
 
 // fro2[0] = |X|_F^2 (one CTA)

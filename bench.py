@@ -149,6 +149,87 @@ def cpu_baseline_sample(n, target, ansatz, budget_s=20.0):
     return {"value": evals_per_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
 
+# ---- config C4: 50-qubit random MPS at bond dimension 256 ----------------------------------------
+def build_mps_workload(n, chi, layers, seed=1):
+    from helpers import random_vidal_mps
+    from adapt_aqc_b200.circuit import Circuit
+    target = random_vidal_mps(n, chi, seed)
+    rng = np.random.default_rng(seed)
+    ansatz = Circuit(n)
+    mid = n // 2 - 1
+    for k in range(layers):
+        a, b = mid + (k % 2), mid + (k % 2) + 1
+        th = rng.uniform(-np.pi, np.pi, 4)
+        ansatz.rz(th[0], a, label="rz"); ansatz.rz(th[1], b, label="rz")
+        ansatz.cx(a, b)
+        ansatz.rz(th[2], a, label="rz"); ansatz.rz(th[3], b, label="rz")
+    return target, ansatz
+
+
+def mps_step(comp):
+    lo, hi = comp.variational_circuit_range()
+    comp.minimizer._reduce_cost(False, (lo, hi))
+
+
+def bench_mps(args, device, with_cpu=True):
+    """evals/s of the MPS path in the reference's contraction order (every evaluation re-applies
+    the un-absorbed gates to the chi=256 target: one 512x512 complex SVD per CNOT, truncated back
+    to chi=256 with Aer's rule) -- the same work per evaluation as AerMPSBackend.evaluate_global_cost."""
+    from adapt_aqc_b200.compiler import AdaptCompiler
+    from adapt_aqc_b200.mps_backend import B200MPSBackend, B200MPSSimulator
+    n, chi, layers = args.mps_qubits, args.mps_chi, args.mps_layers
+    t0 = time.perf_counter()
+    target, ansatz = build_mps_workload(n, chi, layers)
+    gen_s = time.perf_counter() - t0
+    sim = B200MPSSimulator(1e-16, max_chi=chi, device=device)
+    backend = B200MPSBackend(sim)
+    comp = AdaptCompiler(target, backend=backend)
+    comp.full_circuit.data.extend(ansatz.copy().data)
+    comp.evaluate_cost()
+    ctx = sim.context()
+    for _ in range(max(1, args.warmup // 2)):
+        mps_step(comp)
+    ctx.sync()
+    c0, e0 = ctx.counters(), comp.cost_evaluation_counter
+    ctx.profile(True)
+    ctx.mark(0)
+    steps = max(1, args.steps // 2)
+    for _ in range(steps):
+        mps_step(comp)
+    ctx.mark(1)
+    ms = ctx.elapsed_ms()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    c1 = ctx.counters()
+    evals = comp.cost_evaluation_counter - e0
+    out = {
+        "workload": f"C4: {n}-qubit random Vidal MPS, chi={chi} (max_bond_dimension={chi}, threshold 1e-16), "
+                    f"{layers} un-absorbed thinly-dressed CNOT layers; step = one Rotosolve cycle ({evals // steps} evals), "
+                    "reference contraction order (all window gates re-applied per evaluation)",
+        "value": evals / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "evals_per_step": evals // steps,
+        "gpu_launches": int(c1["launches"] - c0["launches"]),
+        "kernel_ms": prof["mps"][0], "kernel_launches": int(prof["mps"][1]),
+        "dmma_flops": int(c1["tensor_flops"] - c0["tensor_flops"]),
+        "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / steps,
+        "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / steps,
+        "target_generation_s": gen_s,
+    }
+    if with_cpu:
+        from oracle.oracle_backends import OracleMPSBackend
+        from oracle import mps_oracle as mo
+        ocomp = AdaptCompiler(target, backend=OracleMPSBackend(mo.OracleMPSSimulator(1e-16, chi)))
+        ocomp.full_circuit.data.extend(ansatz.copy().data)
+        t0 = time.perf_counter()
+        k = 0
+        while k < 3 or (time.perf_counter() - t0 < 8 and k < 20):
+            ocomp.evaluate_cost()
+            k += 1
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": k / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"{k} full evaluations (numpy/LAPACK MPS oracle, {dt:.1f} s)"}
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -195,6 +276,11 @@ def main():
     ap.add_argument("--depth", type=int, default=8)
     ap.add_argument("--layers", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mps", action="store_true", help="skip the secondary C4 (MPS) measurement")
+    ap.add_argument("--mps-only", action="store_true", help="run only the C4 (MPS) measurement and print it")
+    ap.add_argument("--mps-qubits", type=int, default=50)
+    ap.add_argument("--mps-chi", type=int, default=256)
+    ap.add_argument("--mps-layers", type=int, default=2)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -207,6 +293,10 @@ def main():
 
     import adapt_aqc_b200  # noqa: F401
     from adapt_aqc_b200.backends import B200SVBackend
+
+    if args.mps_only:
+        print(json.dumps(bench_mps(args, local_rank, with_cpu=not args.no_cpu_baseline)))
+        return
 
     dist = None
     if world > 1:
@@ -306,6 +396,12 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(n, target, ansatz, budget_s=15.0)
+    if rank == 0 and world == 1 and not args.no_mps:
+        backend._engine.close()          # free the 16 GiB of statevector slots first
+        try:
+            line["mps_c4"] = bench_mps(args, local_rank, with_cpu=not args.no_cpu_baseline)
+        except Exception as exc:  # noqa: BLE001 - the secondary measurement must not hide the main line
+            line["mps_c4"] = {"error": repr(exc)}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

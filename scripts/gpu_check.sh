@@ -11,7 +11,7 @@ python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytes
 tail -5 $OUT/pytest_gpu_$TAG.log
 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/smoke_$TAG.log
 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"; cat $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
-BCMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
+BCMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-mps"
 $BCMD > $OUT/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches_$TAG.csv $BCMD > $OUT/ncu_list_$TAG.log 2>&1
 echo "ncu list rc=$?"

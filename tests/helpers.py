@@ -166,3 +166,34 @@ class FakeEngine:
 
     def upload(self, slot, host, offset=0):
         self.slots[slot][offset:offset + len(host)] = host
+
+
+def random_vidal_mps(n, chi, seed):
+    """Random canonical Vidal-form MPS (QiskitMPS tuple, constants.py:17) with bond dimensions
+    chi_i = min(2^(i+1), 2^(n-1-i), chi) -- SURVEY 8d config C4: complex standard-normal tensors,
+    right-canonicalised by QR, then a left-to-right SVD sweep."""
+    rng = np.random.default_rng(seed)
+    dims = [1] + [int(min(2 ** min(i + 1, n - 1 - i, 30), chi)) for i in range(n - 1)] + [1]
+    B = [rng.normal(size=(2, dims[i], dims[i + 1])) + 1j * rng.normal(size=(2, dims[i], dims[i + 1])) for i in range(n)]
+    for i in range(n - 1, 0, -1):                      # right-canonicalise
+        cl, cr = dims[i], dims[i + 1]
+        M = B[i].transpose(1, 0, 2).reshape(cl, 2 * cr)
+        Q, R = np.linalg.qr(M.conj().T)                # M^H = Q R  ->  M = R^H Q^H
+        B[i] = Q.conj().T.reshape(cl, 2, cr).transpose(1, 0, 2)
+        B[i - 1] = np.einsum("sab,bc->sac", B[i - 1], R.conj().T)
+    B[0] = B[0] / np.linalg.norm(B[0])
+    gammas, lambdas = [], []
+    M = B[0]
+    prev = np.ones(1)
+    for i in range(n - 1):
+        cl, cr = dims[i], dims[i + 1]
+        U, S, Vh = np.linalg.svd(M.reshape(2 * cl, cr), full_matrices=False)
+        A = U.reshape(2, cl, cr)
+        g = A / prev.reshape(1, -1, 1)
+        gammas.append((g[0].copy(), g[1].copy()))
+        lambdas.append(S.copy())
+        M = np.einsum("ab,sbc->sac", S[:, None] * Vh, B[i + 1])
+        prev = S
+    g = M / prev.reshape(1, -1, 1)
+    gammas.append((g[0].copy(), g[1].copy()))
+    return (gammas, lambdas)
