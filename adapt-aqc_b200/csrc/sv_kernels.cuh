@@ -45,8 +45,10 @@ B200_HD uint32_t ins0_32(uint32_t x, int pos) {
     const uint32_t lo = x & ((1u << pos) - 1u);
     return ((x >> pos) << (pos + 1)) | lo;
 }
-// 16-byte-slot swizzle: spreads any 3 of the low 6 index bits over the 8 slots of a 128 B row.
-B200_HD uint32_t swz(uint32_t i) { return i ^ ((i >> 3) & 7u); }
+// 16-byte-slot swizzle: the slot-in-row bits (low 3) are XOR-folded with every higher 3-bit group of
+// the 12-bit tile index, so a quarter-warp whose lanes vary ANY three consecutive tile bits (the
+// three lowest non-register positions of a round) lands on the 8 distinct 16 B slots of a 128 B row.
+B200_HD uint32_t swz(uint32_t i) { return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u); }
 
 B200_HD double2 cmul(const double2 a, const double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));

@@ -286,14 +286,17 @@ class SVCostEvaluator:
         if old is not None and self.cut is not None and self.moves < self.REFRESH_MOVES:
             a0, a1 = self.cut
             m = min(a0, b0)
-            if old[:m] == new[:m]:
+            # moving costs |b0 - a0| gates, rebuilding from the base b0 gates: take the cheaper one
+            if abs(b0 - a0) <= b0 and old[:m] == new[:m]:
                 if b0 > a0:
                     eng.run(SLOT_R, SLOT_R, stream(new[a0:b0]))
                 elif b0 < a0:
                     eng.run(SLOT_R, SLOT_R, stream(old[b0:a0]), inverse=True)
                 r_ok = True
             so, sn = len(old) - a1, len(new) - b1
-            if sn <= so and old[len(old) - sn:] == new[b1:]:
+            if abs(so - sn) > sn:
+                pass                      # rebuilding L from |0..0> is cheaper than moving it
+            elif sn <= so and old[len(old) - sn:] == new[b1:]:
                 if so > sn:
                     eng.run(SLOT_L, SLOT_L, stream(old[a1:len(old) - sn]))
                 l_ok = True
