@@ -410,6 +410,20 @@ int b200_sv_alloc(b200_ctx* ctx, int num_qubits, int n_slots) {
     return 0;
 }
 
+int b200_sv_reserve_slots(b200_ctx* ctx, int num_qubits, int n_slots) {
+    if (!ctx) return set_error("null context");
+    if (num_qubits < 1 || num_qubits > 40) return set_error("num_qubits out of range [1,40]");
+    if (n_slots < 1 || n_slots > 64) return set_error("n_slots out of range [1,64]");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < ctx->slots.size(); ++i)
+        if (ctx->slots[i] && ctx->owned[i]) cudaFree(ctx->slots[i]);
+    ctx->slots.assign(n_slots, nullptr);
+    ctx->owned.assign(n_slots, 0);
+    ctx->nq = num_qubits;
+    return 0;
+}
+
 int b200_sv_attach(b200_ctx* ctx, int slot, void* device_ptr) {
     if (!ctx) return set_error("null context");
     if (ctx->nq <= 0) return set_error("statevector not allocated (call b200_sv_alloc)");

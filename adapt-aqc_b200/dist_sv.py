@@ -1,0 +1,323 @@
+"""Statevectors too large for one GPU: sharding by global qubits (BASELINE config C5).
+
+One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  The 2^n amplitudes are
+split by the top g = log2(world) *physical* index bits: rank r holds the 2^(n-g) amplitudes whose
+global bits equal r.  A logical -> physical qubit permutation is kept per state:
+
+  * gates whose mixing targets are all local run through the single-GPU fused sweep kernels on the
+    local slice (``SVEngine``), unchanged; a control or diagonal qubit that is global only selects
+    or phases the whole slice (decided on the host from the rank's bits);
+  * before a gate that mixes a global qubit, an all-to-all exchange swaps the g global qubits with
+    g local ones (the local qubits used furthest in the future): every rank sends the chunk with
+    top-local bits = p to peer p and receives the peer's chunk -- (1 - 1/G) of the slice crosses
+    NVLink once.  The exchange is done in place through a small staging buffer so that a slot can
+    fill most of the 180 GB.
+
+Read-outs reduce across ranks with one small all-reduce: amplitude 0, all <Z_q>, pair RDMs.
+
+The reference has no distributed path at all; this module is what lets the same
+backend interface reach 34 qubits.  Host-side logic is tested on CPU with gloo, world_size 2
+(tests/test_dist_gloo.py).
+"""
+import numpy as np
+
+from . import gates as G
+
+# gates that act diagonally on every qubit they touch
+_DIAG_1Q = {"z", "s", "sdg", "t", "tdg", "rz", "u1", "p", "id", "i"}
+
+
+def mixing_qubits(ent):
+    """Qubits on which a canonical window entry acts non-diagonally (they must be local)."""
+    name, q0, q1 = ent[0], ent[1], ent[2]
+    if q1 < 0:
+        if name in _DIAG_1Q:
+            return ()
+        if name == "mat1":
+            m = np.frombuffer(ent[6], dtype=np.complex128)
+            return () if (m[1] == 0 and m[2] == 0) else (q0,)
+        return (q0,)
+    if name == "cx":
+        return (q1,)
+    if name == "cz":
+        return ()
+    if name == "mat2":
+        m = np.frombuffer(ent[6], dtype=np.complex128).reshape(4, 4)
+        if np.count_nonzero(m - np.diag(np.diag(m))) == 0:
+            return ()
+    return (q0, q1)
+
+
+class TorchComm:
+    """Thin wrapper over torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device if device is not None else torch.device("cpu")
+        self.bytes_sent = 0
+        self.exchange_ms = 0.0
+
+    def allreduce_sum(self, arr):
+        t = self.torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def exchange_chunks(self, state, staging):
+        """In-place all-to-all of the `world` equal chunks of the 1-D tensor `state`: chunk[p] goes
+        to rank p, whose chunk[rank] comes back into the same place.  `staging`: scratch tensor."""
+        torch, dist = self.torch, self.dist
+        Gw = self.world
+        chunk = state.numel() // Gw
+        piece = min(chunk, staging.numel())
+        timing = state.is_cuda
+        if timing:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        for step in range(1, Gw):
+            peer = self.rank ^ step
+            base = peer * chunk
+            for off in range(0, chunk, piece):
+                cnt = min(piece, chunk - off)
+                mine = state[base + off: base + off + cnt]
+                buf = staging[:cnt]
+                ops = [dist.P2POp(dist.isend, mine, peer), dist.P2POp(dist.irecv, buf, peer)]
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+                mine.copy_(buf)
+                self.bytes_sent += cnt * state.element_size()
+        if timing:
+            e1.record()
+            e1.synchronize()
+            self.exchange_ms += e0.elapsed_time(e1)
+
+
+class ShardedStatevector:
+    """`n_slots` sharded states of `num_qubits` qubits over `comm.world` ranks.
+
+    engine: local engine over n_local = num_qubits - g qubits (SVEngine on the GPU; any object with
+            run/amp/expz/pair_rdm/inner/copy for the CPU tests);
+    slot_tensors: one flat torch tensor (float64, 2 * 2^n_local) per slot, aliasing the engine's
+            slot memory -- what the communicator sends from / receives into."""
+
+    def __init__(self, num_qubits, engine, comm, slot_tensors, staging, sync=None):
+        self.n = int(num_qubits)
+        self.comm = comm
+        self.g = int(np.log2(comm.world))
+        if (1 << self.g) != comm.world:
+            raise ValueError("world size must be a power of two")
+        self.nl = self.n - self.g
+        if self.nl < self.g or engine.num_qubits != self.nl:
+            raise ValueError("local engine must hold num_qubits - log2(world) qubits")
+        self.eng = engine
+        self.slot_tensors = slot_tensors
+        self.staging = staging
+        self._sync = sync or (lambda: None)
+        # perm[slot][logical] = physical position; positions >= nl are rank bits
+        self.perm = [list(range(self.n)) for _ in slot_tensors]
+        self.stats = {"exchanges": 0, "local_runs": 0}
+
+    # ---- layout ----
+    def _rank_bit(self, phys):
+        return (self.comm.rank >> (phys - self.nl)) & 1
+
+    def _is_global(self, slot, logical):
+        return self.perm[slot][logical] >= self.nl
+
+    def _exchange(self, slot, victims):
+        """Swap the g global qubits with the local logical qubits `victims` (len g)."""
+        perm = self.perm[slot]
+        nl, g = self.nl, self.g
+        # 1. move the victims to the top-g local physical positions with local swap gates
+        inv = {p: l for l, p in enumerate(perm)}
+        swaps = []
+        for j, v in enumerate(victims):
+            want = nl - g + j
+            have = perm[v]
+            if have != want:
+                other = inv[want]
+                swaps.append(("swap", have, want, 0.0, 0.0, 0.0, None))
+                perm[v], perm[other] = want, have
+                inv[want], inv[have] = v, other
+        if swaps:
+            self.eng.run(slot, slot, G.GateStream.from_window(swaps))
+            self.stats["local_runs"] += 1
+        # 2. all-to-all: chunk index (top-g local bits) <-> rank bits
+        self._sync()
+        self.comm.exchange_chunks(self.slot_tensors[slot], self.staging)
+        self._sync()
+        for j in range(g):
+            a, b = inv[nl - g + j], inv[nl + j]
+            perm[a], perm[b] = nl + j, nl - g + j
+        self.stats["exchanges"] += 1
+
+    def ensure_local(self, slot, needed, next_use=None):
+        """Make every logical qubit in `needed` local; victims = local qubits not needed, used
+        furthest in the future (next_use[logical], larger = later)."""
+        perm = self.perm[slot]
+        if not any(perm[q] >= self.nl for q in needed):
+            return
+        cands = [l for l in range(self.n) if perm[l] < self.nl and l not in needed]
+        if len(cands) < self.g:
+            raise ValueError("too many qubits must be local at once for this sharding")
+        cands.sort(key=lambda l: (-(next_use[l] if next_use is not None else 0), -perm[l]))
+        self._exchange(slot, cands[:self.g])
+
+    # ---- gate application ----
+    def _localise(self, slot, ent):
+        """Translate one canonical entry to the local physical qubits of this rank; returns a list
+        of entries (possibly empty) -- global control / diagonal qubits are resolved here."""
+        perm, nl = self.perm[slot], self.nl
+        name, q0, q1 = ent[0], ent[1], ent[2]
+        p0 = perm[q0]
+        if q1 < 0:
+            if p0 < nl:
+                return [(name, p0, -1) + ent[3:]]
+            m = G.matrix_of_entry(ent)                      # diagonal on a global qubit: a scalar
+            ph = m[1, 1] if self._rank_bit(p0) else m[0, 0]
+            return [] if ph == 1 else [("mat1", 0, -1, 0.0, 0.0, 0.0, np.diag([ph, ph]).astype(np.complex128).tobytes())]
+        p1 = perm[q1]
+        if p0 < nl and p1 < nl:
+            return [(name, p0, p1) + ent[3:]]
+        if name == "cx":                                    # control is global (target is local by construction)
+            return [("x", p1, -1, 0.0, 0.0, 0.0, None)] if self._rank_bit(p0) else []
+        if name == "cz":
+            if p0 >= nl and p1 >= nl:
+                both = self._rank_bit(p0) and self._rank_bit(p1)
+                return [("mat1", 0, -1, 0.0, 0.0, 0.0, np.diag([-1, -1]).astype(np.complex128).tobytes())] if both else []
+            loc, glob = (p1, p0) if p0 >= nl else (p0, p1)
+            return [("z", loc, -1, 0.0, 0.0, 0.0, None)] if self._rank_bit(glob) else []
+        # diagonal mat2 with a global qubit
+        d = np.diag(np.frombuffer(ent[6], dtype=np.complex128).reshape(4, 4))     # index bit(q0) + 2 bit(q1)
+        if p0 >= nl and p1 >= nl:
+            ph = d[self._rank_bit(p0) + 2 * self._rank_bit(p1)]
+            return [("mat1", 0, -1, 0.0, 0.0, 0.0, np.diag([ph, ph]).astype(np.complex128).tobytes())]
+        if p0 >= nl:
+            b = self._rank_bit(p0)
+            return [("mat1", p1, -1, 0.0, 0.0, 0.0, np.diag([d[b], d[b + 2]]).astype(np.complex128).tobytes())]
+        b = self._rank_bit(p1)
+        return [("mat1", p0, -1, 0.0, 0.0, 0.0, np.diag([d[2 * b], d[2 * b + 1]]).astype(np.complex128).tobytes())]
+
+    def run(self, dst, src, window):
+        """dst <- window applied to src (src = -1: |0..0>).  `window`: canonical entries on logical
+        qubits (gates.canonical_window)."""
+        eng = self.eng
+        if src < 0:
+            self.perm[dst] = list(range(self.n))
+            if self.comm.rank == 0:
+                eng.run(dst, -1, G.GateStream.from_window([]))
+            else:
+                eng.run(dst, -1, G.GateStream.from_window([("mat1", 0, -1, 0.0, 0.0, 0.0,
+                                                               np.zeros((2, 2), dtype=np.complex128).tobytes())]))
+        elif src != dst:
+            eng.copy(dst, src)
+            self.perm[dst] = list(self.perm[src])
+        mix = [mixing_qubits(e) for e in window]
+        # next use (as a mixing target) of every logical qubit, scanning from the back
+        INF = len(window) + 1
+        nxt = [INF] * self.n
+        next_use_at = [None] * len(window)
+        for i in range(len(window) - 1, -1, -1):
+            for q in mix[i]:
+                nxt[q] = i
+            next_use_at[i] = list(nxt)
+        batch = []
+
+        def flush():
+            if batch:
+                eng.run(dst, dst, G.GateStream.from_window(batch))
+                self.stats["local_runs"] += 1
+                batch.clear()
+
+        for i, ent in enumerate(window):
+            if any(self._is_global(dst, q) for q in mix[i]):
+                flush()
+                # bring in this gate's qubits and as many upcoming mixing qubits as are global now
+                needed = set(mix[i])
+                self.ensure_local(dst, needed, next_use_at[i])
+            batch.extend(self._localise(dst, ent))
+        flush()
+
+    # ---- read-outs (every rank returns the same values) ----
+    def amp(self, slot, index=0):
+        perm, nl = self.perm[slot], self.nl
+        phys = 0
+        for l in range(self.n):
+            if (index >> l) & 1:
+                phys |= 1 << perm[l]
+        owner, local = phys >> nl, phys & ((1 << nl) - 1)
+        v = self.eng.amp(slot, local) if owner == self.comm.rank else 0j
+        out = self.comm.allreduce_sum(np.array([v.real, v.imag]))
+        return complex(out[0], out[1])
+
+    def expz(self, slot):
+        perm, nl = self.perm[slot], self.nl
+        z_loc, norm_loc = self.eng.expz(slot)             # unnormalised sums over the local slice
+        vec = np.zeros(self.n + 1)
+        vec[:nl] = z_loc
+        for p in range(nl, self.n):
+            vec[p] = (1 - 2 * self._rank_bit(p)) * norm_loc
+        vec[self.n] = norm_loc
+        tot = self.comm.allreduce_sum(vec)
+        return np.array([tot[perm[l]] for l in range(self.n)]), float(tot[self.n])
+
+    def pair_rdm(self, slot, pairs):
+        """4x4 RDMs (lower logical qubit least significant) for logical `pairs`."""
+        pairs = [tuple(p) for p in pairs]
+        out = {}
+        remaining = list(dict.fromkeys(tuple(sorted(p)) for p in pairs))
+        while remaining:
+            perm = self.perm[slot]
+            ready = [p for p in remaining if perm[p[0]] < self.nl and perm[p[1]] < self.nl]
+            if ready:
+                phys = [(perm[a], perm[b]) for a, b in ready]
+                rho = self.eng.pair_rdm(slot, phys)
+                flat = self.comm.allreduce_sum(np.ascontiguousarray(rho).view(np.float64).reshape(-1))
+                rho = flat.view(np.complex128).reshape(-1, 4, 4)
+                for (a, b), (pa, pb), r in zip(ready, phys, rho):
+                    if pa > pb:       # kernel convention: lower PHYSICAL qubit is the LSB -> swap index bits
+                        r = r[np.ix_([0, 2, 1, 3], [0, 2, 1, 3])]
+                    out[(a, b)] = r
+                remaining = [p for p in remaining if p not in out]
+            if remaining:
+                # make the first blocked pair local; keep the qubits of other remaining pairs if possible
+                weight = [0] * self.n
+                for a, b in remaining:
+                    weight[a] += 1; weight[b] += 1
+                self.ensure_local(slot, set(remaining[0]), next_use=[-w for w in weight])
+        return np.array([out[tuple(sorted(p))] for p in pairs]).reshape(-1, 4, 4)
+
+    def inner(self, l_slot, r_slot):
+        """<L|R>; the two slots must share a layout (true for states produced from the same run)."""
+        if self.perm[l_slot] != self.perm[r_slot]:
+            raise ValueError("inner product needs identical qubit layouts")
+        v = self.eng.inner(l_slot, r_slot, -1)
+        out = self.comm.allreduce_sum(np.array([v.real, v.imag]))
+        return complex(out[0], out[1])
+
+
+def make_gpu_sharded(num_qubits, n_slots=2, staging_bytes=1 << 30, local_rank=0):
+    """Builds a ShardedStatevector over the default process group (NCCL), one rank per GPU."""
+    import torch
+    from .sv_engine import SVEngine
+    dev = torch.device("cuda", local_rank)
+    comm = TorchComm(dev)
+    g = int(np.log2(comm.world))
+    nl = num_qubits - g
+    eng = SVEngine(nl, device=local_rank, n_slots=n_slots, external_memory=True)
+    tensors = []
+    for s in range(n_slots):
+        t = torch.empty(2 << nl, dtype=torch.float64, device=dev)
+        eng.attach(s, t.data_ptr())
+        tensors.append(t)
+    staging = torch.empty(min(staging_bytes // 8, (2 << nl) // comm.world), dtype=torch.float64, device=dev)
+
+    def sync():
+        eng.sync()
+        torch.cuda.synchronize(dev)
+
+    sv = ShardedStatevector(num_qubits, eng, comm, tensors, staging, sync)
+    sv._keepalive = (tensors, staging)
+    return sv

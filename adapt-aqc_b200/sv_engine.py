@@ -34,7 +34,9 @@ SLOT_WORK, SLOT_BASE, SLOT_L, SLOT_R = 0, 1, 2, 3
 class SVEngine:
     """One GPU context holding `n_slots` statevectors of `num_qubits` qubits."""
 
-    def __init__(self, num_qubits, device=0, n_slots=4):
+    def __init__(self, num_qubits, device=0, n_slots=4, external_memory=False):
+        """external_memory=True: slots get their memory from attach() (caller-owned device
+        buffers, e.g. torch tensors that NCCL sends from / receives into)."""
         self._lib = load()
         self._ctx = ctypes.c_void_p()
         check(self._lib.b200_ctx_create(int(device), ctypes.byref(self._ctx)))
@@ -42,10 +44,16 @@ class SVEngine:
         self.num_qubits = int(num_qubits)
         self.n_slots = int(n_slots)
         try:
-            check(self._lib.b200_sv_alloc(self._ctx, self.num_qubits, self.n_slots))
+            if external_memory:
+                check(self._lib.b200_sv_reserve_slots(self._ctx, self.num_qubits, self.n_slots))
+            else:
+                check(self._lib.b200_sv_alloc(self._ctx, self.num_qubits, self.n_slots))
         except B200Error:
             self.close()
             raise
+
+    def attach(self, slot, device_ptr):
+        check(self._lib.b200_sv_attach(self._ctx, int(slot), ctypes.c_void_p(int(device_ptr))))
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:

@@ -97,6 +97,10 @@ int b200_ctx_set_timing(b200_ctx *ctx, int enable);
 /* ---- statevector path ------------------------------------------------------------------- */
 /* (Re)allocate `n_slots` device statevectors of `num_qubits` qubits. */
 int b200_sv_alloc(b200_ctx *ctx, int num_qubits, int n_slots);
+/* Declare `n_slots` empty slots of `num_qubits` qubits without allocating: every slot must be
+ * given memory with b200_sv_attach before use (the sharded multi-GPU path attaches buffers that are
+ * also registered with the NCCL communicator). */
+int b200_sv_reserve_slots(b200_ctx *ctx, int num_qubits, int n_slots);
 /* Use caller-provided device memory (e.g. a torch CUDA tensor's data_ptr()) for one slot. */
 int b200_sv_attach(b200_ctx *ctx, int slot, void *device_ptr);
 int b200_sv_device_ptr(b200_ctx *ctx, int slot, void **out);

@@ -1,0 +1,93 @@
+"""Worker of tests/test_dist_gloo.py: one rank of a gloo process group checking the sharded
+statevector (adapt_aqc_b200.dist_sv) against the oracle.  CPU only: the local engine is the
+emulated kernel path (tests/helpers.FakeEngine)."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import adapt_aqc_b200  # noqa: E402,F401
+from adapt_aqc_b200.dist_sv import ShardedStatevector, TorchComm  # noqa: E402
+from adapt_aqc_b200.gates import GateStream  # noqa: E402
+from helpers import FakeEngine, random_gates  # noqa: E402
+from oracle import sv_oracle as orc  # noqa: E402
+
+
+def load_emu():
+    lib = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libb200aqc_emu.so"))
+    lib.emu_last_error.restype = ctypes.c_char_p
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.emu_sv_run.argtypes = [ctypes.c_int, dp, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                               ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int32)]
+    return lib
+
+
+def gather_state(sv, slot):
+    """Full logical-order statevector on every rank (test only)."""
+    comm = sv.comm
+    local = torch.from_numpy(sv.eng.slots[slot].copy().view(np.float64))
+    parts = [torch.empty_like(local) for _ in range(comm.world)]
+    dist.all_gather(parts, local)
+    phys = np.concatenate([p.numpy().view(np.complex128) for p in parts])      # physical order
+    n, perm = sv.n, sv.perm[slot]
+    idx = np.arange(1 << n)
+    pidx = np.zeros_like(idx)
+    for l in range(n):
+        pidx |= ((idx >> l) & 1) << perm[l]
+    return phys[pidx]
+
+
+def main():
+    dist.init_process_group("gloo")
+    comm = TorchComm()
+    g = int(np.log2(comm.world))
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 7
+    nl = n - g
+    emu = load_emu()
+    eng = FakeEngine(emu, nl, n_slots=2)
+    tensors = [torch.from_numpy(s.view(np.float64)) for s in eng.slots]
+    staging = torch.empty(max(8, (2 << nl) // comm.world // 3), dtype=torch.float64)   # forces multi-piece exchanges
+    sv = ShardedStatevector(n, eng, comm, tensors, staging)
+
+    rng = np.random.default_rng(123)              # same stream on every rank
+    for trial in range(4):
+        gates = random_gates(n, 60, rng)
+        window = GateStream  # noqa: F841
+        from adapt_aqc_b200.gates import canonical_window
+        from helpers import circuit_from_gates
+        circ = circuit_from_gates(n, gates)
+        win = canonical_window(circ)
+        sv.run(0, -1, win)
+        ref = orc.evaluate_circuit(n, gates)
+        got = gather_state(sv, 0)
+        assert np.max(np.abs(got - ref)) < 1e-12, (trial, np.max(np.abs(got - ref)))
+        # read-outs
+        for index in (0, 1, (1 << n) - 1, 1 << (n - 1), 37 % (1 << n)):
+            assert abs(sv.amp(0, index) - ref[index]) < 1e-12
+        z, norm = sv.expz(0)
+        assert np.allclose(z, orc.measure_qubit_expectation_values(ref), atol=1e-12) and abs(norm - 1) < 1e-12
+        pairs = [(a, b) for a in range(n) for b in range(n) if a != b]
+        rho = sv.pair_rdm(0, pairs)
+        for r, (a, b) in zip(rho, pairs):
+            assert np.allclose(r, orc.partial_trace(ref, a, b), atol=1e-12), (a, b)
+        # second segment applied to the (possibly permuted) state, out of place
+        more = random_gates(n, 30, rng)
+        sv.run(1, 0, canonical_window(circuit_from_gates(n, more)))
+        ref2 = orc.apply_gates(orc.evaluate_circuit(n, gates), more)
+        assert np.max(np.abs(gather_state(sv, 1) - ref2)) < 1e-12
+        assert abs(sv.inner(1, 1) - 1) < 1e-12
+    assert sv.stats["exchanges"] > 0, "the test circuits must exercise the global-qubit exchange"
+    if comm.rank == 0:
+        print(f"dist ok: world={comm.world} n={n} exchanges={sv.stats['exchanges']} bytes_sent={comm.bytes_sent}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
