@@ -230,6 +230,62 @@ def bench_mps(args, device, with_cpu=True):
     return out
 
 
+# ---- config C5: statevector sharded over the ranks by global qubits --------------------------------
+def bench_sharded(args, local_rank, world):
+    """One cost evaluation = full_circuit (brickwork target + thin layers) applied to |0..0> on a
+    state of n = sharded_local_qubits + log2(world) qubits, + amplitude 0.  Local gates run in the
+    fused sweep kernels; global qubits are exchanged with NCCL send/recv over NVLink."""
+    import torch
+    import torch.distributed as dist
+    from adapt_aqc_b200.dist_sv import make_gpu_sharded
+    from adapt_aqc_b200.gates import canonical_window
+    g = int(np.log2(world))
+    n = args.sharded_local_qubits + g
+    target, ansatz = build_workload(n, args.sharded_depth, args.sharded_layers)
+    window = canonical_window(target) + canonical_window(ansatz)
+    sv = make_gpu_sharded(n, n_slots=1, local_rank=local_rank)
+    eng, comm = sv.eng, sv.comm
+    sv.run(0, -1, window)                       # warm-up (also JIT of NCCL channels)
+    sv.amp(0, 0)
+    eng.sync(); torch.cuda.synchronize()
+    dist.barrier()
+    comm.bytes_sent, comm.exchange_ms = 0, 0.0
+    sv.stats["exchanges"] = 0
+    c0 = eng.counters()
+    reps = max(1, args.steps)
+    eng.profile(True)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        sv.run(0, -1, window)
+        a0 = sv.amp(0, 0)
+    eng.sync(); torch.cuda.synchronize()
+    dist.barrier()
+    wall = time.perf_counter() - t0
+    prof = eng.profile_read()
+    eng.profile(False)
+    c1 = eng.counters()
+    z, norm = sv.expz(0)
+    t = torch.tensor([wall, comm.exchange_ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, xms = float(t[0]), float(t[1])
+    sweeps = (c1["sweeps"] - c0["sweeps"]) / reps
+    local_bytes = 16 * (1 << (n - g))
+    out = {
+        "workload": f"C5: {n}-qubit brickwork(depth={args.sharded_depth}) + {args.sharded_layers} thin layers from |0..0>, "
+                    f"{n - g} local + {g} global qubits per rank",
+        "qubits": n, "state_bytes_per_gpu": local_bytes, "value": reps / wall, "unit": UNIT, "s_per_eval": wall / reps,
+        "sweeps_per_eval": sweeps, "exchanges_per_eval": sv.stats["exchanges"] / reps,
+        "nvlink_bytes_sent_per_gpu_per_eval": comm.bytes_sent / reps,
+        "exchange_ms_per_eval": xms / reps,
+        "nvlink_GBps_per_direction": (comm.bytes_sent / reps) / (xms / reps * 1e-3) / 1e9 if xms > 0 else None,
+        "sweep_ms_avg": prof["sweep"][0] / max(1, prof["sweep"][1]),
+        "sweep_GBps": 32.0 * (1 << (n - g)) / (prof["sweep"][0] / max(1, prof["sweep"][1]) * 1e-3) / 1e9 if prof["sweep"][1] else None,
+        "norm": norm, "amp0_abs2": abs(a0) ** 2,
+    }
+    eng.close()
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -278,6 +334,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mps", action="store_true", help="skip the secondary C4 (MPS) measurement")
     ap.add_argument("--mps-only", action="store_true", help="run only the C4 (MPS) measurement and print it")
+    ap.add_argument("--sharded-local-qubits", type=int, default=30, help="qubits per rank of the sharded C5 leg (N > 1)")
+    ap.add_argument("--sharded-depth", type=int, default=4)
+    ap.add_argument("--sharded-layers", type=int, default=4)
+    ap.add_argument("--no-sharded", action="store_true")
     ap.add_argument("--mps-qubits", type=int, default=50)
     ap.add_argument("--mps-chi", type=int, default=256)
     ap.add_argument("--mps-layers", type=int, default=2)
@@ -402,6 +462,13 @@ def main():
             line["mps_c4"] = bench_mps(args, local_rank, with_cpu=not args.no_cpu_baseline)
         except Exception as exc:  # noqa: BLE001 - the secondary measurement must not hide the main line
             line["mps_c4"] = {"error": repr(exc)}
+    if dist is not None and not args.no_sharded:
+        backend._engine.close()          # free the replica's statevector slots first
+        try:
+            sharded = bench_sharded(args, local_rank, world)
+        except Exception as exc:  # noqa: BLE001
+            sharded = {"error": repr(exc)}
+        line["sharded_c5"] = sharded
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

@@ -32,10 +32,14 @@ def load_emu():
 def gather_state(sv, slot):
     """Full logical-order statevector on every rank (test only)."""
     comm = sv.comm
-    local = torch.from_numpy(sv.eng.slots[slot].copy().view(np.float64))
+    if hasattr(sv.eng, "download"):
+        host = sv.eng.download(slot)
+    else:
+        host = sv.eng.slots[slot].copy()
+    local = torch.from_numpy(np.ascontiguousarray(host).view(np.float64)).to(comm.device)
     parts = [torch.empty_like(local) for _ in range(comm.world)]
     dist.all_gather(parts, local)
-    phys = np.concatenate([p.numpy().view(np.complex128) for p in parts])      # physical order
+    phys = np.concatenate([p.cpu().numpy().view(np.complex128) for p in parts])      # physical order
     n, perm = sv.n, sv.perm[slot]
     idx = np.arange(1 << n)
     pidx = np.zeros_like(idx)
@@ -45,16 +49,27 @@ def gather_state(sv, slot):
 
 
 def main():
-    dist.init_process_group("gloo")
-    comm = TorchComm()
-    g = int(np.log2(comm.world))
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 7
-    nl = n - g
-    emu = load_emu()
-    eng = FakeEngine(emu, nl, n_slots=2)
-    tensors = [torch.from_numpy(s.view(np.float64)) for s in eng.slots]
-    staging = torch.empty(max(8, (2 << nl) // comm.world // 3), dtype=torch.float64)   # forces multi-piece exchanges
-    sv = ShardedStatevector(n, eng, comm, tensors, staging)
+    on_gpu = len(sys.argv) > 2 and sys.argv[2] == "gpu"
+    if on_gpu:
+        from adapt_aqc_b200.dist_sv import make_gpu_sharded
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a staging buffer of 1/3 chunk forces multi-piece exchanges here too
+        sv = make_gpu_sharded(n, n_slots=2, local_rank=local_rank,
+                              staging_bytes=8 * max(8, (2 << (n - int(np.log2(dist.get_world_size())))) // dist.get_world_size() // 3))
+        comm = sv.comm
+    else:
+        dist.init_process_group("gloo")
+        comm = TorchComm()
+        g = int(np.log2(comm.world))
+        nl = n - g
+        emu = load_emu()
+        eng = FakeEngine(emu, nl, n_slots=2)
+        tensors = [torch.from_numpy(s.view(np.float64)) for s in eng.slots]
+        staging = torch.empty(max(8, (2 << nl) // comm.world // 3), dtype=torch.float64)   # forces multi-piece exchanges
+        sv = ShardedStatevector(n, eng, comm, tensors, staging)
 
     rng = np.random.default_rng(123)              # same stream on every rank
     for trial in range(4):

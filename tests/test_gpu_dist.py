@@ -1,0 +1,30 @@
+"""NCCL version of tests/test_dist_gloo.py: the sharded statevector on >= 2 real GPUs (skipped on a
+one-GPU box).  Same worker, same oracle checks; the local engine is SVEngine on torch-owned
+device buffers and the exchange goes over NVLink."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    from adapt_aqc_b200.lib import load
+    n = ctypes.c_int(0)
+    return n.value if load().b200_device_count(ctypes.byref(n)) == 0 else 0
+
+
+@pytest.mark.parametrize("world,n,port", [(2, 15, 29621), (4, 16, 29622), (8, 17, 29623)])
+def test_sharded_statevector_on_nccl(world, n, port):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"),
+           str(n), "gpu"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "dist ok" in res.stdout
