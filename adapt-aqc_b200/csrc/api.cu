@@ -718,4 +718,27 @@ int b200_sv_plan_stats(int num_qubits, const b200_gate* gates, int n_gates, cons
     return 0;
 }
 
+int b200_sv_plan_detail(int num_qubits, const b200_gate* gates, int n_gates, const double* mats, int n_mats,
+                        int32_t* out, int max_sweeps, int32_t* n_sweeps) {
+    if (!out || !n_sweeps) return set_error("null pointer");
+    if (num_qubits < 1 || num_qubits > 40) return set_error("num_qubits out of range [1,40]");
+    Plan plan;
+    if (make_plan(num_qubits, gates, n_gates, mats, n_mats, false, plan)) return -1;
+    *n_sweeps = (int32_t)plan.sweeps.size();
+    for (int k = 0; k < (int)plan.sweeps.size() && k < max_sweeps; ++k) {
+        const DevSweep& sw = plan.sweeps[k];
+        int ops = 0, dense = 0;
+        for (int r = sw.round_begin; r < sw.round_end; ++r) {
+            ops += plan.rounds[r].op_end - plan.rounds[r].op_begin;
+            for (int o = plan.rounds[r].op_begin; o < plan.rounds[r].op_end; ++o)
+                if (plan.ops[o].kind == K_MAT1 || plan.ops[o].kind == K_MAT2) ++dense;
+        }
+        out[4 * k] = sw.round_end - sw.round_begin;
+        out[4 * k + 1] = ops;
+        out[4 * k + 2] = dense;
+        out[4 * k + 3] = sw.c;
+    }
+    return 0;
+}
+
 }  // extern "C"

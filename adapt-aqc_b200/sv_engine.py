@@ -184,6 +184,15 @@ _M4 = {
 }
 
 
+def plan_detail(num_qubits, stream, max_sweeps=256):
+    """[(rounds, ops, dense ops, contiguous low qubits)] per sweep -- no GPU needed."""
+    out = np.zeros(4 * max_sweeps, dtype=np.int32)
+    ns = ctypes.c_int32()
+    check(load().b200_sv_plan_detail(int(num_qubits), stream.rec_ptr(), len(stream.rec), stream.mats_ptr(),
+                                     len(stream.mats), out.ctypes.data, max_sweeps, ctypes.byref(ns)))
+    return [tuple(int(x) for x in out[4 * k:4 * k + 4]) for k in range(min(ns.value, max_sweeps))]
+
+
 def _support(ent):
     return (ent[1],) if ent[2] < 0 else (ent[1], ent[2])
 

@@ -212,6 +212,11 @@ int b200_mps_stats(b200_mps *mps, uint64_t out[4]);
 int b200_sv_plan_stats(int num_qubits, const b200_gate *gates, int n_gates, const double *mats,
                        int n_mats, int32_t out[4]);
 
+/* Per-sweep detail of the plan: out[4k..4k+3] = {rounds, fused ops, dense (FP64-heavy) ops, number of
+ * leading contiguous low qubits of the tile} for sweep k < max_sweeps; *n_sweeps = total sweeps. */
+int b200_sv_plan_detail(int num_qubits, const b200_gate *gates, int n_gates, const double *mats, int n_mats,
+                        int32_t *out, int max_sweeps, int32_t *n_sweeps);
+
 #ifdef __cplusplus
 }
 #endif
