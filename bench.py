@@ -172,61 +172,74 @@ def mps_step(comp):
 
 
 def bench_mps(args, device, with_cpu=True):
-    """evals/s of the MPS path in the reference's contraction order (every evaluation re-applies
-    the un-absorbed gates to the chi=256 target: one 512x512 complex SVD per CNOT, truncated back
-    to chi=256 with Aer's rule) -- the same work per evaluation as AerMPSBackend.evaluate_global_cost."""
+    """evals/s of the MPS path on config C4, in two truncation settings:
+
+    capped   : max_bond_dimension = chi (Aer's cap), reference contraction order -- every evaluation
+               re-applies the un-absorbed gates to the chi=256 target (one 512x512 complex SVD per
+               CNOT, truncated back to chi), the same work per evaluation as
+               AerMPSBackend.evaluate_global_cost (aer_mps_backend.py:49-57).
+    default  : the reference's default simulator (threshold 1e-16, no cap, aer_mps_backend.py:27):
+               truncation is at roundoff level, so the block transfer-matrix evaluator applies -- SVDs
+               only when the optimiser moves to another layer."""
     from adapt_aqc_b200.compiler import AdaptCompiler
     from adapt_aqc_b200.mps_backend import B200MPSBackend, B200MPSSimulator
     n, chi, layers = args.mps_qubits, args.mps_chi, args.mps_layers
     t0 = time.perf_counter()
     target, ansatz = build_mps_workload(n, chi, layers)
     gen_s = time.perf_counter() - t0
-    sim = B200MPSSimulator(1e-16, max_chi=chi, device=device)
-    backend = B200MPSBackend(sim)
-    comp = AdaptCompiler(target, backend=backend)
-    comp.full_circuit.data.extend(ansatz.copy().data)
-    comp.evaluate_cost()
-    ctx = sim.context()
-    for _ in range(max(1, args.warmup // 2)):
-        mps_step(comp)
-    ctx.sync()
-    c0, e0 = ctx.counters(), comp.cost_evaluation_counter
-    ctx.profile(True)
-    ctx.mark(0)
-    steps = max(1, args.steps // 2)
-    for _ in range(steps):
-        mps_step(comp)
-    ctx.mark(1)
-    ms = ctx.elapsed_ms()
-    prof = ctx.profile_read()
-    ctx.profile(False)
-    c1 = ctx.counters()
-    evals = comp.cost_evaluation_counter - e0
-    out = {
-        "workload": f"C4: {n}-qubit random Vidal MPS, chi={chi} (max_bond_dimension={chi}, threshold 1e-16), "
-                    f"{layers} un-absorbed thinly-dressed CNOT layers; step = one Rotosolve cycle ({evals // steps} evals), "
-                    "reference contraction order (all window gates re-applied per evaluation)",
-        "value": evals / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "evals_per_step": evals // steps,
-        "gpu_launches": int(c1["launches"] - c0["launches"]),
-        "kernel_ms": prof["mps"][0], "kernel_launches": int(prof["mps"][1]),
-        "dmma_flops": int(c1["tensor_flops"] - c0["tensor_flops"]),
-        "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / steps,
-        "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / steps,
-        "target_generation_s": gen_s,
-    }
-    if with_cpu:
-        from oracle.oracle_backends import OracleMPSBackend
-        from oracle import mps_oracle as mo
-        ocomp = AdaptCompiler(target, backend=OracleMPSBackend(mo.OracleMPSSimulator(1e-16, chi)))
-        ocomp.full_circuit.data.extend(ansatz.copy().data)
-        t0 = time.perf_counter()
-        k = 0
-        while k < 3 or (time.perf_counter() - t0 < 8 and k < 20):
-            ocomp.evaluate_cost()
-            k += 1
-        dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": k / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                               "sample": f"{k} full evaluations (numpy/LAPACK MPS oracle, {dt:.1f} s)"}
+    out = {"workload": f"C4: {n}-qubit random Vidal MPS, chi={chi}, {layers} un-absorbed thinly-dressed CNOT layers; "
+                       "step = one Rotosolve cycle over their rotations", "target_generation_s": gen_s}
+    for mode, cap in (("capped", chi), ("default", None)):
+        sim = B200MPSSimulator(1e-16, max_chi=cap, device=device)
+        backend = B200MPSBackend(sim)
+        comp = AdaptCompiler(target, backend=backend)
+        comp.full_circuit.data.extend(ansatz.copy().data)
+        comp.evaluate_cost()
+        ctx = sim.context()
+        for _ in range(max(1, args.warmup // 2)):
+            mps_step(comp)
+        ctx.sync()
+        c0, e0 = ctx.counters(), comp.cost_evaluation_counter
+        ctx.profile(True)
+        ctx.mark(0)
+        steps = max(1, args.steps // 2) if mode == "capped" else max(2, args.steps)
+        for _ in range(steps):
+            mps_step(comp)
+        ctx.mark(1)
+        ms = ctx.elapsed_ms()
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        c1 = ctx.counters()
+        evals = comp.cost_evaluation_counter - e0
+        res = {
+            "truncation": {"threshold": 1e-16, "max_bond_dimension": cap},
+            "evaluation": "reference contraction order" if mode == "capped" else "block transfer matrices",
+            "value": evals / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "evals_per_step": evals // steps,
+            "gpu_launches": int(c1["launches"] - c0["launches"]),
+            "kernel_ms": prof["mps"][0], "kernel_launches": int(prof["mps"][1]),
+            "dmma_flops": int(c1["tensor_flops"] - c0["tensor_flops"]),
+            "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / steps,
+            "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / steps,
+        }
+        if backend._engine is not None:
+            res["max_bond"] = max(max(m.bond_dims()) for m in backend._engine.slots)
+            res["svd"] = {k: int(sum(m.stats()[k] for m in backend._engine.slots)) for k in ("svds", "jacobi_sweeps")}
+        if with_cpu:
+            from oracle.oracle_backends import OracleMPSBackend
+            from oracle import mps_oracle as mo
+            ocomp = AdaptCompiler(target, backend=OracleMPSBackend(mo.OracleMPSSimulator(1e-16, cap)))
+            ocomp.full_circuit.data.extend(ansatz.copy().data)
+            t0 = time.perf_counter()
+            k = 0
+            while k < 2 or (time.perf_counter() - t0 < 6 and k < 20):
+                ocomp.evaluate_cost()
+                k += 1
+            dt = time.perf_counter() - t0
+            res["cpu_baseline"] = {"value": k / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"{k} full evaluations (numpy/LAPACK MPS oracle, {dt:.1f} s)"}
+        out[mode] = res
+        if backend._engine is not None:
+            backend._engine.close()
     return out
 
 
