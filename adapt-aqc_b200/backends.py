@@ -49,6 +49,12 @@ except Exception:  # noqa: BLE001
     _SVBase = AQCBackend
 
 
+# The compact bra lives in the smallest fitting 2^K-amplitude state, K in COMPACT_QUBITS (1 GiB at 26); registers of at most
+# COMPACT_MIN_QUBITS qubits are cheap enough to always use the dense path.
+COMPACT_QUBITS = (12, 19, 26)
+COMPACT_MIN_QUBITS = 12
+
+
 class DeviceStatevector:
     """What ``result.get_statevector()`` returns: a handle on an HBM-resident state.
 
@@ -157,6 +163,7 @@ class B200SVBackend(_SVBase):
     def __init__(self, device=0, simulator=None):
         self.device = device
         self._engine = None
+        self._compact = None
         self._evaluator = None
         self._state_version = 0
         self._last_run_key = None
@@ -178,7 +185,14 @@ class B200SVBackend(_SVBase):
             if self._engine is not None:
                 self._engine.close()
             self._engine = SVEngine(num_qubits, device=self.device, n_slots=4)
-            self._evaluator = SVCostEvaluator(self._engine)
+            for c in self._compact or []:
+                c.close()
+            self._compact = []
+            if num_qubits > COMPACT_MIN_QUBITS:
+                # small extra contexts for the compact bra <L| (see SVCostEvaluator)
+                sizes = sorted({min(k, num_qubits - 2) for k in COMPACT_QUBITS})
+                self._compact = [SVEngine(k, device=self.device, n_slots=1) for k in sizes]
+            self._evaluator = SVCostEvaluator(self._engine, self._compact)
             self._state_version += 1
             self._last_run_key = None
         return self._engine

@@ -683,6 +683,56 @@ int b200_sv_inner2(b200_ctx* ctx, int l_slot, int r_slot, int qa, int qb, double
     return 0;
 }
 
+int b200_sv_inner2_gather(b200_ctx* ctx, int r_slot, const void* compact_state, int K, const int32_t* qmap, int qa,
+                          int qb, double out[32]) {
+    if (check_slot(ctx, r_slot)) return -1;
+    const int n = ctx->nq;
+    if (!compact_state || !qmap || !out) return set_error("null pointer");
+    if (K < 2 || K > n || K > 40) return set_error("inner2_gather: compact size out of range");
+    QMap qm;
+    uint64_t seen = 0;
+    int ca = -1, cb = -1;
+    for (int b = 0; b < K; ++b) {
+        if (qmap[b] < 0 || qmap[b] >= n || (seen >> qmap[b] & 1)) return set_error("inner2_gather: bad qubit map");
+        seen |= 1ull << qmap[b];
+        qm.q[b] = qmap[b];
+        if (qmap[b] == qa) ca = b;
+        if (qmap[b] == qb) cb = b;
+    }
+    if (ca < 0 || cb < 0 || ca == cb) return set_error("inner2_gather: open qubits must be in the map");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Timer tm(ctx);
+    const int lo = std::min(ca, cb), hi = std::max(ca, cb);
+    const int grid = red_grid(ctx, 1ull << (K - 2));
+    {
+        KScope ks(ctx, B200_PROF_INNER);
+        sv_inner2_gather_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>((const double2*)compact_state, K,
+                                                                       (const double2*)ctx->slots[r_slot], qm, lo, hi, ctx->d_partial);
+    }
+    CUDA_TRY(cudaGetLastError());
+    {
+        KScope ks(ctx, B200_PROF_REDUCE);
+        reduce_partials_kernel<<<INNER2_WIDTH, 32, 0, ctx->stream>>>(ctx->d_partial, grid, INNER2_WIDTH, ctx->d_out);
+    }
+    CUDA_TRY(cudaGetLastError());
+    ctx->counters[3] += 32ull << K;
+    ctx->counters[6] += 1;
+    tm.stop();
+    double t[32];
+    if (fetch_out(ctx, t, 32)) return -1;
+    if (ca < cb) {
+        std::memcpy(out, t, sizeof t);
+    } else {
+        auto sw2 = [](int i) { return ((i & 1) << 1) | (i >> 1); };
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                out[2 * (4 * sw2(i) + sw2(j))] = t[2 * (4 * i + j)];
+                out[2 * (4 * sw2(i) + sw2(j)) + 1] = t[2 * (4 * i + j) + 1];
+            }
+    }
+    return 0;
+}
+
 int b200_sv_download(b200_ctx* ctx, int slot, uint64_t offset, uint64_t count, double* host) {
     if (check_slot(ctx, slot)) return -1;
     if (offset + count > (1ull << ctx->nq)) return set_error("download range out of bounds");

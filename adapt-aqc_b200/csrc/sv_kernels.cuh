@@ -573,4 +573,40 @@ sv_inner2_kernel(const double2* __restrict__ L, const double2* __restrict__ Rv, 
     block_sum_store<INNER2_WIDTH>(v, partial + (size_t)blockIdx.x * INNER2_WIDTH);
 }
 
+// K6c.  Transfer matrix against a COMPACT bra.  <L| = suffix^+ applied to <0..0| is supported only on
+// the K qubits the suffix touches: L[x] = ell[c] when x = deposit(c) over qmap, 0 elsewhere.  Then
+// T[i][j] = sum_c conj(ell[c_i]) R[deposit(c)_j] needs a GATHER of 2^K amplitudes of R instead of a
+// pass over all 2^n (for the newest ADAPT layer K = 2: four amplitudes).  ca < cb: compact positions
+// of the open qubits (qmap[ca] = qa, qmap[cb] = qb).
+struct QMap { int32_t q[40]; };
+__global__ void __launch_bounds__(RED_THREADS)
+sv_inner2_gather_kernel(const double2* __restrict__ ell, const int K, const double2* __restrict__ Rv, const QMap qm,
+                        const int ca, const int cb, double* __restrict__ partial) {
+    double2 t[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t[k] = make_double2(0.0, 0.0);
+    const uint64_t groups = 1ull << (K - 2);
+    const uint64_t la = 1ull << ca, lb = 1ull << cb, ra = 1ull << qm.q[ca], rb = 1ull << qm.q[cb];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+        const uint64_t c = ins0_64(ins0_64(g, ca), cb);
+        uint64_t x = 0;
+        for (int b = 0; b < K; ++b) x |= ((c >> b) & 1ull) << qm.q[b];
+        double2 l[4], r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            l[j] = ell[c + ((j & 1) ? la : 0) + ((j & 2) ? lb : 0)];
+            r[j] = Rv[x + ((j & 1) ? ra : 0) + ((j & 2) ? rb : 0)];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[4 * i + j] = cjfma(l[i], r[j], t[4 * i + j]);
+    }
+    double v[INNER2_WIDTH];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { v[2 * k] = t[k].x; v[2 * k + 1] = t[k].y; }
+    block_sum_store<INNER2_WIDTH>(v, partial + (size_t)blockIdx.x * INNER2_WIDTH);
+}
+
 }  // namespace b200

@@ -18,7 +18,7 @@ SYMBOLS = [
     "b200_ctx_set_timing", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_ctx_profile",
     "b200_ctx_profile_read", "b200_sv_alloc", "b200_sv_reserve_slots", "b200_sv_attach", "b200_sv_device_ptr",
     "b200_sv_num_qubits", "b200_sv_init_zero", "b200_sv_copy", "b200_sv_run",
-    "b200_sv_run_inverse", "b200_sv_amp", "b200_sv_expz", "b200_sv_pair_rdm", "b200_sv_inner", "b200_sv_inner2",
+    "b200_sv_run_inverse", "b200_sv_amp", "b200_sv_expz", "b200_sv_pair_rdm", "b200_sv_inner", "b200_sv_inner2", "b200_sv_inner2_gather",
     "b200_sv_download", "b200_sv_upload", "b200_sv_plan_stats", "b200_sv_plan_detail",
     "b200_mps_create", "b200_mps_destroy", "b200_mps_set_truncation", "b200_mps_num_qubits",
     "b200_mps_init_zero", "b200_mps_set", "b200_mps_bond_dims", "b200_mps_get", "b200_mps_copy",
@@ -74,6 +74,7 @@ def load():
     L.b200_sv_pair_rdm.argtypes = [vp, ci, vp, ci, dp]
     L.b200_sv_inner.argtypes = [vp, ci, ci, ci, dp]
     L.b200_sv_inner2.argtypes = [vp, ci, ci, ci, ci, dp]
+    L.b200_sv_inner2_gather.argtypes = [vp, ci, vp, ci, vp, ci, ci, dp]
     L.b200_sv_download.argtypes = [vp, ci, cu64, cu64, vp]
     L.b200_sv_upload.argtypes = [vp, ci, cu64, cu64, vp]
     L.b200_sv_plan_stats.argtypes = [ci, vp, ci, vp, ci, ctypes.POINTER(ctypes.c_int32)]

@@ -112,6 +112,15 @@ class SVEngine:
         check(self._lib.b200_sv_inner2(self._ctx, l_slot, r_slot, int(qa), int(qb), dptr(out)))
         return out.view(np.complex128).reshape(4, 4).copy()
 
+    def inner2_gather(self, r_slot, compact_engine, compact_slot, qmap, qa, qb):
+        """Same T with the bra given compactly: slot `compact_slot` of `compact_engine` (K qubits,
+        same device) holds L on the qubits qmap[0..K)."""
+        qm = np.ascontiguousarray(np.asarray(qmap, dtype=np.int32))
+        out = np.zeros(32)
+        check(self._lib.b200_sv_inner2_gather(self._ctx, r_slot, ctypes.c_void_p(compact_engine.device_ptr(compact_slot)),
+                                              len(qm), qm.ctypes.data, int(qa), int(qb), dptr(out)))
+        return out.view(np.complex128).reshape(4, 4).copy()
+
     def download(self, slot, offset=0, count=None):
         count = (1 << self.num_qubits) - offset if count is None else count
         host = np.empty(count, dtype=np.complex128)
@@ -230,20 +239,42 @@ def embed_entry(ent, pair, override=None):
 
 
 class SVCostEvaluator:
-    """Global-cost evaluation of ``[prefix | window]`` circuits with HBM-resident caches."""
+    """Global-cost evaluation of ``[prefix | window]`` circuits with HBM-resident caches.
 
-    REFRESH_MOVES = 256  # rebuild L/R from scratch after this many incremental moves
+    R (slot R) and L are tracked independently:
+      rwin : the gates R currently contains after the base (R = rwin . base)
+      lwin : the gates the dense L (slot L) contains (L = lwin^+ |0>), or None
+      lkey : identity of the compact L (a 2^K state in the compact engine), or None
+    `compact` (optional): a second, K-qubit engine on the same device.  <L| = suffix^+ <0| is
+    supported only on the qubits the suffix touches; when there are at most K of them L is built
+    from scratch in the compact engine (microseconds) and T comes from a GATHER of 2^K amplitudes
+    of R (``inner2_gather``) instead of a pass over 2^n.
+    """
 
-    def __init__(self, engine: SVEngine):
+    REFRESH_MOVES = 256  # rebuild R / dense L from scratch after this many incremental moves
+
+    def __init__(self, engine, compact=None):
         self.eng = engine
+        # one or several compact engines of increasing size; the smallest that fits is used
+        if compact is None:
+            self.compacts = []
+        elif isinstance(compact, (list, tuple)):
+            self.compacts = sorted(compact, key=lambda e: e.num_qubits)
+        else:
+            self.compacts = [compact]
+        self.compact = self.compacts[-1] if self.compacts else None
         self.base_key = None          # identity of the cached prefix state
-        self.window = None            # canonical window the caches refer to
-        self.cut = None               # (a0, a1): R = W[:a0] base, L = (W[a1:])^+ |0>
+        self.window = None            # last window evaluated
+        self.cut = None               # (b0, b1) of the block T is open on
         self.pair = None              # qubits the transfer matrix T is open on
         self.T = None
-        self.moves = 0
+        self.rwin = None
+        self.lwin = None
+        self.lkey = None
+        self.r_moves = self.l_moves = 0
         self._part_key, self._part = None, None
-        self.stats = {"rebuild_R": 0, "rebuild_L": 0, "moves": 0, "t_passes": 0, "host_evals": 0, "evals": 0}
+        self.stats = {"rebuild_R": 0, "rebuild_L": 0, "moves_R": 0, "moves_L": 0, "compact_L": 0, "t_passes": 0,
+                      "t_gathers": 0, "host_evals": 0, "evals": 0}
 
     # ---- prefix (target) state ----
     def set_base(self, key, prefix_stream):
@@ -259,6 +290,9 @@ class SVCostEvaluator:
         self.cut = None
         self.pair = None
         self.T = None
+        self.rwin = None
+        self.lwin = None
+        self.lkey = None
 
     # ---- block bookkeeping ----
     def _blocks(self, window):
@@ -286,22 +320,15 @@ class SVCostEvaluator:
                 return b
         raise AssertionError("block partition does not cover the window")
 
-    def _prepare_block(self, window, block):
-        """Make R, L and T valid for `block` of `window`, moving the cached states incrementally
-        whenever the part of the circuit they encode is unchanged."""
-        eng = self.eng
-        b0, b1, supp = block
-        old, new = self.window, window
-        n = eng.num_qubits
-        pair = tuple(supp) if (len(supp) == 2 or n == 1) else (supp[0], (supp[0] + 1) % n)
-        if old is not None and self.cut == (b0, b1) and self.pair == pair and self.T is not None \
-                and old[:b0] == new[:b0] and old[b1:] == new[b1:]:
-            self.window = list(new)
-            return
-        stream = G.GateStream.from_window
-        r_ok = l_ok = False
-        if old is not None and self.cut is not None and self.moves < self.REFRESH_MOVES:
-            a0, a1 = self.cut
+    # ---- R: prefix applied to the base ----
+    def _update_R(self, new, b0):
+        """Returns True if slot R changed."""
+        eng, stream = self.eng, G.GateStream.from_window
+        old = self.rwin
+        if old is not None and old == new[:b0]:
+            return False
+        if old is not None and self.r_moves < self.REFRESH_MOVES:
+            a0 = len(old)
             m = min(a0, b0)
             # moving costs |b0 - a0| gates, rebuilding from the base b0 gates: take the cheaper one
             if abs(b0 - a0) <= b0 and old[:m] == new[:m]:
@@ -309,32 +336,95 @@ class SVCostEvaluator:
                     eng.run(SLOT_R, SLOT_R, stream(new[a0:b0]))
                 elif b0 < a0:
                     eng.run(SLOT_R, SLOT_R, stream(old[b0:a0]), inverse=True)
-                r_ok = True
-            so, sn = len(old) - a1, len(new) - b1
-            if abs(so - sn) > sn:
-                pass                      # rebuilding L from |0..0> is cheaper than moving it
-            elif sn <= so and old[len(old) - sn:] == new[b1:]:
-                if so > sn:
-                    eng.run(SLOT_L, SLOT_L, stream(old[a1:len(old) - sn]))
-                l_ok = True
-            elif sn > so and new[len(new) - so:] == old[a1:]:
-                eng.run(SLOT_L, SLOT_L, stream(new[b1:len(new) - so]), inverse=True)
-                l_ok = True
-            if r_ok and l_ok:
-                self.moves += 1
-                self.stats["moves"] += 1
-        if not r_ok:
-            eng.run(SLOT_R, SLOT_BASE, stream(new[:b0]))
-            self.stats["rebuild_R"] += 1
-        if not l_ok:
-            eng.run(SLOT_L, -1, stream(new[b1:]), inverse=True)
-            self.stats["rebuild_L"] += 1
-        if not (r_ok and l_ok):
-            self.moves = 0 if not (r_ok or l_ok) else self.moves
-        self.T = eng.inner(SLOT_L, SLOT_R, pair[0]) if len(pair) == 1 else eng.inner2(SLOT_L, SLOT_R, *pair)
-        self.stats["t_passes"] += 1
+                self.rwin = list(new[:b0])
+                self.r_moves += 1
+                self.stats["moves_R"] += 1
+                return True
+        eng.run(SLOT_R, SLOT_BASE, stream(new[:b0]))
+        self.rwin = list(new[:b0])
+        self.r_moves = 0
+        self.stats["rebuild_R"] += 1
+        return True
+
+    # ---- L: suffix^+ applied to |0..0> ----
+    def _update_L_dense(self, new, b1):
+        eng, stream = self.eng, G.GateStream.from_window
+        old, sfx = self.lwin, new[b1:]
+        if old is not None and old == sfx:
+            return False
+        if old is not None and self.l_moves < self.REFRESH_MOVES:
+            so, sn = len(old), len(sfx)
+            if sn <= so and so - sn <= sn and old[so - sn:] == sfx:
+                eng.run(SLOT_L, SLOT_L, stream(old[:so - sn]))
+                self.lwin = list(sfx); self.l_moves += 1; self.stats["moves_L"] += 1
+                return True
+            if sn > so and sn - so <= sn and sfx[sn - so:] == old:
+                eng.run(SLOT_L, SLOT_L, stream(sfx[:sn - so]), inverse=True)
+                self.lwin = list(sfx); self.l_moves += 1; self.stats["moves_L"] += 1
+                return True
+        eng.run(SLOT_L, -1, stream(sfx), inverse=True)
+        self.lwin = list(sfx)
+        self.l_moves = 0
+        self.stats["rebuild_L"] += 1
+        return True
+
+    def _compact_map(self, sfx, pair):
+        """Qubits the compact bra must carry, or None if it does not fit the compact engine."""
+        if not self.compacts or len(pair) != 2:
+            return None
+        touched = set(pair)
+        for e in sfx:
+            touched.add(e[1])
+            if e[2] >= 0:
+                touched.add(e[2])
+        fits = [c for c in self.compacts if c.num_qubits >= len(touched)]
+        if not fits:
+            return None
+        self.compact = fits[0]
+        qmap = sorted(touched)
+        free = [q for q in range(self.eng.num_qubits) if q not in touched]
+        return qmap + free[:self.compact.num_qubits - len(qmap)]   # pad: unused compact bits stay |0>
+
+    def _update_L_compact(self, new, b1, qmap):
+        sfx = new[b1:]
+        key = (tuple(sfx), tuple(qmap))
+        if key == self.lkey:
+            return False
+        pos = {q: c for c, q in enumerate(qmap)}
+        remapped = [(e[0], pos[e[1]], pos[e[2]] if e[2] >= 0 else -1) + tuple(e[3:]) for e in sfx]
+        self.compact.run(0, -1, G.GateStream.from_window(remapped), inverse=True)
+        self.lkey = key
+        self.stats["compact_L"] += 1
+        return True
+
+    def _prepare_block(self, window, block):
+        """Make R, L and T valid for `block` of `window`."""
+        eng = self.eng
+        b0, b1, supp = block
+        n = eng.num_qubits
+        pair = tuple(supp) if (len(supp) == 2 or n == 1) else (supp[0], (supp[0] + 1) % n)
+        r_changed = self._update_R(window, b0)
+        qmap = self._compact_map(window[b1:], pair)
+        if qmap is not None:
+            l_changed = self._update_L_compact(window, b1, qmap)
+            mode = "compact"
+        else:
+            l_changed = self._update_L_dense(window, b1)
+            mode = "dense"
+        tkey = (b0, b1, pair, mode)
+        if r_changed or l_changed or self.T is None or tkey != self._tkey:
+            if mode == "compact":
+                self.compact.sync()
+                self.T = eng.inner2_gather(SLOT_R, self.compact, 0, qmap, *pair)
+                self.stats["t_gathers"] += 1
+            else:
+                self.T = eng.inner(SLOT_L, SLOT_R, pair[0]) if len(pair) == 1 else eng.inner2(SLOT_L, SLOT_R, *pair)
+                self.stats["t_passes"] += 1
+            self._tkey = tkey
         self.cut, self.pair = (b0, b1), pair
-        self.window = list(new)
+        self.window = list(window)
+
+    _tkey = None
 
     def _operator(self, window, override_index=None, override=None):
         b0, b1 = self.cut

@@ -147,6 +147,15 @@ int b200_sv_inner(b200_ctx *ctx, int l_slot, int r_slot, int q, double out[8]);
  * (adaptaqc/utils/cost_minimiser.py:267-368), for any number of optimiser cycles. */
 int b200_sv_inner2(b200_ctx *ctx, int l_slot, int r_slot, int qa, int qb, double out[32]);
 
+/* Same T as b200_sv_inner2, for a bra that is given COMPACTLY: <L| = (suffix)^+ <0..0| is supported
+ * only on the K qubits the suffix touches, so it is stored as a 2^K-amplitude device array
+ * `compact_state` (e.g. slot memory of a second, K-qubit context on the same device) with
+ * qmap[b] = the full-register qubit of compact bit b.  The kernel gathers the 2^K needed amplitudes
+ * of R instead of reading all 2^n: for the newest ADAPT layer (empty suffix) that is 4 amplitudes.
+ * The caller must have synchronised the context that produced `compact_state`. */
+int b200_sv_inner2_gather(b200_ctx *ctx, int r_slot, const void *compact_state, int K, const int32_t *qmap,
+                          int qa, int qb, double out[32]);
+
 /* Host <-> device transfer of `count` amplitudes starting at `offset` (tests, small n, target
  * upload).  Replaces the Statevector object's `.data`. */
 int b200_sv_download(b200_ctx *ctx, int slot, uint64_t offset, uint64_t count, double *host);

@@ -168,6 +168,27 @@ class FakeEngine:
         Rt = np.moveaxis(R, [n - 1 - qb, n - 1 - qa], [0, 1]).reshape(4, -1)
         return Lt.conj() @ Rt.T
 
+    def inner2_gather(self, r_slot, compact_engine, compact_slot, qmap, qa, qb):
+        """numpy restatement of b200_sv_inner2_gather: scatter the compact bra into the full register."""
+        self.inners += 1
+        n, K = self.num_qubits, compact_engine.num_qubits
+        ell = compact_engine.slots[compact_slot]
+        c = np.arange(1 << K)
+        x = np.zeros_like(c)
+        for b, q in enumerate(qmap):
+            x |= ((c >> b) & 1) << q
+        L = np.zeros(1 << n, dtype=np.complex128)
+        L[x] = ell
+        saved = self.slots[0].copy()
+        self.slots[0][...] = L
+        out = self.inner2(0, r_slot, qa, qb) if r_slot != 0 else None
+        self.slots[0][...] = saved
+        self.inners -= 1
+        return out
+
+    def device_ptr(self, slot):
+        return 0
+
     def download(self, slot, offset=0, count=None):
         return self.slots[slot][offset:None if count is None else offset + count].copy()
 

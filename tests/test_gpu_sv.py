@@ -142,6 +142,29 @@ def test_inner_matches_numpy(n):
     eng.close()
 
 
+def test_inner2_gather_matches_dense_transfer():
+    """Compact bra (K qubits of a second context) against the dense 4x4 transfer matrix."""
+    n, K = 14, 6
+    rng = np.random.default_rng(4450)
+    eng, small = SVEngine(n, n_slots=2), SVEngine(K, n_slots=1)
+    R = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    ell = rng.normal(size=1 << K) + 1j * rng.normal(size=1 << K)
+    R /= np.linalg.norm(R); ell /= np.linalg.norm(ell)
+    for qmap in ([0, 1, 2, 3, 4, 5], [13, 2, 7, 0, 9, 4], [5, 6, 8, 10, 11, 12]):
+        c = np.arange(1 << K)
+        x = np.zeros_like(c)
+        for b, q in enumerate(qmap):
+            x |= ((c >> b) & 1) << q
+        L = np.zeros(1 << n, dtype=np.complex128); L[x] = ell
+        eng.upload(0, L); eng.upload(1, R); small.upload(0, ell)
+        small.sync()
+        for qa, qb in [(qmap[0], qmap[1]), (qmap[3], qmap[1]), (qmap[5], qmap[2])]:
+            dense = eng.inner2(0, 1, qa, qb)
+            got = eng.inner2_gather(1, small, 0, qmap, qa, qb)
+            np.testing.assert_allclose(got, dense, atol=AMP_TOL)
+    eng.close(); small.close()
+
+
 # ---- error behaviour ----------------------------------------------------------------------------
 def test_errors_are_raised_not_swallowed():
     eng = SVEngine(4, n_slots=2)
@@ -237,7 +260,7 @@ def test_evaluator_tracks_rotosolve_edits(n):
             replace_1q_gate(c.full_circuit, idx, name, theta)
         assert abs(comp.evaluate_cost() - oracle_comp.evaluate_cost()) < COST_TOL
     st = backend._evaluator.stats
-    assert st["moves"] > 0 and st["t_passes"] < st["evals"]
+    assert st["moves_R"] > 0 and st["t_passes"] + st["t_gathers"] < st["evals"]
 
 
 def test_shift_costs_equal_individual_evaluations(backend):

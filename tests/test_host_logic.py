@@ -16,11 +16,16 @@ from helpers import FakeEngine, brickwork, circuit_from_gates, random_gates, thi
 
 
 @pytest.fixture
-def fake_backend(emu, monkeypatch):
+def fake_backend(emu, monkeypatch, request):
+    compact_k = getattr(request, "param", None)
+
     def _get_engine(self, num_qubits):
         if self._engine is None or self._engine.num_qubits != num_qubits:
             self._engine = FakeEngine(emu, num_qubits)
-            self._evaluator = SVCostEvaluator(self._engine)
+            compact = None
+            if compact_k is not None and num_qubits > compact_k:
+                compact = FakeEngine(emu, compact_k, n_slots=1)
+            self._evaluator = SVCostEvaluator(self._engine, compact)
             self._state_version += 1
             self._last_run_key = None
         return self._engine
@@ -28,6 +33,7 @@ def fake_backend(emu, monkeypatch):
     return B200SVBackend()
 
 
+@pytest.mark.parametrize("fake_backend", [None, 6], indirect=True)
 @pytest.mark.parametrize("n", [4, 12])
 def test_incremental_evaluator_equals_full_resimulation(fake_backend, n):
     rng = np.random.default_rng(50 + n)
@@ -47,7 +53,9 @@ def test_incremental_evaluator_equals_full_resimulation(fake_backend, n):
             replace_1q_gate(c.full_circuit, idx, name, theta)
         assert abs(comp.evaluate_cost() - ocomp.evaluate_cost()) < 1e-10
     st = fake_backend._evaluator.stats
-    assert st["moves"] > 0 and st["t_passes"] < st["evals"]
+    assert st["moves_R"] > 0 and st["t_passes"] + st["t_gathers"] < st["evals"]
+    if fake_backend._evaluator.compact is not None:
+        assert st["t_gathers"] > 0 and st["compact_L"] > 0
 
 
 def test_structure_change_falls_back_to_resimulation(fake_backend):
@@ -66,6 +74,7 @@ def test_structure_change_falls_back_to_resimulation(fake_backend):
                                ocomp.backend.measure_qubit_expectation_values(ocomp), atol=1e-12)
 
 
+@pytest.mark.parametrize("fake_backend", [None, 2], indirect=True)
 @pytest.mark.parametrize("batched", [False, True])
 def test_compile_decisions_match_oracle_backend(fake_backend, batched):
     ghz = Circuit(4); ghz.h(0)
