@@ -170,6 +170,8 @@ class B200SVBackend(_SVBase):
         self._last_run_sv = None
         self._pair_hint = None
         self._compiler_ref = None
+        self._wcache = None
+        self._changed = None
         self.simulator = simulator if simulator is not None else B200StatevectorSimulator(self)
 
     # checkpointing pickles the whole compiler, backend included (adapt_compiler.py:484-497)
@@ -208,6 +210,7 @@ class B200SVBackend(_SVBase):
     def reset_cache(self):
         """Forget every cached state (call after editing the target part of full_circuit)."""
         self._compiler_ref = None
+        self._wcache = None
         if self._evaluator is not None:
             self._evaluator.base_key = None
             self._evaluator.invalidate()
@@ -236,7 +239,49 @@ class B200SVBackend(_SVBase):
         ev = self._evaluator
         if ev.base_key != key:
             ev.set_base(key, G.GateStream.from_circuit(circuit, 0, lhs))
-        return eng, ev, G.canonical_window(circuit, lhs, None)
+            self._wcache = None
+            self._changed = None
+        window, changed = self._cached_window(circuit, lhs, key)
+        # `_changed` accumulates over calls until the evaluator has seen the window (amp0 /
+        # shift_amplitudes); None = unknown, the evaluator must diff for itself
+        if changed is None or self._changed is None:
+            self._changed = None
+        else:
+            self._changed = sorted(set(self._changed) | set(changed))
+        return eng, ev, window
+
+    def _cached_window(self, circuit, lhs, key):
+        """Canonical window of circuit.data[lhs:], translating only instructions that are new
+        objects since the previous call (the optimiser replaces ONE CircuitInstruction per
+        evaluation, circuit_operations_basic.py:70-99).  Returns (window, changed indices | None)."""
+        data = circuit.data
+        m = len(data) - lhs
+        wc = self._wcache
+        if wc is None or wc[0] != key or len(wc[1]) != m:
+            window = G.canonical_window(circuit, lhs, None)
+            if len(window) != m:          # barriers etc. were dropped: no positional cache
+                self._wcache = None
+                return window, None
+            self._wcache = (key, [data[lhs + i] for i in range(m)], [list(data[lhs + i].operation.params) for i in range(m)],
+                            window)
+            return window, None
+        _, insts, params, window = wc
+        changed = []
+        for i in range(m):
+            inst = data[lhs + i]
+            if inst is not insts[i] or inst.operation.params != params[i]:
+                changed.append(i)
+        if changed:
+            qmap = G.qubit_indices(circuit)
+            for i in changed:
+                ent = G.canonical_window(circuit, lhs + i, lhs + i + 1, qmap)
+                if len(ent) != 1:
+                    self._wcache = None
+                    return G.canonical_window(circuit, lhs, None), None
+                window[i] = ent[0]
+                insts[i] = data[lhs + i]
+                params[i] = list(data[lhs + i].operation.params)
+        return window, changed
 
     # ---- the four backend methods ----
     def evaluate_global_cost(self, compiler):
@@ -246,7 +291,8 @@ class B200SVBackend(_SVBase):
             )
         _, ev, window = self._prepare(compiler)
         self._state_version += 1  # slot WORK may be overwritten
-        amp = ev.amp0(window, focus=len(window) - compiler.rhs_gate_count - 1)
+        amp = ev.amp0(window, focus=len(window) - compiler.rhs_gate_count - 1, changed=self._changed)
+        self._changed = []
         return 1 - (np.absolute(amp)) ** 2
 
     def evaluate_local_cost(self, compiler):
@@ -290,6 +336,7 @@ class B200SVBackend(_SVBase):
         k = gate_index - compiler.lhs_gate_count
         mats = [G.one_qubit_matrix(name, theta) for name, theta in candidates]
         amps = ev.shift_amplitudes(window, k, mats)
+        self._changed = []
         return [1 - (np.absolute(a)) ** 2 for a in amps]
 
     def overlap_between_circuits(self, circuit1, circuit2):

@@ -222,14 +222,37 @@ def partition_blocks(window):
     return blocks
 
 
+def _embed_1q(m, pos, npair):
+    """2x2 matrix `m` acting on bit `pos` of a 1- or 2-qubit index, without np.kron."""
+    if npair == 1:
+        return m
+    out = np.zeros((4, 4), dtype=np.complex128)
+    if pos == 0:
+        out[0:2, 0:2] = m
+        out[2:4, 2:4] = m
+    else:
+        out[0::2, 0::2] = m
+        out[1::2, 1::2] = m
+    return out
+
+
+_EMBED_CACHE = {}
+
+
 def embed_entry(ent, pair, override=None):
     """Matrix of a canonical window entry on the qubits `pair` (index = bit(pair[0]) + 2 bit(pair[1]);
     2x2 when len(pair) == 1).  `override`: replacement 2x2 matrix for a 1-qubit entry."""
     if ent[2] < 0:
-        m = G.matrix_of_entry(ent) if override is None else np.asarray(override, dtype=np.complex128)
-        if len(pair) == 1:
-            return m
-        return np.kron(_I2, m) if ent[1] == pair[0] else np.kron(m, _I2)
+        pos = 0 if ent[1] == pair[0] else 1
+        if override is not None:
+            return _embed_1q(np.asarray(override, dtype=np.complex128), pos, len(pair))
+        key = (ent, pos, len(pair))
+        m = _EMBED_CACHE.get(key)
+        if m is None:
+            if len(_EMBED_CACHE) > 4096:
+                _EMBED_CACHE.clear()
+            m = _EMBED_CACHE[key] = _embed_1q(G.matrix_of_entry(ent), pos, len(pair))
+        return m
     m4 = _M4.get(ent[0])
     if m4 is None:
         m4 = np.frombuffer(ent[6], dtype=np.complex128).reshape(4, 4)
@@ -435,15 +458,22 @@ class SVCostEvaluator:
         return op
 
     # ---- evaluation ----
-    def amp0(self, window, focus=None):
+    def amp0(self, window, focus=None, changed=None):
         """<0| W |base> for the canonical window `window` (one scalar, as the reference asks).
         `focus`: index of the gate the optimiser is most likely to edit next (block choice when the
-        structure changed)."""
+        structure changed).  `changed`: indices at which `window` differs from the previous call's
+        window (None = unknown), so that edits inside the open block skip all bookkeeping."""
         self.stats["evals"] += 1
         if len(window) == 0:
             self.invalidate()
             return self.eng.amp(SLOT_BASE, 0)
-        self._prepare_block(window, self._select_block(window, focus))
+        if (changed is not None and self.T is not None and self.window is not None and len(self.window) == len(window)
+                and all(self.cut[0] <= i < self.cut[1] and window[i][1] == self.window[i][1]
+                        and window[i][2] == self.window[i][2] for i in changed)):
+            for i in changed:
+                self.window[i] = window[i]
+        else:
+            self._prepare_block(window, self._select_block(window, focus))
         self.stats["host_evals"] += 1
         return complex(np.sum(self._operator(window) * self.T))
 

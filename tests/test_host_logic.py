@@ -58,6 +58,43 @@ def test_incremental_evaluator_equals_full_resimulation(fake_backend, n):
         assert st["t_gathers"] > 0 and st["compact_L"] > 0
 
 
+@pytest.mark.parametrize("fake_backend", [None, 5], indirect=True)
+def test_interleaved_backend_calls_keep_the_caches_coherent(fake_backend):
+    """evaluate_circuit / <Z> / shift_costs between cost evaluations consume circuit edits that the
+    evaluator has not seen: the next cost must still equal a full re-simulation."""
+    n = 7
+    rng = np.random.default_rng(77)
+    target, trng = brickwork(n, 2, seed=2)
+    ansatz = thin_ansatz(n, 4, trng)
+    comp = AdaptCompiler(target, backend=fake_backend)
+    comp.full_circuit.data.extend(ansatz.data)
+    ocomp = AdaptCompiler(target, backend=OracleSVBackend())
+    ocomp.full_circuit.data.extend(ansatz.copy().data)
+    rot = [i for i in range(*comp.variational_circuit_range())
+           if comp.full_circuit.data[i].operation.name in ("rx", "ry", "rz")]
+    for step in range(30):
+        for _ in range(int(rng.integers(1, 4))):          # several edits, possibly in different layers
+            idx = rot[int(rng.integers(len(rot)))]
+            name, theta = ["rx", "ry", "rz"][int(rng.integers(3))], float(rng.uniform(-3, 3))
+            for c in (comp, ocomp):
+                replace_1q_gate(c.full_circuit, idx, name, theta)
+        kind = step % 4
+        if kind == 1:
+            np.testing.assert_allclose(fake_backend.measure_qubit_expectation_values(comp),
+                                       ocomp.backend.measure_qubit_expectation_values(ocomp), atol=1e-12)
+            continue                                       # edits consumed without the evaluator seeing them
+        if kind == 2:
+            idx = rot[int(rng.integers(len(rot)))]
+            got = fake_backend.shift_costs(comp, idx, [("ry", 0.3)])[0]
+            replace_1q_gate(ocomp.full_circuit, idx, "ry", 0.3)
+            ref = ocomp.evaluate_cost()
+            replace_1q_gate(ocomp.full_circuit, idx, comp.full_circuit.data[idx].operation.name,
+                            comp.full_circuit.data[idx].operation.params[0])
+            assert abs(got - ref) < 1e-10
+            continue
+        assert abs(comp.evaluate_cost() - ocomp.evaluate_cost()) < 1e-10
+
+
 def test_structure_change_falls_back_to_resimulation(fake_backend):
     n = 5
     target, trng = brickwork(n, 2, seed=9)
