@@ -154,11 +154,23 @@ B200_HD void op_diag(double2 (&a)[1 << R], const DevOp* __restrict__ op, const u
     }
 }
 
+// `pend`: product of the phases of diagonal ops whose qubits are all thread-uniform.  Such a phase
+// multiplies all 2^R amplitudes of the thread alike, so it commutes with every other op of the round
+// and is applied ONCE at the end of the round (1 complex multiply per op instead of 2^R).
 template <int R>
 B200_HD void apply_op(double2 (&a)[1 << R], const DevOp* __restrict__ op, const uint64_t g,
-                                         const double* __restrict__ mat2tab) {
+                                         const double* __restrict__ mat2tab, double2& pend) {
     const int kind = op->kind;
-    if (kind == K_DIAG) { op_diag<R>(a, op, g); return; }
+    if (kind == K_DIAG) {
+        if (op->dmask0 == 0 && op->dmask1 == 0) {
+            const int u0 = op->dq0 >= 0 ? (int)((g >> op->dq0) & 1ull) : 0;
+            const int u1 = op->dq1 >= 0 ? (int)((g >> op->dq1) & 1ull) : 0;
+            pend = cmul(pend, reinterpret_cast<const double2*>(op->m)[u0 + 2 * u1]);
+            return;
+        }
+        op_diag<R>(a, op, g);
+        return;
+    }
     const int cq = op->cq;
     if (cq >= 0 && !((g >> cq) & 1ull)) return;
     const int cmask = op->cmask;
@@ -241,7 +253,12 @@ B200_HD void sweep_round(const double2* __restrict__ src, double2* __restrict__ 
     }
 
     const int ob = rd->op_begin, oe = rd->op_end;
-    for (int o = ob; o < oe; ++o) apply_op<R>(a, ops + o, g, mat2tab);
+    double2 pend = make_double2(1.0, 0.0);
+    for (int o = ob; o < oe; ++o) apply_op<R>(a, ops + o, g, mat2tab, pend);
+    if (pend.x != 1.0 || pend.y != 0.0) {
+#pragma unroll
+        for (int j = 0; j < (1 << R); ++j) a[j] = cmul(a[j], pend);
+    }
 
     if (last) {
         uint64_t gs[R];

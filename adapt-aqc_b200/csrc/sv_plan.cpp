@@ -161,17 +161,27 @@ std::string canonicalize(int nq, const b200_gate* gates, int n_gates, const doub
     return "";
 }
 
+// How op `o` acts on qubit q: 0 = not at all, 1 = diagonally (phase / control), 2 = mixing.
+static int action_on(const COp& o, int q) {
+    if (o.t0 == q || o.t1 == q) return 2;
+    if (o.c == q || o.d0 == q || o.d1 == q) return 1;
+    return 0;
+}
+
 void fuse_single_qubit_runs(std::vector<COp>& ops) {
     std::vector<COp> out;
     out.reserve(ops.size());
-    int last_on[64];
-    for (int q = 0; q < 64; ++q) last_on[q] = -1;
+    // per qubit: index (in `out`) of the latest 1-qubit uncontrolled op that can still absorb
+    //   any_on[q]  : a following 1-qubit op of ANY kind (nothing touched q since)
+    //   diag_on[q] : a following DIAGONAL 1-qubit op (only ops acting diagonally on q came since: a phase
+    //                on q commutes with them, e.g. rz on the control of a cx, or across a cz)
+    int any_on[64], diag_on[64];
+    for (int q = 0; q < 64; ++q) any_on[q] = diag_on[q] = -1;
     for (const COp& op : ops) {
         int q = -1;
         if (single_uncontrolled(op, q)) {
-            const int j = last_on[q];
-            int qj = -1;
-            if (j >= 0 && single_uncontrolled(out[j], qj) && qj == q) {
+            const int j = op.kind == K_DIAG ? diag_on[q] : any_on[q];
+            if (j >= 0) {
                 COp& prev = out[j];
                 if (prev.kind == K_DIAG && op.kind == K_DIAG) {
                     const cplx p0 = op.m[0] * prev.m[0], p1 = op.m[1] * prev.m[1];
@@ -187,12 +197,18 @@ void fuse_single_qubit_runs(std::vector<COp>& ops) {
                 }
                 continue;
             }
+            const int idx = (int)out.size();
+            out.push_back(op);
+            any_on[q] = diag_on[q] = idx;
+            continue;
         }
-        const int idx = (int)out.size();
         out.push_back(op);
         const int qs[5] = {op.t0, op.t1, op.c, op.d0, op.d1};
-        for (int x : qs)
-            if (x >= 0) last_on[x] = idx;
+        for (int x : qs) {
+            if (x < 0) continue;
+            any_on[x] = -1;
+            if (action_on(op, x) == 2) diag_on[x] = -1;
+        }
     }
     ops.swap(out);
 }
