@@ -225,3 +225,35 @@ def random_vidal_mps(n, chi, seed):
     g = M / prev.reshape(1, -1, 1)
     gammas.append((g[0].copy(), g[1].copy()))
     return (gammas, lambdas)
+
+
+def compile_option_cases():
+    """(name, target, AdaptCompiler kwargs, AdaptConfig kwargs): the reference's compile options that
+    change what the backend is asked for (test/recompilers/test_adapt_compiler.py: local cost :142-152,
+    custom layer gate :815-818, starting circuit :795-802, initial single-qubit layer, pair-selection
+    methods :206-237, brickwall :1465-1543, rotosolve options)."""
+    rng = np.random.default_rng(21)
+    n = 4
+    target = Circuit(n)
+    for layer in range(2):
+        for q in range(n):
+            target.u3(*rng.uniform(-np.pi, np.pi, 3), q)
+        for q in range(layer % 2, n - 1, 2):
+            target.cx(q, q + 1)
+    start = Circuit(n); start.x(0); start.h(2)
+    cz_layer = Circuit(2)
+    cz_layer.ry(0, 0, label="ry"); cz_layer.ry(0, 1, label="ry"); cz_layer.cz(0, 1)
+    cz_layer.ry(0, 0, label="ry"); cz_layer.ry(0, 1, label="ry")
+    return [
+        ("default", target, {}, dict(max_layers=4)),
+        ("local_cost", target, dict(optimise_local_cost=True), dict(max_layers=3)),
+        ("starting_circuit", target, dict(starting_circuit=start), dict(max_layers=3)),
+        ("isql", target, dict(initial_single_qubit_layer=True), dict(max_layers=3)),
+        ("custom_cz_layer", target, dict(custom_layer_2q_gate=cz_layer), dict(max_layers=3)),
+        ("no_rotoselect", target, dict(use_rotoselect=False), dict(max_layers=3)),
+        ("expectation", target, {}, dict(max_layers=3, method="expectation")),
+        ("basic", target, {}, dict(max_layers=3, method="basic")),
+        ("brickwall", target, {}, dict(max_layers=4, method="brickwall")),
+        ("rotosolve_every_2", target, {}, dict(max_layers=4, rotosolve_frequency=2, max_layers_to_modify=2)),
+        ("reuse_qubit_mode", target, {}, dict(max_layers=4, reuse_exponent=1, reuse_priority_mode="qubit")),
+    ]

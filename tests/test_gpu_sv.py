@@ -20,7 +20,7 @@ from adapt_aqc_b200.sv_engine import SLOT_BASE, SLOT_L, SLOT_R, SLOT_WORK, SVCos
 from oracle import sv_oracle as orc
 from oracle.oracle_backends import OracleSVBackend, circuit_to_gates
 
-from helpers import brickwork, circuit_from_gates, random_gates, thin_ansatz
+from helpers import brickwork, circuit_from_gates, compile_option_cases, random_gates, thin_ansatz
 
 pytestmark = pytest.mark.gpu
 
@@ -322,6 +322,20 @@ def test_compile_makes_the_same_decisions_as_the_oracle_backend(name, batched):
     assert abs(got.exact_overlap - got.overlap) < 1e-9
     if name != "random4":
         assert got.overlap > 1 - 1e-2
+
+
+@pytest.mark.parametrize("case", compile_option_cases(), ids=lambda c: c[0])
+def test_compile_options_make_the_same_decisions(case):
+    """Every compile option of the reference that changes what the backend is asked for."""
+    name, target, kw, cfg = case
+    ref = AdaptCompiler(target, backend=OracleSVBackend(), adapt_config=AdaptConfig(**cfg), **kw).compile()
+    got = AdaptCompiler(target, backend=B200SVBackend(), adapt_config=AdaptConfig(**cfg), **kw).compile()
+    assert got.qubit_pair_history == ref.qubit_pair_history
+    assert got.method_history == ref.method_history
+    np.testing.assert_allclose(got.global_cost_history, ref.global_cost_history, atol=1e-9)
+    if ref.local_cost_history is not None:
+        np.testing.assert_allclose(got.local_cost_history, ref.local_cost_history, atol=1e-9)
+    assert got.cost_evaluations == ref.cost_evaluations
 
 
 def test_compile_12_qubits_linear_map_matches_oracle():

@@ -12,7 +12,7 @@ from adapt_aqc_b200.minimiser import B200CostMinimiser, replace_1q_gate
 from adapt_aqc_b200.sv_engine import SVCostEvaluator
 from oracle.oracle_backends import OracleSVBackend
 
-from helpers import FakeEngine, brickwork, circuit_from_gates, random_gates, thin_ansatz
+from helpers import FakeEngine, brickwork, circuit_from_gates, compile_option_cases, random_gates, thin_ansatz
 
 
 @pytest.fixture
@@ -139,3 +139,17 @@ def test_bench_step_counts_220_evaluations(fake_backend):
         before = comp.cost_evaluation_counter
         bench.one_step(comp)
         assert comp.cost_evaluation_counter - before == 4 * 7 + 64 * 3
+
+
+@pytest.mark.parametrize("fake_backend", [2], indirect=True)
+@pytest.mark.parametrize("case", compile_option_cases(), ids=lambda c: c[0])
+def test_compile_options_make_the_same_decisions(fake_backend, case):
+    name, target, kw, cfg = case
+    ref = AdaptCompiler(target, backend=OracleSVBackend(), adapt_config=AdaptConfig(**cfg), **kw).compile()
+    got = AdaptCompiler(target, backend=fake_backend, adapt_config=AdaptConfig(**cfg), **kw).compile()
+    assert got.qubit_pair_history == ref.qubit_pair_history
+    assert got.method_history == ref.method_history
+    np.testing.assert_allclose(got.global_cost_history, ref.global_cost_history, atol=1e-9)
+    if ref.local_cost_history is not None:
+        np.testing.assert_allclose(got.local_cost_history, ref.local_cost_history, atol=1e-9)
+    assert got.cost_evaluations == ref.cost_evaluations
