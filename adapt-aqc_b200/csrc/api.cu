@@ -119,14 +119,13 @@ int prof_drain(b200_ctx* ctx) {
     return 0;
 }
 
-// Upload the plan (rounds, ops, mat2 table) in one pinned staging copy.
-int upload_plan(b200_ctx* ctx, const Plan& plan, const DevRound** d_rounds, const DevOp** d_ops,
-                const double** d_mat2) {
-    const size_t b_rounds = plan.rounds.size() * sizeof(DevRound);
+// Upload the small-path program (ops, mat2 table) in one pinned staging copy.  (The tiled path needs no
+// upload: each sweep's program travels as a kernel parameter.)
+int upload_plan(b200_ctx* ctx, const Plan& plan, const DevOp** d_ops, const double** d_mat2) {
     const size_t b_ops = plan.ops.size() * sizeof(DevOp);
     const size_t b_mat2 = plan.mat2.size() * sizeof(double);
     auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    const size_t o_ops = up16(b_rounds), o_mat2 = o_ops + up16(b_ops), total = o_mat2 + up16(b_mat2) + 16;
+    const size_t o_mat2 = up16(b_ops), total = o_mat2 + up16(b_mat2) + 16;
     // The staging buffer may still be in flight from the previous call on this stream.
     if (ctx->plan_in_flight) { CUDA_TRY(cudaEventSynchronize(ctx->ev_plan)); ctx->plan_in_flight = false; }
     if (reserve_host(&ctx->h_plan, &ctx->h_plan_cap, total)) return -1;
@@ -135,15 +134,13 @@ int upload_plan(b200_ctx* ctx, const Plan& plan, const DevRound** d_rounds, cons
         if (reserve_dev(&ctx->d_plan, &ctx->d_plan_cap, total)) return -1;
     }
     char* h = (char*)ctx->h_plan;
-    if (b_rounds) std::memcpy(h, plan.rounds.data(), b_rounds);
-    if (b_ops) std::memcpy(h + o_ops, plan.ops.data(), b_ops);
+    if (b_ops) std::memcpy(h, plan.ops.data(), b_ops);
     if (b_mat2) std::memcpy(h + o_mat2, plan.mat2.data(), b_mat2);
     CUDA_TRY(cudaMemcpyAsync(ctx->d_plan, h, total, cudaMemcpyHostToDevice, ctx->stream));
     ctx->counters[4] += total;
     CUDA_TRY(cudaEventRecord(ctx->ev_plan, ctx->stream));
     ctx->plan_in_flight = true;
-    *d_rounds = (const DevRound*)ctx->d_plan;
-    *d_ops = (const DevOp*)((char*)ctx->d_plan + o_ops);
+    *d_ops = (const DevOp*)ctx->d_plan;
     *d_mat2 = (const double*)((char*)ctx->d_plan + o_mat2);
     return 0;
 }
@@ -156,8 +153,8 @@ int run_plan(b200_ctx* ctx, int dst_slot, int src_slot, const Plan& plan) {
     Timer tm(ctx);
 
     if (plan.small) {
-        const DevRound* d_rounds; const DevOp* d_ops; const double* d_mat2;
-        if (upload_plan(ctx, plan, &d_rounds, &d_ops, &d_mat2)) return -1;
+        const DevOp* d_ops; const double* d_mat2;
+        if (upload_plan(ctx, plan, &d_ops, &d_mat2)) return -1;
         const size_t smem = dim * sizeof(double2);
         {
             KScope ks(ctx, B200_PROF_SMALL);
@@ -187,22 +184,21 @@ int run_plan(b200_ctx* ctx, int dst_slot, int src_slot, const Plan& plan) {
         tm.stop();
         return 0;
     }
-    const DevRound* d_rounds; const DevOp* d_ops; const double* d_mat2;
-    if (upload_plan(ctx, plan, &d_rounds, &d_ops, &d_mat2)) return -1;
     const uint32_t ntiles = (uint32_t)(dim >> TILE_BITS);
-    for (const DevSweep& sw : plan.sweeps) {
-        const int nr = sw.round_end - sw.round_begin;
+    for (const SweepProg& sw : plan.sweeps) {
+        const int nr = sw.nrounds;
         const size_t smem = nr > 1 ? ((size_t)1 << TILE_BITS) * sizeof(double2) : 0;
         const int per_sm = nr > 1 ? ctx->sweep_occ_smem : ctx->sweep_occ_nosmem;
         const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * per_sm * ctx->grid_mult);
         {
             KScope ks(ctx, B200_PROF_SWEEP);
-            sv_sweep_kernel<REG_BITS><<<grid, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, d_rounds, d_ops,
-                                                                                   d_mat2, ntiles);
+            sv_sweep_kernel<REG_BITS><<<grid, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles);
         }
         CUDA_TRY(cudaGetLastError());
         src = dst;
         ctx->counters[1] += 1; ctx->counters[3] += 32 * dim;
+        // host -> device bytes of the program that rode along as the kernel parameter
+        ctx->counters[4] += offsetof(SweepProg, ops) + (size_t)sw.nops * sizeof(POp) + (size_t)sw.nmat2 * 32 * sizeof(double);
     }
     ctx->counters[2] += plan.n_gates_in;
     tm.stop();
@@ -216,6 +212,7 @@ int make_plan(int nq, const b200_gate* gates, int n_gates, const double* mats, i
     const std::string err = canonicalize(nq, gates, n_gates, mats, n_mats, inverse, ops);
     if (!err.empty()) return set_error(err);
     fuse_single_qubit_runs(ops);
+    fuse_diagonals(ops);
     build_plan(nq, ops, plan);
     plan.n_gates_in = n_gates;
     return 0;
@@ -762,8 +759,8 @@ int b200_sv_plan_stats(int num_qubits, const b200_gate* gates, int n_gates, cons
     Plan plan;
     if (make_plan(num_qubits, gates, n_gates, mats, n_mats, false, plan)) return -1;
     out[0] = plan.small ? 1 : (int32_t)plan.sweeps.size();
-    out[1] = plan.small ? 1 : (int32_t)plan.rounds.size();
-    out[2] = (int32_t)plan.ops.size();
+    out[1] = plan.small ? 1 : (int32_t)plan.n_rounds();
+    out[2] = (int32_t)plan.n_ops();
     out[3] = plan.small ? 1 : 0;
     return 0;
 }
@@ -776,14 +773,12 @@ int b200_sv_plan_detail(int num_qubits, const b200_gate* gates, int n_gates, con
     if (make_plan(num_qubits, gates, n_gates, mats, n_mats, false, plan)) return -1;
     *n_sweeps = (int32_t)plan.sweeps.size();
     for (int k = 0; k < (int)plan.sweeps.size() && k < max_sweeps; ++k) {
-        const DevSweep& sw = plan.sweeps[k];
-        int ops = 0, dense = 0;
-        for (int r = sw.round_begin; r < sw.round_end; ++r) {
-            ops += plan.rounds[r].op_end - plan.rounds[r].op_begin;
-            for (int o = plan.rounds[r].op_begin; o < plan.rounds[r].op_end; ++o)
-                if (plan.ops[o].kind == K_MAT1 || plan.ops[o].kind == K_MAT2) ++dense;
-        }
-        out[4 * k] = sw.round_end - sw.round_begin;
+        const SweepProg& sw = plan.sweeps[k];
+        const int ops = sw.nops;
+        int dense = 0;
+        for (int o = 0; o < sw.nops; ++o)
+            if (sw.ops[o].kind == P_MAT1 || sw.ops[o].kind == P_MAT2 || sw.ops[o].kind == P_MAT1LANE) ++dense;
+        out[4 * k] = sw.nrounds;
         out[4 * k + 1] = ops;
         out[4 * k + 2] = dense;
         out[4 * k + 3] = sw.c;

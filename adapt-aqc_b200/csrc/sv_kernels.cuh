@@ -1,10 +1,12 @@
 // sv_kernels.cuh -- sm_100a statevector kernels (complex128, little-endian qubit order).
 //
 //   sv_sweep_kernel<R>  K1/K2: fused gate sweep.  One CTA = one tile of 2^12 amplitudes
-//                       (5 lane qubits + 7 arbitrary qubits); 2^R amplitudes per thread live in
+//                       (the 5 lowest qubits + 7 arbitrary qubits); 2^R amplitudes per thread live in
 //                       registers for a whole round of gates; rounds exchange through swizzled
-//                       shared memory; first round loads from HBM with 512 B-per-warp coalesced
-//                       128-bit accesses and the last round stores the same way.
+//                       shared memory; the first round loads from HBM (128-bit accesses, whole 128 B
+//                       lines per warp access) and the last round stores the same way; gates on the
+//                       three lane qubits of those rounds go through warp shuffles.  The sweep's
+//                       program is a kernel parameter (constant bank, uniform decode).
 //   sv_small_kernel     n <= 11: whole state in one CTA's shared memory (launch-latency path).
 //   sv_expz_kernel      K4: all <Z_q> in one read pass (deterministic two-stage reduction).
 //   sv_rdm3_kernel      K5: three pair-RDMs per read pass, 8 amplitudes per thread in registers.
@@ -21,7 +23,6 @@
 // The per-thread bodies are __host__ __device__ so that tests/emu can run the very same code
 // on the CPU (one loop iteration per CUDA thread) to check the planner and the index math
 // without a GPU.  The product only ever launches the __global__ kernels.
-#define B200_HD __host__ __device__ __forceinline__
 #ifdef __CUDA_ARCH__
 #define B200_LDG(p) __ldg(p)
 #else
@@ -45,10 +46,6 @@ B200_HD uint32_t ins0_32(uint32_t x, int pos) {
     const uint32_t lo = x & ((1u << pos) - 1u);
     return ((x >> pos) << (pos + 1)) | lo;
 }
-// 16-byte-slot swizzle: the slot-in-row bits (low 3) are XOR-folded with every higher 3-bit group of
-// the 12-bit tile index, so a quarter-warp whose lanes vary ANY three consecutive tile bits (the
-// three lowest non-register positions of a round) lands on the 8 distinct 16 B slots of a 128 B row.
-B200_HD uint32_t swz(uint32_t i) { return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u); }
 
 B200_HD double2 cmul(const double2 a, const double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
@@ -69,136 +66,173 @@ B200_HD double2 cjfma(const double2 a, const double2 b, double2 c) {
     c.y = fma(-a.y, b.x, c.y);
     return c;
 }
+B200_HD double2 ld_c(const double* m, int k) { return make_double2(m[2 * k], m[2 * k + 1]); }
 
 // ---------------------------------------------------------------------------------------------
-// register-resident op bodies
+// register-resident op bodies: every register index is a template parameter, so the 2^R amplitudes
+// stay in named registers (no local memory) and the loops unroll to straight-line code
 // ---------------------------------------------------------------------------------------------
 template <int R, int TB>
-B200_HD void op_mat1(double2 (&a)[1 << R], const double* __restrict__ m, const int cmask) {
-    const double2 m00 = make_double2(m[0], m[1]), m01 = make_double2(m[2], m[3]);
-    const double2 m10 = make_double2(m[4], m[5]), m11 = make_double2(m[6], m[7]);
+B200_HD void op_mat1(double2 (&a)[1 << R], const double* __restrict__ m) {
+    const double2 m00 = ld_c(m, 0), m01 = ld_c(m, 1), m10 = ld_c(m, 2), m11 = ld_c(m, 3);
 #pragma unroll
     for (int j = 0; j < (1 << R); ++j) {
         if (j & (1 << TB)) continue;
-        if (cmask == 0 || (j & cmask)) {
-            const double2 x = a[j], y = a[j | (1 << TB)];
-            a[j] = cfma(m01, y, cmul(m00, x));
-            a[j | (1 << TB)] = cfma(m11, y, cmul(m10, x));
-        }
+        const double2 x = a[j], y = a[j | (1 << TB)];
+        a[j] = cfma(m01, y, cmul(m00, x));
+        a[j | (1 << TB)] = cfma(m11, y, cmul(m10, x));
     }
 }
 
 template <int R, int TB>
-B200_HD void op_x(double2 (&a)[1 << R], const int cmask) {
+B200_HD void op_x(double2 (&a)[1 << R]) {
 #pragma unroll
     for (int j = 0; j < (1 << R); ++j) {
         if (j & (1 << TB)) continue;
-        if (cmask == 0 || (j & cmask)) {
-            const double2 x = a[j];
-            a[j] = a[j | (1 << TB)];
-            a[j | (1 << TB)] = x;
-        }
+        const double2 x = a[j];
+        a[j] = a[j | (1 << TB)];
+        a[j | (1 << TB)] = x;
+    }
+}
+
+template <int R, int TB, int CB>
+B200_HD void op_cx(double2 (&a)[1 << R]) {
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) {
+        if ((j & (1 << TB)) || !(j & (1 << CB))) continue;
+        const double2 x = a[j];
+        a[j] = a[j | (1 << TB)];
+        a[j | (1 << TB)] = x;
     }
 }
 
 template <int R, int TB0, int TB1>
-B200_HD void op_mat2(double2 (&a)[1 << R], const double* __restrict__ mm, const int cmask) {
+B200_HD void op_mat2(double2 (&a)[1 << R], const double* __restrict__ mm) {
 #pragma unroll
     for (int j = 0; j < (1 << R); ++j) {
         if (j & ((1 << TB0) | (1 << TB1))) continue;
-        if (cmask == 0 || (j & cmask)) {
-            const double2 v0 = a[j], v1 = a[j | (1 << TB0)], v2 = a[j | (1 << TB1)],
-                          v3 = a[j | (1 << TB0) | (1 << TB1)];
-            double2 o[4];
+        const double2 v0 = a[j], v1 = a[j | (1 << TB0)], v2 = a[j | (1 << TB1)],
+                      v3 = a[j | (1 << TB0) | (1 << TB1)];
+        double2 o[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const double2* row = reinterpret_cast<const double2*>(mm) + 4 * r;
-                double2 acc = cmul(B200_LDG(row + 0), v0);
-                acc = cfma(B200_LDG(row + 1), v1, acc);
-                acc = cfma(B200_LDG(row + 2), v2, acc);
-                acc = cfma(B200_LDG(row + 3), v3, acc);
-                o[r] = acc;
-            }
-            a[j] = o[0];
-            a[j | (1 << TB0)] = o[1];
-            a[j | (1 << TB1)] = o[2];
-            a[j | (1 << TB0) | (1 << TB1)] = o[3];
+        for (int r = 0; r < 4; ++r) {
+            double2 acc = cmul(ld_c(mm, 4 * r), v0);
+            acc = cfma(ld_c(mm, 4 * r + 1), v1, acc);
+            acc = cfma(ld_c(mm, 4 * r + 2), v2, acc);
+            acc = cfma(ld_c(mm, 4 * r + 3), v3, acc);
+            o[r] = acc;
         }
+        a[j] = o[0];
+        a[j | (1 << TB0)] = o[1];
+        a[j | (1 << TB1)] = o[2];
+        a[j | (1 << TB0) | (1 << TB1)] = o[3];
     }
 }
 
-template <int R>
-B200_HD void op_diag(double2 (&a)[1 << R], const DevOp* __restrict__ op, const uint64_t g) {
-    const int dq0 = op->dq0, dq1 = op->dq1, dm0 = op->dmask0, dm1 = op->dmask1;
-    const int u0 = dq0 >= 0 ? (int)((g >> dq0) & 1ull) : 0;
-    const int u1 = dq1 >= 0 ? (int)((g >> dq1) & 1ull) : 0;
-    const double2* ph = reinterpret_cast<const double2*>(op->m);
-    if (dm0 == 0 && dm1 == 0) {
-        const double2 p = ph[u0 + 2 * u1];
-        if (p.x == 1.0 && p.y == 0.0) return;
+// amplitudes with register bit TB set are multiplied by `ratio` (the base phase went into `pend`)
+template <int R, int TB>
+B200_HD void op_diag1(double2 (&a)[1 << R], const double2 ratio) {
 #pragma unroll
-        for (int j = 0; j < (1 << R); ++j) a[j] = cmul(a[j], p);
-    } else if (dm0 != 0 && dm1 != 0) {
-        const double2 p0 = ph[0], p1 = ph[1], p2 = ph[2], p3 = ph[3];
+    for (int j = 0; j < (1 << R); ++j)
+        if (j & (1 << TB)) a[j] = cmul(a[j], ratio);
+}
+
+template <int R, int TB0, int TB1>
+B200_HD void op_diag2(double2 (&a)[1 << R], const double2 r10, const double2 r01, const double2 r11) {
 #pragma unroll
-        for (int j = 0; j < (1 << R); ++j) {
-            const double2 lo = (j & dm0) ? p1 : p0, hi = (j & dm0) ? p3 : p2;
-            a[j] = cmul(a[j], (j & dm1) ? hi : lo);
-        }
-    } else {
-        const int dm = dm0 | dm1;
-        const double2 p0 = dm0 ? ph[2 * u1] : ph[u0];
-        const double2 p1 = dm0 ? ph[1 + 2 * u1] : ph[u0 + 2];
-#pragma unroll
-        for (int j = 0; j < (1 << R); ++j) a[j] = cmul(a[j], (j & dm) ? p1 : p0);
+    for (int j = 0; j < (1 << R); ++j) {
+        const bool b0 = j & (1 << TB0), b1 = j & (1 << TB1);
+        if (b0 && b1) a[j] = cmul(a[j], r11);
+        else if (b0) a[j] = cmul(a[j], r10);
+        else if (b1) a[j] = cmul(a[j], r01);
     }
 }
 
-// `pend`: product of the phases of diagonal ops whose qubits are all thread-uniform.  Such a phase
-// multiplies all 2^R amplitudes of the thread alike, so it commutes with every other op of the round
-// and is applied ONCE at the end of the round (1 complex multiply per op instead of 2^R).
-template <int R>
-B200_HD void apply_op(double2 (&a)[1 << R], const DevOp* __restrict__ op, const uint64_t g,
-                                         const double* __restrict__ mat2tab, double2& pend) {
-    const int kind = op->kind;
-    if (kind == K_DIAG) {
-        if (op->dmask0 == 0 && op->dmask1 == 0) {
-            const int u0 = op->dq0 >= 0 ? (int)((g >> op->dq0) & 1ull) : 0;
-            const int u1 = op->dq1 >= 0 ? (int)((g >> op->dq1) & 1ull) : 0;
-            pend = cmul(pend, reinterpret_cast<const double2*>(op->m)[u0 + 2 * u1]);
-            return;
-        }
-        op_diag<R>(a, op, g);
-        return;
+#define B200_SWITCH_R1(FN, r, ...)                      \
+    switch (r) {                                        \
+    case 0: FN<R, 0>(__VA_ARGS__); break;               \
+    case 1: FN<R, 1>(__VA_ARGS__); break;               \
+    case 2: FN<R, 2>(__VA_ARGS__); break;               \
+    default: FN<R, 3>(__VA_ARGS__); break;              \
     }
-    const int cq = op->cq;
-    if (cq >= 0 && !((g >> cq) & 1ull)) return;
-    const int cmask = op->cmask;
-    const int t0 = op->treg0;
-    if (kind == K_X) {
-        switch (t0) {
-        case 0: op_x<R, 0>(a, cmask); break;
-        case 1: op_x<R, 1>(a, cmask); break;
-        case 2: op_x<R, 2>(a, cmask); break;
-        default: op_x<R, 3>(a, cmask); break;
-        }
-    } else if (kind == K_MAT1) {
-        switch (t0) {
-        case 0: op_mat1<R, 0>(a, op->m, cmask); break;
-        case 1: op_mat1<R, 1>(a, op->m, cmask); break;
-        case 2: op_mat1<R, 2>(a, op->m, cmask); break;
-        default: op_mat1<R, 3>(a, op->m, cmask); break;
-        }
-    } else {  // K_MAT2, treg0 < treg1
-        const double* mm = mat2tab + op->mat2;
-        switch (t0 * 4 + op->treg1) {
-        case 1: op_mat2<R, 0, 1>(a, mm, cmask); break;
-        case 2: op_mat2<R, 0, 2>(a, mm, cmask); break;
-        case 3: op_mat2<R, 0, 3>(a, mm, cmask); break;
-        case 6: op_mat2<R, 1, 2>(a, mm, cmask); break;
-        case 7: op_mat2<R, 1, 3>(a, mm, cmask); break;
-        default: op_mat2<R, 2, 3>(a, mm, cmask); break;
-        }
+// ordered pair r0 < r1
+#define B200_SWITCH_R2(FN, r0, r1, ...)                 \
+    switch ((r0) * 4 + (r1)) {                          \
+    case 1: FN<R, 0, 1>(__VA_ARGS__); break;            \
+    case 2: FN<R, 0, 2>(__VA_ARGS__); break;            \
+    case 3: FN<R, 0, 3>(__VA_ARGS__); break;            \
+    case 6: FN<R, 1, 2>(__VA_ARGS__); break;            \
+    case 7: FN<R, 1, 3>(__VA_ARGS__); break;            \
+    default: FN<R, 2, 3>(__VA_ARGS__); break;           \
+    }
+
+template <int R>
+B200_HD void op_cx_any(double2 (&a)[1 << R], const int t, const int c) {
+    switch (t * 4 + c) {
+    case 1: op_cx<R, 0, 1>(a); break;
+    case 2: op_cx<R, 0, 2>(a); break;
+    case 3: op_cx<R, 0, 3>(a); break;
+    case 4: op_cx<R, 1, 0>(a); break;
+    case 6: op_cx<R, 1, 2>(a); break;
+    case 7: op_cx<R, 1, 3>(a); break;
+    case 8: op_cx<R, 2, 0>(a); break;
+    case 9: op_cx<R, 2, 1>(a); break;
+    case 11: op_cx<R, 2, 3>(a); break;
+    case 12: op_cx<R, 3, 0>(a); break;
+    case 13: op_cx<R, 3, 1>(a); break;
+    default: op_cx<R, 3, 2>(a); break;
+    }
+}
+
+// generic diagonal (non-unitary input with a zero phase entry): phase index = bit(q0) + 2 bit(q1), each
+// bit either a register bit (r >= 0) or a bit of the thread's base index g
+template <int R>
+B200_HD void op_diagraw(double2 (&a)[1 << R], const POp& op, const uint64_t g) {
+    const int u0 = op.dq0 >= 0 ? (int)((g >> op.dq0) & 1ull) : 0;
+    const int u1 = op.dq1 >= 0 ? (int)((g >> op.dq1) & 1ull) : 0;
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) {
+        const int b0 = op.r0 >= 0 ? ((j >> op.r0) & 1) : u0;
+        const int b1 = op.r1 >= 0 ? ((j >> op.r1) & 1) : u1;
+        a[j] = cmul(a[j], ld_c(op.m, b0 + 2 * b1));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lane ops (HBM rounds): the mixing target is one of the warp-lane bits 0..COAL_BITS-1, partners are
+// exchanged through EX (device: __shfl_xor_sync; emulator: a snapshot of the warp's registers)
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+struct ShflExchange {
+    __device__ __forceinline__ double2 operator()(const double2 v, const int /*j*/, const int lane_mask) const {
+        return make_double2(__shfl_xor_sync(0xffffffffu, v.x, lane_mask), __shfl_xor_sync(0xffffffffu, v.y, lane_mask));
+    }
+};
+#endif
+
+// X on lane bit `lb`; control: none, register bit rc, or thread-level (ctl = the control's value for this thread;
+// the partner has the same value because the control is not the target)
+template <int R, class EX>
+B200_HD void op_xlane(double2 (&a)[1 << R], const int lb, const int rc, const bool ctl, const EX& ex) {
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) {
+        if (rc >= 0 && !((j >> rc) & 1)) continue;
+        const double2 v = ex(a[j], j, 1 << lb);
+        if (ctl) a[j] = v;
+    }
+}
+
+// dense 2x2 on lane bit `lb`: every thread computes its own output row
+template <int R, class EX>
+B200_HD void op_mat1lane(double2 (&a)[1 << R], const double* __restrict__ m, const int lb, const uint32_t lane,
+                         const EX& ex) {
+    const bool hi = (lane >> lb) & 1u;
+    const double2 cs = hi ? ld_c(m, 3) : ld_c(m, 0);   // coefficient of the thread's own amplitude
+    const double2 co = hi ? ld_c(m, 2) : ld_c(m, 1);   // coefficient of the partner's
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) {
+        const double2 p = ex(a[j], j, 1 << lb);
+        a[j] = cfma(co, p, cmul(cs, a[j]));
     }
 }
 
@@ -206,100 +240,150 @@ B200_HD void apply_op(double2 (&a)[1 << R], const DevOp* __restrict__ op, const 
 // K1/K2: fused sweep
 // ---------------------------------------------------------------------------------------------
 // Base index of tile `tile`: zero bits inserted at the tile's high qubits.
-B200_HD uint64_t sweep_tile_base(const DevSweep& sw, const uint32_t tile) {
+B200_HD uint64_t sweep_tile_base(const SweepProg& sp, const uint32_t tile) {
     uint64_t y = tile;
-    for (int i = sw.c; i < TILE_BITS; ++i) y = ins0_64(y, sw.tileq[i] - sw.c);
-    return y << sw.c;
+    for (int i = sp.c; i < TILE_BITS; ++i) y = ins0_64(y, sp.tileq[i] - sp.c);
+    return y << sp.c;
 }
 
-// One round of one thread: load 2^R amplitudes (HBM in the first round, shared memory after),
-// apply the round's ops in registers, store (HBM in the last round, shared memory before).
-// The caller separates rounds with a block barrier.
+// Thread `tid`'s tile-local index with zeros at the round's register positions, and its global index.
 template <int R>
-B200_HD void sweep_round(const double2* __restrict__ src, double2* __restrict__ dst, double2* tile_smem,
-                         const DevSweep& sw, const DevRound* __restrict__ rd, const DevOp* __restrict__ ops,
-                         const double* __restrict__ mat2tab, const uint64_t tile_base, const uint32_t tid,
-                         const bool first, const bool last) {
-    const int c = sw.c;
-    int rp[R];
+B200_HD void round_index(const SweepProg& sp, const PRound& rd, const uint64_t tile_base, const uint32_t tid,
+                         uint32_t& tl, uint64_t& g) {
+    tl = tid;
 #pragma unroll
-    for (int k = 0; k < R; ++k) rp[k] = rd->regpos[k];
-    uint32_t tl = tid;
-#pragma unroll
-    for (int k = 0; k < R; ++k) tl = ins0_32(tl, rp[k]);
-    uint64_t g = tile_base | (uint64_t)(tl & ((1u << c) - 1u));
-    for (int i = c; i < TILE_BITS; ++i) g |= (uint64_t)((tl >> i) & 1u) << sw.tileq[i];
+    for (int k = 0; k < R; ++k) tl = ins0_32(tl, rd.regpos[k]);
+    const int c = sp.c;
+    g = tile_base | (uint64_t)(tl & ((1u << c) - 1u));
+    for (int i = c; i < TILE_BITS; ++i) g |= (uint64_t)((tl >> i) & 1u) << sp.tileq[i];
+}
 
-    double2 a[1 << R];
-    if (first) {
-        uint64_t gs[R];
+template <int R>
+B200_HD void round_load_hbm(double2 (&a)[1 << R], const double2* __restrict__ src, const SweepProg& sp,
+                            const PRound& rd, const uint64_t g) {
+    uint64_t gs[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) gs[k] = 1ull << sw.tileq[rp[k]];
+    for (int k = 0; k < R; ++k) gs[k] = 1ull << sp.tileq[rd.regpos[k]];
 #pragma unroll
-        for (int j = 0; j < (1 << R); ++j) {
-            uint64_t off = 0;
+    for (int j = 0; j < (1 << R); ++j) {
+        uint64_t off = 0;
 #pragma unroll
-            for (int k = 0; k < R; ++k) if (j >> k & 1) off += gs[k];
-            a[j] = src[g + off];
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < (1 << R); ++j) {
-            uint32_t off = 0;
-#pragma unroll
-            for (int k = 0; k < R; ++k) if (j >> k & 1) off += 1u << rp[k];
-            a[j] = tile_smem[swz(tl + off)];
-        }
-    }
-
-    const int ob = rd->op_begin, oe = rd->op_end;
-    double2 pend = make_double2(1.0, 0.0);
-    for (int o = ob; o < oe; ++o) apply_op<R>(a, ops + o, g, mat2tab, pend);
-    if (pend.x != 1.0 || pend.y != 0.0) {
-#pragma unroll
-        for (int j = 0; j < (1 << R); ++j) a[j] = cmul(a[j], pend);
-    }
-
-    if (last) {
-        uint64_t gs[R];
-#pragma unroll
-        for (int k = 0; k < R; ++k) gs[k] = 1ull << sw.tileq[rp[k]];
-#pragma unroll
-        for (int j = 0; j < (1 << R); ++j) {
-            uint64_t off = 0;
-#pragma unroll
-            for (int k = 0; k < R; ++k) if (j >> k & 1) off += gs[k];
-            dst[g + off] = a[j];
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < (1 << R); ++j) {
-            uint32_t off = 0;
-#pragma unroll
-            for (int k = 0; k < R; ++k) if (j >> k & 1) off += 1u << rp[k];
-            tile_smem[swz(tl + off)] = a[j];
-        }
+        for (int k = 0; k < R; ++k) if (j >> k & 1) off += gs[k];
+        a[j] = src[g + off];
     }
 }
 
+template <int R>
+B200_HD void round_store_hbm(const double2 (&a)[1 << R], double2* __restrict__ dst, const SweepProg& sp,
+                             const PRound& rd, const uint64_t g) {
+    uint64_t gs[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) gs[k] = 1ull << sp.tileq[rd.regpos[k]];
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) if (j >> k & 1) off += gs[k];
+        dst[g + off] = a[j];
+    }
+}
+
+template <int R>
+B200_HD void round_load_smem(double2 (&a)[1 << R], const double2* tile_smem, const PRound& rd, const uint32_t tls) {
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) a[j] = tile_smem[tls ^ (uint32_t)rd.soff[j]];
+}
+
+template <int R>
+B200_HD void round_store_smem(const double2 (&a)[1 << R], double2* tile_smem, const PRound& rd, const uint32_t tls) {
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) tile_smem[tls ^ (uint32_t)rd.soff[j]] = a[j];
+}
+
+template <int R>
+B200_HD void apply_pend(double2 (&a)[1 << R], const double2 pend) {
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) a[j] = cmul(a[j], pend);
+}
+
+// One op of a round on the thread's registers.  `pend` collects the phases that multiply all 2^R
+// amplitudes of the thread alike: they commute with every register op of the round and are applied once at
+// the end of the round (or before a lane exchange, which they do not commute with: op.flush).  Every field of `op` is warp-uniform (kernel-parameter constant bank).
+template <int R, class EX>
+B200_HD void apply_op(double2 (&a)[1 << R], const SweepProg& sp, const POp& op, const uint64_t g,
+                      const uint32_t lane, double2& pend, const EX& ex) {
+    switch (op.kind) {
+    case P_PEND: {
+        const int u0 = op.dq0 >= 0 ? (int)((g >> op.dq0) & 1ull) : 0;
+        const int u1 = op.dq1 >= 0 ? (int)((g >> op.dq1) & 1ull) : 0;
+        pend = cmul(pend, ld_c(op.m, u0 + 2 * u1));
+        break;
+    }
+    case P_DIAG1: {
+        const int u = op.dq1 >= 0 ? (int)((g >> op.dq1) & 1ull) : 0;
+        pend = cmul(pend, ld_c(op.m, u));
+        const double2 ratio = ld_c(op.m, 2 + u);
+        B200_SWITCH_R1(op_diag1, op.r0, a, ratio)
+        break;
+    }
+    case P_DIAG2: {
+        pend = cmul(pend, ld_c(op.m, 0));
+        const double2 r10 = ld_c(op.m, 1), r01 = ld_c(op.m, 2), r11 = ld_c(op.m, 3);
+        B200_SWITCH_R2(op_diag2, op.r0, op.r1, a, r10, r01, r11)
+        break;
+    }
+    case P_DIAGRAW: op_diagraw<R>(a, op, g); break;
+    case P_XREG:
+        if (op.cq < 0 || ((g >> op.cq) & 1ull)) { B200_SWITCH_R1(op_x, op.r0, a) }
+        break;
+    case P_CXREG: op_cx_any<R>(a, op.r0, op.r1); break;
+    case P_MAT1: B200_SWITCH_R1(op_mat1, op.r0, a, op.m) break;
+    case P_MAT2: B200_SWITCH_R2(op_mat2, op.r0, op.r1, a, sp.mat2[op.mat2]) break;
+    case P_XLANE: {
+        if (op.flush) { apply_pend<R>(a, pend); pend = make_double2(1.0, 0.0); }
+        const bool ctl = op.cq < 0 || ((g >> op.cq) & 1ull);
+        op_xlane<R>(a, op.r0, op.r1, ctl, ex);
+        break;
+    }
+    default:   // P_MAT1LANE
+        if (op.flush) { apply_pend<R>(a, pend); pend = make_double2(1.0, 0.0); }
+        op_mat1lane<R>(a, op.m, op.r0, lane, ex);
+        break;
+    }
+}
+
+#ifdef __CUDACC__
+// The whole program of the sweep is a kernel parameter: op decode is uniform constant-bank loads and
+// uniform branches.  One CTA owns one tile at a time (persistent grid-stride over tiles).
 template <int R>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2)
-sv_sweep_kernel(const double2* __restrict__ src, double2* __restrict__ dst, const DevSweep sw,
-                const DevRound* __restrict__ rounds, const DevOp* __restrict__ ops,
-                const double* __restrict__ mat2tab, const uint32_t ntiles) {
+sv_sweep_kernel(const double2* __restrict__ src, double2* __restrict__ dst, const __grid_constant__ SweepProg sp,
+                const uint32_t ntiles) {
     extern __shared__ __align__(16) double2 tile_smem[];
     static_assert(R == REG_BITS, "register bits");
-    const int nr = sw.round_end - sw.round_begin;
+    const int nr = sp.nrounds;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const ShflExchange ex;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t tile_base = sweep_tile_base(sw, tile);
+        const uint64_t tile_base = sweep_tile_base(sp, tile);
         for (int r = 0; r < nr; ++r) {
-            sweep_round<R>(src, dst, tile_smem, sw, rounds + sw.round_begin + r, ops, mat2tab, tile_base,
-                           threadIdx.x, r == 0, r == nr - 1);
-            if (r != nr - 1) __syncthreads();
+            const PRound& rd = sp.rounds[r];
+            uint32_t tl; uint64_t g;
+            round_index<R>(sp, rd, tile_base, tid, tl, g);
+            const uint32_t tls = swz(tl);
+            double2 a[1 << R];
+            if (r == 0) round_load_hbm<R>(a, src, sp, rd, g);
+            else round_load_smem<R>(a, tile_smem, rd, tls);
+            double2 pend = make_double2(1.0, 0.0);
+            for (int o = rd.op_begin; o < rd.op_end; ++o) apply_op<R>(a, sp, sp.ops[o], g, lane, pend, ex);
+            if (rd.has_pend) apply_pend<R>(a, pend);
+            if (r == nr - 1) round_store_hbm<R>(a, dst, sp, rd, g);
+            else { round_store_smem<R>(a, tile_smem, rd, tls); __syncthreads(); }
         }
         if (nr > 1) __syncthreads();
     }
 }
+#endif  // __CUDACC__
 
 // ---------------------------------------------------------------------------------------------
 // small path: n <= SMALL_MAX_QUBITS, one CTA, state in shared memory

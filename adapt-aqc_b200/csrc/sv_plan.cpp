@@ -213,6 +213,111 @@ void fuse_single_qubit_runs(std::vector<COp>& ops) {
     ops.swap(out);
 }
 
+// ---------------------------------------------------------------------------------------------
+// diagonal fusion: push diagonals forward through CX, merge what meets
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// phase of diagonal op `e` for bit values (ba on qubit a, bb on qubit b); a qubit `e` does not act on is ignored
+inline cplx diag_phase(const COp& e, int a, int ba, int b, int bb) {
+    const int b0 = e.d0 == a ? ba : (e.d0 == b ? bb : 0);
+    const int b1 = e.d1 < 0 ? 0 : (e.d1 == a ? ba : (e.d1 == b ? bb : 0));
+    return e.m[b0 + 2 * b1];
+}
+
+// multiply the 1-qubit diagonal (p0, p1) on qubit q into diagonal op `e` (which acts on q)
+inline void mul_diag1_into(COp& e, int q, cplx p0, cplx p1) {
+    for (int k = 0; k < 4; ++k) {
+        const int bit = e.d0 == q ? (k & 1) : (k >> 1);
+        e.m[k] *= bit ? p1 : p0;
+    }
+}
+
+inline bool same_pair(const COp& e, int a, int b) {
+    return e.d1 >= 0 && ((e.d0 == a && e.d1 == b) || (e.d0 == b && e.d1 == a));
+}
+
+}  // namespace
+
+void fuse_diagonals(std::vector<COp>& ops) {
+    std::vector<COp> out;
+    std::vector<char> dead;
+    out.reserve(ops.size() + 8);
+    int last_mix[64], dcont[64];
+    for (int q = 0; q < 64; ++q) last_mix[q] = dcont[q] = -1;
+    auto live = [&](int e, int q) { return e >= 0 && !dead[e] && last_mix[q] < e; };
+    auto push = [&](const COp& o) { out.push_back(o); dead.push_back(0); return (int)out.size() - 1; };
+
+    for (const COp& op : ops) {
+        if (op.kind == K_DIAG && op.d1 < 0) {
+            const int q = op.d0, e = dcont[q];
+            if (live(e, q)) { mul_diag1_into(out[e], q, op.m[0], op.m[1]); continue; }
+            dcont[q] = push(op);
+        } else if (op.kind == K_DIAG) {
+            const int a = op.d0, b = op.d1;
+            const int e = dcont[a];
+            if (live(e, a) && same_pair(out[e], a, b) && live(e, b)) {
+                for (int k = 0; k < 4; ++k) {
+                    const int ba = out[e].d0 == a ? (k & 1) : (k >> 1), bb = out[e].d0 == a ? (k >> 1) : (k & 1);
+                    out[e].m[k] *= diag_phase(op, a, ba, b, bb);
+                }
+                continue;
+            }
+            COp d = op;
+            for (int q : {a, b}) {
+                const int e1 = dcont[q];
+                if (live(e1, q) && out[e1].d1 < 0) {
+                    mul_diag1_into(d, q, out[e1].m[0], out[e1].m[1]);
+                    dead[e1] = 1;
+                }
+            }
+            dcont[a] = dcont[b] = push(d);
+        } else if (op.kind == K_X && op.c >= 0) {
+            const int c = op.c, t = op.t0;
+            const int e = dcont[t];
+            COp d;
+            bool have = false;
+            if (live(e, t) && out[e].d1 < 0) {                       // D_t . then CX  ==  CX . then parity phase
+                d.kind = K_DIAG; d.d0 = t; d.d1 = c;
+                for (int k = 0; k < 4; ++k) d.m[k] = out[e].m[(k & 1) ^ (k >> 1)];
+                dead[e] = 1; have = true;
+            } else if (live(e, t) && same_pair(out[e], c, t) && live(e, c)) {
+                d.kind = K_DIAG; d.d0 = t; d.d1 = c;
+                for (int k = 0; k < 4; ++k) {
+                    const int bt = k & 1, bc = k >> 1;
+                    d.m[k] = diag_phase(out[e], t, bt ^ bc, c, bc);
+                }
+                dead[e] = 1; have = true;
+            }
+            const int ix = push(op);
+            last_mix[t] = ix;
+            if (have) {
+                const int ec = dcont[c];
+                if (live(ec, c) && out[ec].d1 < 0) {                  // commutes with the control: absorb
+                    mul_diag1_into(d, c, out[ec].m[0], out[ec].m[1]);
+                    dead[ec] = 1;
+                }
+                dcont[t] = dcont[c] = push(d);
+            }
+        } else {
+            const int ix = push(op);
+            if (op.t0 >= 0) last_mix[op.t0] = ix;
+            if (op.t1 >= 0) last_mix[op.t1] = ix;
+        }
+    }
+    ops.clear();
+    for (size_t k = 0; k < out.size(); ++k) {
+        if (dead[k]) continue;
+        const COp& o = out[k];
+        if (o.kind == K_DIAG) {       // drop exact identities
+            bool ident = true;
+            for (int j = 0; j < 4; ++j) ident = ident && o.m[j] == cplx(1, 0);
+            if (ident) continue;
+        }
+        ops.push_back(o);
+    }
+}
+
 namespace {
 
 // Greedy commuting-aware selection: walk `pending` in order and pick every op that (a) commutes
@@ -255,6 +360,69 @@ void fill_small_op(const COp& o, Plan& plan, DevOp& d) {
     }
 }
 
+inline void put(double* m, int k, cplx z) { m[2 * k] = z.real(); m[2 * k + 1] = z.imag(); }
+
+// Translate canonical op `o` for a round whose register qubits are given by reg_of[] (-1 = not a register).
+// Mixing targets that are not registers are lane qubits (only scheduled in HBM rounds, qubit < COAL_BITS).
+void fill_tiled_op(const COp& o, const int* reg_of, SweepProg& sp, POp& d) {
+    std::memset(&d, 0, sizeof d);
+    d.r0 = d.r1 = d.cq = d.dq0 = d.dq1 = d.mat2 = -1;
+    if (o.kind == K_DIAG) {
+        const int ra = reg_of[o.d0], rb = o.d1 >= 0 ? reg_of[o.d1] : -1;
+        bool zero = false;
+        for (int k = 0; k < 4; ++k) zero = zero || std::abs(o.m[k]) < 1e-300;
+        if (ra < 0 && rb < 0) {
+            d.kind = P_PEND; d.dq0 = o.d0; d.dq1 = o.d1;
+            for (int k = 0; k < 4; ++k) put(d.m, k, o.m[k]);
+        } else if (zero) {
+            d.kind = P_DIAGRAW; d.r0 = ra; d.r1 = rb;
+            d.dq0 = ra < 0 ? o.d0 : -1; d.dq1 = (rb < 0 && o.d1 >= 0) ? o.d1 : -1;
+            for (int k = 0; k < 4; ++k) put(d.m, k, o.m[k]);
+        } else if (ra >= 0 && rb >= 0) {
+            d.kind = P_DIAG2;
+            const bool sw = ra > rb;   // kernel wants r0 < r1: swap the two index bits
+            d.r0 = sw ? rb : ra; d.r1 = sw ? ra : rb;
+            const cplx p00 = o.m[0], p10 = sw ? o.m[2] : o.m[1], p01 = sw ? o.m[1] : o.m[2], p11 = o.m[3];
+            put(d.m, 0, p00); put(d.m, 1, p10 / p00); put(d.m, 2, p01 / p00); put(d.m, 3, p11 / p00);
+        } else {
+            d.kind = P_DIAG1;
+            if (ra >= 0) {            // register = d0, thread-level = d1 (may be absent)
+                d.r0 = ra; d.dq1 = o.d1;
+                put(d.m, 0, o.m[0]); put(d.m, 1, o.m[2]);
+                put(d.m, 2, o.m[1] / o.m[0]); put(d.m, 3, o.m[3] / o.m[2]);
+            } else {                  // register = d1, thread-level = d0
+                d.r0 = rb; d.dq1 = o.d0;
+                put(d.m, 0, o.m[0]); put(d.m, 1, o.m[1]);
+                put(d.m, 2, o.m[2] / o.m[0]); put(d.m, 3, o.m[3] / o.m[1]);
+            }
+        }
+    } else if (o.kind == K_X) {
+        const int rt = reg_of[o.t0], rc = o.c >= 0 ? reg_of[o.c] : -1;
+        if (rt >= 0 && rc >= 0) { d.kind = P_CXREG; d.r0 = rt; d.r1 = rc; }
+        else if (rt >= 0) { d.kind = P_XREG; d.r0 = rt; d.cq = o.c; }
+        else { d.kind = P_XLANE; d.r0 = o.t0; d.r1 = rc; d.cq = rc >= 0 ? -1 : o.c; }
+    } else if (o.kind == K_MAT1) {
+        const int rt = reg_of[o.t0];
+        d.kind = rt >= 0 ? P_MAT1 : P_MAT1LANE;
+        d.r0 = rt >= 0 ? rt : o.t0;
+        for (int j = 0; j < 4; ++j) put(d.m, j, o.m[j]);
+    } else {  // K_MAT2
+        d.kind = P_MAT2;
+        d.r0 = reg_of[o.t0]; d.r1 = reg_of[o.t1];
+        cplx mm[16];
+        if (d.r0 < d.r1) {
+            for (int j = 0; j < 16; ++j) mm[j] = o.m[j];
+        } else {  // kernel wants r0 < r1: swap the two index bits
+            auto sw2 = [](int i) { return ((i & 1) << 1) | (i >> 1); };
+            for (int r = 0; r < 4; ++r)
+                for (int cc = 0; cc < 4; ++cc) mm[4 * sw2(r) + sw2(cc)] = o.m[4 * r + cc];
+            std::swap(d.r0, d.r1);
+        }
+        d.mat2 = sp.nmat2++;
+        for (int j = 0; j < 16; ++j) put(sp.mat2[d.mat2], j, mm[j]);
+    }
+}
+
 }  // namespace
 
 void build_plan(int nq, const std::vector<COp>& ops, Plan& plan) {
@@ -273,105 +441,111 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan) {
     for (int k = 0; k < nops; ++k) all[k] = k;
     int n_taken = 0;
     const uint64_t low_mask = (1ull << LANE_BITS) - 1;
+    const uint64_t coal_mask = (1ull << COAL_BITS) - 1;
 
     while (n_taken < nops) {
         // ---- choose the ops of this sweep and its set H of high mixing qubits ----
         uint64_t H = 0;
+        int n_sw = 0, n_m2 = 0;
         std::vector<int> sw_ops = greedy_pick(ops, all, taken, [&](const COp& o) {
+            if (n_sw >= MAX_SWEEP_OPS || (o.kind == K_MAT2 && n_m2 >= MAX_SWEEP_MAT2)) return false;
             const uint64_t need = mix_mask(o) & ~low_mask & ~H;
             if (__builtin_popcountll(H) + __builtin_popcountll(need) > MAX_HIGH) return false;
             H |= need;
+            ++n_sw;
+            if (o.kind == K_MAT2) ++n_m2;
             return true;
         });
-        n_taken += (int)sw_ops.size();
 
         // ---- tile qubit list: lanes, H, padding with the lowest unused qubits ----
         uint64_t tile = low_mask | H;
         for (int q = LANE_BITS; q < nq && __builtin_popcountll(tile) < TILE_BITS; ++q) tile |= 1ull << q;
-        DevSweep sw;
-        std::memset(&sw, 0, sizeof sw);
-        sw.t = TILE_BITS;
+        plan.sweeps.emplace_back();
+        SweepProg& sp = plan.sweeps.back();
+        std::memset(&sp, 0, sizeof sp);
         for (int q = 0, i = 0; q < nq; ++q) {
-            if (tile >> q & 1) { sw.tileq[i] = q; ++i; }
+            if (tile >> q & 1) { sp.tileq[i] = q; ++i; }
         }
         int c = 0;
-        while (c < TILE_BITS && sw.tileq[c] == c) ++c;
-        sw.c = c;
+        while (c < TILE_BITS && sp.tileq[c] == c) ++c;
+        sp.c = c;
 
-        // ---- split the sweep's ops into rounds of <= REG_BITS register (mixing) qubits ----
-        struct RoundTmp { uint64_t regs; std::vector<int> ops; };
+        // ---- split the sweep's ops into rounds ----
+        // HBM round (first / last): register qubits among the tile qubits >= COAL_BITS, up to MAX_LANE_OPS
+        // mixing ops on the lane qubits 0..COAL_BITS-1 served by shuffles, no dense 2-qubit op on a lane qubit.
+        // Middle round (shared memory on both sides): any REG_BITS tile qubits as registers.
+        struct RoundTmp { uint64_t regs; std::vector<int> ops; bool hbm; };
         std::vector<RoundTmp> rounds;
         std::vector<char> rtaken(nops, 1);
         for (int idx : sw_ops) rtaken[idx] = 0;
         int left = (int)sw_ops.size();
         bool first = true;
-        while (left > 0) {
+        while (left > 0 && (int)rounds.size() < MAX_SWEEP_ROUNDS - 1) {
             uint64_t regs = 0;
-            const bool no_low = first;  // the first round loads from HBM: register qubits >= 5
-            std::vector<int> r_ops = greedy_pick(ops, sw_ops, rtaken, [&](const COp& o) {
-                const uint64_t mm = mix_mask(o);
-                if (no_low && (mm & low_mask)) return false;
-                const uint64_t need = mm & ~regs;
+            int lanes = 0;
+            std::vector<char> tk = rtaken;
+            std::vector<int> r_ops = greedy_pick(ops, sw_ops, tk, [&](const COp& o) {
+                const uint64_t mm = mix_mask(o), low = mm & coal_mask;
+                if (low && o.kind == K_MAT2) return false;
+                const int nl = __builtin_popcountll(low);
+                if (lanes + nl > MAX_LANE_OPS) return false;
+                const uint64_t need = mm & ~coal_mask & ~regs;
                 if (__builtin_popcountll(regs) + __builtin_popcountll(need) > REG_BITS) return false;
-                regs |= need;
+                regs |= need; lanes += nl;
                 return true;
             });
+            bool hbm = true;
+            if (!first && (int)r_ops.size() != left) {   // cannot finish here: a shared-memory round instead
+                hbm = false;
+                regs = 0;
+                tk = rtaken;
+                r_ops = greedy_pick(ops, sw_ops, tk, [&](const COp& o) {
+                    const uint64_t need = mix_mask(o) & ~regs;
+                    if (__builtin_popcountll(regs) + __builtin_popcountll(need) > REG_BITS) return false;
+                    regs |= need;
+                    return true;
+                });
+            }
+            rtaken.swap(tk);
             left -= (int)r_ops.size();
-            if (!(first && r_ops.empty())) rounds.push_back({regs, r_ops});
-            else rounds.push_back({0, {}});  // pure load round
+            rounds.push_back({regs, r_ops, hbm});
             first = false;
         }
-        if (rounds.empty()) rounds.push_back({0, {}});
-        if (rounds.back().regs & low_mask) rounds.push_back({0, {}});  // pure store round
+        if (rounds.empty()) rounds.push_back({0, {}, true});
+        if (!rounds.back().hbm) rounds.push_back({0, {}, true});  // pure store round
+        // ops that did not fit the round budget go back to the pool (they commute with everything that
+        // was scheduled ahead of them, see greedy_pick)
+        for (int idx : sw_ops) if (!rtaken[idx]) taken[idx] = 0;
+        n_taken += (int)sw_ops.size() - left;
 
-        sw.round_begin = (int32_t)plan.rounds.size();
-        for (auto& rt : rounds) {
+        sp.nrounds = (int32_t)rounds.size();
+        for (size_t r = 0; r < rounds.size(); ++r) {
+            RoundTmp& rt = rounds[r];
             // pad the register set with the highest free tile positions >= LANE_BITS
             uint64_t regs = rt.regs;
             for (int i = TILE_BITS - 1; i >= LANE_BITS && __builtin_popcountll(regs) < REG_BITS; --i)
-                if (!(regs >> sw.tileq[i] & 1)) regs |= 1ull << sw.tileq[i];
-            DevRound dr;
+                if (!(regs >> sp.tileq[i] & 1)) regs |= 1ull << sp.tileq[i];
+            PRound& dr = sp.rounds[r];
             int reg_of[64];
             for (int q = 0; q < 64; ++q) reg_of[q] = -1;
             int k = 0;
             for (int i = 0; i < TILE_BITS; ++i)
-                if (regs >> sw.tileq[i] & 1) { dr.regpos[k] = i; reg_of[sw.tileq[i]] = k; ++k; }
-            dr.op_begin = (int32_t)plan.ops.size();
-            for (int idx : rt.ops) {
-                const COp& o = ops[idx];
-                DevOp d;
-                std::memset(&d, 0, sizeof d);
-                d.kind = o.kind;
-                d.treg0 = d.treg1 = -1;
-                d.cq = d.dq0 = d.dq1 = -1;
-                d.mat2 = -1;
-                if (o.t0 >= 0) d.treg0 = reg_of[o.t0];
-                if (o.t1 >= 0) d.treg1 = reg_of[o.t1];
-                if (o.c >= 0) { if (reg_of[o.c] >= 0) d.cmask = 1 << reg_of[o.c]; else d.cq = o.c; }
-                if (o.d0 >= 0) { if (reg_of[o.d0] >= 0) d.dmask0 = 1 << reg_of[o.d0]; else d.dq0 = o.d0; }
-                if (o.d1 >= 0) { if (reg_of[o.d1] >= 0) d.dmask1 = 1 << reg_of[o.d1]; else d.dq1 = o.d1; }
-                if (o.kind == K_MAT1 || o.kind == K_DIAG) {
-                    for (int j = 0; j < 4; ++j) { d.m[2 * j] = o.m[j].real(); d.m[2 * j + 1] = o.m[j].imag(); }
-                } else if (o.kind == K_MAT2) {
-                    cplx mm[16];
-                    if (d.treg0 < d.treg1) {
-                        for (int j = 0; j < 16; ++j) mm[j] = o.m[j];
-                    } else {  // kernel wants treg0 < treg1: swap the two index bits
-                        auto sw2 = [](int i) { return ((i & 1) << 1) | (i >> 1); };
-                        for (int r = 0; r < 4; ++r)
-                            for (int cc = 0; cc < 4; ++cc) mm[4 * sw2(r) + sw2(cc)] = o.m[4 * r + cc];
-                        std::swap(d.treg0, d.treg1);
-                    }
-                    d.mat2 = (int32_t)plan.mat2.size();
-                    for (int j = 0; j < 16; ++j) { plan.mat2.push_back(mm[j].real()); plan.mat2.push_back(mm[j].imag()); }
-                }
-                plan.ops.push_back(d);
+                if (regs >> sp.tileq[i] & 1) { dr.regpos[k] = i; reg_of[sp.tileq[i]] = k; ++k; }
+            for (int j = 0; j < (1 << REG_BITS); ++j) {
+                uint32_t off = 0;
+                for (int b = 0; b < REG_BITS; ++b) if (j >> b & 1) off |= 1u << dr.regpos[b];
+                dr.soff[j] = (int32_t)swz(off);
             }
-            dr.op_end = (int32_t)plan.ops.size();
-            plan.rounds.push_back(dr);
+            dr.op_begin = sp.nops;
+            bool pending = false;
+            for (int idx : rt.ops) {
+                POp& po = sp.ops[sp.nops++];
+                fill_tiled_op(ops[idx], reg_of, sp, po);
+                if (po.kind == P_PEND || po.kind == P_DIAG1 || po.kind == P_DIAG2) { dr.has_pend = 1; pending = true; }
+                if (po.kind == P_XLANE || po.kind == P_MAT1LANE) { po.flush = pending ? 1 : 0; pending = false; }
+            }
+            dr.op_end = sp.nops;
         }
-        sw.round_end = (int32_t)plan.rounds.size();
-        plan.sweeps.push_back(sw);
     }
 }
 

@@ -24,15 +24,29 @@
 
 #include "b200aqc.h"
 
+#ifdef __CUDACC__
+#define B200_HD __host__ __device__ __forceinline__
+#else
+#define B200_HD inline
+#endif
+
 namespace b200 {
 
 using cplx = std::complex<double>;
+
+// 16-byte-slot swizzle of the 12-bit tile index: the slot-in-row bits (low 3) are XOR-folded with every
+// higher 3-bit group, so a quarter-warp whose lanes vary ANY three consecutive tile bits (the three
+// lowest non-register positions of a round) lands on the 8 distinct 16 B slots of a 128 B row.
+// XOR-linear: swz(a ^ b) == swz(a) ^ swz(b).
+B200_HD uint32_t swz(uint32_t i) { return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u); }
 
 enum OpKind : int32_t { K_MAT1 = 0, K_X = 1, K_DIAG = 2, K_MAT2 = 3 };
 
 constexpr int TILE_BITS = 12;   // tiled path: 2^12 amplitudes (64 KB) per tile
 constexpr int REG_BITS = 4;     // 16 amplitudes per thread
-constexpr int LANE_BITS = 5;    // lowest 5 qubits always in the tile: 512 B contiguous per warp
+constexpr int LANE_BITS = 5;    // lowest 5 qubits always in the tile: 512 B contiguous per tile row
+constexpr int COAL_BITS = 3;    // HBM rounds keep the 3 lowest qubits on the lanes: every warp access moves whole
+                                // 128 B lines; qubits 3,4 may be register qubits there (4 lines per warp access)
 constexpr int MAX_HIGH = TILE_BITS - LANE_BITS;
 constexpr int SMALL_MAX_QUBITS = 11;  // n <= 11: whole state in one CTA's shared memory
 
@@ -45,46 +59,98 @@ struct COp {
     cplx m[16];            // MAT1: 2x2; DIAG: ph[b0 + 2*b1]; MAT2: 4x4 (index = bit(t0) + 2 bit(t1))
 };
 
-// Device op, 112 bytes.  In the tiled kernel the *mask fields are REGISTER masks (1 << register
-// index); in the small kernel tmask0/tmask1/cq/dq0/dq1 hold global qubit numbers.
+// Device op of the SMALL path (n <= SMALL_MAX_QUBITS, program in global memory), 112 bytes.
+// treg0/treg1/cq/dq0/dq1 hold global qubit numbers.
 struct alignas(16) DevOp {
     int32_t kind;
-    int32_t treg0, treg1;    // register index of mixing targets (tiled) / qubit (small)
-    int32_t cmask;           // register mask of the control, 0 if none or thread-uniform
-    int32_t cq;              // qubit of a thread-uniform control, -1 if none
-    int32_t dmask0, dmask1;  // register masks of diagonal qubits, 0 if thread-uniform / absent
-    int32_t dq0, dq1;        // qubits of thread-uniform diagonal bits, -1 if absent / register
+    int32_t treg0, treg1;    // mixing targets
+    int32_t cmask;           // unused in the small path
+    int32_t cq;              // control qubit, -1 if none
+    int32_t dmask0, dmask1;  // unused in the small path
+    int32_t dq0, dq1;        // diagonal qubits, -1 if absent
     int32_t mat2;            // offset (doubles) into the mat2 table
     int32_t pad0, pad1;
     double m[8];             // MAT1: 2x2 complex row-major; DIAG: 4 phases
 };
 static_assert(sizeof(DevOp) == 112, "DevOp layout");
 
-struct DevRound {
-    int32_t op_begin, op_end;
-    int32_t regpos[REG_BITS];  // tile-local bit positions of the register qubits, ascending
+// ---- tiled path: the whole program of one sweep travels as a KERNEL PARAMETER (constant bank) ----
+// Every field is warp-uniform, so the kernel decodes ops with uniform loads / uniform branches and the
+// register indices select fully unrolled, statically indexed bodies.
+//
+// Where a qubit of an op lives in a round:
+//   register qubit  : one of the round's REG_BITS positions -> index 0..3 into the thread's 2^R amplitudes
+//   lane qubit      : qubits 0..COAL_BITS-1 in a round that loads from / stores to HBM (they are then thread
+//                     bits 0..2 = warp-lane bits): a MIXING target there is served by warp shuffles
+//   thread-level    : anything else; its value is a bit of the thread's base index g
+enum PKind : int32_t {
+    P_PEND = 0,      // diagonal, no register qubit: one phase per thread, folded into the round's `pend`
+    P_DIAG1 = 1,     // diagonal, one register qubit r0 (+ optional thread-level qubit dq1)
+    P_DIAG2 = 2,     // diagonal, two register qubits r0 < r1
+    P_DIAGRAW = 3,   // diagonal with a zero entry (non-unitary input): generic slow path
+    P_XREG = 4,      // X on register r0, optional thread-level control cq
+    P_CXREG = 5,     // X on register r0 controlled by register r1
+    P_MAT1 = 6,      // dense 2x2 on register r0
+    P_MAT2 = 7,      // dense 4x4 on registers r0 < r1 (matrix index `mat2`)
+    P_XLANE = 8,     // X on lane bit r0, control: none / thread-level cq / register r1
+    P_MAT1LANE = 9,  // dense 2x2 on lane bit r0
 };
 
-struct DevSweep {
-    int32_t round_begin, round_end;
-    int32_t t, c;               // tile bits; number of leading contiguous low qubits
-    int32_t tileq[TILE_BITS];   // global qubit of each tile-local bit, ascending
+struct alignas(16) POp {   // 96 bytes
+    int32_t kind;
+    int32_t r0, r1;        // register indices (lane index in r0 for the *LANE kinds); -1 if unused
+    int32_t cq;            // thread-level control qubit, -1 if none
+    int32_t dq0, dq1;      // thread-level diagonal qubits, -1 if absent
+    int32_t mat2;          // P_MAT2: index into SweepProg::mat2
+    int32_t flush;         // lane kinds: phases are pending (they do not commute with a lane exchange): apply first
+    // P_PEND: ph[u0 + 2 u1] (4 complex).  P_DIAG1: base[u], ratio[u] (u = thread-level bit, 4 complex):
+    // amplitudes with the register bit set are multiplied by ratio[u], base[u] goes into `pend`.
+    // P_DIAG2: base, ratio01, ratio10, ratio11.  P_DIAGRAW: ph[4].  P_MAT1 / P_MAT1LANE: 2x2 row-major.
+    double m[8];
 };
+static_assert(sizeof(POp) == 96, "POp layout");
+
+constexpr int MAX_SWEEP_ROUNDS = 16;
+constexpr int MAX_SWEEP_OPS = 96;
+constexpr int MAX_SWEEP_MAT2 = 16;
+constexpr int MAX_LANE_OPS = 2;   // shuffle-served ops per HBM round before a shared-memory round is cheaper
+                                  // (64 SHFL per thread each vs 32 LDS/STS.128 + barrier for a round trip)
+
+struct PRound {
+    int32_t op_begin, op_end;
+    int32_t regpos[REG_BITS];        // tile-local bit positions of the register qubits, ascending
+    int32_t soff[1 << REG_BITS];     // swizzled shared-memory offset of register amplitude j (swz is XOR-linear)
+    int32_t has_pend, pad;           // some op of the round multiplies into the per-thread pending phase
+};
+
+struct alignas(16) SweepProg {
+    int32_t nrounds, nops, nmat2;
+    int32_t c;                  // number of leading contiguous low qubits in tileq
+    int32_t tileq[TILE_BITS];   // global qubit of each tile-local bit, ascending
+    PRound rounds[MAX_SWEEP_ROUNDS];
+    POp ops[MAX_SWEEP_OPS];
+    double mat2[MAX_SWEEP_MAT2][32];
+};
+static_assert(sizeof(SweepProg) <= 32000, "SweepProg must fit the 32 KB kernel-parameter space");
 
 struct Plan {
     int num_qubits = 0;
-    bool small = false;            // single-CTA shared-memory path
-    std::vector<DevSweep> sweeps;  // tiled path
-    std::vector<DevRound> rounds;
-    std::vector<DevOp> ops;        // tiled: grouped by round; small: flat program
-    std::vector<double> mat2;      // 32 doubles per dense 2-qubit op
+    bool small = false;              // single-CTA shared-memory path
+    std::vector<SweepProg> sweeps;   // tiled path
+    std::vector<DevOp> ops;          // small path: flat program
+    std::vector<double> mat2;        // small path: 32 doubles per dense 2-qubit op
     int n_gates_in = 0;
+    int n_rounds() const { int r = 0; for (const auto& s : sweeps) r += s.nrounds; return r; }
+    int n_ops() const { int r = (int)ops.size(); for (const auto& s : sweeps) r += s.nops; return r; }
 };
 
 // Returns empty string on success, else an error message.
 std::string canonicalize(int num_qubits, const b200_gate* gates, int n_gates, const double* mats,
                          int n_mats, bool inverse, std::vector<COp>& out);
 void fuse_single_qubit_runs(std::vector<COp>& ops);
+// Pushes 1-/2-qubit diagonals forward through the CX gates they meet and merges them: a thinly dressed
+// CNOT layer (rz rz cx rz rz) becomes ONE cx + ONE two-qubit diagonal.
+void fuse_diagonals(std::vector<COp>& ops);
 void build_plan(int num_qubits, const std::vector<COp>& ops, Plan& plan);
 
 }  // namespace b200

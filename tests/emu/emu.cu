@@ -2,6 +2,8 @@
 // the sweep / small kernels on the CPU, one loop iteration per CUDA thread, so that the planner
 // (commutation-aware scheduling, tile/round mapping) and the kernels' index math can be checked
 // against the oracle without a GPU (`pytest -m "not gpu"`).  Never loaded by the product.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -23,6 +25,7 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
     g_err = canonicalize(nq, gates, n_gates, mats, n_mats, inverse != 0, ops);
     if (!g_err.empty()) return -1;
     fuse_single_qubit_runs(ops);
+    fuse_diagonals(ops);
     Plan plan;
     build_plan(nq, ops, plan);
     double2* psi = reinterpret_cast<double2*>(state_ri);
@@ -32,8 +35,8 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
     }
     if (stats) {
         stats[0] = plan.small ? 1 : (int32_t)plan.sweeps.size();
-        stats[1] = plan.small ? 1 : (int32_t)plan.rounds.size();
-        stats[2] = (int32_t)plan.ops.size();
+        stats[1] = plan.small ? 1 : (int32_t)plan.n_rounds();
+        stats[2] = (int32_t)plan.n_ops();
         stats[3] = plan.small ? 1 : 0;
     }
     const double* mat2 = plan.mat2.empty() ? nullptr : plan.mat2.data();
@@ -43,16 +46,74 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
             for (uint32_t tid = 0; tid < nthreads; ++tid) small_apply_op(psi, (uint32_t)dim, &op, mat2, tid, nthreads);
         return 0;
     }
+    // Tiled path: the CTA's 256 threads are stepped in lock-step op by op, so the warp shuffles of the
+    // lane ops can be served from a snapshot of the registers (SnapExchange).
+    constexpr int NA = 1 << REG_BITS;
+    struct Regs { double2 a[NA]; };
     std::vector<double2> smem((size_t)1 << TILE_BITS);
+    std::vector<Regs> regs(SWEEP_THREADS), snap(SWEEP_THREADS);
+    std::vector<double2> pend(SWEEP_THREADS);
+    std::vector<uint64_t> gidx(SWEEP_THREADS);
+    std::vector<uint32_t> tls(SWEEP_THREADS);
+    struct SnapExchange {
+        const Regs* snap; uint32_t tid;
+        __host__ __device__ double2 operator()(const double2, const int j, const int lane_mask) const { return snap[tid ^ (uint32_t)lane_mask].a[j]; }
+    };
     const uint32_t ntiles = (uint32_t)(dim >> TILE_BITS);
-    for (const DevSweep& sw : plan.sweeps) {
-        const int nr = sw.round_end - sw.round_begin;
+    if (std::getenv("EMU_DUMP")) {
+        for (const SweepProg& sp : plan.sweeps) {
+            std::printf("sweep: rounds=%d ops=%d c=%d tileq=", sp.nrounds, sp.nops, sp.c);
+            for (int i = 0; i < TILE_BITS; ++i) std::printf("%d ", sp.tileq[i]);
+            std::printf("\n");
+            for (int r = 0; r < sp.nrounds; ++r) {
+                const PRound& rd = sp.rounds[r];
+                std::printf("  round %d regpos=%d,%d,%d,%d pend=%d\n", r, rd.regpos[0], rd.regpos[1], rd.regpos[2], rd.regpos[3], rd.has_pend);
+                for (int o = rd.op_begin; o < rd.op_end; ++o) {
+                    const POp& op = sp.ops[o];
+                    std::printf("    kind=%d r0=%d r1=%d cq=%d dq0=%d dq1=%d flush=%d\n", op.kind, op.r0, op.r1, op.cq, op.dq0, op.dq1, op.flush);
+                }
+            }
+        }
+    }
+    for (const SweepProg& sp : plan.sweeps) {
+        const int nr = sp.nrounds;
         for (uint32_t tile = 0; tile < ntiles; ++tile) {
-            const uint64_t base = sweep_tile_base(sw, tile);
-            for (int r = 0; r < nr; ++r)
-                for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid)
-                    sweep_round<REG_BITS>(psi, psi, smem.data(), sw, plan.rounds.data() + sw.round_begin + r,
-                                          plan.ops.data(), mat2, base, tid, r == 0, r == nr - 1);
+            const uint64_t base = sweep_tile_base(sp, tile);
+            for (int r = 0; r < nr; ++r) {
+                const PRound& rd = sp.rounds[r];
+                for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid) {
+                    uint32_t tl;
+                    round_index<REG_BITS>(sp, rd, base, tid, tl, gidx[tid]);
+                    tls[tid] = swz(tl);
+                    if (r == 0) round_load_hbm<REG_BITS>(regs[tid].a, psi, sp, rd, gidx[tid]);
+                    else round_load_smem<REG_BITS>(regs[tid].a, smem.data(), rd, tls[tid]);
+                    pend[tid] = make_double2(1.0, 0.0);
+                }
+                for (int o = rd.op_begin; o < rd.op_end; ++o) {
+                    POp op = sp.ops[o];
+                    const bool lane_op = op.kind == P_XLANE || op.kind == P_MAT1LANE;
+                    if (lane_op) {
+                        if (r != 0 && r != nr - 1) { g_err = "lane op scheduled in a shared-memory round"; return -1; }
+                        if (op.flush) {   // every lane applies its pending phase before the exchange
+                            for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid) {
+                                apply_pend<REG_BITS>(regs[tid].a, pend[tid]);
+                                pend[tid] = make_double2(1.0, 0.0);
+                            }
+                            op.flush = 0;
+                        }
+                        snap = regs;
+                    }
+                    for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid) {
+                        const SnapExchange ex{snap.data(), tid};
+                        apply_op<REG_BITS>(regs[tid].a, sp, op, gidx[tid], tid & 31u, pend[tid], ex);
+                    }
+                }
+                for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid) {
+                    if (rd.has_pend) apply_pend<REG_BITS>(regs[tid].a, pend[tid]);
+                    if (r == nr - 1) round_store_hbm<REG_BITS>(regs[tid].a, psi, sp, rd, gidx[tid]);
+                    else round_store_smem<REG_BITS>(regs[tid].a, smem.data(), rd, tls[tid]);
+                }
+            }
         }
     }
     return 0;

@@ -57,14 +57,45 @@ def test_brickwork_plus_ansatz_matches_oracle(emu):
     assert stats[0] <= len(gates) // 6
 
 
-def test_low_qubit_mixing_gets_load_and_store_rounds(emu):
-    """A mixing gate on a lane qubit (< 5) can be neither in the first nor in the last round."""
+def test_lane_qubit_mixing_is_served_by_shuffles_or_shared_memory_rounds(emu):
+    """Rounds that touch HBM keep qubits 0..2 on the warp lanes.  Up to two mixing gates there go
+    through shuffles in the same round; more of them (or a dense 2-qubit gate) get shared-memory
+    rounds between a load round and a store round.  Qubits 3 and 4 can be register qubits."""
     n = 13
     gates = [("h", [0], []), ("cx", [0, 1], []), ("ry", [3], [0.4])]
     ref = orc.evaluate_circuit(n, gates)
     got, stats = emu_run(emu, n, gates)
     np.testing.assert_allclose(got, ref, atol=TOL)
-    assert stats[0] == 1 and stats[1] == 3
+    assert stats[0] == 1 and stats[1] == 1
+    gates = [("h", [0], []), ("h", [1], []), ("h", [2], []), ("cx", [2, 0], []), ("ry", [1], [0.4]), ("cx", [9, 1], [])]
+    ref = orc.evaluate_circuit(n, gates)
+    got, stats = emu_run(emu, n, gates)
+    np.testing.assert_allclose(got, ref, atol=TOL)
+    assert stats[0] == 1 and stats[1] >= 2
+
+
+@pytest.mark.parametrize("n", [12, 14])
+def test_lane_ops_every_control_kind(emu, n):
+    """X / dense 1q on each lane qubit with no control, a lane control, a register control and a
+    thread-level control; diagonals with register / thread-level / mixed qubits."""
+    rng = np.random.default_rng(77 + n)
+    for t in range(3):
+        for c in (None, (t + 1) % 3, 3, 4, 7, n - 1):
+            gates = [("h", [q], []) for q in range(n)] + [("rz", [q], [0.1 + 0.3 * q]) for q in range(n)]
+            gates += [("cx", [c, t], [])] if c is not None else [("x", [t], [])]
+            gates += [("u3", [t], list(rng.uniform(-3, 3, 3))), ("cz", [t, 5], []), ("cz", [3, 8], []), ("cz", [0, 1], [])]
+            gates += [("cx", [t, 6], []), ("rz", [6], [0.7]), ("cx", [n - 1, 4], [])]
+            ref = orc.evaluate_circuit(n, gates)
+            got, _ = emu_run(emu, n, gates)
+            np.testing.assert_allclose(got, ref, atol=TOL)
+
+
+def test_thin_layer_is_one_cx_and_one_diagonal():
+    """Diagonal fusion: rz rz cx rz rz -> cx + one 2-qubit phase (2 device ops, 1 round)."""
+    n = 16
+    gates = [("rz", [9], [0.3]), ("rz", [10], [-0.2]), ("cx", [9, 10], []), ("rz", [9], [1.1]), ("rz", [10], [0.5])]
+    st = plan_stats(n, GateStream.from_gates(gates))
+    assert tuple(st[:3]) == (1, 1, 2), st
 
 
 def test_diagonal_and_control_qubits_do_not_need_tile_slots(emu):
