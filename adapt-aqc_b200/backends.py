@@ -120,9 +120,11 @@ class DeviceStatevector:
         if self.num_qubits == 2:
             sv = self.data
             return np.outer(sv, sv.conj())
-        hint = self._owner._current_pair_hint()
+        # The hint may come from another compiler that shares this backend (the reference calls
+        # simulator.run() outside the backend, running.py:58-63): keep only pairs of this register.
+        hint = {p for p in (self._owner._current_pair_hint() or ()) if max(p) < self.num_qubits}
         if hint and tuple(sorted((a, b))) in hint and tuple(sorted((a, b))) not in self._rdm:
-            self.pair_rdms(list(hint))
+            self.pair_rdms(sorted(hint))
         return self.pair_rdms([(a, b)])[0]
 
 

@@ -111,6 +111,7 @@ int prof_drain(b200_ctx* ctx) {
         float f = 0;
         CUDA_TRY(cudaEventElapsedTime(&f, r.a, r.b));
         ctx->prof_ms[r.cls] += f;
+        if (r.cls == B200_PROF_SWEEP && ctx->sweep_log.size() < 65536) ctx->sweep_log.push_back(f);
         ctx->prof_n[r.cls] += 1;
         ctx->prof_pool.push_back(r.a);
         ctx->prof_pool.push_back(r.b);
@@ -187,10 +188,14 @@ int run_plan(b200_ctx* ctx, int dst_slot, int src_slot, const Plan& plan) {
     const uint32_t ntiles = (uint32_t)(dim >> TILE_BITS);
     for (const SweepProg& sw : plan.sweeps) {
         const int nr = sw.nrounds;
-        const size_t smem = nr > 1 ? ((size_t)1 << TILE_BITS) * sizeof(double2) : 0;
-        const int per_sm = nr > 1 ? ctx->sweep_occ_smem : ctx->sweep_occ_nosmem;
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * per_sm * ctx->grid_mult);
-        {
+        if (ctx->sweep_mode == 1) {
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms);
+            KScope ks(ctx, B200_PROF_SWEEP);
+            sv_sweep_pipe_kernel<REG_BITS><<<grid, PIPE_THREADS, PIPE_STAGES * TILE_BYTES, ctx->stream>>>(src, dst, sw, ntiles);
+        } else {
+            const size_t smem = nr > 1 ? ((size_t)1 << TILE_BITS) * sizeof(double2) : 0;
+            const int per_sm = nr > 1 ? ctx->sweep_occ_smem : ctx->sweep_occ_nosmem;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * per_sm * ctx->grid_mult);
             KScope ks(ctx, B200_PROF_SWEEP);
             sv_sweep_kernel<REG_BITS><<<grid, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles);
         }
@@ -283,6 +288,9 @@ int b200_ctx_create(int device, b200_ctx** out) {
     const size_t tile_bytes = ((size_t)1 << TILE_BITS) * sizeof(double2);
     CUDA_TRY(cudaFuncSetAttribute(sv_sweep_kernel<REG_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tile_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(sv_sweep_pipe_kernel<REG_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(PIPE_STAGES * TILE_BYTES)));
+    if (const char* e = std::getenv("B200AQC_SWEEP")) ctx->sweep_mode = std::strcmp(e, "pipe") == 0 ? 1 : 0;
     CUDA_TRY(cudaFuncSetAttribute(sv_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(((size_t)1 << SMALL_MAX_QUBITS) * sizeof(double2))));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sweep_occ_smem, sv_sweep_kernel<REG_BITS>,
@@ -354,6 +362,7 @@ int b200_ctx_profile(b200_ctx* ctx, int enable) {
     ctx->profiling = enable != 0;
     if (enable)
         for (int k = 0; k < B200_PROF_CLASSES; ++k) { ctx->prof_ms[k] = 0; ctx->prof_n[k] = 0; }
+        ctx->sweep_log.clear();
     return 0;
 }
 
@@ -361,6 +370,14 @@ int b200_ctx_profile_read(b200_ctx* ctx, double ms[B200_PROF_CLASSES], uint64_t 
     if (!ctx || !ms || !launches) return set_error("null pointer");
     if (prof_drain(ctx)) return -1;
     for (int k = 0; k < B200_PROF_CLASSES; ++k) { ms[k] = ctx->prof_ms[k]; launches[k] = ctx->prof_n[k]; }
+    return 0;
+}
+
+int b200_ctx_profile_sweeps(b200_ctx* ctx, double* ms, int max_entries, int* n) {
+    if (!ctx || !n || (max_entries > 0 && !ms)) return set_error("null pointer");
+    if (prof_drain(ctx)) return -1;
+    *n = (int)ctx->sweep_log.size();
+    for (int k = 0; k < *n && k < max_entries; ++k) ms[k] = ctx->sweep_log[k];
     return 0;
 }
 

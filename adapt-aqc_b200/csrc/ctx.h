@@ -54,6 +54,7 @@ struct b200_ctx {
     // launch geometry of the sweep kernel
     int sweep_occ_smem = 1, sweep_occ_nosmem = 1;
     int grid_mult = 1;
+    int sweep_mode = 0;   // 0 = direct-load kernel (default), 1 = pipelined bulk-copy kernel (B200AQC_SWEEP=pipe)
 
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -65,6 +66,7 @@ struct b200_ctx {
     struct ProfRec { int cls; cudaEvent_t a, b; };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
+    std::vector<float> sweep_log;   // per-launch ms of the sweep kernel while profiling (b200_ctx_profile_sweeps)
     double prof_ms[B200_PROF_CLASSES] = {0};
     uint64_t prof_n[B200_PROF_CLASSES] = {0};
 

@@ -67,6 +67,15 @@ B200_HD double2 cjfma(const double2 a, const double2 b, double2 c) {
     return c;
 }
 B200_HD double2 ld_c(const double* m, int k) { return make_double2(m[2 * k], m[2 * k + 1]); }
+// runtime selection among register-resident constants WITHOUT dynamic indexing (which would force local memory)
+B200_HD double2 sel2(const double* m, const int base, const int u) {
+    const double2 lo = ld_c(m, base), hi = ld_c(m, base + 1);
+    return make_double2(u ? hi.x : lo.x, u ? hi.y : lo.y);
+}
+B200_HD double2 sel4(const double* m, const int u0, const int u1) {
+    const double2 lo = sel2(m, 0, u0), hi = sel2(m, 2, u0);
+    return make_double2(u1 ? hi.x : lo.x, u1 ? hi.y : lo.y);
+}
 
 // ---------------------------------------------------------------------------------------------
 // register-resident op bodies: every register index is a template parameter, so the 2^R amplitudes
@@ -84,14 +93,25 @@ B200_HD void op_mat1(double2 (&a)[1 << R], const double* __restrict__ m) {
     }
 }
 
+// In-place exchange.  On the device the exchange is an opaque asm block with read-write operands: written as
+// plain assignments it turns the ops switch into a register PERMUTATION at the loop back-edge, which the
+// compiler resolved by copying all 2^R amplitudes (64 moves) on every op of every round (ncu source page,
+// profiles/prof_pipe_r01m: 54 % of the executed instructions were IMAD.MOV/MOV).
+B200_HD void swap_amp(double2& x, double2& y) {
+#ifdef __CUDA_ARCH__
+    asm("{\n\t.reg .f64 t;\n\tmov.f64 t, %0;\n\tmov.f64 %0, %1;\n\tmov.f64 %1, t;\n\t}" : "+d"(x.x), "+d"(y.x));
+    asm("{\n\t.reg .f64 t;\n\tmov.f64 t, %0;\n\tmov.f64 %0, %1;\n\tmov.f64 %1, t;\n\t}" : "+d"(x.y), "+d"(y.y));
+#else
+    const double2 t = x; x = y; y = t;
+#endif
+}
+
 template <int R, int TB>
 B200_HD void op_x(double2 (&a)[1 << R]) {
 #pragma unroll
     for (int j = 0; j < (1 << R); ++j) {
         if (j & (1 << TB)) continue;
-        const double2 x = a[j];
-        a[j] = a[j | (1 << TB)];
-        a[j | (1 << TB)] = x;
+        swap_amp(a[j], a[j | (1 << TB)]);
     }
 }
 
@@ -100,9 +120,7 @@ B200_HD void op_cx(double2 (&a)[1 << R]) {
 #pragma unroll
     for (int j = 0; j < (1 << R); ++j) {
         if ((j & (1 << TB)) || !(j & (1 << CB))) continue;
-        const double2 x = a[j];
-        a[j] = a[j | (1 << TB)];
-        a[j | (1 << TB)] = x;
+        swap_amp(a[j], a[j | (1 << TB)]);
     }
 }
 
@@ -148,53 +166,17 @@ B200_HD void op_diag2(double2 (&a)[1 << R], const double2 r10, const double2 r01
     }
 }
 
-#define B200_SWITCH_R1(FN, r, ...)                      \
-    switch (r) {                                        \
-    case 0: FN<R, 0>(__VA_ARGS__); break;               \
-    case 1: FN<R, 1>(__VA_ARGS__); break;               \
-    case 2: FN<R, 2>(__VA_ARGS__); break;               \
-    default: FN<R, 3>(__VA_ARGS__); break;              \
-    }
-// ordered pair r0 < r1
-#define B200_SWITCH_R2(FN, r0, r1, ...)                 \
-    switch ((r0) * 4 + (r1)) {                          \
-    case 1: FN<R, 0, 1>(__VA_ARGS__); break;            \
-    case 2: FN<R, 0, 2>(__VA_ARGS__); break;            \
-    case 3: FN<R, 0, 3>(__VA_ARGS__); break;            \
-    case 6: FN<R, 1, 2>(__VA_ARGS__); break;            \
-    case 7: FN<R, 1, 3>(__VA_ARGS__); break;            \
-    default: FN<R, 2, 3>(__VA_ARGS__); break;           \
-    }
-
-template <int R>
-B200_HD void op_cx_any(double2 (&a)[1 << R], const int t, const int c) {
-    switch (t * 4 + c) {
-    case 1: op_cx<R, 0, 1>(a); break;
-    case 2: op_cx<R, 0, 2>(a); break;
-    case 3: op_cx<R, 0, 3>(a); break;
-    case 4: op_cx<R, 1, 0>(a); break;
-    case 6: op_cx<R, 1, 2>(a); break;
-    case 7: op_cx<R, 1, 3>(a); break;
-    case 8: op_cx<R, 2, 0>(a); break;
-    case 9: op_cx<R, 2, 1>(a); break;
-    case 11: op_cx<R, 2, 3>(a); break;
-    case 12: op_cx<R, 3, 0>(a); break;
-    case 13: op_cx<R, 3, 1>(a); break;
-    default: op_cx<R, 3, 2>(a); break;
-    }
-}
-
 // generic diagonal (non-unitary input with a zero phase entry): phase index = bit(q0) + 2 bit(q1), each
 // bit either a register bit (r >= 0) or a bit of the thread's base index g
-template <int R>
-B200_HD void op_diagraw(double2 (&a)[1 << R], const POp& op, const uint64_t g) {
+template <int R, class OP>
+B200_HD void op_diagraw_impl(double2 (&a)[1 << R], const OP& op, const uint64_t g) {
     const int u0 = op.dq0 >= 0 ? (int)((g >> op.dq0) & 1ull) : 0;
     const int u1 = op.dq1 >= 0 ? (int)((g >> op.dq1) & 1ull) : 0;
 #pragma unroll
     for (int j = 0; j < (1 << R); ++j) {
         const int b0 = op.r0 >= 0 ? ((j >> op.r0) & 1) : u0;
         const int b1 = op.r1 >= 0 ? ((j >> op.r1) & 1) : u1;
-        a[j] = cmul(a[j], ld_c(op.m, b0 + 2 * b1));
+        a[j] = cmul(a[j], sel4(op.m, b0, b1));
     }
 }
 
@@ -300,56 +282,168 @@ B200_HD void round_store_smem(const double2 (&a)[1 << R], double2* tile_smem, co
     for (int j = 0; j < (1 << R); ++j) tile_smem[tls ^ (uint32_t)rd.soff[j]] = a[j];
 }
 
+// Linear (unswizzled) tile access: the layout the bulk copies of the pipelined kernel land / pick up.
+template <int R>
+B200_HD void round_load_lin(double2 (&a)[1 << R], const double2* tile_smem, const PRound& rd, const uint32_t tl) {
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) {
+        uint32_t off = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) if (j >> k & 1) off |= 1u << rd.regpos[k];
+        a[j] = tile_smem[tl | off];
+    }
+}
+
+template <int R>
+B200_HD void round_store_lin(const double2 (&a)[1 << R], double2* tile_smem, const PRound& rd, const uint32_t tl) {
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) {
+        uint32_t off = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) if (j >> k & 1) off |= 1u << rd.regpos[k];
+        tile_smem[tl | off] = a[j];
+    }
+}
+
+// Global amplitude index of row `row` of a tile: a row is the 2^c contiguous amplitudes of the tile's
+// leading contiguous qubits, the row number spreads over the tile's remaining (scattered) qubits.
+B200_HD uint64_t sweep_row_index(const SweepProg& sp, const uint64_t tile_base, const uint32_t row) {
+    uint64_t g = tile_base;
+    for (int i = sp.c; i < TILE_BITS; ++i) g |= (uint64_t)((row >> (i - sp.c)) & 1u) << sp.tileq[i];
+    return g;
+}
+
 template <int R>
 B200_HD void apply_pend(double2 (&a)[1 << R], const double2 pend) {
 #pragma unroll
     for (int j = 0; j < (1 << R); ++j) a[j] = cmul(a[j], pend);
 }
 
+// Warp-uniform header of an op, read one op AHEAD of its use so that the constant-bank latency of the
+// decode (and of the 8 doubles of phases / matrix entries) hides behind the previous op's arithmetic.
+struct OpHead {
+    int32_t code, flush, r0, r1, cq, dq0, dq1, mat2;
+    double m[8];
+};
+B200_HD OpHead load_head(const POp& op) {
+    OpHead h;
+    h.code = (op.flush >> 8) & 0xff; h.flush = op.flush & 1;
+    h.r0 = op.r0; h.r1 = op.r1; h.cq = op.cq; h.dq0 = op.dq0; h.dq1 = op.dq1; h.mat2 = op.mat2;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h.m[k] = op.m[k];
+    return h;
+}
+
+// The same header by reference: fields are read from the constant bank where they are used (no registers
+// held across the switch) -- for the direct kernel and the emulator.
+struct OpRef {
+    int32_t code, flush;
+    const int32_t &r0, &r1, &cq, &dq0, &dq1, &mat2;
+    const double (&m)[8];
+    B200_HD explicit OpRef(const POp& op)
+        : code((op.flush >> 8) & 0xff), flush(op.flush & 1), r0(op.r0), r1(op.r1), cq(op.cq), dq0(op.dq0),
+          dq1(op.dq1), mat2(op.mat2), m(op.m) {}
+};
+
 // One op of a round on the thread's registers.  `pend` collects the phases that multiply all 2^R
 // amplitudes of the thread alike: they commute with every register op of the round and are applied once at
-// the end of the round (or before a lane exchange, which they do not commute with: op.flush).  Every field of `op` is warp-uniform (kernel-parameter constant bank).
+// the end of the round (or before a lane exchange, which they do not commute with: h.flush).
+// ONE warp-uniform switch selects a fully unrolled, statically indexed body.
+template <int R, class HEAD, class EX>
+B200_HD void apply_decoded(double2 (&a)[1 << R], const SweepProg& sp, const HEAD& h, const uint64_t g,
+                           const uint32_t lane, double2& pend, const EX& ex) {
+#define B200_DIAG1(TB) { const int u = h.dq1 >= 0 ? (int)((g >> h.dq1) & 1ull) : 0;                 \
+                         pend = cmul(pend, sel2(h.m, 0, u)); op_diag1<R, TB>(a, sel2(h.m, 2, u)); } break
+#define B200_DIAG2(T0, T1) { pend = cmul(pend, ld_c(h.m, 0));                                         \
+                             op_diag2<R, T0, T1>(a, ld_c(h.m, 1), ld_c(h.m, 2), ld_c(h.m, 3)); } break
+#define B200_XREG(TB) if (h.cq < 0 || ((g >> h.cq) & 1ull)) op_x<R, TB>(a); break
+    switch (h.code) {
+    case 0: {
+        const int u0 = h.dq0 >= 0 ? (int)((g >> h.dq0) & 1ull) : 0;
+        const int u1 = h.dq1 >= 0 ? (int)((g >> h.dq1) & 1ull) : 0;
+        pend = cmul(pend, sel4(h.m, u0, u1));
+        break;
+    }
+    case 1: B200_DIAG1(0);
+    case 2: B200_DIAG1(1);
+    case 3: B200_DIAG1(2);
+    case 4: B200_DIAG1(3);
+    case 5: B200_DIAG2(0, 1);
+    case 6: B200_DIAG2(0, 2);
+    case 7: B200_DIAG2(0, 3);
+    case 8: B200_DIAG2(1, 2);
+    case 9: B200_DIAG2(1, 3);
+    case 10: B200_DIAG2(2, 3);
+    case 11: op_diagraw_impl<R>(a, h, g); break;
+    case 12: B200_XREG(0);
+    case 13: B200_XREG(1);
+    case 14: B200_XREG(2);
+    case 15: B200_XREG(3);
+    case 16: op_cx<R, 0, 1>(a); break;
+    case 17: op_cx<R, 0, 2>(a); break;
+    case 18: op_cx<R, 0, 3>(a); break;
+    case 19: op_cx<R, 1, 0>(a); break;
+    case 20: op_cx<R, 1, 2>(a); break;
+    case 21: op_cx<R, 1, 3>(a); break;
+    case 22: op_cx<R, 2, 0>(a); break;
+    case 23: op_cx<R, 2, 1>(a); break;
+    case 24: op_cx<R, 2, 3>(a); break;
+    case 25: op_cx<R, 3, 0>(a); break;
+    case 26: op_cx<R, 3, 1>(a); break;
+    case 27: op_cx<R, 3, 2>(a); break;
+    case 28: op_mat1<R, 0>(a, h.m); break;
+    case 29: op_mat1<R, 1>(a, h.m); break;
+    case 30: op_mat1<R, 2>(a, h.m); break;
+    case 31: op_mat1<R, 3>(a, h.m); break;
+    case 32: op_mat2<R, 0, 1>(a, sp.mat2[h.mat2]); break;
+    case 33: op_mat2<R, 0, 2>(a, sp.mat2[h.mat2]); break;
+    case 34: op_mat2<R, 0, 3>(a, sp.mat2[h.mat2]); break;
+    case 35: op_mat2<R, 1, 2>(a, sp.mat2[h.mat2]); break;
+    case 36: op_mat2<R, 1, 3>(a, sp.mat2[h.mat2]); break;
+    case 37: op_mat2<R, 2, 3>(a, sp.mat2[h.mat2]); break;
+    case 38: {
+        if (h.flush) { apply_pend<R>(a, pend); pend = make_double2(1.0, 0.0); }
+        const bool ctl = h.cq < 0 || ((g >> h.cq) & 1ull);
+        op_xlane<R>(a, h.r0, h.r1, ctl, ex);
+        break;
+    }
+    default:   // 39: dense 2x2 on a lane qubit
+        if (h.flush) { apply_pend<R>(a, pend); pend = make_double2(1.0, 0.0); }
+        op_mat1lane<R>(a, h.m, h.r0, lane, ex);
+        break;
+    }
+#undef B200_DIAG1
+#undef B200_DIAG2
+#undef B200_XREG
+}
+
+// emulator entry: one op, decoded on the spot
 template <int R, class EX>
 B200_HD void apply_op(double2 (&a)[1 << R], const SweepProg& sp, const POp& op, const uint64_t g,
                       const uint32_t lane, double2& pend, const EX& ex) {
-    switch (op.kind) {
-    case P_PEND: {
-        const int u0 = op.dq0 >= 0 ? (int)((g >> op.dq0) & 1ull) : 0;
-        const int u1 = op.dq1 >= 0 ? (int)((g >> op.dq1) & 1ull) : 0;
-        pend = cmul(pend, ld_c(op.m, u0 + 2 * u1));
-        break;
+    const OpRef h(op);
+    apply_decoded<R>(a, sp, h, g, lane, pend, ex);
+}
+
+// all ops of a round; PREFETCH: software-pipelined decode (costs ~24 registers: the pipelined kernel has
+// them, the direct kernel with its 128-register cap does not)
+template <int R, bool PREFETCH, class EX>
+B200_HD void round_ops(double2 (&a)[1 << R], const SweepProg& sp, const PRound& rd, const uint64_t g,
+                       const uint32_t lane, const EX& ex) {
+    double2 pend = make_double2(1.0, 0.0);
+    int o = rd.op_begin;
+    const int oe = rd.op_end;
+    if (!PREFETCH) {
+        for (; o < oe; ++o) apply_op<R>(a, sp, sp.ops[o], g, lane, pend, ex);
+    } else if (o < oe) {
+        OpHead h = load_head(sp.ops[o]);
+        for (; o < oe; ++o) {
+            const OpHead nh = load_head(sp.ops[o + 1]);   // ops[] has one slot of slack
+            apply_decoded<R>(a, sp, h, g, lane, pend, ex);
+            h = nh;
+        }
     }
-    case P_DIAG1: {
-        const int u = op.dq1 >= 0 ? (int)((g >> op.dq1) & 1ull) : 0;
-        pend = cmul(pend, ld_c(op.m, u));
-        const double2 ratio = ld_c(op.m, 2 + u);
-        B200_SWITCH_R1(op_diag1, op.r0, a, ratio)
-        break;
-    }
-    case P_DIAG2: {
-        pend = cmul(pend, ld_c(op.m, 0));
-        const double2 r10 = ld_c(op.m, 1), r01 = ld_c(op.m, 2), r11 = ld_c(op.m, 3);
-        B200_SWITCH_R2(op_diag2, op.r0, op.r1, a, r10, r01, r11)
-        break;
-    }
-    case P_DIAGRAW: op_diagraw<R>(a, op, g); break;
-    case P_XREG:
-        if (op.cq < 0 || ((g >> op.cq) & 1ull)) { B200_SWITCH_R1(op_x, op.r0, a) }
-        break;
-    case P_CXREG: op_cx_any<R>(a, op.r0, op.r1); break;
-    case P_MAT1: B200_SWITCH_R1(op_mat1, op.r0, a, op.m) break;
-    case P_MAT2: B200_SWITCH_R2(op_mat2, op.r0, op.r1, a, sp.mat2[op.mat2]) break;
-    case P_XLANE: {
-        if (op.flush) { apply_pend<R>(a, pend); pend = make_double2(1.0, 0.0); }
-        const bool ctl = op.cq < 0 || ((g >> op.cq) & 1ull);
-        op_xlane<R>(a, op.r0, op.r1, ctl, ex);
-        break;
-    }
-    default:   // P_MAT1LANE
-        if (op.flush) { apply_pend<R>(a, pend); pend = make_double2(1.0, 0.0); }
-        op_mat1lane<R>(a, op.m, op.r0, lane, ex);
-        break;
-    }
+    if (rd.has_pend) apply_pend<R>(a, pend);
 }
 
 #ifdef __CUDACC__
@@ -374,13 +468,137 @@ sv_sweep_kernel(const double2* __restrict__ src, double2* __restrict__ dst, cons
             double2 a[1 << R];
             if (r == 0) round_load_hbm<R>(a, src, sp, rd, g);
             else round_load_smem<R>(a, tile_smem, rd, tls);
-            double2 pend = make_double2(1.0, 0.0);
-            for (int o = rd.op_begin; o < rd.op_end; ++o) apply_op<R>(a, sp, sp.ops[o], g, lane, pend, ex);
-            if (rd.has_pend) apply_pend<R>(a, pend);
+            round_ops<R, false>(a, sp, rd, g, lane, ex);
             if (r == nr - 1) round_store_hbm<R>(a, dst, sp, rd, g);
             else { round_store_smem<R>(a, tile_smem, rd, tls); __syncthreads(); }
         }
         if (nr > 1) __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1/K2, pipelined: one persistent CTA per SM, three 64 KB tile buffers in shared memory.
+//   producer warp : bulk async copies (TMA unit, cp.async.bulk -> SASS UBLKCP) HBM -> buffer for tile k+3
+//                   and buffer -> HBM for tile k, one copy per tile row (2^c contiguous amplitudes,
+//                   >= 512 B), completion through mbarriers / bulk groups;
+//   8 compute warps: all rounds of tile k in place in its buffer (first round reads the linear layout
+//                   the copies land, middle rounds use the swizzled layout, last round writes linear).
+// HBM traffic is fully asynchronous to the rounds: the loads of the next two tiles and the store of the
+// previous one are in flight while a tile is being computed.
+// ---------------------------------------------------------------------------------------------
+constexpr int PIPE_STAGES = 3;
+constexpr int PIPE_THREADS = SWEEP_THREADS + 32;
+constexpr uint32_t TILE_BYTES = (1u << TILE_BITS) * 16u;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, const uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, const uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, const uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, const uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, const uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// barrier among the 8 compute warps only (the producer warp never joins it)
+__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SWEEP_THREADS) : "memory"); }
+
+template <int R>
+__global__ void __launch_bounds__(PIPE_THREADS, 1)
+sv_sweep_pipe_kernel(const double2* __restrict__ src, double2* __restrict__ dst, const __grid_constant__ SweepProg sp,
+                     const uint32_t ntiles) {
+    extern __shared__ __align__(128) double2 pipe_smem[];   // PIPE_STAGES tile buffers
+    __shared__ __align__(8) uint64_t full_bar[PIPE_STAGES], done_bar[PIPE_STAGES];
+    static_assert(R == REG_BITS, "register bits");
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (tid == 0) {
+        for (int b = 0; b < PIPE_STAGES; ++b) { mbar_init(&full_bar[b], 1); mbar_init(&done_bar[b], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= SWEEP_THREADS) {
+        // ---------------- producer warp ----------------
+        const int c = sp.c;
+        const uint32_t rows = 1u << (TILE_BITS - c), row_bytes = 16u << c;
+        auto issue_load = [&](const uint32_t k) {
+            const uint32_t b = k % PIPE_STAGES;
+            const uint64_t base = sweep_tile_base(sp, blockIdx.x + k * gridDim.x);
+            if (lane == 0) mbar_arrive_expect_tx(&full_bar[b], TILE_BYTES);
+            __syncwarp();
+            double2* buf = pipe_smem + ((size_t)b << TILE_BITS);
+            for (uint32_t row = lane; row < rows; row += 32)
+                bulk_g2s(buf + ((size_t)row << c), src + sweep_row_index(sp, base, row), row_bytes, &full_bar[b]);
+        };
+        for (uint32_t k = 0; k < my_tiles && k < (uint32_t)PIPE_STAGES; ++k) issue_load(k);
+        for (uint32_t k = 0; k < my_tiles; ++k) {
+            const uint32_t b = k % PIPE_STAGES;
+            mbar_wait(&done_bar[b], (k / PIPE_STAGES) & 1u);
+            const uint64_t base = sweep_tile_base(sp, blockIdx.x + k * gridDim.x);
+            double2* buf = pipe_smem + ((size_t)b << TILE_BITS);
+            for (uint32_t row = lane; row < rows; row += 32)
+                bulk_s2g(dst + sweep_row_index(sp, base, row), buf + ((size_t)row << c), row_bytes);
+            bulk_commit();
+            if (k + PIPE_STAGES < my_tiles) {
+                bulk_wait_read0();       // this lane's rows have left the buffer ...
+                __syncwarp();            // ... and so have every other lane's
+                issue_load(k + PIPE_STAGES);
+            }
+        }
+        bulk_wait0();
+        return;
+    }
+
+    // ---------------- compute warps ----------------
+    const ShflExchange ex;
+    const int nr = sp.nrounds;
+    for (uint32_t k = 0; k < my_tiles; ++k) {
+        const uint32_t b = k % PIPE_STAGES;
+        double2* buf = pipe_smem + ((size_t)b << TILE_BITS);
+        const uint64_t tile_base = sweep_tile_base(sp, blockIdx.x + k * gridDim.x);
+        mbar_wait(&full_bar[b], (k / PIPE_STAGES) & 1u);
+        for (int r = 0; r < nr; ++r) {
+            const PRound& rd = sp.rounds[r];
+            uint32_t tl; uint64_t g;
+            round_index<R>(sp, rd, tile_base, tid, tl, g);
+            const uint32_t tls = swz(tl);
+            const bool lin_in = r == 0, lin_out = r == nr - 1;
+            double2 a[1 << R];
+            if (lin_in) round_load_lin<R>(a, buf, rd, tl);
+            else round_load_smem<R>(a, buf, rd, tls);
+            round_ops<R, true>(a, sp, rd, g, lane, ex);
+            // a round that changes the layout in place must have finished all its reads before any write
+            if (lin_in != lin_out) compute_bar();
+            if (lin_out) round_store_lin<R>(a, buf, rd, tl);
+            else { round_store_smem<R>(a, buf, rd, tls); compute_bar(); }
+        }
+        fence_proxy_async();             // generic-proxy writes -> visible to the bulk copy engine
+        compute_bar();
+        if (tid == 0) mbar_arrive(&done_bar[b]);
     }
 }
 #endif  // __CUDACC__

@@ -543,6 +543,20 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan) {
                 fill_tiled_op(ops[idx], reg_of, sp, po);
                 if (po.kind == P_PEND || po.kind == P_DIAG1 || po.kind == P_DIAG2) { dr.has_pend = 1; pending = true; }
                 if (po.kind == P_XLANE || po.kind == P_MAT1LANE) { po.flush = pending ? 1 : 0; pending = false; }
+                int code = 0;
+                switch (po.kind) {
+                case P_PEND: code = 0; break;
+                case P_DIAG1: code = 1 + po.r0; break;
+                case P_DIAG2: code = 5 + pair_index(po.r0, po.r1); break;
+                case P_DIAGRAW: code = 11; break;
+                case P_XREG: code = 12 + po.r0; break;
+                case P_CXREG: code = 16 + cx_index(po.r0, po.r1); break;
+                case P_MAT1: code = 28 + po.r0; break;
+                case P_MAT2: code = 32 + pair_index(po.r0, po.r1); break;
+                case P_XLANE: code = 38; break;
+                default: code = 39; break;
+                }
+                po.flush |= code << 8;
             }
             dr.op_end = sp.nops;
         }

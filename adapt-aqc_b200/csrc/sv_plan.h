@@ -96,13 +96,22 @@ enum PKind : int32_t {
     P_MAT1LANE = 9,  // dense 2x2 on lane bit r0
 };
 
+// Dispatch code of a tiled op: kind and register selectors folded into ONE warp-uniform switch index.
+//   0 PEND | 1..4 DIAG1(r0) | 5..10 DIAG2(r0<r1) | 11 DIAGRAW | 12..15 XREG(r0) | 16..27 CXREG(t=r0,c=r1)
+//   28..31 MAT1(r0) | 32..37 MAT2(r0<r1) | 38 XLANE | 39 MAT1LANE
+inline int pair_index(int r0, int r1) {   // r0 < r1 < 4 -> 0..5 in the order 01 02 03 12 13 23
+    return r0 == 0 ? r1 - 1 : (r0 == 1 ? r1 + 1 : 5);
+}
+inline int cx_index(int t, int c) { return t * 3 + (c > t ? c - 1 : c); }   // t != c -> 0..11
+
 struct alignas(16) POp {   // 96 bytes
     int32_t kind;
     int32_t r0, r1;        // register indices (lane index in r0 for the *LANE kinds); -1 if unused
     int32_t cq;            // thread-level control qubit, -1 if none
     int32_t dq0, dq1;      // thread-level diagonal qubits, -1 if absent
     int32_t mat2;          // P_MAT2: index into SweepProg::mat2
-    int32_t flush;         // lane kinds: phases are pending (they do not commute with a lane exchange): apply first
+    int32_t flush;         // bit 0 (lane kinds): phases are pending (they do not commute with a lane exchange):
+                           // apply first.  bits 8..15: dispatch code (see above)
     // P_PEND: ph[u0 + 2 u1] (4 complex).  P_DIAG1: base[u], ratio[u] (u = thread-level bit, 4 complex):
     // amplitudes with the register bit set are multiplied by ratio[u], base[u] goes into `pend`.
     // P_DIAG2: base, ratio01, ratio10, ratio11.  P_DIAGRAW: ph[4].  P_MAT1 / P_MAT1LANE: 2x2 row-major.
@@ -128,7 +137,7 @@ struct alignas(16) SweepProg {
     int32_t c;                  // number of leading contiguous low qubits in tileq
     int32_t tileq[TILE_BITS];   // global qubit of each tile-local bit, ascending
     PRound rounds[MAX_SWEEP_ROUNDS];
-    POp ops[MAX_SWEEP_OPS];
+    POp ops[MAX_SWEEP_OPS + 1];   // +1: the kernel prefetches one op ahead
     double mat2[MAX_SWEEP_MAT2][32];
 };
 static_assert(sizeof(SweepProg) <= 32000, "SweepProg must fit the 32 KB kernel-parameter space");

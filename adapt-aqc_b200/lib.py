@@ -16,7 +16,7 @@ SYMBOLS = [
     "b200_abi_version", "b200_last_error", "b200_device_count", "b200_ctx_create",
     "b200_ctx_destroy", "b200_ctx_sync", "b200_ctx_counters", "b200_ctx_last_ms",
     "b200_ctx_set_timing", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_ctx_profile",
-    "b200_ctx_profile_read", "b200_sv_alloc", "b200_sv_reserve_slots", "b200_sv_attach", "b200_sv_device_ptr",
+    "b200_ctx_profile_read", "b200_ctx_profile_sweeps", "b200_sv_alloc", "b200_sv_reserve_slots", "b200_sv_attach", "b200_sv_device_ptr",
     "b200_sv_num_qubits", "b200_sv_init_zero", "b200_sv_copy", "b200_sv_run",
     "b200_sv_run_inverse", "b200_sv_amp", "b200_sv_expz", "b200_sv_pair_rdm", "b200_sv_inner", "b200_sv_inner2", "b200_sv_inner2_gather",
     "b200_sv_download", "b200_sv_upload", "b200_sv_plan_stats", "b200_sv_plan_detail",
@@ -60,6 +60,7 @@ def load():
     L.b200_ctx_elapsed_ms.argtypes = [vp, dp]
     L.b200_ctx_profile.argtypes = [vp, ci]
     L.b200_ctx_profile_read.argtypes = [vp, dp, ctypes.POINTER(cu64)]
+    L.b200_ctx_profile_sweeps.argtypes = [vp, dp, ci, ctypes.POINTER(ci)]
     L.b200_sv_alloc.argtypes = [vp, ci, ci]
     L.b200_sv_attach.argtypes = [vp, ci, vp]
     L.b200_sv_reserve_slots.argtypes = [vp, ci, ci]

@@ -167,6 +167,13 @@ class SVEngine:
         check(self._lib.b200_ctx_profile_read(self._ctx, ms, cnt))
         return {name: (ms[i], cnt[i]) for i, name in enumerate(self.PROF_CLASSES)}
 
+    def profile_sweeps(self, max_entries=4096):
+        """Per-launch device times (ms) of the sweep kernel since profile(True), in launch order."""
+        ms = (ctypes.c_double * max_entries)()
+        n = ctypes.c_int()
+        check(self._lib.b200_ctx_profile_sweeps(self._ctx, ms, max_entries, ctypes.byref(n)))
+        return [ms[i] for i in range(min(n.value, max_entries))]
+
     def set_timing(self, enable=True):
         check(self._lib.b200_ctx_set_timing(self._ctx, 1 if enable else 0))
 

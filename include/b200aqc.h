@@ -90,6 +90,9 @@ enum {
 };
 int b200_ctx_profile(b200_ctx *ctx, int enable);
 int b200_ctx_profile_read(b200_ctx *ctx, double ms[B200_PROF_CLASSES], uint64_t launches[B200_PROF_CLASSES]);
+/* Per-launch device times (ms, launch order) of the sweep kernel since b200_ctx_profile(ctx, 1): *n = number
+ * of launches recorded, the first min(*n, max_entries) go to ms[].  Roofline accounting per sweep. */
+int b200_ctx_profile_sweeps(b200_ctx *ctx, double *ms, int max_entries, int *n);
 /* CUDA-event time (ms) of the kernels launched by the most recent b200_sv_* / b200_mps_* call. */
 int b200_ctx_last_ms(b200_ctx *ctx, double *ms);
 int b200_ctx_set_timing(b200_ctx *ctx, int enable);

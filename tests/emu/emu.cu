@@ -16,7 +16,10 @@ using namespace b200;
 
 static std::string g_err;
 
+static int g_variant = 1;   // 0 = direct-load kernel (sv_sweep_kernel), 1 = pipelined kernel (sv_sweep_pipe_kernel)
+
 extern "C" const char* emu_last_error() { return g_err.c_str(); }
+extern "C" void emu_set_variant(int v) { g_variant = v; }
 
 // state: 2^nq complex128 (host), updated in place.  src_is_zero: start from |0..0>.
 extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_gate* gates, int n_gates,
@@ -54,7 +57,7 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
     std::vector<Regs> regs(SWEEP_THREADS), snap(SWEEP_THREADS);
     std::vector<double2> pend(SWEEP_THREADS);
     std::vector<uint64_t> gidx(SWEEP_THREADS);
-    std::vector<uint32_t> tls(SWEEP_THREADS);
+    std::vector<uint32_t> tls(SWEEP_THREADS), tlin(SWEEP_THREADS);
     struct SnapExchange {
         const Regs* snap; uint32_t tid;
         __host__ __device__ double2 operator()(const double2, const int j, const int lane_mask) const { return snap[tid ^ (uint32_t)lane_mask].a[j]; }
@@ -70,7 +73,7 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
                 std::printf("  round %d regpos=%d,%d,%d,%d pend=%d\n", r, rd.regpos[0], rd.regpos[1], rd.regpos[2], rd.regpos[3], rd.has_pend);
                 for (int o = rd.op_begin; o < rd.op_end; ++o) {
                     const POp& op = sp.ops[o];
-                    std::printf("    kind=%d r0=%d r1=%d cq=%d dq0=%d dq1=%d flush=%d\n", op.kind, op.r0, op.r1, op.cq, op.dq0, op.dq1, op.flush);
+                    std::printf("    kind=%d r0=%d r1=%d cq=%d dq0=%d dq1=%d flush=%d\n", op.kind, op.r0, op.r1, op.cq, op.dq0, op.dq1, op.flush & 1);
                 }
             }
         }
@@ -79,13 +82,19 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
         const int nr = sp.nrounds;
         for (uint32_t tile = 0; tile < ntiles; ++tile) {
             const uint64_t base = sweep_tile_base(sp, tile);
+            const uint32_t rows = 1u << (TILE_BITS - sp.c), row_len = 1u << sp.c;
+            if (g_variant == 1)   // the producer warp's bulk copies: tile rows -> linear buffer
+                for (uint32_t row = 0; row < rows; ++row)
+                    std::memcpy(smem.data() + ((size_t)row << sp.c), psi + sweep_row_index(sp, base, row), row_len * sizeof(double2));
             for (int r = 0; r < nr; ++r) {
                 const PRound& rd = sp.rounds[r];
                 for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid) {
                     uint32_t tl;
                     round_index<REG_BITS>(sp, rd, base, tid, tl, gidx[tid]);
                     tls[tid] = swz(tl);
-                    if (r == 0) round_load_hbm<REG_BITS>(regs[tid].a, psi, sp, rd, gidx[tid]);
+                    tlin[tid] = tl;
+                    if (r == 0 && g_variant == 1) round_load_lin<REG_BITS>(regs[tid].a, smem.data(), rd, tl);
+                    else if (r == 0) round_load_hbm<REG_BITS>(regs[tid].a, psi, sp, rd, gidx[tid]);
                     else round_load_smem<REG_BITS>(regs[tid].a, smem.data(), rd, tls[tid]);
                     pend[tid] = make_double2(1.0, 0.0);
                 }
@@ -94,12 +103,12 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
                     const bool lane_op = op.kind == P_XLANE || op.kind == P_MAT1LANE;
                     if (lane_op) {
                         if (r != 0 && r != nr - 1) { g_err = "lane op scheduled in a shared-memory round"; return -1; }
-                        if (op.flush) {   // every lane applies its pending phase before the exchange
+                        if (op.flush & 1) {   // every lane applies its pending phase before the exchange
                             for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid) {
                                 apply_pend<REG_BITS>(regs[tid].a, pend[tid]);
                                 pend[tid] = make_double2(1.0, 0.0);
                             }
-                            op.flush = 0;
+                            op.flush &= ~1;
                         }
                         snap = regs;
                     }
@@ -110,10 +119,14 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
                 }
                 for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid) {
                     if (rd.has_pend) apply_pend<REG_BITS>(regs[tid].a, pend[tid]);
-                    if (r == nr - 1) round_store_hbm<REG_BITS>(regs[tid].a, psi, sp, rd, gidx[tid]);
+                    if (r == nr - 1 && g_variant == 1) round_store_lin<REG_BITS>(regs[tid].a, smem.data(), rd, tlin[tid]);
+                    else if (r == nr - 1) round_store_hbm<REG_BITS>(regs[tid].a, psi, sp, rd, gidx[tid]);
                     else round_store_smem<REG_BITS>(regs[tid].a, smem.data(), rd, tls[tid]);
                 }
             }
+            if (g_variant == 1)
+                for (uint32_t row = 0; row < rows; ++row)
+                    std::memcpy(psi + sweep_row_index(sp, base, row), smem.data() + ((size_t)row << sp.c), row_len * sizeof(double2));
         }
     }
     return 0;

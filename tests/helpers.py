@@ -102,12 +102,17 @@ def load_golden_mps(seed):
 
 def emu_run(emu, n, gates, psi0=None, inverse=False):
     gs = gates if isinstance(gates, GateStream) else GateStream.from_gates(gates)
-    st = np.zeros(1 << n, dtype=np.complex128) if psi0 is None else np.array(psi0, dtype=np.complex128)
-    stats = (ctypes.c_int32 * 4)()
-    rc = emu.emu_sv_run(n, st.view(np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-                        1 if psi0 is None else 0, gs.rec_ptr(), len(gs), gs.mats_ptr(), len(gs.mats),
-                        int(inverse), stats)
-    assert rc == 0, emu.emu_last_error()
+    outs = []
+    for variant in (0, 1):      # direct-load kernel body, pipelined (bulk-copy) kernel body
+        st = np.zeros(1 << n, dtype=np.complex128) if psi0 is None else np.array(psi0, dtype=np.complex128)
+        stats = (ctypes.c_int32 * 4)()
+        emu.emu_set_variant(variant)
+        rc = emu.emu_sv_run(n, st.view(np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                            1 if psi0 is None else 0, gs.rec_ptr(), len(gs), gs.mats_ptr(), len(gs.mats),
+                            int(inverse), stats)
+        assert rc == 0, emu.emu_last_error()
+        outs.append(st)
+    assert np.array_equal(outs[0], outs[1]), "direct and pipelined sweep bodies disagree"
     return st, tuple(stats)
 
 

@@ -153,3 +153,18 @@ def test_compile_options_make_the_same_decisions(fake_backend, case):
     if ref.local_cost_history is not None:
         np.testing.assert_allclose(got.local_cost_history, ref.local_cost_history, atol=1e-9)
     assert got.cost_evaluations == ref.cost_evaluations
+
+
+def test_backend_shared_by_compilers_of_different_widths(fake_backend):
+    """The reference's default-argument backends are singletons shared by every compiler
+    (aer_sv_backend.py:20, adapt_compiler.py:59).  A wider compiler that is still alive must not leak
+    its coupling map into the pair-RDM batch of a narrower one (entanglement_measures.py:71-75)."""
+    wide_target, _ = brickwork(6, 2, seed=5)
+    wide = AdaptCompiler(wide_target, backend=fake_backend)
+    wide.evaluate_cost()
+    qc = Circuit(3); qc.h(0); qc.cx(0, 1)
+    narrow = AdaptCompiler(qc, backend=fake_backend)
+    ems = narrow._get_all_qubit_pair_entanglement_measures()
+    np.testing.assert_allclose(ems, [1.0, 0.0, 0.0], atol=1e-7)
+    ref = AdaptCompiler(wide_target, backend=OracleSVBackend())._get_all_qubit_pair_entanglement_measures()
+    np.testing.assert_allclose(wide._get_all_qubit_pair_entanglement_measures(), ref, atol=1e-9)
