@@ -169,7 +169,8 @@ int run_plan(b200_ctx* ctx, int dst_slot, int src_slot, const Plan& plan) {
         return 0;
     }
 
-    if (src == nullptr) {
+    if (src == nullptr && (plan.sweeps.empty() || ctx->sweep_mode == 1)) {
+        // (the direct sweep kernel takes |0..0> as an implicit source: no fill pass, no read pass)
         {
             KScope ks(ctx, B200_PROF_FILL);
             sv_init_zero_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(dst, dim);
@@ -196,12 +197,14 @@ int run_plan(b200_ctx* ctx, int dst_slot, int src_slot, const Plan& plan) {
             const size_t smem = nr > 1 ? ((size_t)1 << TILE_BITS) * sizeof(double2) : 0;
             const int per_sm = nr > 1 ? ctx->sweep_occ_smem : ctx->sweep_occ_nosmem;
             const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * per_sm * ctx->grid_mult);
-            KScope ks(ctx, B200_PROF_SWEEP);
+            // a sweep from the implicit |0..0> only writes (16 * 2^n bytes): accounted with the fills, so
+            // that the SWEEP class holds read+write passes only (roofline accounting, bench.py)
+            KScope ks(ctx, src == nullptr ? B200_PROF_FILL : B200_PROF_SWEEP);
             sv_sweep_kernel<REG_BITS><<<grid, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles);
         }
         CUDA_TRY(cudaGetLastError());
+        ctx->counters[1] += 1; ctx->counters[3] += (src == nullptr ? 16 : 32) * dim;
         src = dst;
-        ctx->counters[1] += 1; ctx->counters[3] += 32 * dim;
         // host -> device bytes of the program that rode along as the kernel parameter
         ctx->counters[4] += offsetof(SweepProg, ops) + (size_t)sw.nops * sizeof(POp) + (size_t)sw.nmat2 * 32 * sizeof(double);
     }

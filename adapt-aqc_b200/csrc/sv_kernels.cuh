@@ -240,9 +240,16 @@ B200_HD void round_index(const SweepProg& sp, const PRound& rd, const uint64_t t
     for (int i = c; i < TILE_BITS; ++i) g |= (uint64_t)((tl >> i) & 1u) << sp.tileq[i];
 }
 
+// src == nullptr: the source is |0..0> (no read pass, no separate fill pass)
 template <int R>
 B200_HD void round_load_hbm(double2 (&a)[1 << R], const double2* __restrict__ src, const SweepProg& sp,
                             const PRound& rd, const uint64_t g) {
+    if (src == nullptr) {
+#pragma unroll
+        for (int j = 0; j < (1 << R); ++j) a[j] = make_double2(0.0, 0.0);
+        if (g == 0) a[0].x = 1.0;
+        return;
+    }
     uint64_t gs[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) gs[k] = 1ull << sp.tileq[rd.regpos[k]];

@@ -120,6 +120,19 @@ def measured_peak_hbm():
     return 6650.0, "fallback"
 
 
+def measured_traffic(n):
+    """DRAM bytes per launch of the sweep kernel from the committed `ncu --set full` capture
+    (profiles/sweep_traffic.json, taken at n = 28); None for other sizes."""
+    p = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+    try:
+        t = json.load(open(p))
+        if int(t["algorithmic_bytes_per_launch"]) == 32 * (1 << n):
+            return float(t["traffic_bytes_per_launch"])
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def cpu_baseline_sample(n, target, ansatz, budget_s=20.0):
     """CPU restatement of the reference path, bounded sample: the reference re-simulates ALL G
     gates of full_circuit from |0..0> for every evaluation; time the first k gates at full size
@@ -450,7 +463,7 @@ def main():
     achieved = alg_bytes / (sweep_ms / max(1, sweep_n) * 1e-3) / 1e9 if sweep_n else None
     roofline = {"bound": "hbm", "kernel": "sv_sweep_kernel", "achieved": achieved, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                "traffic": None, "bytes_per_launch": alg_bytes, "launches": int(sweep_n),
+                "traffic": measured_traffic(n), "bytes_per_launch": alg_bytes, "launches": int(sweep_n),
                 "avg_launch_ms": sweep_ms / max(1, sweep_n),
                 "share_of_step": sweep_ms / dev_ms if world == 1 else None,
                 "other_kernels_ms": {k: round(v[0], 3) for k, v in prof.items() if k != "sweep" and v[1]}}

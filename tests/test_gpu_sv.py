@@ -192,7 +192,13 @@ def test_counters_and_timing():
     after = eng.counters()
     assert ms > 0
     assert after["sweeps"] > before["sweeps"] and after["launches"] > before["launches"]
-    assert after["bytes"] - before["bytes"] == (after["sweeps"] - before["sweeps"]) * 32 * (1 << n)
+    # algorithmic bytes: 32 * 2^n per sweep (read + write), except that the first sweep of a run from
+    # |0..0> has no read pass (the kernel synthesises the source)
+    assert after["bytes"] - before["bytes"] == ((after["sweeps"] - before["sweeps"]) * 32 - 16) * (1 << n)
+    mid = eng.counters()
+    eng.run(0, 0, GateStream.from_circuit(target))
+    end = eng.counters()
+    assert end["bytes"] - mid["bytes"] == (end["sweeps"] - mid["sweeps"]) * 32 * (1 << n)
     eng.close()
 
 
