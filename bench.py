@@ -256,6 +256,54 @@ def bench_mps(args, device, with_cpu=True):
     return out
 
 
+# ---- compile wall-time (BASELINE metric, second half): a whole ADAPT-AQC compile of C3 -----------
+def bench_compile(args, device, cpu_evals_per_s=None):
+    """AdaptCompiler.compile() (adapt_compiler.py:246) on the C3 target: ISL pair selection from pair
+    RDMs on a linear coupling map (P = n - 1 pairs), Rotoselect on each new layer, Rotosolve over the
+    window, `--compile-layers` layers.  Wall time includes every host-side step (circuit edits, plan
+    building, 4x4 measures); the final exact overlap is computed on the device."""
+    from adapt_aqc_b200.backends import B200SVBackend
+    from adapt_aqc_b200.compiler import AdaptCompiler, AdaptConfig
+    from adapt_aqc_b200.minimiser import B200CostMinimiser
+    n = args.qubits
+    target, _ = build_workload(n, args.depth, 0)
+    cmap = [(i, i + 1) for i in range(n - 1)]
+    out = {"workload": f"C3 compile: {n}-qubit brickwork(depth={args.depth}) target, AdaptConfig(max_layers={args.compile_layers}, "
+                       f"method='ISL'), linear coupling map (P={n - 1})"}
+    for name, mcls in (("batched", B200CostMinimiser), ("reference_minimiser", None)):
+        backend = B200SVBackend(device=device)
+        comp = AdaptCompiler(target, backend=backend, coupling_map=cmap, minimiser_cls=mcls,
+                             adapt_config=AdaptConfig(max_layers=args.compile_layers, method="ISL"))
+        comp.evaluate_cost()              # U|0> once (also the reference's first call, adapt_compiler.py:334)
+        eng = backend._engine
+        eng.sync()
+        c0 = eng.counters()
+        eng.profile(True)
+        t0 = time.perf_counter()
+        res = comp.compile()
+        eng.sync()
+        wall = time.perf_counter() - t0
+        prof = eng.profile_read()
+        eng.profile(False)
+        c1 = eng.counters()
+        layers = len(res.qubit_pair_history)
+        evals = int(comp.cost_evaluation_counter)
+        r = {"wall_s": wall, "layers": layers, "cost_evaluations": evals, "final_global_cost": float(res.global_cost_history[-1]),
+             "overlap": float(res.overlap), "evals_per_s": evals / wall, "gpu_launches": int(c1["launches"] - c0["launches"]),
+             "sweeps": int(c1["sweeps"] - c0["sweeps"]),
+             "kernel_ms": {k: round(v[0], 2) for k, v in prof.items() if v[1]},
+             "kernel_launches": {k: int(v[1]) for k, v in prof.items() if v[1]}}
+        if cpu_evals_per_s:
+            # the reference re-simulates everything per evaluation and once more per candidate pair per layer
+            sims = evals + layers * (n - 1)
+            r["cpu_estimate_s"] = sims / cpu_evals_per_s
+            r["cpu_estimate_note"] = (f"{sims} full re-simulations (evaluations + one per candidate pair per layer, "
+                                      "adapt_compiler.py:964-975) at the measured CPU rate of this box; estimate, not timed")
+        out[name] = r
+        backend._engine.close()
+    return out
+
+
 # ---- config C5: statevector sharded over the ranks by global qubits --------------------------------
 def bench_sharded(args, local_rank, world):
     """One cost evaluation = full_circuit (brickwork target + thin layers) applied to |0..0> on a
@@ -364,6 +412,8 @@ def main():
     ap.add_argument("--sharded-depth", type=int, default=4)
     ap.add_argument("--sharded-layers", type=int, default=4)
     ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--no-compile", action="store_true", help="skip the compile wall-time leg")
+    ap.add_argument("--compile-layers", type=int, default=6)
     ap.add_argument("--mps-qubits", type=int, default=50)
     ap.add_argument("--mps-chi", type=int, default=256)
     ap.add_argument("--mps-layers", type=int, default=2)
@@ -482,8 +532,16 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(n, target, ansatz, budget_s=15.0)
+    if rank == 0 and world == 1 and not args.no_compile:
+        backend._engine.close()
+        try:
+            cpu_rate = line.get("cpu_baseline", {}).get("value")
+            line["compile_c3"] = bench_compile(args, local_rank, cpu_rate)
+        except Exception as exc:  # noqa: BLE001
+            line["compile_c3"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_mps:
-        backend._engine.close()          # free the 16 GiB of statevector slots first
+        if backend._engine is not None:
+            backend._engine.close()          # free the 16 GiB of statevector slots first
         try:
             line["mps_c4"] = bench_mps(args, local_rank, with_cpu=not args.no_cpu_baseline)
         except Exception as exc:  # noqa: BLE001 - the secondary measurement must not hide the main line
