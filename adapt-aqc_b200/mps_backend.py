@@ -102,6 +102,12 @@ class B200MPSSimulator:
         self._pool = {}            # num_qubits -> [DeviceMPS]
         self._uploaded = {}        # id(host mps object) -> (host object, DeviceMPS): set_mps cache
         self.runs = 0
+        # prefix checkpoints of the most recent run: states right after each 2-qubit gate (= each SVD)
+        self._ckpt_key = None      # (n, truncation settings)
+        self._ckpt_base = None     # the host target MPS object the checkpoints start from (None: |0..0>)
+        self._ckpt_window = []     # canonical window of the run that produced them
+        self._ckpts = []           # [(prefix length, DeviceMPS)], ascending
+        self.ckpt_stats = {"resumed_gates": 0, "applied_gates": 0, "svds_skipped": 0}
 
     def __getstate__(self):
         return {"thr": self.options.matrix_product_state_truncation_threshold,
@@ -162,8 +168,51 @@ class B200MPSSimulator:
             stop -= 1
         window = G.canonical_window(circuit, start, stop)
         if window:
-            out.apply(G.GateStream.from_window(window))
+            self._apply_with_checkpoints(out, window, data[0].operation.params[0] if start else None)
         return out
+
+    MAX_CHECKPOINTS = 24
+
+    def _drop_checkpoints(self, keep=0):
+        while len(self._ckpts) > keep:
+            self._recycle(self._ckpts.pop()[1])
+
+    def _apply_with_checkpoints(self, out, window, base_obj):
+        """Apply `window` to `out` (which holds the base state), resuming from the longest prefix the
+        previous run shares with it.  The reference re-applies every un-absorbed gate on every evaluation
+        (aer_mps_backend.py:76-78) although the optimiser changed ONE rotation: the state right after
+        each 2-qubit gate (each SVD + truncation) of the previous run is kept on the device, and a run
+        whose gate list starts with the same gates resumes from it.  Same gates in the same order with the
+        same truncation rule give the same state, so the result is identical to a full re-run."""
+        o = self.options
+        key = (out.num_qubits, o.matrix_product_state_truncation_threshold, o.matrix_product_state_max_bond_dimension)
+        if key != self._ckpt_key or base_obj is not self._ckpt_base:      # (the host target object is kept alive here)
+            self._drop_checkpoints()
+            self._ckpt_key, self._ckpt_base, self._ckpt_window = key, base_obj, []
+        old = self._ckpt_window
+        common = 0
+        while common < len(old) and common < len(window) and old[common] == window[common]:
+            common += 1
+        self._drop_checkpoints(sum(1 for plen, _ in self._ckpts if plen <= common))
+        pos = 0
+        if self._ckpts:
+            pos, h = self._ckpts[-1]
+            out.copy_from(h)
+            self.ckpt_stats["resumed_gates"] += pos
+            self.ckpt_stats["svds_skipped"] += len(self._ckpts)
+        two_q = [i for i in range(pos, len(window)) if window[i][2] >= 0]
+        for i in two_q:
+            out.apply(G.GateStream.from_window(window[pos:i + 1]))
+            self.ckpt_stats["applied_gates"] += i + 1 - pos
+            pos = i + 1
+            if len(self._ckpts) < self.MAX_CHECKPOINTS:
+                h = self._acquire(out.num_qubits)
+                h.copy_from(out)
+                self._ckpts.append((pos, h))
+        if pos < len(window):
+            out.apply(G.GateStream.from_window(window[pos:]))
+            self.ckpt_stats["applied_gates"] += len(window) - pos
+        self._ckpt_window = list(window)
 
     def run(self, circuit, **_options):
         """Aer-shaped entry: ``sim.run(qc, shots=1).result().data(0)[label]`` gives the QiskitMPS."""

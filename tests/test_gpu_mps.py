@@ -281,3 +281,43 @@ def test_device_view_is_listlike_and_backend_pickles():
     b2 = pickle.loads(pickle.dumps(b))
     assert b2.simulator.options.matrix_product_state_truncation_threshold == 1e-12
     assert b2.simulator.options.matrix_product_state_max_bond_dimension == 16
+
+
+def test_prefix_checkpoints_reproduce_full_reruns_bit_for_bit():
+    """B200MPSSimulator.simulate resumes from the state after the last 2-qubit gate the previous run
+    shares with the new gate list.  Under truncation (bond cap AND threshold) the resumed result must be
+    IDENTICAL to a run from the base state by a simulator without history -- edits walk over every
+    position of the un-absorbed window like Rotosolve does (cost_minimiser.py:344-368)."""
+    n = 10
+    rng = np.random.default_rng(3)
+    base = _generic_circuit(n, 6, 11)
+    target = mo.mps_from_circuit(base.copy(), sim=mo.OracleMPSSimulator(1e-16, None))
+    for thr, max_chi in [(1e-16, 6), (1e-5, None)]:
+        sim = B200MPSSimulator(thr, max_chi)
+        qc = Circuit(n)
+        qc.set_matrix_product_state(target)
+        rot = []
+        for layer in range(4):
+            a = int(rng.integers(n - 1))
+            for q in (a, a + 1):
+                rot.append(len(qc.data)); qc.rz(float(rng.uniform(-3, 3)), q, label="rz")
+            qc.cx(a, a + 1)
+            for q in (a, a + 1):
+                rot.append(len(qc.data)); qc.ry(float(rng.uniform(-3, 3)), q, label="ry")
+        order = list(rot) + list(rng.permutation(rot))
+        for idx in order:
+            qc.data[idx].operation.params[0] = float(rng.uniform(-3, 3))
+            h = sim.simulate(qc)
+            got = h.get()
+            sim._recycle(h)
+            fresh = B200MPSSimulator(thr, max_chi)
+            h2 = fresh.simulate(qc)
+            ref = h2.get()
+            h2.close()
+            fresh.context().close()
+            assert [len(l) for l in got[1]] == [len(l) for l in ref[1]]
+            for (g0, g1), (r0, r1) in zip(got[0], ref[0]):
+                assert np.array_equal(g0, r0) and np.array_equal(g1, r1)
+            for la, lb in zip(got[1], ref[1]):
+                assert np.array_equal(la, lb)
+        assert sim.ckpt_stats["svds_skipped"] > 0 and sim.ckpt_stats["resumed_gates"] > 0
