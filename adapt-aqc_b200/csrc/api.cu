@@ -459,6 +459,61 @@ int b200_sv_device_ptr(b200_ctx* ctx, int slot, void** out) {
     return 0;
 }
 
+int b200_sv_ipc_export(b200_ctx* ctx, int slot, unsigned char handle[64]) {
+    if (check_slot(ctx, slot)) return -1;
+    if (!handle) return set_error("null pointer");
+    if (!ctx->owned[slot]) return set_error("ipc_export: slot memory is caller-owned (attach): export it from its owner");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, ctx->slots[slot]));
+    std::memcpy(handle, &h, 64);
+    return 0;
+}
+
+int b200_sv_ipc_open(b200_ctx* ctx, const unsigned char handle[64], void** peer_ptr) {
+    if (!ctx || !handle || !peer_ptr) return set_error("null pointer");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int b200_sv_ipc_close(b200_ctx* ctx, void* peer_ptr) {
+    if (!ctx) return set_error("null context");
+    if (!peer_ptr) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaIpcCloseMemHandle(peer_ptr));
+    return 0;
+}
+
+int b200_sv_peer_swap(b200_ctx* ctx, int slot, void* const* peer_ptrs, int world, int rank) {
+    if (check_slot(ctx, slot)) return -1;
+    if (!peer_ptrs) return set_error("null pointer");
+    if (world < 2 || world > PEER_MAX_WORLD || (world & (world - 1))) return set_error("peer_swap: world must be a power of two in [2,16]");
+    if (rank < 0 || rank >= world) return set_error("peer_swap: rank out of range");
+    const uint64_t dim = 1ull << ctx->nq;
+    if (dim / world < 2) return set_error("peer_swap: slice too small for this world size");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    PeerTable pt;
+    for (int p = 0; p < PEER_MAX_WORLD; ++p) pt.p[p] = nullptr;
+    for (int p = 0; p < world; ++p) {
+        if (p != rank && !peer_ptrs[p]) return set_error("peer_swap: missing peer pointer");
+        pt.p[p] = (double2*)peer_ptrs[p];
+    }
+    const uint64_t chunk = dim / world;
+    Timer tm(ctx);
+    {
+        KScope ks(ctx, B200_PROF_FILL);
+        sv_peer_swap_kernel<<<ctx->num_sms * 4, 512, 0, ctx->stream>>>((double2*)ctx->slots[slot], pt, world, rank, chunk);
+    }
+    CUDA_TRY(cudaGetLastError());
+    ctx->counters[6] += 1;
+    tm.stop();
+    return 0;
+}
+
 int b200_sv_num_qubits(b200_ctx* ctx, int* out) {
     if (!ctx || !out) return set_error("null pointer");
     *out = ctx->nq;

@@ -608,6 +608,50 @@ sv_sweep_pipe_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
         if (tid == 0) mbar_arrive(&done_bar[b]);
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// K7: global-qubit exchange over NVLink peer memory.  The local slice is `world` chunks; chunk[p] of this
+// rank and chunk[rank] of rank p trade places, for every p at once, IN PLACE and without staging: every
+// amplitude pair is owned by exactly one thread in the whole system (the lower rank of a pair takes the
+// first half of the chunk, the higher rank the second half), which loads both sides (the remote one over
+// NVLink), and stores them swapped (the remote store again over NVLink).  Each GPU thus reads and writes
+// half a chunk per peer: both NVLink directions of every rank carry the same load.  Replaces NCCL
+// send/recv through a staging buffer plus a copy-back.  Ranks synchronise before and after (host side).
+// ---------------------------------------------------------------------------------------------
+constexpr int PEER_MAX_WORLD = 16;
+struct PeerTable { double2* p[PEER_MAX_WORLD]; };
+
+__global__ void __launch_bounds__(512)
+sv_peer_swap_kernel(double2* __restrict__ local, const PeerTable peers, const int world, const int rank,
+                    const uint64_t chunk) {
+    const uint64_t half = chunk >> 1;
+    const uint64_t total = (uint64_t)(world - 1) * half;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    constexpr int U = 4;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += stride * U) {
+        double2 a[U], b[U];
+        double2* mine[U];
+        double2* theirs[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t idx = base + (uint64_t)u * stride;
+            mine[u] = nullptr;
+            if (idx < total) {
+                const int s = (int)(idx / half) + 1;
+                const int peer = rank ^ s;
+                const uint64_t i = idx % half + (rank < peer ? 0 : half);
+                mine[u] = local + (uint64_t)peer * chunk + i;
+                theirs[u] = peers.p[peer] + (uint64_t)rank * chunk + i;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (mine[u]) { a[u] = *mine[u]; b[u] = __ldcg(theirs[u]); }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (mine[u]) { *mine[u] = b[u]; __stcg(theirs[u], a[u]); }
+    }
+}
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------------------------------------

@@ -71,23 +71,35 @@ class TorchComm:
         torch, dist = self.torch, self.dist
         Gw = self.world
         chunk = state.numel() // Gw
-        piece = min(chunk, staging.numel())
         timing = state.is_cuda
         if timing:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        for step in range(1, Gw):
-            peer = self.rank ^ step
-            base = peer * chunk
-            for off in range(0, chunk, piece):
-                cnt = min(piece, chunk - off)
-                mine = state[base + off: base + off + cnt]
-                buf = staging[:cnt]
-                ops = [dist.P2POp(dist.isend, mine, peer), dist.P2POp(dist.irecv, buf, peer)]
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
-                mine.copy_(buf)
-                self.bytes_sent += cnt * state.element_size()
+        # Double-buffered staging: the transfer of piece k+1 is issued (it runs on NCCL's stream) before
+        # this stream copies piece k back into place, so the copy-back hides behind the next transfer.
+        half = max(1, staging.numel() // 2)
+        piece = min(chunk, half)
+        bufs = (staging[:piece], staging[half:half + piece]) if 2 * piece <= staging.numel() else (staging[:piece],)
+        jobs = [(self.rank ^ step, off) for step in range(1, Gw) for off in range(0, chunk, piece)]
+
+        def issue(k):
+            peer, off = jobs[k]
+            cnt = min(piece, chunk - off)
+            mine = state[peer * chunk + off: peer * chunk + off + cnt]
+            buf = bufs[k % len(bufs)][:cnt]
+            works = dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, peer), dist.P2POp(dist.irecv, buf, peer)])
+            return works, mine, buf
+
+        pending = issue(0) if jobs else None
+        for k in range(len(jobs)):
+            works, mine, buf = pending
+            pending = issue(k + 1) if (k + 1 < len(jobs) and len(bufs) > 1) else None
+            for w in works:
+                w.wait()
+            mine.copy_(buf)
+            self.bytes_sent += mine.numel() * state.element_size()
+            if pending is None and k + 1 < len(jobs):
+                pending = issue(k + 1)
         if timing:
             e1.record()
             e1.synchronize()
@@ -118,6 +130,7 @@ class ShardedStatevector:
         # perm[slot][logical] = physical position; positions >= nl are rank bits
         self.perm = [list(range(self.n)) for _ in slot_tensors]
         self.stats = {"exchanges": 0, "local_runs": 0}
+        self.peer_ptrs = None      # [slot][rank] -> device pointer into that rank's slot (CUDA IPC), or None: NCCL path
 
     # ---- layout ----
     def _rank_bit(self, phys):
@@ -146,12 +159,28 @@ class ShardedStatevector:
             self.stats["local_runs"] += 1
         # 2. all-to-all: chunk index (top-g local bits) <-> rank bits
         self._sync()
-        self.comm.exchange_chunks(self.slot_tensors[slot], self.staging)
+        if self.peer_ptrs is not None:
+            self._peer_exchange(slot)
+        else:
+            self.comm.exchange_chunks(self.slot_tensors[slot], self.staging)
         self._sync()
         for j in range(g):
             a, b = inv[nl - g + j], inv[nl + j]
             perm[a], perm[b] = nl + j, nl - g + j
         self.stats["exchanges"] += 1
+
+    def _peer_exchange(self, slot):
+        """One fused kernel per rank over NVLink peer memory (b200_sv_peer_swap): no staging, no copy-back.
+        Ranks meet before (every slice is final) and after (every remote store has landed)."""
+        import time
+        comm = self.comm
+        comm.dist.barrier()
+        t0 = time.perf_counter()
+        self.eng.peer_swap(slot, self.peer_ptrs[slot], comm.rank)
+        self.eng.sync()
+        comm.exchange_ms += 1e3 * (time.perf_counter() - t0)
+        comm.dist.barrier()
+        comm.bytes_sent += (comm.world - 1) * (16 << self.nl) // comm.world
 
     def ensure_local(self, slot, needed, next_use=None):
         """Make every logical qubit in `needed` local; victims = local qubits not needed, used
@@ -298,26 +327,59 @@ class ShardedStatevector:
         return complex(out[0], out[1])
 
 
-def make_gpu_sharded(num_qubits, n_slots=2, staging_bytes=1 << 30, local_rank=0):
-    """Builds a ShardedStatevector over the default process group (NCCL), one rank per GPU."""
+class _CudaAlias:
+    """Lets torch view library-owned device memory (torch.as_tensor over __cuda_array_interface__)."""
+
+    def __init__(self, ptr, n_doubles):
+        self.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def make_gpu_sharded(num_qubits, n_slots=2, staging_bytes=1 << 30, local_rank=0, exchange=None):
+    """Builds a ShardedStatevector over the default process group (NCCL), one rank per GPU.
+
+    exchange: "peer" (default) = the slots are opened on every rank through CUDA IPC and global qubits are
+    exchanged by b200_sv_peer_swap over NVLink peer memory; "nccl" = send/recv through a staging buffer
+    (also the fallback when IPC is not available).  Env B200AQC_EXCHANGE overrides."""
+    import os
     import torch
+    import torch.distributed as dist
     from .sv_engine import SVEngine
     dev = torch.device("cuda", local_rank)
     comm = TorchComm(dev)
     g = int(np.log2(comm.world))
     nl = num_qubits - g
-    eng = SVEngine(nl, device=local_rank, n_slots=n_slots, external_memory=True)
-    tensors = []
-    for s in range(n_slots):
-        t = torch.empty(2 << nl, dtype=torch.float64, device=dev)
-        eng.attach(s, t.data_ptr())
-        tensors.append(t)
-    staging = torch.empty(min(staging_bytes // 8, (2 << nl) // comm.world), dtype=torch.float64, device=dev)
+    exchange = os.environ.get("B200AQC_EXCHANGE", exchange or "peer")
+    eng = SVEngine(nl, device=local_rank, n_slots=n_slots)
+    tensors = [torch.as_tensor(_CudaAlias(eng.device_ptr(s), 2 << nl), device=dev) for s in range(n_slots)]
+    staging = None
+    peer_ptrs = None
+    if exchange == "peer" and comm.world > 1:
+        try:
+            mine = [eng.ipc_export(s) for s in range(n_slots)]
+            ok = True
+        except Exception:  # noqa: BLE001
+            mine, ok = None, False
+        table = [None] * comm.world
+        dist.all_gather_object(table, mine)
+        if ok and all(t is not None for t in table):
+            try:
+                peer_ptrs = [[None if r == comm.rank else eng.ipc_open(table[r][s]) for r in range(comm.world)]
+                             for s in range(n_slots)]
+            except Exception:  # noqa: BLE001
+                peer_ptrs = None
+        flags = [None] * comm.world
+        dist.all_gather_object(flags, peer_ptrs is not None)
+        if not all(flags):
+            peer_ptrs = None          # every rank must take the same path
+    if peer_ptrs is None:
+        staging = torch.empty(min(staging_bytes // 8, (2 << nl) // comm.world), dtype=torch.float64, device=dev)
 
     def sync():
         eng.sync()
         torch.cuda.synchronize(dev)
 
     sv = ShardedStatevector(num_qubits, eng, comm, tensors, staging, sync)
+    sv.peer_ptrs = peer_ptrs
+    sv.exchange_mode = "peer" if peer_ptrs is not None else "nccl"
     sv._keepalive = (tensors, staging)
     return sv

@@ -55,6 +55,26 @@ class SVEngine:
     def attach(self, slot, device_ptr):
         check(self._lib.b200_sv_attach(self._ctx, int(slot), ctypes.c_void_p(int(device_ptr))))
 
+    # ---- NVLink peer memory (sharded statevector, dist_sv) ----
+    def ipc_export(self, slot):
+        """64-byte CUDA IPC handle of a library-owned slot (to be opened by the other ranks)."""
+        buf = ctypes.create_string_buffer(64)
+        check(self._lib.b200_sv_ipc_export(self._ctx, int(slot), buf))
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = ctypes.c_void_p()
+        check(self._lib.b200_sv_ipc_open(self._ctx, bytes(handle), ctypes.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        check(self._lib.b200_sv_ipc_close(self._ctx, ctypes.c_void_p(ptr)))
+
+    def peer_swap(self, slot, peer_ptrs, rank):
+        """In-place exchange of chunk[p] with rank p's chunk[rank] for all p (one kernel over NVLink)."""
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(p or 0) for p in peer_ptrs])
+        check(self._lib.b200_sv_peer_swap(self._ctx, int(slot), arr, len(peer_ptrs), int(rank)))
+
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
             self._lib.b200_ctx_destroy(self._ctx)

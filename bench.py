@@ -347,7 +347,7 @@ def bench_sharded(args, local_rank, world):
     out = {
         "workload": f"C5: {n}-qubit brickwork(depth={args.sharded_depth}) + {args.sharded_layers} thin layers from |0..0>, "
                     f"{n - g} local + {g} global qubits per rank",
-        "qubits": n, "state_bytes_per_gpu": local_bytes, "value": reps / wall, "unit": UNIT, "s_per_eval": wall / reps,
+        "qubits": n, "exchange": getattr(sv, "exchange_mode", "nccl"), "state_bytes_per_gpu": local_bytes, "value": reps / wall, "unit": UNIT, "s_per_eval": wall / reps,
         "sweeps_per_eval": sweeps, "exchanges_per_eval": sv.stats["exchanges"] / reps,
         "nvlink_bytes_sent_per_gpu_per_eval": comm.bytes_sent / reps,
         "exchange_ms_per_eval": xms / reps,

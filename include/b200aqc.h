@@ -107,6 +107,17 @@ int b200_sv_reserve_slots(b200_ctx *ctx, int num_qubits, int n_slots);
 /* Use caller-provided device memory (e.g. a torch CUDA tensor's data_ptr()) for one slot. */
 int b200_sv_attach(b200_ctx *ctx, int slot, void *device_ptr);
 int b200_sv_device_ptr(b200_ctx *ctx, int slot, void **out);
+/* Multi-GPU statevector sharded by global qubits (one process per GPU): peer access to another rank's
+ * slot through CUDA IPC, and the in-place exchange of global with local qubits over NVLink peer memory
+ * (replaces the NCCL send/recv + staging + copy-back of dist_sv.TorchComm.exchange_chunks; the reference
+ * has no multi-device path -- SURVEY 8e).  `handle` is a cudaIpcMemHandle_t (64 bytes) of a library-owned
+ * slot; peer_ptrs[p] = pointer opened from rank p's handle (entry `rank` ignored).  peer_swap trades
+ * chunk[p] of this rank's slot with chunk[rank] of rank p's, for all p, in one kernel; the caller
+ * synchronises the ranks before and after. */
+int b200_sv_ipc_export(b200_ctx *ctx, int slot, unsigned char handle[64]);
+int b200_sv_ipc_open(b200_ctx *ctx, const unsigned char handle[64], void **peer_ptr);
+int b200_sv_ipc_close(b200_ctx *ctx, void *peer_ptr);
+int b200_sv_peer_swap(b200_ctx *ctx, int slot, void *const *peer_ptrs, int world, int rank);
 int b200_sv_num_qubits(b200_ctx *ctx, int *out);
 
 /* slot <- |0...0> */

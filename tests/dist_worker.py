@@ -100,7 +100,8 @@ def main():
         assert abs(sv.inner(1, 1) - 1) < 1e-12
     assert sv.stats["exchanges"] > 0, "the test circuits must exercise the global-qubit exchange"
     if comm.rank == 0:
-        print(f"dist ok: world={comm.world} n={n} exchanges={sv.stats['exchanges']} bytes_sent={comm.bytes_sent}")
+        print(f"dist ok: world={comm.world} n={n} exchanges={sv.stats['exchanges']} bytes_sent={comm.bytes_sent} "
+              f"exchange={getattr(sv, 'exchange_mode', 'nccl')}")
     dist.destroy_process_group()
 
 

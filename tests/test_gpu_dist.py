@@ -18,13 +18,18 @@ def _ngpu():
     return n.value if load().b200_device_count(ctypes.byref(n)) == 0 else 0
 
 
-@pytest.mark.parametrize("world,n,port", [(2, 15, 29621), (4, 16, 29622), (8, 17, 29623)])
-def test_sharded_statevector_on_nccl(world, n, port):
+@pytest.mark.parametrize("world,n,port,exchange", [(2, 15, 29621, "peer"), (2, 15, 29624, "nccl"), (4, 16, 29622, "peer"),
+                                                   (8, 17, 29623, "peer"), (8, 17, 29625, "nccl")])
+def test_sharded_statevector_on_nccl(world, n, port, exchange):
+    """exchange = "peer": global qubits are swapped by b200_sv_peer_swap over NVLink peer memory (CUDA IPC);
+    "nccl": send/recv through a staging buffer."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ, B200AQC_EXCHANGE=exchange)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"),
            str(n), "gpu"]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "dist ok" in res.stdout
+    assert f"exchange={exchange}" in res.stdout, res.stdout[-500:]
