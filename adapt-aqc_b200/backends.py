@@ -170,6 +170,7 @@ class B200SVBackend(_SVBase):
         self._state_version = 0
         self._last_run_key = None
         self._last_run_sv = None
+        self._last_run_insts = None
         self._pair_hint = None
         self._compiler_ref = None
         self._wcache = None
@@ -199,6 +200,7 @@ class B200SVBackend(_SVBase):
             self._evaluator = SVCostEvaluator(self._engine, self._compact)
             self._state_version += 1
             self._last_run_key = None
+            self._last_run_insts = None
         return self._engine
 
     def _prefix_key(self, compiler):
@@ -217,15 +219,24 @@ class B200SVBackend(_SVBase):
             self._evaluator.base_key = None
             self._evaluator.invalidate()
         self._last_run_key = None
+        self._last_run_insts = None
 
     def _simulate(self, circuit, pair_hint=None):
         """Full circuit from |0..0> into slot WORK (facade path, no caching assumptions except an
         identical-circuit shortcut: the reference re-runs the same circuit once per pair)."""
         eng = self._get_engine(circuit.num_qubits)
+        data = circuit.data
+        live = self._last_run_sv is not None and self._last_run_sv._version == self._state_version
+        # same instruction objects with the same parameters as the previous run (the reference asks for
+        # the same circuit once per candidate pair, adapt_compiler.py:964-975): no re-canonicalisation
+        fp = self._last_run_insts
+        if live and fp is not None and len(fp) == len(data) and all(
+                inst is f[0] and inst.operation.params == f[1] for inst, f in zip(data, fp)):
+            return self._last_run_sv
         window = G.canonical_window(circuit)
         key = tuple(window)
-        if self._last_run_key is not None and key == self._last_run_key and self._last_run_sv is not None \
-                and self._last_run_sv._version == self._state_version:
+        self._last_run_insts = [(inst, list(inst.operation.params)) for inst in data]
+        if live and self._last_run_key is not None and key == self._last_run_key:
             return self._last_run_sv
         eng.run(SLOT_WORK, -1, G.GateStream.from_window(window))
         self._state_version += 1
@@ -306,7 +317,7 @@ class B200SVBackend(_SVBase):
         eng.run(SLOT_WORK, SLOT_BASE, G.GateStream.from_window(window))
         self._state_version += 1
         sv = DeviceStatevector(self, self._state_version)
-        self._last_run_key, self._last_run_sv = None, sv
+        self._last_run_key, self._last_run_sv, self._last_run_insts = None, sv, None
         return sv
 
     def measure_qubit_expectation_values(self, compiler):

@@ -611,68 +611,77 @@ int b200_sv_pair_rdm(b200_ctx* ctx, int slot, const int32_t* pairs, int n_pairs,
         if (a < 0 || b < 0 || a >= n || b >= n || a == b)
             return set_error("pair " + std::to_string(p) + ": qubits out of range");
     }
-    // Cover the requested pairs with qubit triples (three pair-RDMs per read pass).
+    // Cover the requested pairs with qubit quadruples (six pair-RDMs per read pass), triples (three) or
+    // single pairs, greedily by newly covered pairs per pass.  Results of many passes are staged in d_out
+    // and fetched together (one synchronisation per ~40 passes instead of one per pass).
     std::vector<char> want(n * n, 0), have(n * n, 0);
     std::vector<double> acc((size_t)n * n * 16, 0.0);  // indexed [lo*n+hi][16]
     for (int p = 0; p < n_pairs; ++p) {
         const int lo = std::min(pairs[2 * p], pairs[2 * p + 1]), hi = std::max(pairs[2 * p], pairs[2 * p + 1]);
         want[lo * n + hi] = 1;
     }
+    auto need = [&](int u, int v) { const int l = std::min(u, v), h = std::max(u, v); return want[l * n + h] && !have[l * n + h] ? 1 : 0; };
+    struct Pending { int off, npairs; int pl[6][2]; };
+    std::vector<Pending> pending;
+    int out_off = 0;
+    auto flush = [&]() -> int {
+        if (pending.empty()) return 0;
+        std::vector<double> r(out_off);
+        if (fetch_out(ctx, r.data(), out_off)) return -1;
+        for (const Pending& pd : pending)
+            for (int t = 0; t < pd.npairs; ++t)
+                std::memcpy(&acc[(size_t)(pd.pl[t][0] * n + pd.pl[t][1]) * 16], r.data() + pd.off + 16 * t, 16 * sizeof(double));
+        pending.clear();
+        out_off = 0;
+        return 0;
+    };
     Timer tm(ctx);
-    std::vector<double> host;
     for (int lo = 0; lo < n; ++lo)
         for (int hi = lo + 1; hi < n; ++hi) {
             if (!want[lo * n + hi] || have[lo * n + hi]) continue;
-            int best = -1, best_gain = -1;
-            if (n >= 3) {
-                for (int c = 0; c < n; ++c) {
-                    if (c == lo || c == hi) continue;
-                    auto need = [&](int u, int v) { const int l = std::min(u, v), h = std::max(u, v); return want[l * n + h] && !have[l * n + h] ? 1 : 0; };
-                    const int gain = need(lo, c) + need(hi, c);
-                    if (gain > best_gain) { best_gain = gain; best = c; }
+            int c3 = -1, g3 = 1, c4a = -1, c4b = -1, g4 = 1;
+            for (int c = 0; c < n && n >= 3; ++c) {
+                if (c == lo || c == hi) continue;
+                const int gc = 1 + need(lo, c) + need(hi, c);
+                if (gc > g3) { g3 = gc; c3 = c; }
+                for (int d = c + 1; d < n && n >= 4; ++d) {
+                    if (d == lo || d == hi) continue;
+                    const int gd = gc + need(lo, d) + need(hi, d) + need(c, d);
+                    if (gd > g4) { g4 = gd; c4a = c; c4b = d; }
                 }
             }
-            if (best < 0 || best_gain == 0) {
-                const int grid = red_grid(ctx, 1ull << (n - 2));
-                {
-                    KScope ks(ctx, B200_PROF_RDM);
-                    sv_rdm2_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>(psi, n, lo, hi, ctx->d_partial);
-                }
-                CUDA_TRY(cudaGetLastError());
-                {
-                    KScope ks(ctx, B200_PROF_REDUCE);
-                    reduce_partials_kernel<<<16, 32, 0, ctx->stream>>>(ctx->d_partial, grid, 16, ctx->d_out);
-                }
-                CUDA_TRY(cudaGetLastError());
-                ctx->counters[3] += 16ull << n;
-                double r[16];
-                if (fetch_out(ctx, r, 16)) return -1;
-                std::memcpy(&acc[(size_t)(lo * n + hi) * 16], r, sizeof r);
-                have[lo * n + hi] = 1;
-            } else {
-                int q[3] = {lo, hi, best};
-                std::sort(q, q + 3);
-                const int grid = red_grid(ctx, 1ull << (n - 3));
-                {
-                    KScope ks(ctx, B200_PROF_RDM);
-                    sv_rdm3_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>(psi, n, q[0], q[1], q[2], ctx->d_partial);
-                }
-                CUDA_TRY(cudaGetLastError());
-                {
-                    KScope ks(ctx, B200_PROF_REDUCE);
-                    reduce_partials_kernel<<<RDM3_WIDTH, 32, 0, ctx->stream>>>(ctx->d_partial, grid, RDM3_WIDTH, ctx->d_out);
-                }
-                CUDA_TRY(cudaGetLastError());
-                ctx->counters[3] += 16ull << n;
-                double r[RDM3_WIDTH];
-                if (fetch_out(ctx, r, RDM3_WIDTH)) return -1;
-                const int pl[3][2] = {{q[0], q[1]}, {q[0], q[2]}, {q[1], q[2]}};
-                for (int t = 0; t < 3; ++t) {
-                    std::memcpy(&acc[(size_t)(pl[t][0] * n + pl[t][1]) * 16], r + 16 * t, 16 * sizeof(double));
-                    have[pl[t][0] * n + pl[t][1]] = 1;
-                }
+            int q[4] = {lo, hi, -1, -1}, nq = 2;
+            if (g4 > g3 && g4 >= 3) { q[2] = c4a; q[3] = c4b; nq = 4; }      // a quad pass costs ~1.2 triple passes
+            else if (g3 >= 2) { q[2] = c3; nq = 3; }
+            std::sort(q, q + nq);
+            const int width = nq == 4 ? RDM4_WIDTH : (nq == 3 ? RDM3_WIDTH : 16);
+            if (out_off + width > (int)OUT_DOUBLES && flush()) return -1;
+            const int grid = red_grid(ctx, 1ull << (n - nq));
+            {
+                KScope ks(ctx, B200_PROF_RDM);
+                if (nq == 4) sv_rdm4_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>(psi, n, q[0], q[1], q[2], q[3], ctx->d_partial);
+                else if (nq == 3) sv_rdm3_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>(psi, n, q[0], q[1], q[2], ctx->d_partial);
+                else sv_rdm2_kernel<<<grid, RED_THREADS, 0, ctx->stream>>>(psi, n, q[0], q[1], ctx->d_partial);
             }
+            CUDA_TRY(cudaGetLastError());
+            {
+                KScope ks(ctx, B200_PROF_REDUCE);
+                reduce_partials_kernel<<<width, 32, 0, ctx->stream>>>(ctx->d_partial, grid, width, ctx->d_out + out_off);
+            }
+            CUDA_TRY(cudaGetLastError());
+            ctx->counters[3] += 16ull << n;
+            Pending pd;
+            pd.off = out_off; pd.npairs = 0;
+            for (int i = 0; i < nq; ++i)
+                for (int j = i + 1; j < nq; ++j) {
+                    pd.pl[pd.npairs][0] = q[i]; pd.pl[pd.npairs][1] = q[j];
+                    have[q[i] * n + q[j]] = 1;
+                    ++pd.npairs;
+                }
+            pending.push_back(pd);
+            out_off += width;
         }
+    if (flush()) return -1;
     tm.stop();
     // expand the packed Hermitian accumulators into row-major 4x4 complex
     static const int off_r[6] = {1, 2, 3, 2, 3, 3}, off_c[6] = {0, 0, 0, 1, 1, 2};

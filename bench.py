@@ -267,10 +267,11 @@ def bench_compile(args, device, cpu_evals_per_s=None):
     from adapt_aqc_b200.minimiser import B200CostMinimiser
     n = args.qubits
     target, _ = build_workload(n, args.depth, 0)
-    cmap = [(i, i + 1) for i in range(n - 1)]
+    linear = [(i, i + 1) for i in range(n - 1)]
     out = {"workload": f"C3 compile: {n}-qubit brickwork(depth={args.depth}) target, AdaptConfig(max_layers={args.compile_layers}, "
-                       f"method='ISL'), linear coupling map (P={n - 1})"}
-    for name, mcls in (("batched", B200CostMinimiser), ("reference_minimiser", None)):
+                       f"method='ISL'); coupling map linear (P={n - 1}) or the reference default all-to-all (P={n * (n - 1) // 2})"}
+    for name, mcls, cmap in (("linear_batched", B200CostMinimiser, linear), ("linear_reference_minimiser", None, linear),
+                             ("all_to_all_reference_minimiser", None, None)):
         backend = B200SVBackend(device=device)
         comp = AdaptCompiler(target, backend=backend, coupling_map=cmap, minimiser_cls=mcls,
                              adapt_config=AdaptConfig(max_layers=args.compile_layers, method="ISL"))
@@ -295,7 +296,7 @@ def bench_compile(args, device, cpu_evals_per_s=None):
              "kernel_launches": {k: int(v[1]) for k, v in prof.items() if v[1]}}
         if cpu_evals_per_s:
             # the reference re-simulates everything per evaluation and once more per candidate pair per layer
-            sims = evals + layers * (n - 1)
+            sims = evals + layers * len(comp.coupling_map)
             r["cpu_estimate_s"] = sims / cpu_evals_per_s
             r["cpu_estimate_note"] = (f"{sims} full re-simulations (evaluations + one per candidate pair per layer, "
                                       "adapt_compiler.py:964-975) at the measured CPU rate of this box; estimate, not timed")
