@@ -268,7 +268,33 @@ int apply_adjacent(b200_mps* m, int i, const cplx u4[16]) {
         }
         CUDA_TRY(cudaGetLastError());
         bool coop_done = false;
-        if (ctx->coop_ok) {
+        // blocked cooperative SVD: 2*WB columns of X and W per CTA in shared memory
+        constexpr int WB = 4;
+        const size_t jb_smem = (size_t)2 * WB * (p + q) * sizeof(double2);
+        if (ctx->coop_ok && jb_smem <= 200 * 1024 && !std::getenv("B200AQC_JACOBI_SCALAR")) {
+            const int NB = (((q + WB - 1) / WB) + 1) & ~1;
+            CUDA_TRY(cudaFuncSetAttribute(jacobi_block_kernel<WB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_block_kernel<WB>, JB_GROUP * WB, jb_smem));
+            if ((long long)per_sm * ctx->num_sms >= NB / 2) {
+                CUDA_TRY(cudaMemsetAsync(st->flag.p, 0, 4 * sizeof(int), s));
+                double2* Xp = (double2*)st->X.p; double2* Wp = (double2*)st->W.p;
+                int pp = p, qq = q, NN = NB, ms_ = max_sweeps;
+                const double* fr = fro2; int* ctrl = (int*)st->flag.p;
+                void* args[] = {&Xp, &Wp, &pp, &qq, &NN, &ms_, &fr, &ctrl};
+                {
+                    MScope ms(ctx);
+                    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)jacobi_block_kernel<WB>, dim3(NB / 2), dim3(JB_GROUP * WB), args, jb_smem, s));
+                }
+                int done[3] = {0, 0, 0};
+                CUDA_TRY(cudaMemcpyAsync(done, st->flag.p, sizeof done, cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+                ctx->counters[5] += sizeof done;
+                sweeps = done[2];
+                coop_done = true;
+            }
+        }
+        if (!coop_done && ctx->coop_ok) {
             // one cooperative launch for the whole SVD (needs all N/2 CTAs co-resident)
             int per_sm = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_coop_kernel, 128, 0));

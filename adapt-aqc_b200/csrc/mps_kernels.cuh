@@ -366,6 +366,136 @@ jacobi_coop_kernel(double2* __restrict__ X, double2* __restrict__ W, const int p
     if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[2] = sweep;
 }
 
+// Blocked variant of the cooperative SVD: the columns are grouped in blocks of WB; in every outer round
+// CTA k owns one PAIR of blocks (round-robin tournament over the blocks), keeps its 2*WB columns of X
+// and of W in shared memory and rotates every cross pair (i in block A, j in block B) there -- WB local
+// rounds of WB disjoint pairs, one warp per pair -- before the grid-wide barrier.  The first outer
+// round of a sweep also rotates the pairs inside each block, so a sweep still visits every column pair
+// exactly once.  Compared with one pair per CTA per barrier this divides the number of grid barriers
+// (and of trips through L2) per sweep by WB; the sweep count is the same (checked against the scalar
+// ordering on the C4 two-site matrices).
+__device__ __forceinline__ void jacobi_grid_barrier(unsigned* bar, const unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*((volatile unsigned*)bar) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// ctrl[0..1] = per-sweep rotation flags (ping-pong), ctrl[2] = sweeps done, ctrl[3] = barrier counter (all
+// zero at launch).  NB = number of blocks (even, NB * WB >= q).  Dynamic shared memory: 2*WB*(p+q) double2.
+// 128 threads (4 warps) cooperate on one column pair: WB pairs per local round -> 128*WB threads per CTA
+// (one warp per pair left every latency exposed: 20 us per outer round instead of ~6).
+constexpr int JB_GROUP = 128;
+template <int WB>
+__global__ void __launch_bounds__(JB_GROUP * WB)
+jacobi_block_kernel(double2* __restrict__ X, double2* __restrict__ W, const int p, const int q, const int NB,
+                    const int max_sweeps, const double* __restrict__ fro2, int* __restrict__ ctrl) {
+    extern __shared__ __align__(16) double2 jb_smem[];
+    __shared__ double red[WB][JB_GROUP / 32][4];
+    constexpr int NT = JB_GROUP * WB;
+    const int lane = threadIdx.x & 31;
+    const int grp = threadIdx.x / JB_GROUP, gt = threadIdx.x % JB_GROUP, gw = gt >> 5;
+    const int ld = p + q;
+    const double tiny2 = 1e-34 * (*fro2);
+    const double tol = jacobi_tol(p);
+    unsigned* bar = (unsigned*)(ctrl + 3);
+    unsigned epoch = 0;
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        int* flag = ctrl + (sweep & 1);
+        int mine = 0;
+        for (int r = 0; r < NB - 1; ++r) {
+            int A, B;
+            rr_pair(NB, r, blockIdx.x, A, B);
+            // ---- block pair -> shared memory (column c of the pair at jb_smem + c*ld: X rows, then W rows) ----
+#pragma unroll 4
+            for (int e = threadIdx.x; e < 2 * WB * p; e += NT) {
+                const int c = e / p, i = e - c * p;
+                const int col = c < WB ? A * WB + c : B * WB + (c - WB);
+                if (col < q) jb_smem[(size_t)c * ld + i] = __ldcg(X + (size_t)col * p + i);
+            }
+#pragma unroll 4
+            for (int e = threadIdx.x; e < 2 * WB * q; e += NT) {
+                const int c = e / q, i = e - c * q;
+                const int col = c < WB ? A * WB + c : B * WB + (c - WB);
+                if (col < q) jb_smem[(size_t)c * ld + p + i] = __ldcg(W + (size_t)col * q + i);
+            }
+            __syncthreads();
+            const int nloc = r == 0 ? 2 * WB - 1 : WB;
+            for (int t = 0; t < nloc; ++t) {
+                int i, j;
+                if (r == 0) rr_pair(2 * WB, t, grp, i, j);
+                else { i = grp; j = WB + (grp + t) % WB; }
+                const int ci = i < WB ? A * WB + i : B * WB + (i - WB);
+                const int cj = j < WB ? A * WB + j : B * WB + (j - WB);
+                const bool valid = ci < q && cj < q;
+                double2* ca = jb_smem + (size_t)i * ld;
+                double2* cb = jb_smem + (size_t)j * ld;
+                double al = 0, be = 0, gr = 0, gi = 0;
+                if (valid) {
+#pragma unroll 4
+                    for (int k = gt; k < p; k += JB_GROUP) {
+                        const double2 u = ca[k], v = cb[k];
+                        al = fma(u.x, u.x, fma(u.y, u.y, al));
+                        be = fma(v.x, v.x, fma(v.y, v.y, be));
+                        gr = fma(u.x, v.x, fma(u.y, v.y, gr));
+                        gi = fma(u.x, v.y, fma(-u.y, v.x, gi));
+                    }
+                }
+                al = warp_sum_d(al); be = warp_sum_d(be); gr = warp_sum_d(gr); gi = warp_sum_d(gi);
+                if (lane == 0) { red[grp][gw][0] = al; red[grp][gw][1] = be; red[grp][gw][2] = gr; red[grp][gw][3] = gi; }
+                __syncthreads();
+                al = (red[grp][0][0] + red[grp][1][0]) + (red[grp][2][0] + red[grp][3][0]);
+                be = (red[grp][0][1] + red[grp][1][1]) + (red[grp][2][1] + red[grp][3][1]);
+                gr = (red[grp][0][2] + red[grp][1][2]) + (red[grp][2][2] + red[grp][3][2]);
+                gi = (red[grp][0][3] + red[grp][1][3]) + (red[grp][2][3] + red[grp][3][3]);
+                const double g = sqrt(gr * gr + gi * gi);
+                if (valid && !(g == 0.0 || g <= tol * sqrt(al * be) || al <= tiny2 || be <= tiny2)) {
+                    const double zeta = (be - al) / (2.0 * g);
+                    const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double c = 1.0 / sqrt(1.0 + tt * tt), sn = c * tt;
+                    const double2 ph = make_double2(gr / g, gi / g);
+                    const double2 sm = make_double2(-sn * ph.x, sn * ph.y);
+                    const double2 sp = make_double2(sn * ph.x, sn * ph.y);
+#pragma unroll 4
+                    for (int k = gt; k < ld; k += JB_GROUP) {
+                        const double2 u = ca[k], v = cb[k];
+                        double2 nu = z_mul(sm, v); nu.x = fma(c, u.x, nu.x); nu.y = fma(c, u.y, nu.y);
+                        double2 nv = z_mul(sp, u); nv.x = fma(c, v.x, nv.x); nv.y = fma(c, v.y, nv.y);
+                        ca[k] = nu; cb[k] = nv;
+                    }
+                    mine = 1;
+                }
+                __syncthreads();
+            }
+            // ---- back to global ----
+#pragma unroll 4
+            for (int e = threadIdx.x; e < 2 * WB * p; e += NT) {
+                const int c = e / p, i = e - c * p;
+                const int col = c < WB ? A * WB + c : B * WB + (c - WB);
+                if (col < q) __stcg(X + (size_t)col * p + i, jb_smem[(size_t)c * ld + i]);
+            }
+#pragma unroll 4
+            for (int e = threadIdx.x; e < 2 * WB * q; e += NT) {
+                const int c = e / q, i = e - c * q;
+                const int col = c < WB ? A * WB + c : B * WB + (c - WB);
+                if (col < q) __stcg(W + (size_t)col * q + i, jb_smem[(size_t)c * ld + p + i]);
+            }
+            jacobi_grid_barrier(bar, ++epoch * gridDim.x);
+        }
+        if (__syncthreads_or(mine) && threadIdx.x == 0) atomicOr(flag, 1);
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[(sweep + 1) & 1] = 0;   // next sweep's flag
+        jacobi_grid_barrier(bar, ++epoch * gridDim.x);
+        const int any = *((volatile int*)flag);
+        if (!any) { ++sweep; break; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[2] = sweep;
+}
+
 // fro2[0] = |X|_F^2 (one CTA)
 __global__ void __launch_bounds__(256)
 jacobi_fro_kernel(const double2* __restrict__ X, const size_t nelem, double* __restrict__ fro2) {
