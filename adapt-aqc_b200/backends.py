@@ -14,6 +14,7 @@ because the reference calls it directly, bypassing the backend, once per candida
 Everything is evaluated on the GPU through libb200aqc.so; there is no CPU path.
 """
 import abc
+import os
 import weakref
 
 import numpy as np
@@ -53,6 +54,9 @@ except Exception:  # noqa: BLE001
 # COMPACT_MIN_QUBITS qubits are cheap enough to always use the dense path.
 COMPACT_QUBITS = (12, 19, 26)
 COMPACT_MIN_QUBITS = 12
+# Projected tail (SVCostEvaluator): K-qubit engines (4 slots each; 1 GiB in total at K = 24) on which the blocks of the
+# window are optimised once the remaining gates touch at most K qubits.  B200AQC_PROJECT=0 disables.
+PROJECT_QUBITS = (16, 20, 24)
 
 
 class DeviceStatevector:
@@ -197,7 +201,13 @@ class B200SVBackend(_SVBase):
                 # small extra contexts for the compact bra <L| (see SVCostEvaluator)
                 sizes = sorted({min(k, num_qubits - 2) for k in COMPACT_QUBITS})
                 self._compact = [SVEngine(k, device=self.device, n_slots=1) for k in sizes]
-            self._evaluator = SVCostEvaluator(self._engine, self._compact)
+            for c in getattr(self, "_projected", None) or []:
+                c.close()
+            self._projected = []
+            if num_qubits > COMPACT_MIN_QUBITS and os.environ.get("B200AQC_PROJECT", "1") != "0":
+                self._projected = [SVEngine(k, device=self.device, n_slots=4) for k in PROJECT_QUBITS
+                                   if COMPACT_MIN_QUBITS <= k <= num_qubits - SVCostEvaluator.PROJECT_MIN_SAVING]
+            self._evaluator = SVCostEvaluator(self._engine, self._compact, self._projected)
             self._state_version += 1
             self._last_run_key = None
             self._last_run_insts = None

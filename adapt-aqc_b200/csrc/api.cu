@@ -814,6 +814,31 @@ int b200_sv_inner2_gather(b200_ctx* ctx, int r_slot, const void* compact_state, 
     return 0;
 }
 
+int b200_sv_gather(b200_ctx* ctx, int slot, const int32_t* qmap, int K, void* dst) {
+    if (check_slot(ctx, slot)) return -1;
+    if (!qmap || !dst) return set_error("null pointer");
+    const int n = ctx->nq;
+    if (K < 1 || K > n || K > 40) return set_error("gather: K out of range");
+    QMap qm;
+    uint64_t seen = 0;
+    for (int b = 0; b < K; ++b) {
+        if (qmap[b] < 0 || qmap[b] >= n || (seen >> qmap[b] & 1)) return set_error("gather: qmap must hold distinct qubits of the register");
+        seen |= 1ull << qmap[b];
+        qm.q[b] = qmap[b];
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Timer tm(ctx);
+    {
+        KScope ks(ctx, B200_PROF_INNER);
+        sv_gather_kernel<<<red_grid(ctx, 1ull << K), RED_THREADS, 0, ctx->stream>>>((const double2*)ctx->slots[slot], qm, K, (double2*)dst);
+    }
+    CUDA_TRY(cudaGetLastError());
+    ctx->counters[3] += 32ull << K;
+    ctx->counters[6] += 1;
+    tm.stop();
+    return 0;
+}
+
 int b200_sv_download(b200_ctx* ctx, int slot, uint64_t offset, uint64_t count, double* host) {
     if (check_slot(ctx, slot)) return -1;
     if (offset + count > (1ull << ctx->nq)) return set_error("download range out of bounds");

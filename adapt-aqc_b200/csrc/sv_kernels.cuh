@@ -1016,4 +1016,18 @@ sv_inner2_gather_kernel(const double2* __restrict__ ell, const int K, const doub
     block_sum_store<INNER2_WIDTH>(v, partial + (size_t)blockIdx.x * INNER2_WIDTH);
 }
 
+// K6d.  Projection of a state onto |0> of every qubit OUTSIDE qmap: phi[c] = psi[deposit(c)], c < 2^K.
+// When every remaining gate of the window acts only on the K qubits of qmap, <0..0| W |psi> equals
+// <0_K| W_K |phi>: the rest of the optimisation runs on a 2^K-amplitude state (sv_engine "projected tail").
+__global__ void __launch_bounds__(RED_THREADS)
+sv_gather_kernel(const double2* __restrict__ psi, const QMap qm, const int K, double2* __restrict__ phi) {
+    const uint64_t dim = 1ull << K;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < dim; c += stride) {
+        uint64_t x = 0;
+        for (int b = 0; b < K; ++b) x |= ((c >> b) & 1ull) << qm.q[b];
+        phi[c] = psi[x];
+    }
+}
+
 }  // namespace b200

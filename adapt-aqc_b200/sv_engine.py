@@ -141,6 +141,17 @@ class SVEngine:
                                               len(qm), qm.ctypes.data, int(qa), int(qb), dptr(out)))
         return out.view(np.complex128).reshape(4, 4).copy()
 
+    def gather(self, slot, qmap, dst_engine, dst_slot):
+        """dst[c] = slot[deposit(c, qmap)]: the state projected onto |0> of every qubit outside qmap, into
+        slot `dst_slot` of the len(qmap)-qubit engine `dst_engine` (same device).  Synchronous."""
+        qm = np.ascontiguousarray(np.asarray(qmap, dtype=np.int32))
+        if len(qm) != dst_engine.num_qubits:
+            raise ValueError("qmap must name one qubit per qubit of the destination engine")
+        dst_engine.sync()
+        check(self._lib.b200_sv_gather(self._ctx, int(slot), qm.ctypes.data, len(qm),
+                                       ctypes.c_void_p(dst_engine.device_ptr(dst_slot))))
+        self.sync()
+
     def download(self, slot, offset=0, count=None):
         count = (1 << self.num_qubits) - offset if count is None else count
         host = np.empty(count, dtype=np.complex128)
@@ -302,9 +313,21 @@ class SVCostEvaluator:
     """
 
     REFRESH_MOVES = 256  # rebuild R / dense L from scratch after this many incremental moves
+    PROJECT_MIN_SAVING = 3  # project only onto engines at least this many qubits smaller than the register
 
-    def __init__(self, engine, compact=None):
+    def __init__(self, engine, compact=None, projected=None):
+        """projected: optional K-qubit engines (4 slots each, same device) for the PROJECTED TAIL: once the
+        gates of window[m:] act on at most K qubits S, <0|W|base> = <0_S| W[m:] |phi> with
+        |phi> = <0_rest| W[:m] |base> (a gather of 2^K amplitudes of R, ``gather``), so every evaluation
+        of the blocks in window[m:] -- R/L moves, transfer passes -- runs on the 2^K-amplitude engine
+        through a nested evaluator, and no sweep over the 2^n register is needed while the optimiser
+        stays in the tail."""
         self.eng = engine
+        self.projected = sorted(projected or [], key=lambda e: e.num_qubits)
+        self._sub = {}                # id(projected engine) -> nested SVCostEvaluator
+        self._proj_state = None       # (engine id, m, qmap) of the phi currently held by that engine
+        self._split_key, self._split = None, None
+        self._tail_cache = None       # (proj key, remapped tail window)
         # one or several compact engines of increasing size; the smallest that fits is used
         if compact is None:
             self.compacts = []
@@ -324,7 +347,7 @@ class SVCostEvaluator:
         self.r_moves = self.l_moves = 0
         self._part_key, self._part = None, None
         self.stats = {"rebuild_R": 0, "rebuild_L": 0, "moves_R": 0, "moves_L": 0, "compact_L": 0, "t_passes": 0,
-                      "t_gathers": 0, "host_evals": 0, "evals": 0}
+                      "t_gathers": 0, "host_evals": 0, "evals": 0, "projections": 0, "projected_evals": 0}
 
     # ---- prefix (target) state ----
     def set_base(self, key, prefix_stream):
@@ -336,6 +359,10 @@ class SVCostEvaluator:
         self.invalidate()
 
     def invalidate(self):
+        self._proj_state = None
+        for sub in self._sub.values():
+            sub.base_key = None
+            sub.invalidate()
         self.window = None
         self.cut = None
         self.pair = None
@@ -369,6 +396,71 @@ class SVCostEvaluator:
             if b[0] <= target < b[1]:
                 return b
         raise AssertionError("block partition does not cover the window")
+
+    # ---- projected tail ----
+    def _tail_split(self, window):
+        """(m, qubits): window[m:] is the longest block-aligned tail whose support fits the largest
+        projected engine; None if there is no such engine or no saving."""
+        if not self.projected:
+            return None
+        blocks = self._blocks(window)
+        if self._split_key is not self._part_key:
+            kmax = self.projected[-1].num_qubits
+            supp, m = set(), len(window)
+            for (s0, _, sp) in reversed(blocks):
+                new = supp | set(sp)
+                if len(new) > kmax:
+                    break
+                supp, m = new, s0
+            ok = m < len(window) and len(supp) + self.PROJECT_MIN_SAVING <= self.eng.num_qubits
+            self._split_key, self._split = self._part_key, ((m, sorted(supp)) if ok else None)
+        return self._split
+
+    def _projected(self, window, target, changed):
+        """If window[target] lies in the projected tail: (nested evaluator, tail window in the engine's qubit
+        numbering, changed indices relative to the tail | None, m); else None.  Makes phi valid."""
+        split = self._tail_split(window)
+        if split is None or target < split[0]:
+            return None
+        m, supp = split
+        fits = [e for e in self.projected if e.num_qubits >= len(supp) and
+                e.num_qubits + self.PROJECT_MIN_SAVING <= self.eng.num_qubits]
+        if not fits:
+            return None
+        peng = fits[0]
+        free = [q for q in range(self.eng.num_qubits) if q not in set(supp)]
+        qmap = supp + free[:peng.num_qubits - len(supp)]     # padded qubits carry no gate: <0| projects them out
+        sub = self._sub.get(id(peng))
+        if sub is None:
+            # (no compact-bra engines for the nested evaluator: they are owned by this one, and a pass over
+            # 2^K amplitudes is cheap anyway)
+            sub = self._sub[id(peng)] = SVCostEvaluator(peng)
+        r_changed = self._update_R(window, m) if m > 0 else False
+        state = (id(peng), m, tuple(qmap), self.base_key)
+        if r_changed or state != self._proj_state:
+            self.eng.gather(SLOT_R if m > 0 else SLOT_BASE, qmap, peng, SLOT_BASE)
+            sub.base_key = ("projected", self.stats["projections"])
+            sub.invalidate()
+            self._proj_state = state
+            self.stats["projections"] += 1
+            self._tail_cache = None
+        # the dense evaluator's T / window no longer describe the circuit once the tail is edited here
+        self.T = None
+        self.window = None
+        pos = {q: c for c, q in enumerate(qmap)}
+        tc = self._tail_cache
+        sub_changed = None
+        if (tc is not None and tc[0] == state and len(tc[1]) == len(window) - m and changed is not None
+                and all(i >= m for i in changed)):
+            tail = tc[1]
+            for i in changed:
+                e = window[i]
+                tail[i - m] = (e[0], pos[e[1]], pos[e[2]] if e[2] >= 0 else -1) + tuple(e[3:])
+            sub_changed = [i - m for i in changed]
+        else:
+            tail = [(e[0], pos[e[1]], pos[e[2]] if e[2] >= 0 else -1) + tuple(e[3:]) for e in window[m:]]
+            self._tail_cache = (state, tail)
+        return sub, tail, sub_changed, m
 
     # ---- R: prefix applied to the base ----
     def _update_R(self, new, b0):
@@ -494,6 +586,13 @@ class SVCostEvaluator:
         if len(window) == 0:
             self.invalidate()
             return self.eng.amp(SLOT_BASE, 0)
+        if self.projected:
+            target = max(changed) if changed else (len(window) - 1 if focus is None else min(max(focus, 0), len(window) - 1))
+            pj = self._projected(window, target, changed)
+            if pj is not None:
+                sub, tail, sub_changed, m = pj
+                self.stats["projected_evals"] += 1
+                return sub.amp0(tail, focus=None if focus is None else max(focus - m, 0), changed=sub_changed)
         if (changed is not None and self.T is not None and self.window is not None and len(self.window) == len(window)
                 and all(self.cut[0] <= i < self.cut[1] and window[i][1] == self.window[i][1]
                         and window[i][2] == self.window[i][2] for i in changed)):
@@ -507,6 +606,13 @@ class SVCostEvaluator:
     # ---- batched API (K6): every shift value of one gate from one transfer pass ----
     def shift_amplitudes(self, window, k, candidates):
         """<0|psi> for each replacement 2x2 matrix in `candidates` at window position k."""
+        if self.projected:
+            pj = self._projected(window, k, None)
+            if pj is not None:
+                sub, tail, _, m = pj
+                self.stats["evals"] += len(candidates)
+                self.stats["projected_evals"] += len(candidates)
+                return sub.shift_amplitudes(tail, k - m, candidates)
         for b in self._blocks(window):
             if b[0] <= k < b[1]:
                 self._prepare_block(window, b)

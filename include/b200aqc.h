@@ -170,6 +170,11 @@ int b200_sv_inner2(b200_ctx *ctx, int l_slot, int r_slot, int qa, int qb, double
 int b200_sv_inner2_gather(b200_ctx *ctx, int r_slot, const void *compact_state, int K, const int32_t *qmap,
                           int qa, int qb, double out[32]);
 
+/* Projection onto |0> of every qubit outside qmap: dst[c] = slot[deposit(c, qmap)], c < 2^K (dst = device
+ * memory of 2^K amplitudes on the same device, e.g. a slot of a K-qubit context).  Once the remaining gates
+ * of the window (utils/cost_minimiser.py:267-368 walks them layer by layer) act only on these K qubits, every
+ * further cost evaluation <0|W|psi> = <0_K|W_K|dst> runs on the 2^K-amplitude state. */
+int b200_sv_gather(b200_ctx *ctx, int slot, const int32_t *qmap, int K, void *dst);
 /* Host <-> device transfer of `count` amplitudes starting at `offset` (tests, small n, target
  * upload).  Replaces the Statevector object's `.data`. */
 int b200_sv_download(b200_ctx *ctx, int slot, uint64_t offset, uint64_t count, double *host);

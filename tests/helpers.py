@@ -191,6 +191,14 @@ class FakeEngine:
         self.inners -= 1
         return out
 
+    def gather(self, slot, qmap, dst_engine, dst_slot):
+        """numpy restatement of b200_sv_gather."""
+        c = np.arange(1 << len(qmap))
+        x = np.zeros_like(c)
+        for b, q in enumerate(qmap):
+            x |= ((c >> b) & 1) << q
+        dst_engine.slots[dst_slot][...] = self.slots[slot][x]
+
     def device_ptr(self, slot):
         return 0
 

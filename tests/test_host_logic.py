@@ -17,7 +17,8 @@ from helpers import FakeEngine, brickwork, circuit_from_gates, compile_option_ca
 
 @pytest.fixture
 def fake_backend(emu, monkeypatch, request):
-    compact_k = getattr(request, "param", None)
+    param = getattr(request, "param", None)
+    compact_k, proj_k = param if isinstance(param, tuple) else (param, None)
 
     def _get_engine(self, num_qubits):
         if self._engine is None or self._engine.num_qubits != num_qubits:
@@ -25,7 +26,10 @@ def fake_backend(emu, monkeypatch, request):
             compact = None
             if compact_k is not None and num_qubits > compact_k:
                 compact = FakeEngine(emu, compact_k, n_slots=1)
-            self._evaluator = SVCostEvaluator(self._engine, compact)
+            projected = None
+            if proj_k is not None and num_qubits >= proj_k + SVCostEvaluator.PROJECT_MIN_SAVING:
+                projected = [FakeEngine(emu, proj_k, n_slots=4)]
+            self._evaluator = SVCostEvaluator(self._engine, compact, projected)
             self._state_version += 1
             self._last_run_key = None
         return self._engine
@@ -33,7 +37,7 @@ def fake_backend(emu, monkeypatch, request):
     return B200SVBackend()
 
 
-@pytest.mark.parametrize("fake_backend", [None, 6], indirect=True)
+@pytest.mark.parametrize("fake_backend", [None, 6, (None, 8), (4, 8)], indirect=True)
 @pytest.mark.parametrize("n", [4, 12])
 def test_incremental_evaluator_equals_full_resimulation(fake_backend, n):
     rng = np.random.default_rng(50 + n)
@@ -111,7 +115,7 @@ def test_structure_change_falls_back_to_resimulation(fake_backend):
                                ocomp.backend.measure_qubit_expectation_values(ocomp), atol=1e-12)
 
 
-@pytest.mark.parametrize("fake_backend", [None, 2], indirect=True)
+@pytest.mark.parametrize("fake_backend", [None, 2, (None, 2), (None, 3)], indirect=True)
 @pytest.mark.parametrize("batched", [False, True])
 def test_compile_decisions_match_oracle_backend(fake_backend, batched):
     ghz = Circuit(4); ghz.h(0)
@@ -141,7 +145,7 @@ def test_bench_step_counts_220_evaluations(fake_backend):
         assert comp.cost_evaluation_counter - before == 4 * 7 + 64 * 3
 
 
-@pytest.mark.parametrize("fake_backend", [2], indirect=True)
+@pytest.mark.parametrize("fake_backend", [2, (2, 3)], indirect=True)
 @pytest.mark.parametrize("case", compile_option_cases(), ids=lambda c: c[0])
 def test_compile_options_make_the_same_decisions(fake_backend, case):
     name, target, kw, cfg = case
