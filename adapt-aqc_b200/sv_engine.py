@@ -372,9 +372,15 @@ class SVCostEvaluator:
         self.lkey = None
 
     # ---- block bookkeeping ----
-    def _blocks(self, window):
+    def _blocks(self, window, changed=None):
+        """Block partition of `window`, cached on the qubits of its gates.  `changed` (indices that differ
+        from the window of the previous call): only those entries are checked against the cached structure."""
+        pk = self._part_key
+        if (changed is not None and pk is not None and len(pk) == len(window)
+                and all(pk[i] == (window[i][1], window[i][2]) for i in changed)):
+            return self._part
         key = tuple((e[1], e[2]) for e in window)
-        if key != self._part_key:
+        if key != pk:
             self._part_key, self._part = key, partition_blocks(window)
         return self._part
 
@@ -398,12 +404,12 @@ class SVCostEvaluator:
         raise AssertionError("block partition does not cover the window")
 
     # ---- projected tail ----
-    def _tail_split(self, window):
+    def _tail_split(self, window, changed=None):
         """(m, qubits): window[m:] is the longest block-aligned tail whose support fits the largest
         projected engine; None if there is no such engine or no saving."""
         if not self.projected:
             return None
-        blocks = self._blocks(window)
+        blocks = self._blocks(window, changed)
         if self._split_key is not self._part_key:
             kmax = self.projected[-1].num_qubits
             supp, m = set(), len(window)
@@ -419,7 +425,7 @@ class SVCostEvaluator:
     def _projected(self, window, target, changed):
         """If window[target] lies in the projected tail: (nested evaluator, tail window in the engine's qubit
         numbering, changed indices relative to the tail | None, m); else None.  Makes phi valid."""
-        split = self._tail_split(window)
+        split = self._tail_split(window, changed)
         if split is None or target < split[0]:
             return None
         m, supp = split
