@@ -213,6 +213,10 @@ class B200SVBackend(_SVBase):
             self._last_run_insts = None
         return self._engine
 
+    def engines(self):
+        """Every device context this backend launches kernels on (the register + the compact / projected ones)."""
+        return [e for e in [self._engine] + list(self._compact or []) + list(getattr(self, "_projected", None) or []) if e is not None]
+
     def _prefix_key(self, compiler):
         lhs = compiler.lhs_gate_count
         ref = self._compiler_ref() if self._compiler_ref is not None else None

@@ -327,6 +327,7 @@ class SVCostEvaluator:
         self._sub = {}                # id(projected engine) -> nested SVCostEvaluator
         self._proj_state = None       # (engine id, m, qmap) of the phi currently held by that engine
         self._split_key, self._split = None, None
+        self._split_info = None       # (split, (engine, qmap, position of each qubit, nested evaluator) | None)
         self._tail_cache = None       # (proj key, remapped tail window)
         # one or several compact engines of increasing size; the smallest that fits is used
         if compact is None:
@@ -429,22 +430,34 @@ class SVCostEvaluator:
         if split is None or target < split[0]:
             return None
         m, supp = split
-        fits = [e for e in self.projected if e.num_qubits >= len(supp) and
-                e.num_qubits + self.PROJECT_MIN_SAVING <= self.eng.num_qubits]
-        if not fits:
+        info = self._split_info
+        if info is None or info[0] is not split:
+            fits = [e for e in self.projected if e.num_qubits >= len(supp) and
+                    e.num_qubits + self.PROJECT_MIN_SAVING <= self.eng.num_qubits]
+            if not fits:
+                self._split_info = (split, None)
+                return None
+            peng = fits[0]
+            used = set(supp)
+            free = [q for q in range(self.eng.num_qubits) if q not in used]
+            qmap = supp + free[:peng.num_qubits - len(supp)]     # padded qubits carry no gate: <0| projects them out
+            sub = self._sub.get(id(peng))
+            if sub is None:
+                # (no compact-bra engines for the nested evaluator: they are owned by this one, and a pass over
+                # 2^K amplitudes is cheap anyway)
+                sub = self._sub[id(peng)] = SVCostEvaluator(peng)
+            info = self._split_info = (split, (peng, tuple(qmap), {q: c for c, q in enumerate(qmap)}, sub))
+        if info[1] is None:
             return None
-        peng = fits[0]
-        free = [q for q in range(self.eng.num_qubits) if q not in set(supp)]
-        qmap = supp + free[:peng.num_qubits - len(supp)]     # padded qubits carry no gate: <0| projects them out
-        sub = self._sub.get(id(peng))
-        if sub is None:
-            # (no compact-bra engines for the nested evaluator: they are owned by this one, and a pass over
-            # 2^K amplitudes is cheap anyway)
-            sub = self._sub[id(peng)] = SVCostEvaluator(peng)
-        r_changed = self._update_R(window, m) if m > 0 else False
-        state = (id(peng), m, tuple(qmap), self.base_key)
+        peng, qmap, pos, sub = info[1]
+        if (m > 0 and changed is not None and self._proj_state is not None and self._proj_state[1] == m
+                and self.rwin is not None and len(self.rwin) == m and all(i >= m for i in changed)):
+            r_changed = False        # only tail gates changed since phi was gathered from this R
+        else:
+            r_changed = self._update_R(window, m) if m > 0 else False
+        state = (id(peng), m, qmap, self.base_key)
         if r_changed or state != self._proj_state:
-            self.eng.gather(SLOT_R if m > 0 else SLOT_BASE, qmap, peng, SLOT_BASE)
+            self.eng.gather(SLOT_R if m > 0 else SLOT_BASE, list(qmap), peng, SLOT_BASE)
             sub.base_key = ("projected", self.stats["projections"])
             sub.invalidate()
             self._proj_state = state
@@ -453,7 +466,6 @@ class SVCostEvaluator:
         # the dense evaluator's T / window no longer describe the circuit once the tail is edited here
         self.T = None
         self.window = None
-        pos = {q: c for c, q in enumerate(qmap)}
         tc = self._tail_cache
         sub_changed = None
         if (tc is not None and tc[0] == state and len(tc[1]) == len(window) - m and changed is not None

@@ -279,6 +279,7 @@ def bench_compile(args, device, cpu_evals_per_s=None):
         eng = backend._engine
         eng.sync()
         c0 = eng.counters()
+        l0 = sum(e.counters()["launches"] for e in backend.engines())
         eng.profile(True)
         t0 = time.perf_counter()
         res = comp.compile()
@@ -287,10 +288,11 @@ def bench_compile(args, device, cpu_evals_per_s=None):
         prof = eng.profile_read()
         eng.profile(False)
         c1 = eng.counters()
+        l1 = sum(e.counters()["launches"] for e in backend.engines())
         layers = len(res.qubit_pair_history)
         evals = int(comp.cost_evaluation_counter)
         r = {"wall_s": wall, "layers": layers, "cost_evaluations": evals, "final_global_cost": float(res.global_cost_history[-1]),
-             "overlap": float(res.overlap), "evals_per_s": evals / wall, "gpu_launches": int(c1["launches"] - c0["launches"]),
+             "overlap": float(res.overlap), "evals_per_s": evals / wall, "gpu_launches": int(l1 - l0),
              "sweeps": int(c1["sweeps"] - c0["sweeps"]),
              "kernel_ms": {k: round(v[0], 2) for k, v in prof.items() if v[1]},
              "kernel_launches": {k: int(v[1]) for k, v in prof.items() if v[1]}}
@@ -458,7 +460,12 @@ def main():
         one_step(comp)
     eng.sync()
     sampler = ClockSampler(local_rank)
+
+    def all_launches():
+        return sum(e.counters()["launches"] for e in backend.engines())
+
     c0 = eng.counters()
+    l0 = all_launches()
     e0 = comp.cost_evaluation_counter
     barrier()
     sampler.start()
@@ -475,7 +482,7 @@ def main():
     clocks = sampler.stop()
     c1 = eng.counters()
     evals = comp.cost_evaluation_counter - e0
-    launches = c1["launches"] - c0["launches"]
+    launches = all_launches() - l0       # register engine + the compact / projected engines
 
     # ---- e2e leg: the reference-facing one-scalar-per-call interface ----------------------------
     backend2 = backend            # same engine / same cached U|0>: the interface is what changes
