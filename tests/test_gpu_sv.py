@@ -435,3 +435,37 @@ def test_c3_size_properties():
     np.testing.assert_allclose(rho[1], bell, atol=1e-12)
     np.testing.assert_allclose(rho[2], np.eye(4) / 4, atol=1e-12)
     eng.close()
+
+
+def test_c3_evaluator_equals_device_resimulation():
+    """BASELINE config C3 at full size: the incremental evaluator (block transfer matrices, compact bra,
+    projected tail on the 16/20/24-qubit contexts) against a from-scratch simulation of the whole
+    circuit on the device -- itself parity-tested against the oracle at the sizes the oracle can run.
+    Edits walk over head layers (dense path) and tail layers (projected path) and back."""
+    n = 28
+    _, trng = brickwork(n, 1, seed=1234)
+    layers = thin_ansatz(n, 16, trng)
+    target = Circuit(n)
+    for q in range(n):
+        target.ry(float(trng.uniform(0.5, 2.5)), q)            # dense superposition on every qubit
+    target.data.extend(layers.copy().data)
+    ansatz = target.inverse()            # exact solution: after small edits the costs are of order 0.1
+    backend = B200SVBackend()
+    comp = AdaptCompiler(target, backend=backend)
+    comp.full_circuit.data.extend(ansatz.copy().data)
+    rng = np.random.default_rng(5)
+    lo, hi = comp.variational_circuit_range()
+    rot = [i for i in range(lo, hi) if comp.full_circuit.data[i].operation.name in ("rx", "ry", "rz")]
+    from adapt_aqc_b200.minimiser import replace_1q_gate
+    visits = [rot[0], rot[1], rot[-1], rot[-2], rot[len(rot) // 2], rot[5], rot[-9], rot[2], rot[-1]]
+    for idx in visits:
+        for rep in range(2):
+            replace_1q_gate(comp.full_circuit, idx, ["rx", "ry", "rz"][int(rng.integers(3))], float(rng.uniform(-0.6, 0.6)))
+            got = comp.evaluate_cost()
+        sv = backend.simulator.run(comp.full_circuit).result().get_statevector()      # full re-simulation
+        ref = 1 - abs(sv[0]) ** 2
+        assert abs(got - ref) < 1e-10, (idx, got, ref)
+        assert 1e-3 < ref < 1 - 1e-6, ref          # the costs stay away from both trivial values
+    st = backend._evaluator.stats
+    assert st["projected_evals"] > 0 and st["t_passes"] + st["t_gathers"] > 0
+    backend._engine.close()
