@@ -102,8 +102,15 @@ int grid_for(size_t work, int threads = 256) { return (int)std::max<size_t>(1, s
 
 int gemm(b200_ctx* ctx, const GemmArgs& g) {
     if (g.M <= 0 || g.N <= 0) return 0;
-    dim3 grid((g.N + GM_TILE - 1) / GM_TILE, (g.M + GM_TILE - 1) / GM_TILE);
-    {
+    // 64 x 64 tiles with a register-prefetch pipeline once the problem fills the machine with them; the
+    // 32 x 32 kernel keeps more CTAs in flight on small ones
+    const long long tiles64 = (long long)((g.N + G2_TILE - 1) / G2_TILE) * ((g.M + G2_TILE - 1) / G2_TILE);
+    if (tiles64 >= ctx->num_sms / 4 && g.K >= 2 * G2_K && !std::getenv("B200AQC_GEMM32")) {
+        dim3 grid((g.N + G2_TILE - 1) / G2_TILE, (g.M + G2_TILE - 1) / G2_TILE);
+        MScope ms(ctx);
+        zgemm_dmma64_kernel<<<grid, 256, 0, ctx->stream>>>(g);
+    } else {
+        dim3 grid((g.N + GM_TILE - 1) / GM_TILE, (g.M + GM_TILE - 1) / GM_TILE);
         MScope ms(ctx);
         zgemm_dmma_kernel<<<grid, 128, 0, ctx->stream>>>(g);
     }

@@ -76,23 +76,36 @@ zgemm_dmma_kernel(const GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) { cre[i][j][0] = cre[i][j][1] = cim[i][j][0] = cim[i][j][1] = 0.0; }
 
-    for (int k0 = 0; k0 < g.K; k0 += GK_TILE) {
-        // stage A (32 x 16) and B (16 x 32), zero-padded at the edges
-        for (int e = tid; e < GM_TILE * GK_TILE; e += 128) {
+    // The next K tile travels global -> registers while the DMMAs of the current one are issued (these GEMMs
+    // are skinny: few CTAs, one K loop of 16-64 tiles each -- exposed load latency was most of the time).
+    double2 pa[4], pb[4];
+    auto fetch = [&](const int k0) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int e = tid + 128 * t;
             const int r = e / GK_TILE, c = e % GK_TILE;
-            double2 v = make_double2(0.0, 0.0);
-            if (m0 + r < g.M && k0 + c < g.K) v = g.A[(long long)(m0 + r) * g.sam + (long long)(k0 + c) * g.sak];
-            As_re[r][c] = v.x;
-            As_im[r][c] = g.conj_a ? -v.y : v.y;
+            pa[t] = make_double2(0.0, 0.0);
+            if (m0 + r < g.M && k0 + c < g.K) pa[t] = g.A[(long long)(m0 + r) * g.sam + (long long)(k0 + c) * g.sak];
+            const int rb = e / GM_TILE, cb = e % GM_TILE;
+            pb[t] = make_double2(0.0, 0.0);
+            if (k0 + rb < g.K && n0 + cb < g.N) pb[t] = g.B[(long long)(k0 + rb) * g.sbk + (long long)(n0 + cb) * g.sbn];
         }
-        for (int e = tid; e < GK_TILE * GM_TILE; e += 128) {
-            const int r = e / GM_TILE, c = e % GM_TILE;
-            double2 v = make_double2(0.0, 0.0);
-            if (k0 + r < g.K && n0 + c < g.N) v = g.B[(long long)(k0 + r) * g.sbk + (long long)(n0 + c) * g.sbn];
-            Bs_re[r][c] = v.x;
-            Bs_im[r][c] = v.y;
+    };
+    auto stage = [&]() {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int e = tid + 128 * t;
+            As_re[e / GK_TILE][e % GK_TILE] = pa[t].x;
+            As_im[e / GK_TILE][e % GK_TILE] = g.conj_a ? -pa[t].y : pa[t].y;
+            Bs_re[e / GM_TILE][e % GM_TILE] = pb[t].x;
+            Bs_im[e / GM_TILE][e % GM_TILE] = pb[t].y;
         }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < g.K; k0 += GK_TILE) {
+        stage();
         __syncthreads();
+        if (k0 + GK_TILE < g.K) fetch(k0 + GK_TILE);
 #pragma unroll
         for (int kk = 0; kk < GK_TILE; kk += 4) {
             double are[2], aim[2], bre[2], bim[2];
@@ -130,6 +143,108 @@ zgemm_dmma_kernel(const GemmArgs g) {
                     if (g.rowscale) s *= g.rowscale[m % g.rs_mod];
                     if (g.colscale) s *= g.colscale[n % g.cs_mod];
                     double2 v = make_double2(cre[i][j][c] * s, cim[i][j][c] * s);
+                    double2* dst = g.C + (long long)m * g.scm + (long long)n * g.scn;
+                    if (g.accumulate) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+                    *dst = v;
+                }
+            }
+}
+
+// Large-problem variant: 64 x 64 CTA tile, 8 warps (4 x 2, each a 16 x 32 sub-tile = 2 x 4 DMMA fragments,
+// 32 accumulator doubles per thread), K tile 16.  The next K tile is fetched from global memory into
+// registers BEFORE the DMMAs of the current one are issued and written to shared memory after them, so
+// the global-load latency hides behind the tensor work.  Row strides 20 / 68 doubles make every half-warp
+// fragment load hit 16 distinct 8-byte banks.  Per k4-step and warp: 12 LDS.64 feed 32 DMMAs.
+constexpr int G2_TILE = 64;
+constexpr int G2_K = 16;
+constexpr int G2_LDA = G2_K + 4;      // 20
+constexpr int G2_LDB = G2_TILE + 4;   // 68
+
+__global__ void __launch_bounds__(256, 2)
+zgemm_dmma64_kernel(const GemmArgs g) {
+    __shared__ double As_re[G2_TILE][G2_LDA], As_im[G2_TILE][G2_LDA];
+    __shared__ double Bs_re[G2_K][G2_LDB], Bs_im[G2_K][G2_LDB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * G2_TILE, n0 = blockIdx.x * G2_TILE;
+    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;
+    double cre[2][4][2], cim[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { cre[i][j][0] = cre[i][j][1] = cim[i][j][0] = cim[i][j][1] = 0.0; }
+
+    // element (r, c) of the A tile handled by this thread in pass t: the unit-stride dimension runs fastest
+    const bool a_k_fast = g.sak <= g.sam;     // A(m,k): k contiguous (row-major) or m contiguous
+    const bool b_n_fast = g.sbn <= g.sbk;
+    double2 pa[4], pb[4];
+    auto fetch = [&](const int k0) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int e = tid + 256 * t;
+            const int r = a_k_fast ? e / G2_K : e % G2_TILE, c = a_k_fast ? e % G2_K : e / G2_TILE;
+            pa[t] = make_double2(0.0, 0.0);
+            if (m0 + r < g.M && k0 + c < g.K) pa[t] = g.A[(long long)(m0 + r) * g.sam + (long long)(k0 + c) * g.sak];
+            const int rb = b_n_fast ? e / G2_TILE : e % G2_K, cb = b_n_fast ? e % G2_TILE : e / G2_K;
+            pb[t] = make_double2(0.0, 0.0);
+            if (k0 + rb < g.K && n0 + cb < g.N) pb[t] = g.B[(long long)(k0 + rb) * g.sbk + (long long)(n0 + cb) * g.sbn];
+        }
+    };
+    auto stage = [&]() {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int e = tid + 256 * t;
+            const int r = a_k_fast ? e / G2_K : e % G2_TILE, c = a_k_fast ? e % G2_K : e / G2_TILE;
+            As_re[r][c] = pa[t].x;
+            As_im[r][c] = g.conj_a ? -pa[t].y : pa[t].y;
+            const int rb = b_n_fast ? e / G2_TILE : e % G2_K, cb = b_n_fast ? e % G2_TILE : e / G2_K;
+            Bs_re[rb][cb] = pb[t].x;
+            Bs_im[rb][cb] = pb[t].y;
+        }
+    };
+    fetch(0);
+    stage();
+    __syncthreads();
+    for (int k0 = 0; k0 < g.K; k0 += G2_K) {
+        const bool more = k0 + G2_K < g.K;
+        if (more) fetch(k0 + G2_K);                 // in flight during the DMMAs below
+#pragma unroll
+        for (int kk = 0; kk < G2_K; kk += 4) {
+            double are[2], aim[2], bre[4], bim[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                are[i] = As_re[wm + 8 * i + (lane >> 2)][kk + (lane & 3)];
+                aim[i] = As_im[wm + 8 * i + (lane >> 2)][kk + (lane & 3)];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                bre[j] = Bs_re[kk + (lane & 3)][wn + 8 * j + (lane >> 2)];
+                bim[j] = Bs_im[kk + (lane & 3)][wn + 8 * j + (lane >> 2)];
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dmma884(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
+                    dmma884(cre[i][j][0], cre[i][j][1], -aim[i], bim[j]);
+                    dmma884(cim[i][j][0], cim[i][j][1], are[i], bim[j]);
+                    dmma884(cim[i][j][0], cim[i][j][1], aim[i], bre[j]);
+                }
+        }
+        __syncthreads();
+        if (more) { stage(); __syncthreads(); }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int m = m0 + wm + 8 * i + (lane >> 2), n = n0 + wn + 8 * j + 2 * (lane & 3) + c;
+                if (m < g.M && n < g.N) {
+                    double sc = 1.0;
+                    if (g.rowscale) sc *= g.rowscale[m % g.rs_mod];
+                    if (g.colscale) sc *= g.colscale[n % g.cs_mod];
+                    double2 v = make_double2(cre[i][j][c] * sc, cim[i][j][c] * sc);
                     double2* dst = g.C + (long long)m * g.scm + (long long)n * g.scn;
                     if (g.accumulate) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
                     *dst = v;
