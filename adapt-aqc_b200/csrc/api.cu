@@ -814,29 +814,43 @@ int b200_sv_inner2_gather(b200_ctx* ctx, int r_slot, const void* compact_state, 
     return 0;
 }
 
-int b200_sv_gather(b200_ctx* ctx, int slot, const int32_t* qmap, int K, void* dst) {
+static int gather_impl(b200_ctx* ctx, int slot, const int32_t* qmap, int K, void* dst, int rank_bits, int rank) {
     if (check_slot(ctx, slot)) return -1;
     if (!qmap || !dst) return set_error("null pointer");
     const int n = ctx->nq;
-    if (K < 1 || K > n || K > 40) return set_error("gather: K out of range");
+    if (K < 1 || K > n + rank_bits || K > 40) return set_error("gather: K out of range");
     QMap qm;
     uint64_t seen = 0;
+    uint32_t covered = 0;
     for (int b = 0; b < K; ++b) {
-        if (qmap[b] < 0 || qmap[b] >= n || (seen >> qmap[b] & 1)) return set_error("gather: qmap must hold distinct qubits of the register");
+        if (qmap[b] < 0 || qmap[b] >= n + rank_bits || (seen >> qmap[b] & 1))
+            return set_error("gather: qmap must hold distinct qubits of the register");
         seen |= 1ull << qmap[b];
+        if (qmap[b] >= n) covered |= 1u << (qmap[b] - n);
         qm.q[b] = qmap[b];
     }
+    const int contributes = ((uint32_t)rank & ~covered) == 0 ? 1 : 0;
     CUDA_TRY(cudaSetDevice(ctx->device));
     Timer tm(ctx);
     {
         KScope ks(ctx, B200_PROF_INNER);
-        sv_gather_kernel<<<red_grid(ctx, 1ull << K), RED_THREADS, 0, ctx->stream>>>((const double2*)ctx->slots[slot], qm, K, (double2*)dst);
+        sv_gather_kernel<<<red_grid(ctx, 1ull << K), RED_THREADS, 0, ctx->stream>>>(
+            (const double2*)ctx->slots[slot], qm, K, (double2*)dst, n, (uint32_t)rank & covered, contributes);
     }
     CUDA_TRY(cudaGetLastError());
     ctx->counters[3] += 32ull << K;
     ctx->counters[6] += 1;
     tm.stop();
     return 0;
+}
+
+int b200_sv_gather(b200_ctx* ctx, int slot, const int32_t* qmap, int K, void* dst) {
+    return gather_impl(ctx, slot, qmap, K, dst, 0, 0);
+}
+
+int b200_sv_gather_ranked(b200_ctx* ctx, int slot, const int32_t* qmap, int K, int rank_bits, int rank, void* dst) {
+    if (rank_bits < 0 || rank_bits > 8 || rank < 0 || rank >= (1 << rank_bits)) return set_error("gather: rank out of range");
+    return gather_impl(ctx, slot, qmap, K, dst, rank_bits, rank);
 }
 
 int b200_sv_download(b200_ctx* ctx, int slot, uint64_t offset, uint64_t count, double* host) {

@@ -1019,14 +1019,24 @@ sv_inner2_gather_kernel(const double2* __restrict__ ell, const int K, const doub
 // K6d.  Projection of a state onto |0> of every qubit OUTSIDE qmap: phi[c] = psi[deposit(c)], c < 2^K.
 // When every remaining gate of the window acts only on the K qubits of qmap, <0..0| W |psi> equals
 // <0_K| W_K |phi>: the rest of the optimisation runs on a 2^K-amplitude state (sv_engine "projected tail").
+// Sharded registers (dist_sv): entries of qmap >= n_local name RANK bits.  This rank contributes the
+// amplitudes whose rank bits equal its own (`rank_want` on the covered bits; `contributes` = its other
+// rank bits are all zero) and zeros elsewhere; the ranks' results are summed afterwards.
 __global__ void __launch_bounds__(RED_THREADS)
-sv_gather_kernel(const double2* __restrict__ psi, const QMap qm, const int K, double2* __restrict__ phi) {
+sv_gather_kernel(const double2* __restrict__ psi, const QMap qm, const int K, double2* __restrict__ phi,
+                 const int n_local, const uint32_t rank_want, const int contributes) {
     const uint64_t dim = 1ull << K;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < dim; c += stride) {
         uint64_t x = 0;
-        for (int b = 0; b < K; ++b) x |= ((c >> b) & 1ull) << qm.q[b];
-        phi[c] = psi[x];
+        uint32_t rb = 0;
+        for (int b = 0; b < K; ++b) {
+            const uint64_t bit = (c >> b) & 1ull;
+            const int q = qm.q[b];
+            if (q < n_local) x |= bit << q;
+            else rb |= (uint32_t)bit << (q - n_local);
+        }
+        phi[c] = (contributes && rb == rank_want) ? psi[x] : make_double2(0.0, 0.0);
     }
 }
 

@@ -60,6 +60,17 @@ class TorchComm:
         self.bytes_sent = 0
         self.exchange_ms = 0.0
 
+    def allreduce_engine_slot(self, engine, slot):
+        """Sum slot `slot` of `engine` (a whole small register, replicated per rank) over the ranks, in place."""
+        if hasattr(engine, "slots"):                      # CPU stand-in engine (gloo tests)
+            a = engine.slots[slot]
+            a[...] = self.allreduce_sum(a.view(np.float64)).view(np.complex128)
+            return
+        engine.sync()
+        t = self.torch.as_tensor(_CudaAlias(engine.device_ptr(slot), 2 << engine.num_qubits), device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        self.torch.cuda.synchronize(self.device)
+
     def allreduce_sum(self, arr):
         t = self.torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
@@ -327,6 +338,63 @@ class ShardedStatevector:
         return complex(out[0], out[1])
 
 
+class ShardedEngine:
+    """SVEngine-shaped view of a ShardedStatevector, so that the backend / the incremental evaluator
+    (sv_engine.SVCostEvaluator with dense_blocks = False) can drive a register that spans several GPUs:
+    gate streams, amplitude / <Z> / pair-RDM read-outs, and the PROJECTION of the register onto |0> of all
+    but K qubits (each rank gathers the amplitudes it owns, one all-reduce of 2^K amplitudes assembles them
+    on every rank), after which the optimisation of the tail runs on a K-qubit engine replicated per rank.
+    Every rank must issue the same calls in the same order."""
+
+    def __init__(self, sharded):
+        self.sv = sharded
+        self.num_qubits = sharded.n
+
+    def run(self, dst, src, stream, inverse=False):
+        window = stream.window
+        if window is None:
+            raise ValueError("the sharded engine needs gate streams built with GateStream.from_window / from_circuit")
+        self.sv.run(dst, src, G.invert_window(window) if inverse else window)
+
+    def copy(self, dst, src):
+        self.sv.eng.copy(dst, src)
+        self.sv.perm[dst] = list(self.sv.perm[src])
+
+    def amp(self, slot, index=0):
+        return self.sv.amp(slot, index)
+
+    def expz(self, slot):
+        return self.sv.expz(slot)
+
+    def pair_rdm(self, slot, pairs):
+        return self.sv.pair_rdm(slot, pairs)
+
+    def gather(self, slot, qmap, dst_engine, dst_slot):
+        sv = self.sv
+        phys = [sv.perm[slot][q] for q in qmap]            # positions >= nl are rank bits
+        sv.eng.gather_ranked(slot, phys, sv.g, sv.comm.rank, dst_engine, dst_slot)
+        sv._sync()
+        sv.comm.allreduce_engine_slot(dst_engine, dst_slot)
+
+    def download(self, slot, offset=0, count=None):
+        raise MemoryError("a sharded statevector is not downloaded to one host")
+
+    def sync(self):
+        self.sv._sync()
+
+    def counters(self):
+        return self.sv.eng.counters()
+
+    def profile(self, enable=True):
+        self.sv.eng.profile(enable)
+
+    def profile_read(self):
+        return self.sv.eng.profile_read()
+
+    def close(self):
+        self.sv.eng.close()
+
+
 class _CudaAlias:
     """Lets torch view library-owned device memory (torch.as_tensor over __cuda_array_interface__)."""
 
@@ -383,3 +451,66 @@ def make_gpu_sharded(num_qubits, n_slots=2, staging_bytes=1 << 30, local_rank=0,
     sv.exchange_mode = "peer" if peer_ptrs is not None else "nccl"
     sv._keepalive = (tensors, staging)
     return sv
+
+
+def _sharded_backend_class():
+    from .backends import PROJECT_QUBITS, B200SVBackend
+    from .sv_engine import SVCostEvaluator, SVEngine
+
+    class B200ShardedSVBackend(B200SVBackend):
+        """``B200SVBackend`` for registers larger than one GPU: the statevector is sharded by global qubits over
+        the ranks of the default process group (one process per GPU; every rank runs the same compiler and
+        issues the same backend calls).  Cost evaluations of the blocks in the projected tail run on a
+        K-qubit engine replicated per rank (one gather + all-reduce of 2^K amplitudes per projection); blocks
+        outside it re-simulate the window from the resident U|0> (fused sweeps + peer-memory exchanges);
+        <Z> and pair RDMs are sharded read-outs with one small all-reduce."""
+
+        def __init__(self, local_rank=0, exchange=None):
+            super().__init__(device=local_rank)
+            self.exchange = exchange
+
+        def __getstate__(self):
+            return {"device": self.device, "exchange": self.exchange}
+
+        def __setstate__(self, state):
+            self.__init__(local_rank=state.get("device", 0), exchange=state.get("exchange"))
+
+        def _make_engines(self, num_qubits):
+            """(ShardedEngine, [projected engines]) -- overridden by the CPU tests."""
+            sv = make_gpu_sharded(num_qubits, n_slots=4, local_rank=self.device, exchange=self.exchange)
+            sizes = [k for k in PROJECT_QUBITS if 12 <= k <= min(num_qubits - SVCostEvaluator.PROJECT_MIN_SAVING, sv.nl)]
+            return ShardedEngine(sv), [SVEngine(k, device=self.device, n_slots=4) for k in sizes]
+
+        def overlap_between_circuits(self, circuit1, circuit2):
+            """|<psi1|psi2>|^2 = |<0| U1^+ U2 |0>|^2: both circuits on ONE sharded slot (two independently
+            simulated slots would end up in different qubit layouts), then amplitude 0."""
+            eng = self._get_engine(circuit1.num_qubits)
+            from .sv_engine import SLOT_WORK
+            eng.run(SLOT_WORK, -1, G.GateStream.from_circuit(circuit2))
+            eng.run(SLOT_WORK, SLOT_WORK, G.GateStream.from_circuit(circuit1), inverse=True)
+            self._state_version += 1
+            return np.absolute(eng.amp(SLOT_WORK, 0)) ** 2
+
+        def _get_engine(self, num_qubits):
+            if self._engine is None or self._engine.num_qubits != num_qubits:
+                for e in [self._engine] + list(getattr(self, "_projected", None) or []):
+                    if e is not None:
+                        e.close()
+                self._engine, self._projected = self._make_engines(num_qubits)
+                self._compact = []
+                self._evaluator = SVCostEvaluator(self._engine, None, self._projected)
+                self._evaluator.dense_blocks = False
+                self._state_version += 1
+                self._last_run_key = None
+                self._last_run_insts = None
+            return self._engine
+
+    return B200ShardedSVBackend
+
+
+def __getattr__(name):          # B200ShardedSVBackend is built on first use (keeps `import dist_sv` light)
+    if name == "B200ShardedSVBackend":
+        cls = _sharded_backend_class()
+        globals()[name] = cls
+        return cls
+    raise AttributeError(name)

@@ -86,11 +86,12 @@ def canonical_window(circuit, start=0, stop=None, qmap="auto"):
 class GateStream:
     """Packed gate records + dense-matrix pool, ready for the C-ABI."""
 
-    __slots__ = ("rec", "mats")
+    __slots__ = ("rec", "mats", "window")
 
-    def __init__(self, rec=None, mats=None):
+    def __init__(self, rec=None, mats=None, window=None):
         self.rec = rec if rec is not None else np.zeros(0, dtype=GATE_DTYPE)
         self.mats = mats if mats is not None else np.zeros(0, dtype=np.float64)
+        self.window = window          # the canonical entries the records were packed from (from_window)
 
     def __len__(self):
         return len(self.rec)
@@ -115,7 +116,7 @@ class GateStream:
             q0s[k] = q0
             q1s[k] = q1
             ps[k, 0] = p0; ps[k, 1] = p1; ps[k, 2] = p2
-        return cls(rec, np.concatenate(mats) if mats else None)
+        return cls(rec, np.concatenate(mats) if mats else None, window)
 
     @classmethod
     def from_gates(cls, gates):
@@ -141,6 +142,31 @@ class GateStream:
 
     def mats_ptr(self):
         return self.mats.ctypes.data if len(self.mats) else None
+
+
+_SELF_INVERSE = ("id", "i", "x", "y", "z", "h", "cx", "cz", "swap")
+_INVERSE_NAME = {"s": "sdg", "sdg": "s", "t": "tdg", "tdg": "t"}
+
+
+def invert_window(window):
+    """Canonical entries of the inverse circuit (reversed order, every gate inverted)."""
+    out = []
+    for ent in reversed(window):
+        name, q0, q1, p0, p1, p2, mb = ent
+        if mb is not None:
+            d = 4 if q1 >= 0 else 2
+            m = np.frombuffer(mb, dtype=np.complex128).reshape(d, d)
+            out.append((name, q0, q1, 0.0, 0.0, 0.0, np.ascontiguousarray(m.conj().T).tobytes()))
+        elif name in _SELF_INVERSE:
+            out.append(ent)
+        elif name in ROTATIONS or name in ("u1", "p"):
+            out.append((name, q0, q1, -p0, p1, p2, None))
+        elif name in _INVERSE_NAME:
+            out.append((_INVERSE_NAME[name], q0, q1, p0, p1, p2, None))
+        else:       # u2 / u3 / sx ...: as a dense matrix
+            m = np.asarray(matrix_of_entry(ent), dtype=np.complex128)
+            out.append(("mat1", q0, -1, 0.0, 0.0, 0.0, np.ascontiguousarray(m.conj().T).tobytes()))
+    return out
 
 
 def one_qubit_matrix(name, theta):

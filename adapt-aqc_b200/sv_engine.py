@@ -152,6 +152,14 @@ class SVEngine:
                                        ctypes.c_void_p(dst_engine.device_ptr(dst_slot))))
         self.sync()
 
+    def gather_ranked(self, slot, qmap, rank_bits, rank, dst_engine, dst_slot):
+        """One rank's part of ``gather`` on a register sharded over 2^rank_bits ranks (dist_sv): qmap entries
+        >= num_qubits name rank bits.  Asynchronous on this engine's stream (the caller synchronises)."""
+        qm = np.ascontiguousarray(np.asarray(qmap, dtype=np.int32))
+        dst_engine.sync()
+        check(self._lib.b200_sv_gather_ranked(self._ctx, int(slot), qm.ctypes.data, len(qm), int(rank_bits), int(rank),
+                                              ctypes.c_void_p(dst_engine.device_ptr(dst_slot))))
+
     def download(self, slot, offset=0, count=None):
         count = (1 << self.num_qubits) - offset if count is None else count
         host = np.empty(count, dtype=np.complex128)
@@ -323,6 +331,9 @@ class SVCostEvaluator:
         through a nested evaluator, and no sweep over the 2^n register is needed while the optimiser
         stays in the tail."""
         self.eng = engine
+        # False (sharded registers, dist_sv.ShardedEngine): no dense bra / transfer passes over the register --
+        # blocks outside the projected tail are evaluated by re-simulating the window from the base state
+        self.dense_blocks = True
         self.projected = sorted(projected or [], key=lambda e: e.num_qubits)
         self._sub = {}                # id(projected engine) -> nested SVCostEvaluator
         self._proj_state = None       # (engine id, m, qmap) of the phi currently held by that engine
@@ -611,6 +622,10 @@ class SVCostEvaluator:
                 sub, tail, sub_changed, m = pj
                 self.stats["projected_evals"] += 1
                 return sub.amp0(tail, focus=None if focus is None else max(focus - m, 0), changed=sub_changed)
+        if not self.dense_blocks:
+            self.stats["resimulations"] = self.stats.get("resimulations", 0) + 1
+            self.eng.run(SLOT_WORK, SLOT_BASE, G.GateStream.from_window(window))
+            return self.eng.amp(SLOT_WORK, 0)
         if (changed is not None and self.T is not None and self.window is not None and len(self.window) == len(window)
                 and all(self.cut[0] <= i < self.cut[1] and window[i][1] == self.window[i][1]
                         and window[i][2] == self.window[i][2] for i in changed)):
@@ -631,6 +646,13 @@ class SVCostEvaluator:
                 self.stats["evals"] += len(candidates)
                 self.stats["projected_evals"] += len(candidates)
                 return sub.shift_amplitudes(tail, k - m, candidates)
+        if not self.dense_blocks:
+            out = []
+            for cand in candidates:
+                w = list(window)
+                w[k] = ("mat1", window[k][1], -1, 0.0, 0.0, 0.0, np.ascontiguousarray(cand, dtype=np.complex128).tobytes())
+                out.append(self.amp0(w))
+            return out
         for b in self._blocks(window):
             if b[0] <= k < b[1]:
                 self._prepare_block(window, b)

@@ -175,6 +175,10 @@ int b200_sv_inner2_gather(b200_ctx *ctx, int r_slot, const void *compact_state, 
  * of the window (utils/cost_minimiser.py:267-368 walks them layer by layer) act only on these K qubits, every
  * further cost evaluation <0|W|psi> = <0_K|W_K|dst> runs on the 2^K-amplitude state. */
 int b200_sv_gather(b200_ctx *ctx, int slot, const int32_t *qmap, int K, void *dst);
+/* Same for one slice of a register sharded by global qubits: qmap entries >= num_qubits name rank bit
+ * (entry - num_qubits).  The rank writes the amplitudes it owns and zeros elsewhere; summing the ranks'
+ * results (all-reduce) gives the projection of the whole register. */
+int b200_sv_gather_ranked(b200_ctx *ctx, int slot, const int32_t *qmap, int K, int rank_bits, int rank, void *dst);
 /* Host <-> device transfer of `count` amplitudes starting at `offset` (tests, small n, target
  * upload).  Replaces the Statevector object's `.data`. */
 int b200_sv_download(b200_ctx *ctx, int slot, uint64_t offset, uint64_t count, double *host);

@@ -48,9 +48,60 @@ def gather_state(sv, slot):
     return phys[pidx]
 
 
+def compile_main(n, on_gpu):
+    """mode `compile`: the ADAPT loop on a sharded register (B200ShardedSVBackend) makes the same decisions
+    as on the oracle backend -- pair RDMs and <Z> are sharded read-outs, cost evaluations run in the
+    projected tail (gather + all-reduce) or by re-simulation on the sharded register."""
+    from adapt_aqc_b200.compiler import AdaptCompiler, AdaptConfig
+    from adapt_aqc_b200.dist_sv import B200ShardedSVBackend, ShardedEngine
+    from adapt_aqc_b200.sv_engine import SVCostEvaluator
+    from helpers import brickwork
+    from oracle.oracle_backends import OracleSVBackend
+    if on_gpu:
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        backend = B200ShardedSVBackend(local_rank)
+        proj_k = None
+    else:
+        dist.init_process_group("gloo")
+        emu = load_emu()
+        proj_k = 4
+
+        class CpuSharded(B200ShardedSVBackend):
+            def _make_engines(self, num_qubits):
+                comm = TorchComm()
+                nl = num_qubits - int(np.log2(comm.world))
+                eng = FakeEngine(emu, nl, n_slots=4)
+                tensors = [torch.from_numpy(s.view(np.float64)) for s in eng.slots]
+                staging = torch.empty(max(8, (2 << nl) // comm.world // 3), dtype=torch.float64)
+                sv = ShardedStatevector(num_qubits, eng, comm, tensors, staging)
+                return ShardedEngine(sv), [FakeEngine(emu, proj_k, n_slots=4)]
+        backend = CpuSharded()
+    target, _ = brickwork(n, 2, seed=21)
+    cfg = dict(max_layers=4 if not on_gpu else 5)
+    got = AdaptCompiler(target, backend=backend, adapt_config=AdaptConfig(**cfg)).compile()
+    st = dict(backend._evaluator.stats)
+    if n <= 16 or on_gpu:
+        # reference: the oracle on the CPU; at GPU sizes the single-GPU backend (parity-tested against the oracle)
+        from adapt_aqc_b200.backends import B200SVBackend
+        ref_backend = B200SVBackend(device=int(os.environ.get("LOCAL_RANK", "0"))) if on_gpu else OracleSVBackend()
+        ref = AdaptCompiler(target, backend=ref_backend, adapt_config=AdaptConfig(**cfg)).compile()
+        assert got.qubit_pair_history == ref.qubit_pair_history, (got.qubit_pair_history, ref.qubit_pair_history)
+        assert np.allclose(got.global_cost_history, ref.global_cost_history, atol=1e-9)
+        assert got.cost_evaluations == ref.cost_evaluations
+    assert st["projected_evals"] > 0, st
+    if dist.get_rank() == 0:
+        print(f"dist compile ok: world={dist.get_world_size()} n={n} layers={len(got.qubit_pair_history)} "
+              f"evals={got.cost_evaluations} cost={got.global_cost_history[-1]:.6f} stats={st}")
+    dist.destroy_process_group()
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 7
     on_gpu = len(sys.argv) > 2 and sys.argv[2] == "gpu"
+    if len(sys.argv) > 3 and sys.argv[3] == "compile":
+        return compile_main(n, on_gpu)
     if on_gpu:
         from adapt_aqc_b200.dist_sv import make_gpu_sharded
         local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -199,6 +199,22 @@ class FakeEngine:
             x |= ((c >> b) & 1) << q
         dst_engine.slots[dst_slot][...] = self.slots[slot][x]
 
+    def gather_ranked(self, slot, qmap, rank_bits, rank, dst_engine, dst_slot):
+        """numpy restatement of b200_sv_gather_ranked."""
+        n = self.num_qubits
+        c = np.arange(1 << len(qmap))
+        x = np.zeros_like(c)
+        rb = np.zeros_like(c)
+        covered = 0
+        for b, q in enumerate(qmap):
+            if q < n:
+                x |= ((c >> b) & 1) << q
+            else:
+                rb |= ((c >> b) & 1) << (q - n)
+                covered |= 1 << (q - n)
+        ok = (rb == (rank & covered)) & ((rank & ~covered) == 0)
+        dst_engine.slots[dst_slot][...] = np.where(ok, self.slots[slot][x], 0)
+
     def device_ptr(self, slot):
         return 0
 

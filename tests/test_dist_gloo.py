@@ -19,3 +19,17 @@ def test_sharded_statevector_matches_oracle(emu, world, n, port):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "dist ok" in res.stdout
+
+
+@pytest.mark.parametrize("world,n,port", [(2, 8, 29613), (4, 9, 29614)])
+def test_compile_on_a_sharded_register_matches_oracle(emu, world, n, port):
+    """B200ShardedSVBackend: the ADAPT loop over a register sharded by global qubits -- projected-tail
+    evaluations (ranked gather + all-reduce), re-simulation fallback, sharded <Z> / pair-RDM read-outs --
+    makes the decisions of the oracle backend."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"),
+           str(n), "cpu", "compile"]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "dist compile ok" in res.stdout

@@ -33,3 +33,16 @@ def test_sharded_statevector_on_nccl(world, n, port, exchange):
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "dist ok" in res.stdout
     assert f"exchange={exchange}" in res.stdout, res.stdout[-500:]
+
+
+@pytest.mark.parametrize("world,n,port", [(2, 20, 29631), (8, 22, 29632)])
+def test_compile_on_a_sharded_register(world, n, port):
+    """B200ShardedSVBackend on real GPUs: same pairs, costs and evaluation count as the single-GPU backend."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"),
+           str(n), "gpu", "compile"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "dist compile ok" in res.stdout
