@@ -360,6 +360,43 @@ def bench_sharded(args, local_rank, world):
         "norm": norm, "amp0_abs2": abs(a0) ** 2,
     }
     eng.close()
+    del sv
+    torch.cuda.empty_cache()
+    if not args.no_compile:
+        out["compile"] = bench_sharded_compile(args, local_rank, n)
+    return out
+
+
+def bench_sharded_compile(args, local_rank, n):
+    """AdaptCompiler.compile() on the sharded register (B200ShardedSVBackend): U|0> resident across the ranks,
+    ISL pair selection from sharded pair-RDM passes on a linear map, Rotoselect / Rotosolve in the projected
+    tail (one gather + all-reduce of 2^K amplitudes per projection, then a K-qubit engine per rank)."""
+    import torch.distributed as dist
+    from adapt_aqc_b200.compiler import AdaptCompiler, AdaptConfig
+    from adapt_aqc_b200.dist_sv import B200ShardedSVBackend
+    target, _ = build_workload(n, args.sharded_depth, 0)
+    backend = B200ShardedSVBackend(local_rank)
+    comp = AdaptCompiler(target, backend=backend, coupling_map=[(i, i + 1) for i in range(n - 1)],
+                         adapt_config=AdaptConfig(max_layers=args.sharded_compile_layers, method="ISL"))
+    comp.evaluate_cost()
+    backend._engine.sync()
+    dist.barrier()
+    sv = backend._engine.sv
+    sv.stats["exchanges"] = 0
+    t0 = time.perf_counter()
+    res = comp.compile()
+    backend._engine.sync()
+    dist.barrier()
+    wall = time.perf_counter() - t0
+    st = dict(backend._evaluator.stats)
+    out = {"workload": f"{n}-qubit brickwork(depth={args.sharded_depth}) target, AdaptConfig(max_layers={args.sharded_compile_layers}, "
+                       f"method='ISL'), linear coupling map (P={n - 1}), register sharded over the ranks",
+           "wall_s": wall, "layers": len(res.qubit_pair_history), "cost_evaluations": int(comp.cost_evaluation_counter),
+           "final_global_cost": float(res.global_cost_history[-1]), "exchanges": int(sv.stats["exchanges"]),
+           "projections": st.get("projections"), "projected_evals": st.get("projected_evals"),
+           "resimulations": st.get("resimulations", 0)}
+    for e in backend.engines():
+        e.close()
     return out
 
 
@@ -417,6 +454,7 @@ def main():
     ap.add_argument("--no-sharded", action="store_true")
     ap.add_argument("--no-compile", action="store_true", help="skip the compile wall-time leg")
     ap.add_argument("--compile-layers", type=int, default=6)
+    ap.add_argument("--sharded-compile-layers", type=int, default=4)
     ap.add_argument("--mps-qubits", type=int, default=50)
     ap.add_argument("--mps-chi", type=int, default=256)
     ap.add_argument("--mps-layers", type=int, default=2)
@@ -439,6 +477,9 @@ def main():
 
     dist = None
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
