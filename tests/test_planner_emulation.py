@@ -122,3 +122,20 @@ def test_plan_for_c3_workload_is_a_few_sweeps():
     a_stats = plan_stats(n, GateStream.from_circuit(ansatz))
     assert t_stats[0] <= 24, t_stats
     assert a_stats[0] <= 3, a_stats
+
+
+@pytest.mark.parametrize("n", [3, 12])
+def test_invert_window_is_the_inverse_circuit(emu, n):
+    """gates.invert_window (used by the sharded engine, which has no inverse entry point of its own)
+    against the library's inverse canonicalisation, on every opcode."""
+    from adapt_aqc_b200.gates import canonical_window, invert_window
+    from helpers import circuit_from_gates
+    rng = np.random.default_rng(300 + n)
+    gates = random_gates(n, 70, rng)
+    window = canonical_window(circuit_from_gates(n, gates))
+    psi, _ = emu_run(emu, n, GateStream.from_window(window))
+    back, _ = emu_run(emu, n, GateStream.from_window(invert_window(window)), psi0=psi)
+    via_flag, _ = emu_run(emu, n, GateStream.from_window(window), psi0=psi, inverse=True)
+    e0 = np.zeros(1 << n, dtype=np.complex128); e0[0] = 1
+    np.testing.assert_allclose(back, e0, atol=TOL)
+    np.testing.assert_allclose(via_flag, e0, atol=TOL)
