@@ -376,6 +376,17 @@ class ShardedEngine:
         sv._sync()
         sv.comm.allreduce_engine_slot(dst_engine, dst_slot)
 
+    def inner2_gather(self, r_slot, compact_engine, compact_slot, qmap, qa, qb):
+        """Transfer matrix against a compact bra: the 2^K amplitudes of the sharded R on qmap are gathered
+        (ranked gather + all-reduce) into a spare slot of the compact engine, then the ordinary transfer
+        pass runs between the two 2^K-amplitude states."""
+        if getattr(compact_engine, "n_slots", len(getattr(compact_engine, "slots", [0, 0]))) < 2:
+            raise ValueError("the compact engine of a sharded backend needs two slots")
+        spare = 1 if compact_slot == 0 else 0
+        qmap = list(qmap)
+        self.gather(r_slot, qmap, compact_engine, spare)
+        return compact_engine.inner2(compact_slot, spare, qmap.index(qa), qmap.index(qb))
+
     def download(self, slot, offset=0, count=None):
         raise MemoryError("a sharded statevector is not downloaded to one host")
 
@@ -476,10 +487,13 @@ def _sharded_backend_class():
             self.__init__(local_rank=state.get("device", 0), exchange=state.get("exchange"))
 
         def _make_engines(self, num_qubits):
-            """(ShardedEngine, [projected engines]) -- overridden by the CPU tests."""
+            """(ShardedEngine, [compact-bra engines, 2 slots], [projected engines, 4 slots]) -- overridden by the CPU tests."""
+            from .backends import COMPACT_QUBITS
             sv = make_gpu_sharded(num_qubits, n_slots=4, local_rank=self.device, exchange=self.exchange)
             sizes = [k for k in PROJECT_QUBITS if 12 <= k <= min(num_qubits - SVCostEvaluator.PROJECT_MIN_SAVING, sv.nl)]
-            return ShardedEngine(sv), [SVEngine(k, device=self.device, n_slots=4) for k in sizes]
+            csizes = sorted({min(k, sv.nl) for k in COMPACT_QUBITS})
+            return (ShardedEngine(sv), [SVEngine(k, device=self.device, n_slots=2) for k in csizes],
+                    [SVEngine(k, device=self.device, n_slots=4) for k in sizes])
 
         def overlap_between_circuits(self, circuit1, circuit2):
             """|<psi1|psi2>|^2 = |<0| U1^+ U2 |0>|^2: both circuits on ONE sharded slot (two independently
@@ -493,12 +507,11 @@ def _sharded_backend_class():
 
         def _get_engine(self, num_qubits):
             if self._engine is None or self._engine.num_qubits != num_qubits:
-                for e in [self._engine] + list(getattr(self, "_projected", None) or []):
+                for e in [self._engine] + list(getattr(self, "_projected", None) or []) + list(self._compact or []):
                     if e is not None:
                         e.close()
-                self._engine, self._projected = self._make_engines(num_qubits)
-                self._compact = []
-                self._evaluator = SVCostEvaluator(self._engine, None, self._projected)
+                self._engine, self._compact, self._projected = self._make_engines(num_qubits)
+                self._evaluator = SVCostEvaluator(self._engine, self._compact, self._projected)
                 self._evaluator.dense_blocks = False
                 self._state_version += 1
                 self._last_run_key = None

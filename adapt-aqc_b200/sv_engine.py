@@ -568,6 +568,16 @@ class SVCostEvaluator:
         self.stats["compact_L"] += 1
         return True
 
+    def _open_block_ok(self, window, changed):
+        """The edits stay inside the block T is open on (the fast path of amp0 applies)."""
+        return (changed is not None and self.T is not None and self.window is not None and len(self.window) == len(window)
+                and all(self.cut[0] <= i < self.cut[1] for i in changed))
+
+    def _compact_ok(self, window, block):
+        """dense_blocks = False: a block can be served only with a compact bra (gather of R)."""
+        b0, b1, supp = block
+        return len(supp) == 2 and self._compact_map(window[b1:], tuple(supp)) is not None
+
     def _prepare_block(self, window, block):
         """Make R, L and T valid for `block` of `window`."""
         eng = self.eng
@@ -622,8 +632,11 @@ class SVCostEvaluator:
                 sub, tail, sub_changed, m = pj
                 self.stats["projected_evals"] += 1
                 return sub.amp0(tail, focus=None if focus is None else max(focus - m, 0), changed=sub_changed)
-        if not self.dense_blocks:
+        if not self.dense_blocks and not self._open_block_ok(window, changed) \
+                and not self._compact_ok(window, self._select_block(window, focus)):
             self.stats["resimulations"] = self.stats.get("resimulations", 0) + 1
+            self.T = None
+            self.window = None
             self.eng.run(SLOT_WORK, SLOT_BASE, G.GateStream.from_window(window))
             return self.eng.amp(SLOT_WORK, 0)
         if (changed is not None and self.T is not None and self.window is not None and len(self.window) == len(window)
@@ -646,7 +659,7 @@ class SVCostEvaluator:
                 self.stats["evals"] += len(candidates)
                 self.stats["projected_evals"] += len(candidates)
                 return sub.shift_amplitudes(tail, k - m, candidates)
-        if not self.dense_blocks:
+        if not self.dense_blocks and not any(b[0] <= k < b[1] and self._compact_ok(window, b) for b in self._blocks(window)):
             out = []
             for cand in candidates:
                 w = list(window)

@@ -76,7 +76,7 @@ def compile_main(n, on_gpu):
                 tensors = [torch.from_numpy(s.view(np.float64)) for s in eng.slots]
                 staging = torch.empty(max(8, (2 << nl) // comm.world // 3), dtype=torch.float64)
                 sv = ShardedStatevector(num_qubits, eng, comm, tensors, staging)
-                return ShardedEngine(sv), [FakeEngine(emu, proj_k, n_slots=4)]
+                return ShardedEngine(sv), [FakeEngine(emu, 5, n_slots=2)], [FakeEngine(emu, proj_k, n_slots=4)]
         backend = CpuSharded()
     target, _ = brickwork(n, 2, seed=21)
     cfg = dict(max_layers=4 if not on_gpu else 5)
