@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+RESULT_OUT = sys.stdout
 METRIC = "cost_evals_per_sec"
 UNIT = "evals/s"
 
@@ -424,7 +425,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 def workload_config(args):
@@ -464,6 +465,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # stdout carries exactly ONE JSON line (rank 0): native libraries that write to fd 1 (NCCL prints its
+    # version banner there) are sent to stderr, the result line goes to a private copy of the real stdout
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -472,7 +480,7 @@ def main():
     from adapt_aqc_b200.backends import B200SVBackend
 
     if args.mps_only:
-        print(json.dumps(bench_mps(args, local_rank, with_cpu=not args.no_cpu_baseline)))
+        print(json.dumps(bench_mps(args, local_rank, with_cpu=not args.no_cpu_baseline)), file=RESULT_OUT, flush=True)
         return
 
     dist = None
@@ -602,7 +610,7 @@ def main():
             sharded = {"error": repr(exc)}
         line["sharded_c5"] = sharded
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
