@@ -853,6 +853,32 @@ int b200_sv_gather_ranked(b200_ctx* ctx, int slot, const int32_t* qmap, int K, i
     return gather_impl(ctx, slot, qmap, K, dst, rank_bits, rank);
 }
 
+int b200_sv_scatter(b200_ctx* ctx, int slot, const int32_t* qmap, int K, const void* src) {
+    if (check_slot(ctx, slot)) return -1;
+    if (!qmap || !src) return set_error("null pointer");
+    const int n = ctx->nq;
+    if (K < 1 || K > n || K > 40) return set_error("scatter: K out of range");
+    QMap qm;
+    uint64_t inside = 0;
+    for (int b = 0; b < K; ++b) {
+        if (qmap[b] < 0 || qmap[b] >= n || (inside >> qmap[b] & 1)) return set_error("scatter: qmap must hold distinct qubits of the register");
+        inside |= 1ull << qmap[b];
+        qm.q[b] = qmap[b];
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t dim = 1ull << n;
+    Timer tm(ctx);
+    {
+        KScope ks(ctx, B200_PROF_FILL);
+        sv_scatter_kernel<<<ctx->num_sms * 8, RED_THREADS, 0, ctx->stream>>>((double2*)ctx->slots[slot], dim, qm, K, inside, (const double2*)src);
+    }
+    CUDA_TRY(cudaGetLastError());
+    ctx->counters[3] += 16 * dim;
+    ctx->counters[6] += 1;
+    tm.stop();
+    return 0;
+}
+
 int b200_sv_download(b200_ctx* ctx, int slot, uint64_t offset, uint64_t count, double* host) {
     if (check_slot(ctx, slot)) return -1;
     if (offset + count > (1ull << ctx->nq)) return set_error("download range out of bounds");

@@ -152,6 +152,13 @@ class SVEngine:
                                        ctypes.c_void_p(dst_engine.device_ptr(dst_slot))))
         self.sync()
 
+    def scatter(self, slot, qmap, src_engine, src_slot):
+        """slot[x] = src[extract(x, qmap)] where all qubits outside qmap are 0, and 0 elsewhere (inverse of gather)."""
+        qm = np.ascontiguousarray(np.asarray(qmap, dtype=np.int32))
+        src_engine.sync()
+        check(self._lib.b200_sv_scatter(self._ctx, int(slot), qm.ctypes.data, len(qm),
+                                        ctypes.c_void_p(src_engine.device_ptr(src_slot))))
+
     def gather_ranked(self, slot, qmap, rank_bits, rank, dst_engine, dst_slot):
         """One rank's part of ``gather`` on a register sharded over 2^rank_bits ranks (dist_sv): qmap entries
         >= num_qubits name rank bits.  Asynchronous on this engine's stream (the caller synchronises)."""
@@ -396,7 +403,7 @@ class SVCostEvaluator:
             self._part_key, self._part = key, partition_blocks(window)
         return self._part
 
-    def _select_block(self, window, focus):
+    def _select_block(self, window, focus, changed=None):
         blocks = self._blocks(window)
         old, target = self.window, None
         if old is not None and self.cut is not None and len(old) == len(window):
@@ -408,6 +415,8 @@ class SVCostEvaluator:
                     if b[0] == a0 and b[1] == a1:
                         return b
             target = outside[-1] if outside else (diff[-1] if diff else None)
+        if target is None and changed:
+            target = max(changed)       # no previous window to diff against (e.g. after a projected phase)
         if target is None:
             target = len(window) - 1 if focus is None else min(max(focus, 0), len(window) - 1)
         for b in blocks:
@@ -434,20 +443,16 @@ class SVCostEvaluator:
             self._split_key, self._split = self._part_key, ((m, sorted(supp)) if ok else None)
         return self._split
 
-    def _projected(self, window, target, changed):
-        """If window[target] lies in the projected tail: (nested evaluator, tail window in the engine's qubit
-        numbering, changed indices relative to the tail | None, m); else None.  Makes phi valid."""
-        split = self._tail_split(window, changed)
-        if split is None or target < split[0]:
-            return None
+    def _proj_info(self, split):
+        """(split, (engine, qmap, position of each qubit, nested evaluator) | None) for a tail split, cached."""
         m, supp = split
         info = self._split_info
         if info is None or info[0] is not split:
             fits = [e for e in self.projected if e.num_qubits >= len(supp) and
                     e.num_qubits + self.PROJECT_MIN_SAVING <= self.eng.num_qubits]
             if not fits:
-                self._split_info = (split, None)
-                return None
+                info = self._split_info = (split, None)
+                return info
             peng = fits[0]
             used = set(supp)
             free = [q for q in range(self.eng.num_qubits) if q not in used]
@@ -458,6 +463,16 @@ class SVCostEvaluator:
                 # 2^K amplitudes is cheap anyway)
                 sub = self._sub[id(peng)] = SVCostEvaluator(peng)
             info = self._split_info = (split, (peng, tuple(qmap), {q: c for c, q in enumerate(qmap)}, sub))
+        return info
+
+    def _projected(self, window, target, changed):
+        """If window[target] lies in the projected tail: (nested evaluator, tail window in the engine's qubit
+        numbering, changed indices relative to the tail | None, m); else None.  Makes phi valid."""
+        split = self._tail_split(window, changed)
+        if split is None or target < split[0]:
+            return None
+        m, supp = split
+        info = self._proj_info(split)
         if info[1] is None:
             return None
         peng, qmap, pos, sub = info[1]
@@ -533,7 +548,22 @@ class SVCostEvaluator:
                 eng.run(SLOT_L, SLOT_L, stream(sfx[:sn - so]), inverse=True)
                 self.lwin = list(sfx); self.l_moves += 1; self.stats["moves_L"] += 1
                 return True
-        eng.run(SLOT_L, -1, stream(sfx), inverse=True)
+        # rebuild.  When the suffix contains the whole projected tail, tail^+ |0> is supported on the tail's K
+        # qubits: build it on the K-qubit engine (cheap sweeps), embed it into the register (one write pass)
+        # and apply only the remaining head gates with sweeps over 2^n
+        split = self._tail_split(new) if (self.projected and self.dense_blocks) else None
+        info = self._proj_info(split)[1] if split is not None else None
+        if info is not None and b1 <= split[0] < len(new) and hasattr(eng, "scatter"):
+            m = split[0]
+            peng, qmap, pos, _ = info
+            tail = [(e[0], pos[e[1]], pos[e[2]] if e[2] >= 0 else -1) + tuple(e[3:]) for e in new[m:]]
+            peng.run(SLOT_WORK, -1, stream(tail), inverse=True)
+            eng.scatter(SLOT_L, list(qmap), peng, SLOT_WORK)
+            if b1 < m:
+                eng.run(SLOT_L, SLOT_L, stream(new[b1:m]), inverse=True)
+            self.stats["scattered_L"] = self.stats.get("scattered_L", 0) + 1
+        else:
+            eng.run(SLOT_L, -1, stream(sfx), inverse=True)
         self.lwin = list(sfx)
         self.l_moves = 0
         self.stats["rebuild_L"] += 1
@@ -633,7 +663,7 @@ class SVCostEvaluator:
                 self.stats["projected_evals"] += 1
                 return sub.amp0(tail, focus=None if focus is None else max(focus - m, 0), changed=sub_changed)
         if not self.dense_blocks and not self._open_block_ok(window, changed) \
-                and not self._compact_ok(window, self._select_block(window, focus)):
+                and not self._compact_ok(window, self._select_block(window, focus, changed)):
             self.stats["resimulations"] = self.stats.get("resimulations", 0) + 1
             self.T = None
             self.window = None
@@ -645,7 +675,7 @@ class SVCostEvaluator:
             for i in changed:
                 self.window[i] = window[i]
         else:
-            self._prepare_block(window, self._select_block(window, focus))
+            self._prepare_block(window, self._select_block(window, focus, changed))
         self.stats["host_evals"] += 1
         return complex(np.sum(self._operator(window) * self.T))
 

@@ -175,6 +175,9 @@ int b200_sv_inner2_gather(b200_ctx *ctx, int r_slot, const void *compact_state, 
  * of the window (utils/cost_minimiser.py:267-368 walks them layer by layer) act only on these K qubits, every
  * further cost evaluation <0|W|psi> = <0_K|W_K|dst> runs on the 2^K-amplitude state. */
 int b200_sv_gather(b200_ctx *ctx, int slot, const int32_t *qmap, int K, void *dst);
+/* The inverse embedding: slot[x] = src[extract(x, qmap)] where every qubit outside qmap is 0, and 0 elsewhere
+ * (a bra <L| = suffix^+ <0| whose tail was built on the K-qubit context is placed into the register). */
+int b200_sv_scatter(b200_ctx *ctx, int slot, const int32_t *qmap, int K, const void *src);
 /* Same for one slice of a register sharded by global qubits: qmap entries >= num_qubits name rank bit
  * (entry - num_qubits).  The rank writes the amplitudes it owns and zeros elsewhere; summing the ranks'
  * results (all-reduce) gives the projection of the whole register. */

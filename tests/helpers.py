@@ -199,6 +199,15 @@ class FakeEngine:
             x |= ((c >> b) & 1) << q
         dst_engine.slots[dst_slot][...] = self.slots[slot][x]
 
+    def scatter(self, slot, qmap, src_engine, src_slot):
+        """numpy restatement of b200_sv_scatter."""
+        c = np.arange(1 << len(qmap))
+        x = np.zeros_like(c)
+        for b, q in enumerate(qmap):
+            x |= ((c >> b) & 1) << q
+        self.slots[slot][...] = 0
+        self.slots[slot][x] = src_engine.slots[src_slot]
+
     def gather_ranked(self, slot, qmap, rank_bits, rank, dst_engine, dst_slot):
         """numpy restatement of b200_sv_gather_ranked."""
         n = self.num_qubits

@@ -59,8 +59,10 @@ def test_incremental_evaluator_equals_full_resimulation(fake_backend, n):
             assert abs(comp.evaluate_cost() - ocomp.evaluate_cost()) < 1e-10
     st = fake_backend._evaluator.stats
     assert st["moves_R"] > 0 and st["t_passes"] + st["t_gathers"] < st["evals"]
-    if fake_backend._evaluator.compact is not None:
+    if fake_backend._evaluator.compact is not None and not fake_backend._evaluator.projected:
         assert st["t_gathers"] > 0 and st["compact_L"] > 0
+    if fake_backend._evaluator.projected:
+        assert st["projected_evals"] > 0 and st["projections"] > 0
 
 
 @pytest.mark.parametrize("fake_backend", [None, 5], indirect=True)
