@@ -361,6 +361,7 @@ class SVCostEvaluator:
         self.pair = None              # qubits the transfer matrix T is open on
         self.T = None
         self.rwin = None
+        self.r_slot = SLOT_R          # slot that holds R (SLOT_BASE while the prefix is empty)
         self.lwin = None
         self.lkey = None
         self.r_moves = self.l_moves = 0
@@ -483,7 +484,7 @@ class SVCostEvaluator:
             r_changed = self._update_R(window, m) if m > 0 else False
         state = (id(peng), m, qmap, self.base_key)
         if r_changed or state != self._proj_state:
-            self.eng.gather(SLOT_R if m > 0 else SLOT_BASE, list(qmap), peng, SLOT_BASE)
+            self.eng.gather(self.r_slot if m > 0 else SLOT_BASE, list(qmap), peng, SLOT_BASE)
             sub.base_key = ("projected", self.stats["projections"])
             sub.invalidate()
             self._proj_state = state
@@ -513,7 +514,11 @@ class SVCostEvaluator:
         old = self.rwin
         if old is not None and old == new[:b0]:
             return False
-        if old is not None and self.r_moves < self.REFRESH_MOVES:
+        if b0 == 0:
+            # empty prefix: R IS the base state -- read slot BASE instead of copying it (self.r_slot)
+            self.rwin, self.r_slot, self.r_moves = [], SLOT_BASE, 0
+            return True
+        if old is not None and self.r_moves < self.REFRESH_MOVES and self.r_slot == SLOT_R:
             a0 = len(old)
             m = min(a0, b0)
             # moving costs |b0 - a0| gates, rebuilding from the base b0 gates: take the cheaper one
@@ -528,6 +533,7 @@ class SVCostEvaluator:
                 return True
         eng.run(SLOT_R, SLOT_BASE, stream(new[:b0]))
         self.rwin = list(new[:b0])
+        self.r_slot = SLOT_R
         self.r_moves = 0
         self.stats["rebuild_R"] += 1
         return True
@@ -626,10 +632,11 @@ class SVCostEvaluator:
         if r_changed or l_changed or self.T is None or tkey != self._tkey:
             if mode == "compact":
                 self.compact.sync()
-                self.T = eng.inner2_gather(SLOT_R, self.compact, 0, qmap, *pair)
+                self.T = eng.inner2_gather(self.r_slot, self.compact, 0, qmap, *pair)
                 self.stats["t_gathers"] += 1
             else:
-                self.T = eng.inner(SLOT_L, SLOT_R, pair[0]) if len(pair) == 1 else eng.inner2(SLOT_L, SLOT_R, *pair)
+                self.T = (eng.inner(SLOT_L, self.r_slot, pair[0]) if len(pair) == 1
+                          else eng.inner2(SLOT_L, self.r_slot, *pair))
                 self.stats["t_passes"] += 1
             self._tkey = tkey
         self.cut, self.pair = (b0, b1), pair
