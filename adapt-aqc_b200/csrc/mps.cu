@@ -7,7 +7,7 @@
 // lambdas, apply the gate, SVD, truncate with Aer's rule, divide the outer lambdas back out; swaps
 // for non-neighbours), with every tensor operation on the device:
 //   contraction / transfer matrices : zgemm_dmma_kernel (FP64 tensor cores)
-//   SVD                              : one-sided Jacobi (jacobi_cta_kernel / jacobi_round_kernel)
+//   SVD                              : one-sided Jacobi (jacobi_cta_kernel / jacobi_block_kernel; coop + per-round fallbacks)
 //   truncation                       : singular values (<= 4 KB) are read back, Aer's reduce_zeros
 //                                      rule picks the kept count (the launch geometry of the
 //                                      following kernels depends on it), the rest stays on device.

@@ -23,12 +23,6 @@
 // The per-thread bodies are __host__ __device__ so that tests/emu can run the very same code
 // on the CPU (one loop iteration per CUDA thread) to check the planner and the index math
 // without a GPU.  The product only ever launches the __global__ kernels.
-#ifdef __CUDA_ARCH__
-#define B200_LDG(p) __ldg(p)
-#else
-#define B200_LDG(p) (*(p))
-#endif
-
 namespace b200 {
 
 constexpr int SWEEP_THREADS = 1 << (TILE_BITS - REG_BITS);  // 256
