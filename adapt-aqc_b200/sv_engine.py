@@ -341,6 +341,7 @@ class SVCostEvaluator:
         # False (sharded registers, dist_sv.ShardedEngine): no dense bra / transfer passes over the register --
         # blocks outside the projected tail are evaluated by re-simulating the window from the base state
         self.dense_blocks = True
+        self.prefetch_L = True        # see _prefetch_next_L
         self.projected = sorted(projected or [], key=lambda e: e.num_qubits)
         self._sub = {}                # id(projected engine) -> nested SVCostEvaluator
         self._proj_state = None       # (engine id, m, qmap) of the phi currently held by that engine
@@ -614,6 +615,25 @@ class SVCostEvaluator:
         b0, b1, supp = block
         return len(supp) == 2 and self._compact_map(window[b1:], tuple(supp)) is not None
 
+    def _prefetch_next_L(self, window, b1):
+        """T of the open block has been read back, so slot L is free: enqueue (asynchronously) the bra of the
+        NEXT block -- Rotosolve walks the blocks in order (cost_minimiser.py:267-316) -- while the host
+        evaluates the open one.  Only bookkeeping (lwin) records it: if the optimiser goes elsewhere the
+        usual move / rebuild logic starts from this state."""
+        nxt = next((b for b in self._blocks(window) if b[0] == b1), None)
+        if nxt is None or self.lwin is None or self.l_moves >= self.REFRESH_MOVES:
+            return
+        n0, n1, supp = nxt
+        if len(supp) == 2 and self._compact_map(window[n1:], tuple(supp)) is not None:
+            return          # the next block will use a compact bra
+        split = self._tail_split(window)
+        if split is not None and n0 >= split[0]:
+            return          # ... or the projected tail
+        self.eng.run(SLOT_L, SLOT_L, G.GateStream.from_window(window[n0:n1]))
+        self.lwin = list(window[n1:])
+        self.l_moves += 1
+        self.stats["prefetched_L"] = self.stats.get("prefetched_L", 0) + 1
+
     def _prepare_block(self, window, block):
         """Make R, L and T valid for `block` of `window`."""
         eng = self.eng
@@ -639,6 +659,8 @@ class SVCostEvaluator:
                           else eng.inner2(SLOT_L, self.r_slot, *pair))
                 self.stats["t_passes"] += 1
             self._tkey = tkey
+            if mode == "dense" and self.prefetch_L:
+                self._prefetch_next_L(window, b1)
         self.cut, self.pair = (b0, b1), pair
         self.window = list(window)
 
