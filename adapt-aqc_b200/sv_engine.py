@@ -641,6 +641,12 @@ class SVCostEvaluator:
         n = eng.num_qubits
         pair = tuple(supp) if (len(supp) == 2 or n == 1) else (supp[0], (supp[0] + 1) % n)
         r_changed = self._update_R(window, b0)
+        if (not r_changed and self.T is not None and self._tkey is not None and self._tkey[:3] == (b0, b1, pair)
+                and self._t_sfx == window[b1:]):
+            # T is still valid for this block (slot L may already hold the prefetched bra of the next one)
+            self.cut, self.pair = (b0, b1), pair
+            self.window = list(window)
+            return
         qmap = self._compact_map(window[b1:], pair)
         if qmap is not None:
             l_changed = self._update_L_compact(window, b1, qmap)
@@ -659,12 +665,14 @@ class SVCostEvaluator:
                           else eng.inner2(SLOT_L, self.r_slot, *pair))
                 self.stats["t_passes"] += 1
             self._tkey = tkey
+            self._t_sfx = list(window[b1:])
             if mode == "dense" and self.prefetch_L:
                 self._prefetch_next_L(window, b1)
         self.cut, self.pair = (b0, b1), pair
         self.window = list(window)
 
     _tkey = None
+    _t_sfx = None
 
     def _operator(self, window, override_index=None, override=None):
         b0, b1 = self.cut

@@ -152,6 +152,32 @@ def test_bench_step_counts_220_evaluations(fake_backend):
         assert comp.cost_evaluation_counter - before == 4 * 7 + 64 * 3
 
 
+@pytest.mark.parametrize("fake_backend", [(None, 6)], indirect=True)
+def test_bench_step_device_work_is_the_same_through_both_front_ends(fake_backend):
+    """The one-scalar-per-call reference interface and the batched minimiser must cost the device the same
+    passes per step: one transfer pass per head block, bras prefetched or moved once, no thrash between a
+    prefetched bra and the block that is still open (a regression once doubled the passes of one of them)."""
+    import bench
+    n = 10
+    target, ansatz = bench.build_workload(n, 2, 16)
+    per_mode = []
+    for batched in (True, False):
+        fake_backend.reset_cache()
+        comp = bench.make_compiler(target, ansatz, fake_backend, batched)
+        comp.evaluate_cost()
+        bench.one_step(comp)                      # reach the steady state
+        ev = fake_backend._evaluator
+        s0 = dict(ev.stats)
+        bench.one_step(comp)
+        d = {k: ev.stats.get(k, 0) - s0.get(k, 0) for k in ev.stats}
+        head_blocks = sum(1 for b in ev._blocks(ev.window or []) ) if ev.window else None
+        per_mode.append(d)
+        assert d["projected_evals"] > 0
+        assert d["t_passes"] <= 16 and d["moves_L"] + d["rebuild_L"] + d.get("prefetched_L", 0) <= 17, d
+    for k in ("t_passes", "moves_L", "rebuild_L"):
+        assert abs(per_mode[0][k] - per_mode[1][k]) <= 1, (k, per_mode)
+
+
 @pytest.mark.parametrize("fake_backend", [2, (2, 3)], indirect=True)
 @pytest.mark.parametrize("case", compile_option_cases(), ids=lambda c: c[0])
 def test_compile_options_make_the_same_decisions(fake_backend, case):
