@@ -868,9 +868,14 @@ int b200_sv_scatter(b200_ctx* ctx, int slot, const int32_t* qmap, int K, const v
     CUDA_TRY(cudaSetDevice(ctx->device));
     const uint64_t dim = 1ull << n;
     Timer tm(ctx);
+    {   // a plain zero fill at write bandwidth, then 2^K scattered stores (one pass with the test inside ran at half of it)
+        KScope ks(ctx, B200_PROF_FILL);
+        sv_zero_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>((double2*)ctx->slots[slot], dim);
+    }
+    CUDA_TRY(cudaGetLastError());
     {
         KScope ks(ctx, B200_PROF_FILL);
-        sv_scatter_kernel<<<ctx->num_sms * 8, RED_THREADS, 0, ctx->stream>>>((double2*)ctx->slots[slot], dim, qm, K, inside, (const double2*)src);
+        sv_scatter_kernel<<<red_grid(ctx, 1ull << K), RED_THREADS, 0, ctx->stream>>>((double2*)ctx->slots[slot], qm, K, (const double2*)src);
     }
     CUDA_TRY(cudaGetLastError());
     ctx->counters[3] += 16 * dim;

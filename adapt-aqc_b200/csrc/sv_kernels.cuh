@@ -1036,18 +1036,21 @@ sv_gather_kernel(const double2* __restrict__ psi, const QMap qm, const int K, do
 
 // Inverse of the projection: psi[x] = phi[extract(x)] where every qubit outside qmap is 0, and 0 elsewhere.
 // (<L| = suffix^+ <0| whose tail part was built on the K-qubit engine is embedded into the register.)
-__global__ void __launch_bounds__(RED_THREADS)
-sv_scatter_kernel(double2* __restrict__ psi, const uint64_t dim, const QMap qm, const int K, const uint64_t inside,
-                  const double2* __restrict__ phi) {
+__global__ void sv_zero_kernel(double2* __restrict__ psi, const uint64_t dim) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < dim; x += stride) {
-        double2 v = make_double2(0.0, 0.0);
-        if ((x & ~inside) == 0) {
-            uint64_t c = 0;
-            for (int b = 0; b < K; ++b) c |= ((x >> qm.q[b]) & 1ull) << b;
-            v = phi[c];
-        }
-        psi[x] = v;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride)
+        psi[i] = make_double2(0.0, 0.0);
+}
+
+// (after sv_zero_kernel) psi[deposit(c)] = phi[c]: 2^K scattered 16-byte stores
+__global__ void __launch_bounds__(RED_THREADS)
+sv_scatter_kernel(double2* __restrict__ psi, const QMap qm, const int K, const double2* __restrict__ phi) {
+    const uint64_t dim = 1ull << K;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < dim; c += stride) {
+        uint64_t x = 0;
+        for (int b = 0; b < K; ++b) x |= ((c >> b) & 1ull) << qm.q[b];
+        psi[x] = phi[c];
     }
 }
 

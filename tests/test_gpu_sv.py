@@ -469,3 +469,25 @@ def test_c3_evaluator_equals_device_resimulation():
     st = backend._evaluator.stats
     assert st["projected_evals"] > 0 and st["t_passes"] + st["t_gathers"] > 0
     backend._engine.close()
+
+
+@pytest.mark.parametrize("n,K", [(14, 12), (18, 13)])
+def test_gather_and_scatter_match_numpy(n, K):
+    """b200_sv_gather / b200_sv_scatter: projection onto |0> of the qubits outside qmap and its adjoint."""
+    rng = np.random.default_rng(60 + n)
+    big, small = SVEngine(n, n_slots=2), SVEngine(K, n_slots=1)
+    psi = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    big.upload(0, psi)
+    qmap = sorted(int(q) for q in rng.choice(n, K, replace=False))
+    qmap = qmap[3:] + qmap[:3]                      # not sorted: compact bit b <-> register qubit qmap[b]
+    c = np.arange(1 << K)
+    x = np.zeros_like(c)
+    for b, q in enumerate(qmap):
+        x |= ((c >> b) & 1) << q
+    big.gather(0, qmap, small, 0)
+    np.testing.assert_array_equal(small.download(0), psi[x])
+    big.scatter(1, qmap, small, 0)
+    ref = np.zeros(1 << n, dtype=np.complex128)
+    ref[x] = psi[x]
+    np.testing.assert_array_equal(big.download(1), ref)
+    big.close(); small.close()
