@@ -172,6 +172,36 @@ class B200MPSSimulator:
         return out
 
     MAX_CHECKPOINTS = 24
+    _DIAGONAL_1Q = ("rz", "z", "s", "sdg", "t", "tdg", "u1", "p", "id", "i")
+
+    @classmethod
+    def _commute_phases_past_controls(cls, window):
+        """A diagonal 1-qubit gate on the CONTROL of a following cx / on either qubit of a cz commutes with it
+        exactly; moving it behind the 2-qubit gate lets a run that only changed that rotation resume from the
+        checkpoint taken after the 2-qubit gate (no new SVD: the two-site matrix gets a unitary diagonal on
+        its row or column index, which leaves its singular values and the kept subspace untouched)."""
+        out = list(window)
+        for i in range(len(out)):
+            e = out[i]
+            if e[2] < 0 or e[0] not in ("cx", "cz"):
+                continue
+            free = {e[1]} if e[0] == "cx" else {e[1], e[2]}
+            j = i - 1
+            moved = []
+            blocked = set()
+            while j >= 0 and out[j][2] < 0:                  # only look through 1-qubit gates
+                g = out[j]
+                if g[1] in free and g[1] not in blocked:
+                    if g[0] in cls._DIAGONAL_1Q and g[6] is None:
+                        moved.append(j)
+                    else:
+                        blocked.add(g[1])
+                j -= 1
+            if moved:
+                gates = [out[k] for k in sorted(moved)]
+                keep = [out[k] for k in range(j + 1, i) if k not in moved]
+                out[j + 1:i + 1] = keep + [e] + gates
+        return out
 
     def _drop_checkpoints(self, keep=0):
         while len(self._ckpts) > keep:
@@ -185,6 +215,7 @@ class B200MPSSimulator:
         whose gate list starts with the same gates resumes from it.  Same gates in the same order with the
         same truncation rule give the same state, so the result is identical to a full re-run."""
         o = self.options
+        window = self._commute_phases_past_controls(window)
         key = (out.num_qubits, o.matrix_product_state_truncation_threshold, o.matrix_product_state_max_bond_dimension)
         if key != self._ckpt_key or base_obj is not self._ckpt_base:      # (the host target object is kept alive here)
             self._drop_checkpoints()
