@@ -176,31 +176,34 @@ class B200MPSSimulator:
 
     @classmethod
     def _commute_phases_past_controls(cls, window):
-        """A diagonal 1-qubit gate on the CONTROL of a following cx / on either qubit of a cz commutes with it
-        exactly; moving it behind the 2-qubit gate lets a run that only changed that rotation resume from the
-        checkpoint taken after the 2-qubit gate (no new SVD: the two-site matrix gets a unitary diagonal on
-        its row or column index, which leaves its singular values and the kept subspace untouched)."""
+        """Normal form for checkpoint matching: every 1-qubit gate is moved as LATE as exact commutation allows
+        -- past gates on other qubits, and, if it is diagonal, past a cx it controls or a cz it takes part in.
+        (One right-to-left pass; gates on the same qubit never overtake each other.)  A run that only changed
+        such a rotation then resumes from a checkpoint behind the 2-qubit gates it commutes with: no new SVD.
+        The circuit is unchanged (exact commutations); moving a unitary diagonal across an SVD leaves the
+        singular values and the kept subspace untouched."""
         out = list(window)
-        for i in range(len(out)):
-            e = out[i]
-            if e[2] < 0 or e[0] not in ("cx", "cz"):
+        if len(out) > 512:
+            return out
+        for j in range(len(out) - 2, -1, -1):
+            g = out[j]
+            if g[2] >= 0:
                 continue
-            free = {e[1]} if e[0] == "cx" else {e[1], e[2]}
-            j = i - 1
-            moved = []
-            blocked = set()
-            while j >= 0 and out[j][2] < 0:                  # only look through 1-qubit gates
-                g = out[j]
-                if g[1] in free and g[1] not in blocked:
-                    if g[0] in cls._DIAGONAL_1Q and g[6] is None:
-                        moved.append(j)
-                    else:
-                        blocked.add(g[1])
-                j -= 1
-            if moved:
-                gates = [out[k] for k in sorted(moved)]
-                keep = [out[k] for k in range(j + 1, i) if k not in moved]
-                out[j + 1:i + 1] = keep + [e] + gates
+            q = g[1]
+            diag = g[0] in cls._DIAGONAL_1Q and g[6] is None
+            k = j
+            while k + 1 < len(out):
+                h = out[k + 1]
+                if h[2] < 0:
+                    ok = h[1] != q
+                elif q not in (h[1], h[2]):
+                    ok = True
+                else:
+                    ok = diag and ((h[0] == "cx" and h[1] == q) or h[0] == "cz")
+                if not ok:
+                    break
+                out[k], out[k + 1] = h, g
+                k += 1
         return out
 
     def _drop_checkpoints(self, keep=0):

@@ -205,3 +205,37 @@ def test_backend_shared_by_compilers_of_different_widths(fake_backend):
     np.testing.assert_allclose(ems, [1.0, 0.0, 0.0], atol=1e-7)
     ref = AdaptCompiler(wide_target, backend=OracleSVBackend())._get_all_qubit_pair_entanglement_measures()
     np.testing.assert_allclose(wide._get_all_qubit_pair_entanglement_measures(), ref, atol=1e-9)
+
+
+def test_mps_checkpoint_normal_form_is_the_same_circuit():
+    """B200MPSSimulator._commute_phases_past_controls (checkpoint matching of the capped MPS path): every
+    1-qubit gate as late as exact commutation allows.  Same unitary on random circuits; on two thinly dressed
+    layers only the rotations on the cx TARGETS stay in front of a 2-qubit gate."""
+    from adapt_aqc_b200.gates import canonical_window
+    from adapt_aqc_b200.mps_backend import B200MPSSimulator
+    from oracle import sv_oracle as orc
+    norm = B200MPSSimulator._commute_phases_past_controls
+    rng = np.random.default_rng(8)
+    n = 5
+    npar = {"rx": 1, "ry": 1, "rz": 1, "u1": 1, "p": 1, "u2": 2, "u3": 3, "u": 3}
+
+    def to_gates(win):
+        return [(e[0], [e[1]] + ([e[2]] if e[2] >= 0 else []), [e[3], e[4], e[5]][:npar.get(e[0], 0)]) for e in win]
+
+    for trial in range(60):
+        gates = []
+        for _ in range(30):
+            q = int(rng.integers(n)); q2 = int((q + 1 + rng.integers(n - 1)) % n)
+            gates.append([("rz", [q], [float(rng.uniform(-3, 3))]), ("cx", [q, q2], []), ("cz", [q, q2], []), ("ry", [q], [0.3]),
+                          ("t", [q], []), ("h", [q], []), ("u1", [q], [0.7]), ("swap", [q, q2], [])][int(rng.integers(8))])
+        win = canonical_window(circuit_from_gates(n, gates))
+        w2 = norm(win)
+        assert sorted(map(repr, win)) == sorted(map(repr, w2))
+        np.testing.assert_allclose(orc.evaluate_circuit(n, to_gates(w2)), orc.evaluate_circuit(n, to_gates(win)), atol=1e-12)
+    a, b, c = 1, 2, 3
+    thin = [("rz", a, -1, .1, 0, 0, None), ("rz", b, -1, .2, 0, 0, None), ("cx", a, b, 0, 0, 0, None), ("rz", a, -1, .3, 0, 0, None),
+            ("rz", b, -1, .4, 0, 0, None), ("rz", b, -1, .5, 0, 0, None), ("rz", c, -1, .6, 0, 0, None), ("cx", b, c, 0, 0, 0, None),
+            ("rz", b, -1, .7, 0, 0, None), ("rz", c, -1, .8, 0, 0, None)]
+    w2 = norm(thin)
+    last_2q = max(i for i, e in enumerate(w2) if e[2] >= 0)
+    assert [e[3] for e in w2[:last_2q] if e[2] < 0] == [.2, .6]          # only the rotations on the cx targets
