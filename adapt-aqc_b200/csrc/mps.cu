@@ -838,11 +838,11 @@ int b200_mps_amps(b200_mps* m, const uint64_t* bitstrings, int count, double* ou
     CUDA_TRY(cudaMemcpyAsync(st->bits.p, bitstrings, count * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     ctx->counters[4] += count * sizeof(uint64_t);
     const int maxchi = max_bond(m);
-    const size_t smem = (size_t)2 * maxchi * sizeof(double2);
+    const size_t smem = (size_t)(2 + AMPS_SLICES) * maxchi * sizeof(double2);
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(mps_amps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         MScope ms(ctx);
-        mps_amps_kernel<<<count, 256, smem, ctx->stream>>>(tab, (const uint64_t*)st->bits.p, maxchi, (double2*)st->outz.p);
+        mps_amps_kernel<<<count, AMPS_THREADS, smem, ctx->stream>>>(tab, (const uint64_t*)st->bits.p, maxchi, (double2*)st->outz.p);
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, st->outz.p, count * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
