@@ -504,6 +504,42 @@ __device__ __forceinline__ void jacobi_grid_barrier(unsigned* bar, const unsigne
 // zero at launch).  NB = number of blocks (even, NB * WB >= q).  Dynamic shared memory: 2*WB*(p+q) double2.
 // 128 threads (4 warps) cooperate on one column pair: WB pairs per local round -> 128*WB threads per CTA
 // (one warp per pair left every latency exposed: 20 us per outer round instead of ~6).
+// Copies the 2*WB columns of block pair (A, B) of a column-major matrix G (`rows` rows, `q` valid columns)
+// between global memory and rows [row0, row0 + rows) of the shared-memory columns (stride ld); LOAD: global
+// -> shared (L2 loads), else shared -> global.  Element e = c * rows + i is walked with stride NT.
+template <int WB, int NT, bool LOAD>
+__device__ __forceinline__ void jb_copy(double2* __restrict__ smem, double2* __restrict__ G, const int rows, const int q,
+                                        const int row0, const int ld, const int A, const int B) {
+    const int total = 2 * WB * rows;
+    int c = 0, i = threadIdx.x;
+    while (i >= rows) { i -= rows; ++c; }
+    const int dc = NT / rows, di = NT - dc * rows;       // advance of (c, i) per step (loop-invariant division)
+    for (int e = threadIdx.x; e < total; e += 4 * NT) {
+        int cc[4], ii[4];
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            cc[u] = c; ii[u] = i;
+            c += dc; i += di;
+            if (i >= rows) { i -= rows; ++c; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int col = cc[u] < WB ? A * WB + cc[u] : B * WB + (cc[u] - WB);
+            const bool ok = cc[u] < 2 * WB && col < q;
+            if (LOAD) { if (ok) v[u] = __ldcg(G + (size_t)col * rows + ii[u]); }
+            else { if (ok) v[u] = smem[(size_t)cc[u] * ld + row0 + ii[u]]; }
+            cc[u] = ok ? cc[u] : -1;
+            if (!LOAD && ok) __stcg(G + (size_t)col * rows + ii[u], v[u]);
+        }
+        if (LOAD) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (cc[u] >= 0) smem[(size_t)cc[u] * ld + row0 + ii[u]] = v[u];
+        }
+    }
+}
+
 constexpr int JB_GROUP = 128;
 template <int WB>
 __global__ void __launch_bounds__(JB_GROUP * WB)
@@ -527,18 +563,9 @@ jacobi_block_kernel(double2* __restrict__ X, double2* __restrict__ W, const int 
             int A, B;
             rr_pair(NB, r, blockIdx.x, A, B);
             // ---- block pair -> shared memory (column c of the pair at jb_smem + c*ld: X rows, then W rows) ----
-#pragma unroll 4
-            for (int e = threadIdx.x; e < 2 * WB * p; e += NT) {
-                const int c = e / p, i = e - c * p;
-                const int col = c < WB ? A * WB + c : B * WB + (c - WB);
-                if (col < q) jb_smem[(size_t)c * ld + i] = __ldcg(X + (size_t)col * p + i);
-            }
-#pragma unroll 4
-            for (int e = threadIdx.x; e < 2 * WB * q; e += NT) {
-                const int c = e / q, i = e - c * q;
-                const int col = c < WB ? A * WB + c : B * WB + (c - WB);
-                if (col < q) jb_smem[(size_t)c * ld + p + i] = __ldcg(W + (size_t)col * q + i);
-            }
+            // (c, i) advance incrementally: no integer division on the copy path; 4 loads in flight per thread
+            jb_copy<WB, NT, true>(jb_smem, X, p, q, 0, ld, A, B);
+            jb_copy<WB, NT, true>(jb_smem, W, q, q, p, ld, A, B);
             __syncthreads();
             const int nloc = r == 0 ? 2 * WB - 1 : WB;
             for (int t = 0; t < nloc; ++t) {
@@ -588,18 +615,8 @@ jacobi_block_kernel(double2* __restrict__ X, double2* __restrict__ W, const int 
                 __syncthreads();
             }
             // ---- back to global ----
-#pragma unroll 4
-            for (int e = threadIdx.x; e < 2 * WB * p; e += NT) {
-                const int c = e / p, i = e - c * p;
-                const int col = c < WB ? A * WB + c : B * WB + (c - WB);
-                if (col < q) __stcg(X + (size_t)col * p + i, jb_smem[(size_t)c * ld + i]);
-            }
-#pragma unroll 4
-            for (int e = threadIdx.x; e < 2 * WB * q; e += NT) {
-                const int c = e / q, i = e - c * q;
-                const int col = c < WB ? A * WB + c : B * WB + (c - WB);
-                if (col < q) __stcg(W + (size_t)col * q + i, jb_smem[(size_t)c * ld + p + i]);
-            }
+            jb_copy<WB, NT, false>(jb_smem, X, p, q, 0, ld, A, B);
+            jb_copy<WB, NT, false>(jb_smem, W, q, q, p, ld, A, B);
             jacobi_grid_barrier(bar, ++epoch * gridDim.x);
         }
         if (__syncthreads_or(mine) && threadIdx.x == 0) atomicOr(flag, 1);
