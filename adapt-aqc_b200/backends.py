@@ -362,7 +362,7 @@ class B200SVBackend(_SVBase):
         _, ev, window = self._prepare(compiler)
         k = gate_index - compiler.lhs_gate_count
         mats = [G.one_qubit_matrix(name, theta) for name, theta in candidates]
-        amps = ev.shift_amplitudes(window, k, mats)
+        amps = ev.shift_amplitudes(window, k, mats, self._changed)
         self._changed = []
         return [1 - (np.absolute(a)) ** 2 for a in amps]
 

@@ -717,23 +717,23 @@ class SVCostEvaluator:
         return complex(np.sum(self._operator(window) * self.T))
 
     # ---- batched API (K6): every shift value of one gate from one transfer pass ----
-    def shift_amplitudes(self, window, k, candidates):
-        """<0|psi> for each replacement 2x2 matrix in `candidates` at window position k."""
+    def shift_amplitudes(self, window, k, candidates, changed=None):
+        """<0|psi> for each replacement 2x2 matrix in `candidates` at window position k.  `changed`: as in amp0."""
         if self.projected:
-            pj = self._projected(window, k, None)
+            pj = self._projected(window, k, changed)
             if pj is not None:
-                sub, tail, _, m = pj
+                sub, tail, sub_changed, m = pj
                 self.stats["evals"] += len(candidates)
                 self.stats["projected_evals"] += len(candidates)
-                return sub.shift_amplitudes(tail, k - m, candidates)
-        if not self.dense_blocks and not any(b[0] <= k < b[1] and self._compact_ok(window, b) for b in self._blocks(window)):
+                return sub.shift_amplitudes(tail, k - m, candidates, sub_changed)
+        if not self.dense_blocks and not any(b[0] <= k < b[1] and self._compact_ok(window, b) for b in self._blocks(window, changed)):
             out = []
             for cand in candidates:
                 w = list(window)
                 w[k] = ("mat1", window[k][1], -1, 0.0, 0.0, 0.0, np.ascontiguousarray(cand, dtype=np.complex128).tobytes())
                 out.append(self.amp0(w))
             return out
-        for b in self._blocks(window):
+        for b in self._blocks(window, changed):
             if b[0] <= k < b[1]:
                 self._prepare_block(window, b)
                 break
