@@ -169,16 +169,30 @@ def invert_window(window):
     return out
 
 
+_ROT_CACHE = {}
+
+
 def one_qubit_matrix(name, theta):
-    """2x2 matrix of rx/ry/rz(theta) (standard qiskit definitions)."""
+    """2x2 matrix of rx/ry/rz(theta) (standard qiskit definitions).  Cached (read-only arrays): the optimiser
+    asks for the same few shift angles of every gate (cost_minimiser.py:344-368)."""
+    key = (name, float(theta))
+    m = _ROT_CACHE.get(key)
+    if m is not None:
+        return m
     c, s = np.cos(theta / 2), np.sin(theta / 2)
     if name == "rx":
-        return np.array([[c, -1j * s], [-1j * s, c]])
-    if name == "ry":
-        return np.array([[c, -s], [s, c]], dtype=np.complex128)
-    if name == "rz":
-        return np.array([[np.exp(-0.5j * theta), 0], [0, np.exp(0.5j * theta)]])
-    raise ValueError(f"not a rotation: {name}")
+        m = np.array([[c, -1j * s], [-1j * s, c]])
+    elif name == "ry":
+        m = np.array([[c, -s], [s, c]], dtype=np.complex128)
+    elif name == "rz":
+        m = np.array([[np.exp(-0.5j * theta), 0], [0, np.exp(0.5j * theta)]])
+    else:
+        raise ValueError(f"not a rotation: {name}")
+    m.flags.writeable = False
+    if len(_ROT_CACHE) > 8192:
+        _ROT_CACHE.clear()
+    _ROT_CACHE[key] = m
+    return m
 
 
 _R2 = 1 / np.sqrt(2)
