@@ -293,11 +293,8 @@ class B200SVBackend(_SVBase):
                             window)
             return window, None
         _, insts, params, window = wc
-        changed = []
-        for i in range(m):
-            inst = data[lhs + i]
-            if inst is not insts[i] or inst.operation.params != params[i]:
-                changed.append(i)
+        changed = [i for i, (inst, old, par) in enumerate(zip(data[lhs:] if lhs else data, insts, params))
+                   if inst is not old or inst.operation.params != par]
         if changed:
             qmap = G.qubit_indices(circuit)
             for i in changed:
