@@ -143,6 +143,19 @@ class ShardedStatevector:
         self.stats = {"exchanges": 0, "local_runs": 0}
         self.peer_ptrs = None      # [slot][rank] -> device pointer into that rank's slot (CUDA IPC), or None: NCCL path
 
+    def close(self):
+        """Collective: every rank unmaps its peers' slots (CUDA IPC) before any rank frees its own."""
+        if self.peer_ptrs is not None:
+            self._sync()
+            self.comm.dist.barrier()
+            for row in self.peer_ptrs:
+                for ptr in row:
+                    if ptr:
+                        self.eng.ipc_close(ptr)
+            self.peer_ptrs = None
+            self.comm.dist.barrier()
+        self.eng.close()
+
     # ---- layout ----
     def _rank_bit(self, phys):
         return (self.comm.rank >> (phys - self.nl)) & 1
@@ -403,7 +416,7 @@ class ShardedEngine:
         return self.sv.eng.profile_read()
 
     def close(self):
-        self.sv.eng.close()
+        self.sv.close()
 
 
 class _CudaAlias:

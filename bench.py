@@ -360,7 +360,7 @@ def bench_sharded(args, local_rank, world):
         "sweep_GBps": 32.0 * (1 << (n - g)) / (prof["sweep"][0] / max(1, prof["sweep"][1]) * 1e-3) / 1e9 if prof["sweep"][1] else None,
         "norm": norm, "amp0_abs2": abs(a0) ** 2,
     }
-    eng.close()
+    sv.close()
     del sv
     torch.cuda.empty_cache()
     if not args.no_compile:

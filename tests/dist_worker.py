@@ -91,6 +91,8 @@ def compile_main(n, on_gpu):
         assert np.allclose(got.global_cost_history, ref.global_cost_history, atol=1e-9)
         assert got.cost_evaluations == ref.cost_evaluations
     assert st["projected_evals"] > 0, st
+    if on_gpu:
+        backend._engine.close()
     if dist.get_rank() == 0:
         print(f"dist compile ok: world={dist.get_world_size()} n={n} layers={len(got.qubit_pair_history)} "
               f"evals={got.cost_evaluations} cost={got.global_cost_history[-1]:.6f} stats={st}")
@@ -150,6 +152,8 @@ def main():
         assert np.max(np.abs(gather_state(sv, 1) - ref2)) < 1e-12
         assert abs(sv.inner(1, 1) - 1) < 1e-12
     assert sv.stats["exchanges"] > 0, "the test circuits must exercise the global-qubit exchange"
+    if on_gpu:
+        sv.close()
     if comm.rank == 0:
         print(f"dist ok: world={comm.world} n={n} exchanges={sv.stats['exchanges']} bytes_sent={comm.bytes_sent} "
               f"exchange={getattr(sv, 'exchange_mode', 'nccl')}")
