@@ -590,7 +590,7 @@ int b200_sv_expz(b200_ctx* ctx, int slot, double* out) {
         CUDA_TRY(cudaGetLastError());
         {
             KScope ks(ctx, B200_PROF_REDUCE);
-            sv_expz_final_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_partial, nblocks, n, tb, ctx->d_out);
+            sv_expz_final_kernel<<<n + 1, RED_THREADS, 0, ctx->stream>>>(ctx->d_partial, nblocks, n, tb, ctx->d_out);
         }
         CUDA_TRY(cudaGetLastError());
     }

@@ -793,20 +793,32 @@ sv_expz_kernel(const double2* __restrict__ psi, const int tb, const int kb, doub
     block_sum_store<EXPZ_WIDTH>(v, partial + (size_t)blockIdx.x * EXPZ_WIDTH);
 }
 
-// out[q] = <Z_q> (q < n), out[n] = norm^2
-__global__ void sv_expz_final_kernel(const double* __restrict__ partial, const int nblocks, const int n,
-                                     const int tb, double* __restrict__ out) {
-    const int q = threadIdx.x;
+// out[q] = <Z_q> (q < n), out[n] = norm^2.  One CTA per output: 256 threads add the block partials in a
+// strided, fixed order and meet in a fixed shuffle / shared-memory tree (deterministic for a given grid).
+// (One thread per output walking all ~16k block partials took 0.5 ms -- half of the read pass itself.)
+__global__ void __launch_bounds__(RED_THREADS)
+sv_expz_final_kernel(const double* __restrict__ partial, const int nblocks, const int n, const int tb,
+                     double* __restrict__ out) {
+    __shared__ double sh[2][RED_THREADS / 32];
+    const int q = blockIdx.x;
     if (q > n) return;
     double total = 0, sq = 0;
-    for (int b = 0; b < nblocks; ++b) {
+    for (int b = threadIdx.x; b < nblocks; b += RED_THREADS) {
         const double* pb = partial + (size_t)b * EXPZ_WIDTH;
         total += pb[0];
         if (q < 8) sq += pb[1 + q];
         else if (q < tb) sq += ((b >> (q - 8)) & 1) ? pb[0] : 0.0;
         else if (q < n) sq += pb[9 + (q - tb)];
     }
-    out[q] = q < n ? total - 2.0 * sq : total;
+    total = warp_sum(total);
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = total; sh[1][threadIdx.x >> 5] = sq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0, s2 = 0;
+        for (int w = 0; w < RED_THREADS / 32; ++w) { t += sh[0][w]; s2 += sh[1][w]; }
+        out[q] = q < n ? t - 2.0 * s2 : t;
+    }
 }
 
 // generic small/odd-size fallback: one block, thread q walks the whole state (n <= 14)
