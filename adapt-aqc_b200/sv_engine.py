@@ -739,4 +739,20 @@ class SVCostEvaluator:
                 break
         self.stats["evals"] += len(candidates)
         self.stats["host_evals"] += len(candidates)
-        return [complex(np.sum(self._operator(window, k, c) * self.T)) for c in candidates]
+        # The product of the block's gates in front of position k is the same for every candidate: fold it
+        # once.  Same association order as _operator (later gates multiply from the left), so every candidate
+        # gets bit-identical arithmetic.
+        b0, b1 = self.cut
+        pre = None
+        for i in range(b0, k):
+            m = embed_entry(window[i], self.pair)
+            pre = m if pre is None else m @ pre
+        post = [embed_entry(window[i], self.pair) for i in range(k + 1, b1)]
+        out = []
+        for c in candidates:
+            m = embed_entry(window[k], self.pair, c)
+            op = m if pre is None else m @ pre
+            for pm in post:
+                op = pm @ op
+            out.append(complex(np.sum(op * self.T)))
+        return out
