@@ -704,6 +704,9 @@ class SVCostEvaluator:
             self.stats["resimulations"] = self.stats.get("resimulations", 0) + 1
             self.T = None
             self.window = None
+            # slot R / phi were NOT advanced to this window: a later tail-only edit must not take the
+            # "only tail gates changed since phi was gathered" shortcut of _projected
+            self._proj_state = None
             self.eng.run(SLOT_WORK, SLOT_BASE, G.GateStream.from_window(window))
             return self.eng.amp(SLOT_WORK, 0)
         if (changed is not None and self.T is not None and self.window is not None and len(self.window) == len(window)

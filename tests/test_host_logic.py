@@ -239,3 +239,43 @@ def test_mps_checkpoint_normal_form_is_the_same_circuit():
     w2 = norm(thin)
     last_2q = max(i for i, e in enumerate(w2) if e[2] >= 0)
     assert [e[3] for e in w2[:last_2q] if e[2] < 0] == [.2, .6]          # only the rotations on the cx targets
+
+
+def test_resimulation_then_tail_edit_does_not_reuse_a_stale_projection(emu):
+    """Sharded-register mode (dense_blocks=False): a head-gate edit is served by re-simulation, which leaves slot R /
+    phi at the OLD head; the next tail-only edit must re-gather phi instead of taking the "only tail gates changed"
+    shortcut (round-1 advisor finding: 2.7e-3 error in the order tail edit, head edit, tail edit)."""
+    from adapt_aqc_b200.gates import canonical_window
+    from oracle import sv_oracle as orc
+    from oracle.oracle_backends import circuit_to_gates
+    n = 12
+    target, trng = brickwork(n, 3, seed=3)
+    # head layers spread over the register (suffix touches > 8 qubits -> no compact / projected path), tail on 0..3
+    ansatz = Circuit(n)
+    pairs = [(0, 1), (4, 5), (8, 9), (10, 11), (2, 3), (6, 7), (1, 2), (0, 1), (2, 3)]
+    for a, b in pairs:
+        th = trng.uniform(-np.pi, np.pi, 4)
+        ansatz.rz(th[0], a, label="rz"); ansatz.rz(th[1], b, label="rz"); ansatz.cx(a, b)
+        ansatz.rz(th[2], a, label="rz"); ansatz.rz(th[3], b, label="rz")
+    eng = FakeEngine(emu, n)
+    ev = SVCostEvaluator(eng, None, [FakeEngine(emu, 8, n_slots=4)])
+    ev.dense_blocks = False
+    from adapt_aqc_b200.gates import GateStream
+    ev.set_base("t", GateStream.from_circuit(target))
+    base_gates = circuit_to_gates(target)
+
+    def check(window, changed):
+        got = ev.amp0(list(window), changed=changed)
+        c = Circuit(n)
+        c.data = list(ansatz.data)
+        ref = orc.evaluate_circuit(n, base_gates + circuit_to_gates(c))[0]
+        assert abs(got - ref) < 1e-10, (got, ref)
+
+    window = canonical_window(ansatz)
+    check(window, None)
+    tail_idx, head_idx = len(window) - 1, 0
+    for step, idx in enumerate([tail_idx, head_idx, tail_idx, tail_idx - 5, head_idx + 1, tail_idx]):
+        replace_1q_gate(ansatz, idx, "rz", 0.37 * (step + 1))
+        window[idx] = canonical_window(ansatz, idx, idx + 1)[0]
+        check(window, [idx])
+    assert ev.stats.get("resimulations", 0) >= 2 and ev.stats["projected_evals"] >= 3
