@@ -59,6 +59,29 @@ COMPACT_MIN_QUBITS = 12
 PROJECT_QUBITS = (16, 20, 24)
 
 
+def _fingerprint(inst, qmap):
+    """[instruction object, snapshot of its params, value key | None] (mutable: the object slot is refreshed)."""
+    return [inst, list(inst.operation.params), G.instruction_key(inst, qmap)]
+
+
+def _same_instruction(inst, fp, qmap):
+    """Is `inst` the gate recorded in fingerprint `fp`?  Same object with unmodified params, or equal by value."""
+    old, params, key = fp
+    if inst is old:
+        try:
+            if inst.operation.params == params:
+                return True
+        except ValueError:            # array-valued parameters (unitary gates) compared element-wise
+            pass
+        return False
+    if key is None:
+        return False
+    if G.instruction_key(inst, qmap) == key:
+        fp[0] = inst                  # the next call may hit the identity shortcut
+        return True
+    return False
+
+
 class DeviceStatevector:
     """What ``result.get_statevector()`` returns: a handle on an HBM-resident state.
 
@@ -241,15 +264,16 @@ class B200SVBackend(_SVBase):
         eng = self._get_engine(circuit.num_qubits)
         data = circuit.data
         live = self._last_run_sv is not None and self._last_run_sv._version == self._state_version
-        # same instruction objects with the same parameters as the previous run (the reference asks for
-        # the same circuit once per candidate pair, adapt_compiler.py:964-975): no re-canonicalisation
+        # same instructions (by value; object identity is only a shortcut) as the previous run -- the reference asks
+        # for the same circuit once per candidate pair (adapt_compiler.py:964-975): no re-canonicalisation
         fp = self._last_run_insts
-        if live and fp is not None and len(fp) == len(data) and all(
-                inst is f[0] and inst.operation.params == f[1] for inst, f in zip(data, fp)):
+        qmap = G.qubit_indices(circuit)
+        cur = list(data)
+        if live and fp is not None and len(fp) == len(cur) and all(_same_instruction(inst, f, qmap) for inst, f in zip(cur, fp)):
             return self._last_run_sv
         window = G.canonical_window(circuit)
         key = tuple(window)
-        self._last_run_insts = [(inst, list(inst.operation.params)) for inst in data]
+        self._last_run_insts = [_fingerprint(inst, qmap) for inst in cur]
         if live and self._last_run_key is not None and key == self._last_run_key:
             return self._last_run_sv
         eng.run(SLOT_WORK, -1, G.GateStream.from_window(window))
@@ -289,22 +313,25 @@ class B200SVBackend(_SVBase):
             if len(window) != m:          # barriers etc. were dropped: no positional cache
                 self._wcache = None
                 return window, None
-            self._wcache = (key, [data[lhs + i] for i in range(m)], [list(data[lhs + i].operation.params) for i in range(m)],
-                            window)
-            return window, None
-        _, insts, params, window = wc
-        changed = [i for i, (inst, old, par) in enumerate(zip(data[lhs:] if lhs else data, insts, params))
-                   if inst is not old or inst.operation.params != par]
-        if changed:
             qmap = G.qubit_indices(circuit)
-            for i in changed:
-                ent = G.canonical_window(circuit, lhs + i, lhs + i + 1, qmap)
-                if len(ent) != 1:
-                    self._wcache = None
-                    return G.canonical_window(circuit, lhs, None), None
-                window[i] = ent[0]
-                insts[i] = data[lhs + i]
-                params[i] = list(data[lhs + i].operation.params)
+            self._wcache = (key, [_fingerprint(inst, qmap) for inst in (data[lhs:] if lhs else data)], window, qmap)
+            return window, None
+        _, fps, window, qmap = wc
+        # value comparison (name, params, qubits); `is` only short-cuts it: qiskit >= 1.0 hands out a fresh
+        # CircuitInstruction per data[i] access, so identity alone would flag every gate on every call
+        cur = data[lhs:] if lhs else data
+        try:        # (identity test inlined: this line runs once per gate per cost evaluation)
+            changed = [i for i, (inst, f) in enumerate(zip(cur, fps))
+                       if not (inst is f[0] and inst.operation.params == f[1]) and not _same_instruction(inst, f, qmap)]
+        except ValueError:          # array-valued parameters
+            changed = [i for i, (inst, f) in enumerate(zip(cur, fps)) if not _same_instruction(inst, f, qmap)]
+        for i in changed:
+            ent = G.canonical_window(circuit, lhs + i, lhs + i + 1, qmap)
+            if len(ent) != 1:
+                self._wcache = None
+                return G.canonical_window(circuit, lhs, None), None
+            window[i] = ent[0]
+            fps[i] = _fingerprint(data[lhs + i], qmap)
         return window, changed
 
     # ---- the four backend methods ----
@@ -357,7 +384,12 @@ class B200SVBackend(_SVBase):
                 "soften_global_cost is currently only implemented for AerMPSBackend"
             )
         _, ev, window = self._prepare(compiler)
-        k = gate_index - compiler.lhs_gate_count
+        lhs = compiler.lhs_gate_count
+        k = gate_index - lhs
+        if len(window) != len(compiler.full_circuit.data) - lhs:     # barriers / delays were dropped from the window
+            k = G.window_index(compiler.full_circuit, lhs, gate_index)
+        if not 0 <= k < len(window) or window[k][2] >= 0:
+            raise ValueError(f"full_circuit index {gate_index} is not a 1-qubit gate of the variational window")
         mats = [G.one_qubit_matrix(name, theta) for name, theta in candidates]
         amps = ev.shift_amplitudes(window, k, mats, self._changed)
         self._changed = []

@@ -83,6 +83,36 @@ def canonical_window(circuit, start=0, stop=None, qmap="auto"):
     return out
 
 
+def instruction_key(inst, qmap=None):
+    """Value identity of one circuit instruction: (name, params, qubit indices), or None for instructions whose
+    parameters are not plain numbers (e.g. a `unitary` carrying a matrix) -- those only match by object identity.
+
+    qiskit >= 1.0 materialises a fresh ``CircuitInstruction`` on every ``QuantumCircuit.data[i]`` access, so the
+    incremental translator diffs circuits on these values, never on ``id()`` alone."""
+    op = inst.operation
+    name = op.name
+    if name not in GATE_TABLE and name not in IGNORED:
+        return None
+    qs = inst.qubits
+    if qmap is not None:
+        qs = [qmap[q] for q in qs]
+    try:
+        return (name, tuple(float(p) for p in op.params), tuple(int(q) for q in qs))
+    except (TypeError, ValueError):        # unbound Parameter etc.
+        return None
+
+
+def window_index(circuit, start, gate_index):
+    """Position in ``canonical_window(circuit, start, None)`` of the instruction at circuit index `gate_index`
+    (the canonical window drops barriers / delays, so it is not always gate_index - start)."""
+    data = circuit.data
+    if not start <= gate_index < len(data):
+        raise IndexError(f"gate index {gate_index} outside the window [{start}, {len(data)})")
+    if data[gate_index].operation.name in IGNORED:
+        raise ValueError(f"instruction {gate_index} ({data[gate_index].operation.name}) carries no gate")
+    return sum(1 for i in range(start, gate_index) if data[i].operation.name not in IGNORED)
+
+
 class GateStream:
     """Packed gate records + dense-matrix pool, ready for the C-ABI."""
 

@@ -427,28 +427,28 @@ class B200MPSBackend(_MPSBase):
         return self._evaluator
 
     def _base_and_window(self, compiler):
+        """(device base state | None, cache key, canonical window, circuit index of the window's first gate)"""
         circuit = compiler.full_circuit
         data = circuit.data
-        lhs = compiler.lhs_gate_count
         if len(data) and data[0].operation.name == "set_matrix_product_state":
             host = data[0].operation.params[0]
             base = self.simulator.device_copy_of(host)
             key = ("mps", id(host))
-            window = G.canonical_window(circuit, 1, None)
+            window, start = G.canonical_window(circuit, 1, None), 1
         else:   # circuit target that was not converted (not produced by the reference's prepare_circuit)
-            base, key, window = None, ("zero", circuit.num_qubits), G.canonical_window(circuit, 0, None)
-        return base, key, window, lhs
+            base, key, window, start = None, ("zero", circuit.num_qubits), G.canonical_window(circuit, 0, None), 0
+        return base, key, window, start
 
-    def amp0(self, compiler):
+    def amp0(self, compiler, with_start=False):
         ev = self._get_evaluator(compiler.full_circuit.num_qubits)
-        base, key, window, _ = self._base_and_window(compiler)
+        base, key, window, start = self._base_and_window(compiler)
         if base is not None:
             ev.set_base_handle(key, base)
         elif ev.base_key != key:
             self._engine.slots[SLOT_BASE].init_zero()
             ev.base_key = key
             ev.invalidate()
-        return ev, window
+        return (ev, window, start) if with_start else (ev, window)
 
     # ---- the backend methods (aer_mps_backend.py:49-93) ----
     def evaluate_global_cost(self, compiler):
@@ -493,7 +493,13 @@ class B200MPSBackend(_MPSBase):
     def shift_costs(self, compiler, gate_index, candidates):
         if not self._use_incremental(compiler):
             raise NotImplementedError("batched shifts need roundoff-level truncation (see _use_incremental)")
-        ev, window = self.amp0(compiler)
-        k = gate_index - compiler.lhs_gate_count
+        ev, window, start = self.amp0(compiler, with_start=True)
+        # the window starts right after the set_matrix_product_state instruction (index 1), or at 0 for a circuit
+        # target that was not converted -- not necessarily at lhs_gate_count
+        k = gate_index - start
+        if len(window) != len(compiler.full_circuit.data) - start:   # barriers / delays were dropped from the window
+            k = G.window_index(compiler.full_circuit, start, gate_index)
+        if not 0 <= k < len(window) or window[k][2] >= 0:
+            raise ValueError(f"full_circuit index {gate_index} is not a 1-qubit gate")
         mats = [G.one_qubit_matrix(name, theta) for name, theta in candidates]
         return [1 - np.absolute(a) ** 2 for a in ev.shift_amplitudes(window, k, mats)]
