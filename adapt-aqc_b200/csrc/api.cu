@@ -886,7 +886,8 @@ int b200_sv_scatter(b200_ctx* ctx, int slot, const int32_t* qmap, int K, const v
 
 int b200_sv_download(b200_ctx* ctx, int slot, uint64_t offset, uint64_t count, double* host) {
     if (check_slot(ctx, slot)) return -1;
-    if (offset + count > (1ull << ctx->nq)) return set_error("download range out of bounds");
+    if (!host && count) return set_error("null host buffer");
+    if (offset > (1ull << ctx->nq) || count > (1ull << ctx->nq) - offset) return set_error("download range out of bounds");
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaMemcpyAsync(host, (const double2*)ctx->slots[slot] + offset, count * sizeof(double2),
                              cudaMemcpyDeviceToHost, ctx->stream));
@@ -897,7 +898,8 @@ int b200_sv_download(b200_ctx* ctx, int slot, uint64_t offset, uint64_t count, d
 
 int b200_sv_upload(b200_ctx* ctx, int slot, uint64_t offset, uint64_t count, const double* host) {
     if (check_slot(ctx, slot)) return -1;
-    if (offset + count > (1ull << ctx->nq)) return set_error("upload range out of bounds");
+    if (!host && count) return set_error("null host buffer");
+    if (offset > (1ull << ctx->nq) || count > (1ull << ctx->nq) - offset) return set_error("upload range out of bounds");
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaMemcpyAsync((double2*)ctx->slots[slot] + offset, host, count * sizeof(double2),
                              cudaMemcpyHostToDevice, ctx->stream));

@@ -179,19 +179,31 @@ int apply_1q(b200_mps* m, int q, const cplx g[4]) {
     return 0;
 }
 
-// Aer's reduce_zeros: number of singular values kept (S descending) and their renormalised values.
+// Aer's reduce_zeros (qiskit-aer 0.16, src/simulators/matrix_product_state/svd.cpp -- not vendored in the reference
+// tree, restated from the published source): number of singular values kept (S descending) and their renormalised
+// values.  Two details of that function are easy to get wrong, so both are a named rule (b200_mps_set_chop_rule):
+//   B200_CHOP_AER (default): num_of_SV counts values with std::norm(S[i]) > CHOP_THRESHOLD -- std::norm of a real is its
+//     SQUARE, i.e. sigma^2 > 1e-16 (sigma > 1e-8); and the tail-drop loop only lowers the kept count when it BREAKS: if
+//     every value down to S[1] fits under the threshold the count is left unchanged (nothing is dropped).
+//   B200_CHOP_SIGMA: the round-1 reading -- sigma > 1e-16, and a loop that runs out keeps exactly one value.
+constexpr double CHOP_THRESHOLD = 1e-16;
+int g_chop_rule = 0;   // B200_CHOP_AER
+
 int reduce_zeros(const std::vector<double>& S, int max_chi, double thr, std::vector<double>& kept) {
+    const bool aer = g_chop_rule == 0;
     int sv_num = 0;
-    for (double s : S) if (s > 1e-16) ++sv_num;
+    for (double s : S) if ((aer ? s * s : s) > CHOP_THRESHOLD) ++sv_num;
     int new_num = sv_num;
     if (max_chi > 0 && max_chi < sv_num) new_num = max_chi;
     double sum_sq = 0.0;
     int i = new_num - 1;
+    bool broke = false;
     for (; i > 0; --i) {
         if (sum_sq + S[i] * S[i] < thr) sum_sq += S[i] * S[i];
-        else break;
+        else { broke = true; break; }
     }
-    new_num = std::max(1, i + 1);
+    if (broke || !aer) new_num = i + 1;
+    new_num = std::max(1, new_num);
     kept.assign(S.begin(), S.begin() + new_num);
     if (new_num < sv_num) {
         double nrm = 0;
@@ -611,6 +623,7 @@ int b200_mps_init_zero(b200_mps* m) {
 int b200_mps_set(b200_mps* m, const int32_t* bond_dims, const double* gammas, const double* lambdas) {
     if (check_mps(m)) return -1;
     if (!bond_dims && m->n > 1) return set_error("null bond_dims");
+    if (!gammas || (!lambdas && m->n > 1)) return set_error("null gammas / lambdas");
     b200_ctx* ctx = m->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
     for (int i = 0; i + 1 < m->n; ++i)
@@ -814,6 +827,21 @@ int b200_mps_transfer(b200_mps* a, b200_mps* b, const int32_t* qubits, int n_ope
             out[2 * (4 * ii + jj)] = host[4 * i + j].x;
             out[2 * (4 * ii + jj) + 1] = host[4 * i + j].y;
         }
+    return 0;
+}
+
+int b200_mps_set_chop_rule(int rule) {
+    if (rule != 0 && rule != 1) return set_error("chop rule must be B200_CHOP_AER (0) or B200_CHOP_SIGMA (1)");
+    g_chop_rule = rule;
+    return 0;
+}
+
+int b200_mps_reduce_zeros(const double* s_desc, int n, int max_bond_dimension, double truncation_threshold, int* n_kept,
+                          double* kept_out) {
+    if (!s_desc || !n_kept || !kept_out || n <= 0) return set_error("b200_mps_reduce_zeros: null or empty input");
+    std::vector<double> S(s_desc, s_desc + n), kept;
+    *n_kept = reduce_zeros(S, max_bond_dimension, truncation_threshold, kept);
+    for (int i = 0; i < *n_kept; ++i) kept_out[i] = kept[i];
     return 0;
 }
 

@@ -269,6 +269,7 @@ class MPSOps:
 
     def __init__(self, default_sim):
         self._default_sim = default_sim
+        self._sims_by_threshold = {}      # trunc_thr -> B200MPSSimulator sharing the default simulator's device context
 
     # -- conversions --
     @staticmethod
@@ -309,8 +310,13 @@ class MPSOps:
         """Appends the save instruction to `qc` in place like aqc_research does (callers pass
         copies, aer_mps_backend.py:77), runs the circuit on the device."""
         if sim is None:
-            sim = self._default_sim if trunc_thr == self._default_sim.options.matrix_product_state_truncation_threshold \
-                else B200MPSSimulator(trunc_thr, device=self._default_sim.device)
+            sim = self._default_sim
+            if trunc_thr != sim.options.matrix_product_state_truncation_threshold:
+                # one cached simulator per threshold, on the default simulator's context (no new device context per call)
+                sim = self._sims_by_threshold.get(trunc_thr)
+                if sim is None:
+                    sim = self._sims_by_threshold[trunc_thr] = B200MPSSimulator(trunc_thr, device=self._default_sim.device)
+                    sim._context = self._default_sim.context()
         if hasattr(qc, "save_matrix_product_state"):
             qc.save_matrix_product_state()
         handle = sim.simulate(qc)

@@ -46,6 +46,24 @@ def pack_preprocessed(pp):
     return bond, gflat, lflat
 
 
+CHOP_AER, CHOP_SIGMA = 0, 1      # include/b200aqc.h: B200_CHOP_AER / B200_CHOP_SIGMA
+
+
+def set_chop_rule(rule):
+    """Process-wide reading of Aer's reduce_zeros (see include/b200aqc.h, b200_mps_set_chop_rule)."""
+    check(load().b200_mps_set_chop_rule({"aer": CHOP_AER, "sigma": CHOP_SIGMA}.get(rule, rule)))
+
+
+def reduce_zeros(singular_values, max_bond_dimension=None, truncation_threshold=1e-16):
+    """(kept count, kept values) of the library's truncation rule on a descending vector (host only, no GPU)."""
+    s = np.ascontiguousarray(singular_values, dtype=np.float64)
+    out = np.zeros(len(s))
+    k = ctypes.c_int(0)
+    check(load().b200_mps_reduce_zeros(dptr(s), len(s), int(max_bond_dimension or 0), float(truncation_threshold),
+                                       ctypes.byref(k), dptr(out)))
+    return k.value, out[:k.value].copy()
+
+
 class MPSContext:
     """One GPU context for MPS work (one CUDA stream)."""
 

@@ -214,8 +214,8 @@ int b200_mps_get(b200_mps *mps, double *gammas, double *lambdas);
 int b200_mps_copy(b200_mps *dst, b200_mps *src);
 /* Applies the gate stream: 1-qubit gates contract the physical index; 2-qubit gates contract the
  * two sites (complex GEMM on FP64 tensor cores), run the on-device Jacobi SVD and truncate with
- * Aer's rule (keep > 1e-16, cap at max bond, drop smallest while the sum of squares stays below
- * the threshold, renormalise if anything was dropped); non-neighbours are swapped together and
+ * Aer's rule (see b200_mps_set_chop_rule: chop, cap at max bond, drop smallest while the sum of squares
+ * stays below the threshold, renormalise if anything was dropped); non-neighbours are swapped together and
  * back.  Replaces the Aer MPS run inside mps_from_circuit (aer_mps_backend.py:78;
  * adaptaqc/compilers/adapt/adapt_compiler.py:1129-1131). */
 int b200_mps_apply(b200_mps *mps, const b200_gate *gates, int n_gates, const double *mats, int n_mats);
@@ -239,6 +239,19 @@ int b200_mps_expz(b200_mps *mps, double *out /* n+1 */);
 /* 4x4 reduced density matrices, same conventions as b200_sv_pair_rdm: aqc_research.partial_trace
  * (adaptaqc/utils/entanglement_measures.py:76-79). */
 int b200_mps_pair_rdm(b200_mps *mps, const int32_t *pairs, int n_pairs, double *out /* 32*n_pairs */);
+/* Truncation rule of the 2-qubit gates = qiskit-aer's reduce_zeros (svd.cpp, called from the Aer MPS run the
+ * reference starts at adaptaqc/backends/aer_mps_backend.py:37-42,78).  The Aer source is not part of the reference
+ * tree; its rule is restated and the two ambiguous details are selectable so that both readings stay testable:
+ *   B200_CHOP_AER   (default) count values with sigma^2 > 1e-16 (std::norm of a real), and leave the count unchanged
+ *                   when the tail-drop loop runs out without a break;
+ *   B200_CHOP_SIGMA count values with sigma > 1e-16, a loop that runs out keeps one value (round-1 behaviour).
+ * Process-wide.  b200_mps_reduce_zeros applies the current rule to a descending vector on the host (no GPU):
+ * *n_kept values, renormalised if anything was dropped, are written to kept_out (capacity n). */
+#define B200_CHOP_AER 0
+#define B200_CHOP_SIGMA 1
+int b200_mps_set_chop_rule(int rule);
+int b200_mps_reduce_zeros(const double *s_desc, int n, int max_bond_dimension, double truncation_threshold,
+                          int *n_kept, double *kept_out);
 /* out = {SVDs run, Jacobi sweeps run, current max bond dimension, 0}. */
 int b200_mps_stats(b200_mps *mps, uint64_t out[4]);
 

@@ -13,7 +13,7 @@ pinned against the statevector oracle and the 54 paper/random_mps fixtures.
     2-qubit gate on neighbours = contract two sites with the surrounding lambdas, apply the 4x4
     matrix, SVD of the (2 chi_l x 2 chi_r) matrix, truncate, divide the outer lambdas back out;
     non-neighbours are brought together with swap gates.  Truncation ("reduce_zeros"): keep
-    singular values > 1e-16, cap at max_bond_dimension, then drop the smallest while the running
+    singular values with sigma^2 > 1e-16 (see set_chop_rule), cap at max_bond_dimension, then drop the smallest while the running
     sum of their squares stays below truncation_threshold; if anything was dropped renormalise
     the kept values to unit 2-norm.
 (2) aqc_research.mps_operations (unpinned git dependency, setup.py:22): mps_from_circuit,
@@ -65,21 +65,45 @@ def gate_matrix(name, params):
 # ---------------------------------------------------------------------------------------------
 # (1) Aer's MPS simulator
 # ---------------------------------------------------------------------------------------------
+CHOP_AER, CHOP_SIGMA = "aer", "sigma"
+CHOP_RULE = CHOP_AER
+
+
+def set_chop_rule(rule):
+    """Select how Aer's reduce_zeros is read (the Aer source is not vendored in the reference tree):
+
+    "aer"   (default) num_of_SV counts ``std::norm(S[i]) > CHOP_THRESHOLD`` -- the norm of a real number is its
+            square, so sigma^2 > 1e-16 -- and the tail-drop loop lowers the count only when it breaks;
+    "sigma" round-1 reading: sigma > 1e-16, and a loop that runs out keeps one value.
+    Mirrors ``b200_mps_set_chop_rule`` of the product so that both readings can be parity-tested."""
+    global CHOP_RULE
+    if rule not in (CHOP_AER, CHOP_SIGMA):
+        raise ValueError(rule)
+    CHOP_RULE = rule
+
+
 def reduce_zeros(S, max_bond_dimension, truncation_threshold):
-    """Number of singular values kept + the (possibly renormalised) values.  S descending."""
-    sv_num = int(np.count_nonzero(S > CHOP_THRESHOLD))
+    """Number of singular values kept + the (possibly renormalised) values.  S descending.
+    Restates reduce_zeros / num_of_SV of qiskit-aer 0.16 svd.cpp (reached from aer_mps_backend.py:37-42,78)."""
+    S = np.asarray(S, dtype=np.float64)
+    aer = CHOP_RULE == CHOP_AER
+    sv_num = int(np.count_nonzero((S * S if aer else S) > CHOP_THRESHOLD))
     new_num = sv_num
     if max_bond_dimension is not None and max_bond_dimension < sv_num:
         new_num = int(max_bond_dimension)
     sum_squares = 0.0
     i = new_num - 1
+    broke = False
     while i > 0:
         if sum_squares + S[i] ** 2 < truncation_threshold:
             sum_squares += S[i] ** 2
             i -= 1
         else:
+            broke = True
             break
-    new_num = i + 1
+    if broke or not aer:
+        new_num = i + 1
+    new_num = max(1, new_num)
     kept = np.array(S[:new_num], dtype=np.float64)
     if new_num < sv_num:
         kept = kept / np.sqrt(np.sum(kept ** 2))
