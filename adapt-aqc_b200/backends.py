@@ -82,6 +82,13 @@ def _same_instruction(inst, fp, qmap):
     return False
 
 
+_LAST_ACTIVE = None      # weakref to the B200SVBackend that touched the device last (registration: exact overlap)
+
+
+def last_active_backend():
+    return _LAST_ACTIVE() if _LAST_ACTIVE is not None else None
+
+
 class DeviceStatevector:
     """What ``result.get_statevector()`` returns: a handle on an HBM-resident state.
 
@@ -213,6 +220,9 @@ class B200SVBackend(_SVBase):
 
     # ---- engine management ----
     def _get_engine(self, num_qubits):
+        global _LAST_ACTIVE
+        if _LAST_ACTIVE is None or _LAST_ACTIVE() is not self:
+            _LAST_ACTIVE = weakref.ref(self)
         if self._engine is None or self._engine.num_qubits != num_qubits:
             if self._engine is not None:
                 self._engine.close()
@@ -407,24 +417,6 @@ class B200SVBackend(_SVBase):
         return np.absolute(eng.inner(SLOT_L, SLOT_R, -1)) ** 2
 
 
-def install():
-    """Registration hook for a real ``adaptaqc`` installation: the one reference function that
-    touches Aer's Statevector type directly (adaptaqc/utils/entanglement_measures.py:325-340) is
-    wrapped so that a DeviceStatevector answers ``partial_trace`` itself (all candidate pairs from
-    one batch of RDM passes).  A no-op when the reference package is not importable."""
-    if not HAVE_REFERENCE:
-        return False
-    import adaptaqc.utils.entanglement_measures as rem  # pragma: no cover
-
-    original = rem.partial_trace                         # pragma: no cover
-
-    def partial_trace(statevector, qubit_1, qubit_2):    # pragma: no cover
-        if isinstance(statevector, DeviceStatevector):
-            return statevector.partial_trace(qubit_1, qubit_2)
-        return original(statevector, qubit_1, qubit_2)
-
-    rem.partial_trace = partial_trace                    # pragma: no cover
-    return True                                          # pragma: no cover
-
+from .registration import install  # noqa: E402  (re-exported: adapt_aqc_b200.backends.install)
 
 install()

@@ -519,24 +519,28 @@ int right_step(b200_ctx* ctx, const b200_mps* a, const b200_mps* b, int i, const
     return 0;
 }
 
-// Right environments of <m|m>: F_i (chi_{i-1} x chi_{i-1}), i = 0..n, packed back to back in `buf`.
-int right_envs(b200_mps* m, DevBuf& buf, DevBuf& tmp, std::vector<size_t>& foff) {
-    b200_ctx* ctx = m->ctx;
+// Right environments of <a|b>: F_i (chi^a_{i-1} x chi^b_{i-1}), i = 0..n, packed back to back in `buf`.
+int right_envs(b200_mps* a, b200_mps* b, DevBuf& buf, DevBuf& tmp, std::vector<size_t>& foff) {
+    b200_ctx* ctx = a->ctx;
     cudaStream_t s = ctx->stream;
-    const int n = m->n;
+    const int n = a->n;
     foff.assign(n + 2, 0);
-    for (int i = 0; i <= n; ++i) { const size_t c = i == 0 ? 1 : m->chi[i - 1]; foff[i + 1] = foff[i] + c * c; }
+    for (int i = 0; i <= n; ++i) {
+        const size_t ca = i == 0 ? 1 : a->chi[i - 1], cb = i == 0 ? 1 : b->chi[i - 1];
+        foff[i + 1] = foff[i] + ca * cb;
+    }
     if (reserve(buf, foff[n + 1] * sizeof(double2), s)) return -1;
-    const size_t mc = max_bond(m);
-    if (reserve(tmp, mc * mc * sizeof(double2), s)) return -1;
+    const size_t mc2 = (size_t)max_bond(a) * max_bond(b);
+    if (reserve(tmp, mc2 * sizeof(double2), s)) return -1;
     double2* F = (double2*)buf.p;
     const double2 one = make_double2(1.0, 0.0);
     CUDA_TRY(cudaMemcpyAsync(F + foff[n], &one, sizeof(double2), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     for (int i = n - 1; i >= 0; --i)
-        if (right_step(ctx, m, m, i, F + foff[i + 1], (double2*)tmp.p, F + foff[i])) return -1;
+        if (right_step(ctx, a, b, i, F + foff[i + 1], (double2*)tmp.p, F + foff[i])) return -1;
     return 0;
 }
+int right_envs(b200_mps* m, DevBuf& buf, DevBuf& tmp, std::vector<size_t>& foff) { return right_envs(m, m, buf, tmp, foff); }
 
 const double2 kOne = {1.0, 0.0};
 
@@ -953,25 +957,22 @@ int b200_mps_expz(b200_mps* m, double* out) {
     return 0;
 }
 
-// out[p] = 4x4 reduced density matrix (row-major, 32 doubles) of pairs[2p], pairs[2p+1]; the lower
-// qubit is the least-significant index; rho[ket][bra].  Replaces aqc_research partial_trace
-// (adaptaqc/utils/entanglement_measures.py:76-79), once per candidate pair per layer
-// (adaptaqc/compilers/adapt/adapt_compiler.py:960-975).  Left/right environments are built once;
-// pairs sharing their lower qubit share the propagation of the four open environments.
-int b200_mps_pair_rdm(b200_mps* m, const int32_t* pairs, int n_pairs, double* out) {
-    if (check_mps(m)) return -1;
-    if (n_pairs < 0 || (n_pairs > 0 && (!pairs || !out))) return set_error("null pointer");
-    if (n_pairs == 0) return 0;
-    b200_ctx* ctx = m->ctx;
+// Shared body of b200_mps_pair_rdm / b200_mps_pair_transfer: for every requested pair, the 16 values
+//   V[(s,s'),(t,t')] = <a| (|s s'><t t'| on (lo, hi)) |b>      (s, t: physical indices at lo; s', t' at hi; s = bra)
+// written at out16[p] + (transposed ? 4*ket + bra : 4*bra + ket), bra = s + 2 s', ket = t + 2 t'.
+// Left/right environments of <a|b> are built once; pairs sharing their lower qubit share the propagation of the
+// four open environments.
+static int pair_open_values(b200_mps* ma, b200_mps* mb, const int32_t* pairs, int n_pairs, bool transposed, double* out) {
+    b200_ctx* ctx = ma->ctx;
     MpsState* st = state(ctx);
     cudaStream_t s = ctx->stream;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    const int n = m->n;
+    const int n = ma->n;
     for (int p = 0; p < n_pairs; ++p) {
         const int a = pairs[2 * p], b = pairs[2 * p + 1];
         if (a < 0 || b < 0 || a >= n || b >= n || a == b) return set_error("pair " + std::to_string(p) + ": qubits out of range");
     }
-    const size_t mc = max_bond(m), mc2 = mc * mc;
+    const size_t mc2 = (size_t)max_bond(ma) * max_bond(mb);
     // env[0], env[1]: left env ping-pong; env[2]: GEMM temp; env[3]: all F; env[4]: 4 open envs (+4 ping-pong);
     // env[5]: closing temps
     for (int k : {0, 1, 2})
@@ -980,7 +981,7 @@ int b200_mps_pair_rdm(b200_mps* m, const int32_t* pairs, int n_pairs, double* ou
     if (reserve(st->env[5], 2 * mc2 * sizeof(double2), s)) return -1;
     if (reserve(st->outz, (size_t)16 * n_pairs * sizeof(double2), s)) return -1;
     std::vector<size_t> foff;
-    if (right_envs(m, st->env[3], st->env[2], foff)) return -1;
+    if (right_envs(ma, mb, st->env[3], st->env[2], foff)) return -1;
     const double2* F = (const double2*)st->env[3].p;
 
     // group the requested pairs by their lower qubit
@@ -1004,36 +1005,36 @@ int b200_mps_pair_rdm(b200_mps* m, const int32_t* pairs, int n_pairs, double* ou
             double2* O2 = O + 4 * mc2;
             for (int t = 0; t < 2; ++t)
                 for (int sb = 0; sb < 2; ++sb)
-                    if (transfer_one(ctx, m, m, lo, E, tmp, O + (size_t)(sb + 2 * t) * mc2, sb, t, false)) return -1;
+                    if (transfer_one(ctx, ma, mb, lo, E, tmp, O + (size_t)(sb + 2 * t) * mc2, sb, t, false)) return -1;
             for (int site = lo + 1; site <= far; ++site) {
                 for (auto& hp : by_lo[lo]) {
                     if (hp.first != site) continue;
-                    const int cr = m->chi[site];
-                    // close at `site`: value[(s,t),(s',t')] = < A_{s'}^H O_{st} A_{t'}, F_{site+1} >
+                    const int nel = ma->chi[site] * mb->chi[site];
+                    // close at `site`: value[(s,t),(s',t')] = < A_{s'}^H O_{st} B_{t'}, F_{site+1} >
                     for (int st_ = 0; st_ < 4; ++st_)
                         for (int tp = 0; tp < 2; ++tp)
                             for (int sp = 0; sp < 2; ++sp) {
                                 double2* Y = (double2*)st->env[5].p;
-                                if (transfer_one(ctx, m, m, site, O + (size_t)st_ * mc2, tmp, Y, sp, tp, false)) return -1;
+                                if (transfer_one(ctx, ma, mb, site, O + (size_t)st_ * mc2, tmp, Y, sp, tp, false)) return -1;
                                 const int sb = st_ & 1, t = st_ >> 1;
                                 const int ket = t + 2 * tp, bra = sb + 2 * sp;
                                 {
                                     MScope ms(ctx);
-                                    mps_dot_elem_kernel<<<1, 256, 0, s>>>(Y, F + foff[site + 1], cr * cr,
-                                                                          (double2*)st->outz.p + (size_t)16 * hp.second + 4 * ket + bra);
+                                    mps_dot_elem_kernel<<<1, 256, 0, s>>>(Y, F + foff[site + 1], nel,
+                                        (double2*)st->outz.p + (size_t)16 * hp.second + (transposed ? 4 * ket + bra : 4 * bra + ket));
                                 }
                                 CUDA_TRY(cudaGetLastError());
                             }
                 }
                 if (site < far) {   // propagate the four open environments through `site`
                     for (int st_ = 0; st_ < 4; ++st_)
-                        if (transfer_step(ctx, m, m, site, O + (size_t)st_ * mc2, tmp, O2 + (size_t)st_ * mc2)) return -1;
+                        if (transfer_step(ctx, ma, mb, site, O + (size_t)st_ * mc2, tmp, O2 + (size_t)st_ * mc2)) return -1;
                     std::swap(O, O2);
                 }
             }
         }
         if (lo < max_lo) {
-            if (transfer_step(ctx, m, m, lo, E, tmp, (double2*)st->env[1 - cur].p)) return -1;
+            if (transfer_step(ctx, ma, mb, lo, E, tmp, (double2*)st->env[1 - cur].p)) return -1;
             cur = 1 - cur;
         }
     }
@@ -1041,6 +1042,43 @@ int b200_mps_pair_rdm(b200_mps* m, const int32_t* pairs, int n_pairs, double* ou
     CUDA_TRY(cudaStreamSynchronize(s));
     ctx->counters[5] += (size_t)16 * n_pairs * sizeof(double2);
     ctx->counters[6] += 1;
+    return 0;
+}
+
+// out[p] = 4x4 reduced density matrix (row-major, 32 doubles) of pairs[2p], pairs[2p+1]; the lower
+// qubit is the least-significant index; rho[ket][bra].  Replaces aqc_research partial_trace
+// (adaptaqc/utils/entanglement_measures.py:76-79), once per candidate pair per layer
+// (adaptaqc/compilers/adapt/adapt_compiler.py:960-975).
+int b200_mps_pair_rdm(b200_mps* m, const int32_t* pairs, int n_pairs, double* out) {
+    if (check_mps(m)) return -1;
+    if (n_pairs < 0 || (n_pairs > 0 && (!pairs || !out))) return set_error("null pointer");
+    if (n_pairs == 0) return 0;
+    return pair_open_values(m, m, pairs, n_pairs, true, out);
+}
+
+// out[p] = T_p[i][j] = <a| (|i><j| on pairs[2p], pairs[2p+1]) |b>, i = bra, j = ket, index = bit(pairs[2p]) +
+// 2 bit(pairs[2p+1]) (the order the pair is given in), row-major 4x4 complex.  All pairs from ONE left and ONE right
+// environment sweep of <a|b>.  With <a| = <s| (starting state) and |b> = |psi>, sum_ij O[i][j] T_p[i][j] = <s|O_p|psi>
+// for any two-qubit operator O: every (pair, generator) overlap of general_grad_of_pairs
+// (adaptaqc/utils/gradients.py:23-124) is 4x4 host algebra on these matrices.
+int b200_mps_pair_transfer(b200_mps* a, b200_mps* b, const int32_t* pairs, int n_pairs, double* out) {
+    if (check_mps(a) || check_mps(b)) return -1;
+    if (a->ctx != b->ctx || a->n != b->n) return set_error("mps_pair_transfer: handles differ in context or size");
+    if (n_pairs < 0 || (n_pairs > 0 && (!pairs || !out))) return set_error("null pointer");
+    if (n_pairs == 0) return 0;
+    if (pair_open_values(a, b, pairs, n_pairs, false, out)) return -1;
+    auto sw2 = [](int i) { return ((i & 1) << 1) | (i >> 1); };
+    for (int p = 0; p < n_pairs; ++p) {
+        if (pairs[2 * p] < pairs[2 * p + 1]) continue;      // given as (hi, lo): re-index bit(first) + 2 bit(second)
+        double t[32];
+        double* o = out + (size_t)32 * p;
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                t[2 * (4 * sw2(i) + sw2(j))] = o[2 * (4 * i + j)];
+                t[2 * (4 * sw2(i) + sw2(j)) + 1] = o[2 * (4 * i + j) + 1];
+            }
+        std::memcpy(o, t, sizeof t);
+    }
     return 0;
 }
 

@@ -24,7 +24,7 @@ SYMBOLS = [
     "b200_mps_create", "b200_mps_destroy", "b200_mps_set_truncation", "b200_mps_num_qubits",
     "b200_mps_init_zero", "b200_mps_set", "b200_mps_bond_dims", "b200_mps_get", "b200_mps_copy",
     "b200_mps_apply", "b200_mps_apply_inverse", "b200_mps_transfer", "b200_mps_amps", "b200_mps_dot",
-    "b200_mps_expz", "b200_mps_pair_rdm", "b200_mps_stats", "b200_mps_set_chop_rule", "b200_mps_reduce_zeros",
+    "b200_mps_expz", "b200_mps_pair_rdm", "b200_mps_pair_transfer", "b200_mps_stats", "b200_mps_set_chop_rule", "b200_mps_reduce_zeros",
 ]
 
 
@@ -106,6 +106,7 @@ def load():
     L.b200_mps_expz.argtypes = [vp, dp]
     L.b200_mps_pair_rdm.argtypes = [vp, vp, ci, dp]
     L.b200_mps_stats.argtypes = [vp, ctypes.POINTER(cu64)]
+    L.b200_mps_pair_transfer.argtypes = [vp, vp, vp, ci, dp]
     L.b200_mps_set_chop_rule.argtypes = [ci]
     L.b200_mps_reduce_zeros.argtypes = [dp, ci, ci, ctypes.c_double, ctypes.POINTER(ci), dp]
     del i32p

@@ -116,6 +116,13 @@ class B200MPSSimulator:
     def __setstate__(self, st):
         self.__init__(st["thr"], st["max_chi"], device=st.get("device", 0))
 
+    @property
+    def ops(self):
+        """The aqc_research.mps_operations-shaped functions bound to this simulator (registration.install_mps)."""
+        if getattr(self, "_ops", None) is None:
+            self._ops = MPSOps(self)
+        return self._ops
+
     # ---- handles ----
     def context(self):
         if self._context is None:
@@ -150,9 +157,10 @@ class B200MPSSimulator:
         return m
 
     # ---- simulation ----
-    def simulate(self, circuit):
+    def simulate(self, circuit, use_checkpoints=True):
         """Run ``[set_matrix_product_state?] gates... [save_matrix_product_state?]`` and return a
-        DeviceMPS handle owned by the caller."""
+        DeviceMPS handle owned by the caller.  use_checkpoints=False: a side computation (e.g. the starting state of
+        the gradient heuristic) that must not evict the prefix checkpoints of the circuit being optimised."""
         self.runs += 1
         n = circuit.num_qubits
         out = self._acquire(n)
@@ -167,8 +175,10 @@ class B200MPSSimulator:
         while stop > start and data[stop - 1].operation.name == "save_matrix_product_state":
             stop -= 1
         window = G.canonical_window(circuit, start, stop)
-        if window:
+        if window and use_checkpoints:
             self._apply_with_checkpoints(out, window, data[0].operation.params[0] if start else None)
+        elif window:
+            out.apply(G.GateStream.from_window(window))
         return out
 
     MAX_CHECKPOINTS = 24
@@ -399,7 +409,7 @@ class B200MPSBackend(_MPSBase):
 
     def __init__(self, simulator=None, device=0, incremental=True):
         self.simulator = simulator if simulator is not None else B200MPSSimulator(device=device)
-        self.mps_ops = MPSOps(self.simulator)
+        self.mps_ops = self.simulator.ops
         self.incremental = incremental
         self._engine = None
         self._evaluator = None
@@ -494,6 +504,64 @@ class B200MPSBackend(_MPSBase):
         if tmp:
             self.simulator._recycle(h)
         return out
+
+    # ---- general-gradient pair heuristic ----
+    @staticmethod
+    def _two_qubit_unitary(circuit):
+        """4x4 matrix (index = bit(qubit 0) + 2 bit(qubit 1)) of a 2-qubit circuit of basis gates."""
+        from .sv_engine import embed_entry
+        if circuit.num_qubits != 2:
+            raise ValueError("generators / ansatz of general_grad_of_pairs act on two qubits")
+        u = np.eye(4, dtype=np.complex128)
+        for ent in G.canonical_window(circuit):
+            u = embed_entry(ent, (0, 1)) @ u
+        return u
+
+    def general_grad_of_pairs(self, circuit, inverse_zero_ansatz, generators, degeneracies, coupling_map,
+                              starting_circuit=None):
+        """adaptaqc/utils/gradients.py:23-124 with the same arguments and the same return value
+        (g_pair = sqrt(sum_k deg_k Im(<s|G_k|psi><psi|U^+(0)|s>)^2) for every pair), from ONE simulation of |psi> and ONE
+        batched read-out instead of P x (#generators + 1) simulator runs + mps_dot calls.
+
+        Every operator involved acts on the pair only, so with T_p[i][j] = <s|(|i><j| on p)|psi>
+            <s|G_k|psi>     = sum_ij (M_k^+)[i][j] T_p[i][j]        (generators[k] is the circuit of G_k^+, matrix M_k)
+            <psi|U^+(0)|s>  = conj(sum_ij (M_0^+)[i][j] T_p[i][j])  (inverse_zero_ansatz has matrix M_0)
+        For |s> = |0..0> (no starting circuit) T_p[0][j] is the amplitude of |psi> on the bitstring that has j on the
+        pair and zeros elsewhere: all 4 P amplitudes come from ONE kernel launch (b200_mps_amps).  With a starting
+        circuit T_p comes from one left + one right environment sweep of <s|psi> (b200_mps_pair_transfer)."""
+        sim = self.simulator
+        pairs = [(int(c), int(t)) for c, t in coupling_map]
+        psi = sim.simulate(circuit)
+        try:
+            if starting_circuit is None or len(starting_circuit.data) == 0:
+                bits = [((j & 1) << c) | ((j >> 1) << t) for c, t in pairs for j in range(4)]
+                amps = psi.amps(bits).reshape(len(pairs), 4)
+                T = np.zeros((len(pairs), 4, 4), dtype=np.complex128)
+                T[:, 0, :] = amps
+            else:
+                s_state = sim.simulate(starting_circuit, use_checkpoints=False)
+                try:
+                    T = s_state.pair_transfer(psi, pairs)
+                finally:
+                    sim._recycle(s_state)
+        finally:
+            sim._recycle(psi)
+        return self.gradients_from_pair_transfers(T, inverse_zero_ansatz, generators, degeneracies)
+
+    @classmethod
+    def gradients_from_pair_transfers(cls, T, inverse_zero_ansatz, generators, degeneracies):
+        """The 4x4 host algebra of general_grad_of_pairs: T[p][i][j] = <s|(|i><j| on pair p)|psi>."""
+        m0 = cls._two_qubit_unitary(inverse_zero_ansatz).conj().T
+        gens = [cls._two_qubit_unitary(g).conj().T for g in generators]
+        gradients = []
+        for Tp in T:
+            zero_overlap = np.conj(np.sum(m0 * Tp))
+            total = 0
+            for mk, deg in zip(gens, degeneracies):
+                overlap = np.sum(mk * Tp)
+                total += (-1 * np.imag(overlap * zero_overlap)) ** 2 * deg
+            gradients.append(np.sqrt(total))
+        return gradients
 
     # ---- batched extension (B200CostMinimiser) ----
     def shift_costs(self, compiler, gate_index, candidates):

@@ -208,6 +208,15 @@ class DeviceMPS:
         check(self._lib.b200_mps_transfer(self._h, other._h, q.ctypes.data, len(q), dptr(out)))
         return out.view(np.complex128).reshape(d, d).copy()
 
+    def pair_transfer(self, other, pairs):
+        """T_p[i][j] = <self|(|i><j| on pair p)|other> for every pair, index = bit(pair[0]) + 2 bit(pair[1]):
+        all pairs from one left + one right environment sweep."""
+        pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        out = np.zeros((len(pairs), 16), dtype=np.complex128)
+        if len(pairs):
+            check(self._lib.b200_mps_pair_transfer(self._h, other._h, pairs.ctypes.data, len(pairs), dptr(out.view(np.float64))))
+        return out.reshape(-1, 4, 4)
+
     def expz(self):
         out = np.zeros(self.num_qubits + 1)
         check(self._lib.b200_mps_expz(self._h, dptr(out)))

@@ -31,23 +31,18 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 RESULT_OUT = sys.stdout
 METRIC = "cost_evals_per_sec"
 UNIT = "evals/s"
 
 
-def build_workload(n, depth, layers, seed=1234):
-    from helpers import brickwork, thin_ansatz
-    target, rng = brickwork(n, depth, seed)
-    ansatz = thin_ansatz(n, layers, rng)
-    return target, ansatz
+from harness.workloads import build_mps_workload, build_workload  # noqa: E402
 
 
 def make_compiler(target, ansatz, backend, batched):
-    from adapt_aqc_b200.compiler import AdaptCompiler
-    from adapt_aqc_b200.minimiser import B200CostMinimiser
+    from harness.compiler import AdaptCompiler
+    from harness.minimiser import B200CostMinimiser
     comp = AdaptCompiler(target, backend=backend, minimiser_cls=B200CostMinimiser if batched else None)
     comp.full_circuit.data.extend(ansatz.copy().data)
     return comp
@@ -164,22 +159,6 @@ def cpu_baseline_sample(n, target, ansatz, budget_s=20.0):
 
 
 # ---- config C4: 50-qubit random MPS at bond dimension 256 ----------------------------------------
-def build_mps_workload(n, chi, layers, seed=1):
-    from helpers import random_vidal_mps
-    from adapt_aqc_b200.circuit import Circuit
-    target = random_vidal_mps(n, chi, seed)
-    rng = np.random.default_rng(seed)
-    ansatz = Circuit(n)
-    mid = n // 2 - 1
-    for k in range(layers):
-        a, b = mid + (k % 2), mid + (k % 2) + 1
-        th = rng.uniform(-np.pi, np.pi, 4)
-        ansatz.rz(th[0], a, label="rz"); ansatz.rz(th[1], b, label="rz")
-        ansatz.cx(a, b)
-        ansatz.rz(th[2], a, label="rz"); ansatz.rz(th[3], b, label="rz")
-    return target, ansatz
-
-
 def mps_step(comp):
     lo, hi = comp.variational_circuit_range()
     comp.minimizer._reduce_cost(False, (lo, hi))
@@ -195,7 +174,7 @@ def bench_mps(args, device, with_cpu=True):
     default  : the reference's default simulator (threshold 1e-16, no cap, aer_mps_backend.py:27):
                truncation is at roundoff level, so the block transfer-matrix evaluator applies -- SVDs
                only when the optimiser moves to another layer."""
-    from adapt_aqc_b200.compiler import AdaptCompiler
+    from harness.compiler import AdaptCompiler
     from adapt_aqc_b200.mps_backend import B200MPSBackend, B200MPSSimulator
     n, chi, layers = args.mps_qubits, args.mps_chi, args.mps_layers
     t0 = time.perf_counter()
@@ -264,8 +243,8 @@ def bench_compile(args, device, cpu_evals_per_s=None):
     window, `--compile-layers` layers.  Wall time includes every host-side step (circuit edits, plan
     building, 4x4 measures); the final exact overlap is computed on the device."""
     from adapt_aqc_b200.backends import B200SVBackend
-    from adapt_aqc_b200.compiler import AdaptCompiler, AdaptConfig
-    from adapt_aqc_b200.minimiser import B200CostMinimiser
+    from harness.compiler import AdaptCompiler, AdaptConfig
+    from harness.minimiser import B200CostMinimiser
     n = args.qubits
     target, _ = build_workload(n, args.depth, 0)
     linear = [(i, i + 1) for i in range(n - 1)]
@@ -373,7 +352,7 @@ def bench_sharded_compile(args, local_rank, n):
     ISL pair selection from sharded pair-RDM passes on a linear map, Rotoselect / Rotosolve in the projected
     tail (one gather + all-reduce of 2^K amplitudes per projection, then a K-qubit engine per rank)."""
     import torch.distributed as dist
-    from adapt_aqc_b200.compiler import AdaptCompiler, AdaptConfig
+    from harness.compiler import AdaptCompiler, AdaptConfig
     from adapt_aqc_b200.dist_sv import B200ShardedSVBackend
     target, _ = build_workload(n, args.sharded_depth, 0)
     backend = B200ShardedSVBackend(local_rank)

@@ -12,7 +12,7 @@ import copy as _copy
 
 import numpy as np
 
-from . import gates as G
+from adapt_aqc_b200 import gates as G
 
 _SELF_INVERSE = {"x", "y", "z", "h", "cx", "cz", "swap", "id"}
 _INVERSE_NAME = {"s": "sdg", "sdg": "s", "t": "tdg", "tdg": "t"}

@@ -661,6 +661,10 @@ class AdaptCompiler:
         from . import gradients as gr
         end = len(self.full_circuit) - (len(self.starting_circuit) if self.starting_circuit is not None else 0)
         circuit = extract_inner_circuit(self.full_circuit, (0, end))
+        # same dispatch as adapt_aqc_b200.registration.install_gradients performs on a real adaptaqc installation
+        if hasattr(self.backend, "general_grad_of_pairs"):
+            return self.backend.general_grad_of_pairs(circuit, self.inverse_zero_ansatz, self.generators, self.degeneracies,
+                                                      self.coupling_map, self.starting_circuit)
         return gr.general_grad_of_pairs(circuit, self.inverse_zero_ansatz, self.generators, self.degeneracies,
                                         self.coupling_map, self.starting_circuit, self.backend)
 

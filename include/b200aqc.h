@@ -239,6 +239,13 @@ int b200_mps_expz(b200_mps *mps, double *out /* n+1 */);
 /* 4x4 reduced density matrices, same conventions as b200_sv_pair_rdm: aqc_research.partial_trace
  * (adaptaqc/utils/entanglement_measures.py:76-79). */
 int b200_mps_pair_rdm(b200_mps *mps, const int32_t *pairs, int n_pairs, double *out /* 32*n_pairs */);
+/* out[p] = T_p[i][j] = <a| (|i><j| on pairs[2p], pairs[2p+1]) |b>: i = bra, j = ket, index = bit(pairs[2p]) +
+ * 2 bit(pairs[2p+1]); 32 doubles per pair, row-major.  ALL pairs from one left + one right environment sweep of
+ * <a|b> (pairs sharing their lower qubit share the open environments).  Replaces the P x (#generators + 1) Aer MPS
+ * runs + mps_dot calls of general_grad_of_pairs (adaptaqc/utils/gradients.py:23-124, called at
+ * adaptaqc/compilers/adapt/adapt_compiler.py:839-856): with <a| = <s| (the starting state) and |b> = |psi>,
+ * <s|G|psi> = sum_ij G[i][j] T_p[i][j] for every generator G on the pair. */
+int b200_mps_pair_transfer(b200_mps *a, b200_mps *b, const int32_t *pairs, int n_pairs, double *out /* 32*n_pairs */);
 /* Truncation rule of the 2-qubit gates = qiskit-aer's reduce_zeros (svd.cpp, called from the Aer MPS run the
  * reference starts at adaptaqc/backends/aer_mps_backend.py:37-42,78).  The Aer source is not part of the reference
  * tree; its rule is restated and the two ambiguous details are selectable so that both readings stay testable:

@@ -52,7 +52,7 @@ def compile_main(n, on_gpu):
     """mode `compile`: the ADAPT loop on a sharded register (B200ShardedSVBackend) makes the same decisions
     as on the oracle backend -- pair RDMs and <Z> are sharded read-outs, cost evaluations run in the
     projected tail (gather + all-reduce) or by re-simulation on the sharded register."""
-    from adapt_aqc_b200.compiler import AdaptCompiler, AdaptConfig
+    from harness.compiler import AdaptCompiler, AdaptConfig
     from adapt_aqc_b200.dist_sv import B200ShardedSVBackend, ShardedEngine
     from adapt_aqc_b200.sv_engine import SVCostEvaluator
     from helpers import brickwork

@@ -72,18 +72,22 @@ def test_no_silent_cpu_fallback():
     with pytest.raises(blib.B200Error):
         SVEngine(3)
     from adapt_aqc_b200.backends import B200SVBackend
-    from adapt_aqc_b200.circuit import Circuit
-    from adapt_aqc_b200.compiler import AdaptCompiler
+    from harness.circuit import Circuit
+    from harness.compiler import AdaptCompiler
     qc = Circuit(2); qc.h(0)
     with pytest.raises(blib.B200Error):
         AdaptCompiler(qc, backend=B200SVBackend()).evaluate_cost()
 
 
-def test_product_never_imports_the_oracle():
+def test_product_never_imports_the_harness_or_the_oracle():
+    """The package holds product code only: the oracle (CPU restatement of the reference's arithmetic) and the harness
+    (qiskit-free mirror of the reference's compile loop) are test infrastructure and must stay outside it."""
     pkg = os.path.join(ROOT, "adapt-aqc_b200")
+    assert not any(os.path.exists(os.path.join(pkg, f)) for f in ("compiler.py", "circuit.py", "measures.py", "gradients.py"))
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "sv_oracle" not in text and "libsv_oracle" not in text, f
+                assert "import harness" not in text and "from harness" not in text, f

@@ -8,9 +8,9 @@ import pytest
 
 from adapt_aqc_b200 import gates as G
 from adapt_aqc_b200.backends import B200SVBackend
-from adapt_aqc_b200.circuit import Circuit, CircuitInstruction, Gate
-from adapt_aqc_b200.compiler import AdaptCompiler
-from adapt_aqc_b200.minimiser import replace_1q_gate
+from harness.circuit import Circuit, CircuitInstruction, Gate
+from harness.compiler import AdaptCompiler
+from harness.minimiser import replace_1q_gate
 from adapt_aqc_b200.sv_engine import SVCostEvaluator
 from oracle.oracle_backends import OracleSVBackend
 

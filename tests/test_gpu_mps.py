@@ -4,11 +4,11 @@ same truncation threshold; untruncated amplitude-level checks use 1e-10."""
 import numpy as np
 import pytest
 
-from adapt_aqc_b200 import measures as em
-from adapt_aqc_b200.circuit import Circuit
-from adapt_aqc_b200.compiler import CMAP_LINEAR, AdaptCompiler, AdaptConfig, generate_coupling_map
+from harness import measures as em
+from harness.circuit import Circuit
+from harness.compiler import CMAP_LINEAR, AdaptCompiler, AdaptConfig, generate_coupling_map
 from adapt_aqc_b200.gates import GateStream
-from adapt_aqc_b200.minimiser import B200CostMinimiser
+from harness.minimiser import B200CostMinimiser
 from adapt_aqc_b200.mps_backend import B200MPSBackend, B200MPSSimulator, DeviceMPSView
 from adapt_aqc_b200.mps_engine import MPSContext
 from oracle import mps_oracle as mo

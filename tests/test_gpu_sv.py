@@ -10,12 +10,12 @@ import numpy as np
 import pytest
 
 from adapt_aqc_b200 import lib as blib
-from adapt_aqc_b200 import measures as em
+from harness import measures as em
 from adapt_aqc_b200.backends import B200SVBackend
-from adapt_aqc_b200.circuit import Circuit
-from adapt_aqc_b200.compiler import (CMAP_LINEAR, AdaptCompiler, AdaptConfig, generate_coupling_map)
+from harness.circuit import Circuit
+from harness.compiler import (CMAP_LINEAR, AdaptCompiler, AdaptConfig, generate_coupling_map)
 from adapt_aqc_b200.gates import GateStream
-from adapt_aqc_b200.minimiser import B200CostMinimiser
+from harness.minimiser import B200CostMinimiser
 from adapt_aqc_b200.sv_engine import SLOT_BASE, SLOT_L, SLOT_R, SLOT_WORK, SVCostEvaluator, SVEngine
 from oracle import sv_oracle as orc
 from oracle.oracle_backends import OracleSVBackend, circuit_to_gates
@@ -269,7 +269,7 @@ def test_evaluator_tracks_rotosolve_edits(n):
     oracle_comp.full_circuit.data.extend([d for d in ansatz.copy().data])
     rot = [i for i in range(*comp.variational_circuit_range())
            if comp.full_circuit.data[i].operation.name in ("rx", "ry", "rz")]
-    from adapt_aqc_b200.minimiser import replace_1q_gate
+    from harness.minimiser import replace_1q_gate
     for step in range(60):
         idx = rot[int(rng.integers(len(rot)))] if step % 7 else rot[step % len(rot)]
         name = ["rx", "ry", "rz"][int(rng.integers(3))]
@@ -289,7 +289,7 @@ def test_shift_costs_equal_individual_evaluations(backend):
     comp.full_circuit.data.extend(ansatz.data)
     ocomp = AdaptCompiler(target, backend=OracleSVBackend())
     ocomp.full_circuit.data.extend(ansatz.copy().data)
-    from adapt_aqc_b200.minimiser import replace_1q_gate
+    from harness.minimiser import replace_1q_gate
     idx = comp.variational_circuit_range()[0] + 8
     h = np.pi / 2
     cands = [("rx", 0.0)] + [(g, s) for g in ("rx", "ry", "rz") for s in (h, -h)]
@@ -456,7 +456,7 @@ def test_c3_evaluator_equals_device_resimulation():
     rng = np.random.default_rng(5)
     lo, hi = comp.variational_circuit_range()
     rot = [i for i in range(lo, hi) if comp.full_circuit.data[i].operation.name in ("rx", "ry", "rz")]
-    from adapt_aqc_b200.minimiser import replace_1q_gate
+    from harness.minimiser import replace_1q_gate
     visits = [rot[0], rot[1], rot[-1], rot[-2], rot[len(rot) // 2], rot[5], rot[-9], rot[2], rot[-1]]
     for idx in visits:
         for rep in range(2):

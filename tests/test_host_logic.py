@@ -6,9 +6,9 @@ import numpy as np
 import pytest
 
 from adapt_aqc_b200.backends import B200SVBackend
-from adapt_aqc_b200.circuit import Circuit
-from adapt_aqc_b200.compiler import AdaptCompiler, AdaptConfig
-from adapt_aqc_b200.minimiser import B200CostMinimiser, replace_1q_gate
+from harness.circuit import Circuit
+from harness.compiler import AdaptCompiler, AdaptConfig
+from harness.minimiser import B200CostMinimiser, replace_1q_gate
 from adapt_aqc_b200.sv_engine import SVCostEvaluator
 from oracle.oracle_backends import OracleSVBackend
 

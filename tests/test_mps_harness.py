@@ -4,10 +4,10 @@ general-gradient analytic value)."""
 import numpy as np
 import pytest
 
-from adapt_aqc_b200 import gradients as gr
-from adapt_aqc_b200 import measures as em
-from adapt_aqc_b200.circuit import Circuit
-from adapt_aqc_b200.compiler import AdaptCompiler, AdaptConfig
+from harness import gradients as gr
+from harness import measures as em
+from harness.circuit import Circuit
+from harness.compiler import AdaptCompiler, AdaptConfig
 from oracle import mps_oracle as mo
 from oracle.oracle_backends import OracleMPSBackend, OracleSVBackend
 
@@ -149,3 +149,46 @@ def _dense(circ):
             full = m if tuple(inst.qubits) == (0, 1) else m[np.ix_([0, 2, 1, 3], [0, 2, 1, 3])]
         u = full @ u
     return u
+
+
+def _dense_state(circ):
+    from oracle import sv_oracle as orc
+    from oracle.oracle_backends import circuit_to_gates
+    return orc.evaluate_circuit(circ.num_qubits, circuit_to_gates(circ))
+
+
+def _pair_transfers_dense(s, psi, pairs):
+    """T_p[i][j] = <s|(|i><j| on pair p)|psi>, index = bit(pair[0]) + 2 bit(pair[1]), from dense little-endian vectors."""
+    n = int(np.log2(psi.size))
+    out = []
+    for a, b in pairs:
+        S = np.moveaxis(s.reshape([2] * n), [n - 1 - b, n - 1 - a], [0, 1]).reshape(4, -1)       # row = 2 bit(b) + bit(a)
+        P = np.moveaxis(psi.reshape([2] * n), [n - 1 - b, n - 1 - a], [0, 1]).reshape(4, -1)
+        out.append(S.conj() @ P.T)
+    return np.array(out)
+
+
+@pytest.mark.parametrize("rotoselect", [True, False])
+@pytest.mark.parametrize("with_start", [False, True])
+def test_pair_transfer_gradient_algebra_equals_the_reference_chain(rotoselect, with_start):
+    """B200MPSBackend.general_grad_of_pairs gets every (pair, generator) overlap of
+    adaptaqc/utils/gradients.py:23-124 as 4x4 algebra on T_p = <s|(|i><j|)_p|psi>.  Here T_p is built from dense
+    vectors (the device read-out itself is GPU-tested) and the algebra is compared with the reference's chain -- one
+    simulation + one mps_dot per (pair, generator) -- run on the oracle backend."""
+    from adapt_aqc_b200.mps_backend import B200MPSBackend
+    n = 5
+    target = _random_target(n, 11)
+    start = None
+    if with_start:
+        start = Circuit(n); start.x(1); start.h(3); start.cx(3, 4); start.ry(0.4, 0)
+    cmap = [(0, 1), (1, 2), (2, 3), (3, 4), (0, 2), (4, 1), (3, 0)]           # incl. non-neighbours and (hi, lo) order
+    comp = AdaptCompiler(target, backend=OracleMPSBackend(), coupling_map=cmap, starting_circuit=start,
+                         use_rotoselect=rotoselect, adapt_config=AdaptConfig(method="general_gradient"))
+    ref = comp._get_all_qubit_pair_gradients()
+    psi = _dense_state(target)       # the chain uses full_circuit WITHOUT the inverse starting circuit (adapt_compiler.py:839-846)
+    s = _dense_state(start) if start is not None else np.eye(1 << n)[0].astype(np.complex128)
+    T = _pair_transfers_dense(s, psi, cmap)
+    got = B200MPSBackend.gradients_from_pair_transfers(T, comp.inverse_zero_ansatz, comp.generators, comp.degeneracies)
+    np.testing.assert_allclose(got, ref, atol=1e-10)
+    if rotoselect or with_start:      # (rz-only generators on |0..0> give a real product: zero gradient)
+        assert max(ref) > 1e-3

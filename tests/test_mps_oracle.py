@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from adapt_aqc_b200.circuit import Circuit
+from harness.circuit import Circuit
 from oracle import mps_oracle as mo
 from oracle import sv_oracle as orc
 from oracle.oracle_backends import circuit_to_gates
@@ -112,17 +112,28 @@ def test_readme_mps_example_costs():
 
 
 def test_truncation_rule():
-    """Aer reduce_zeros: chop <= 1e-16, cap at max chi, drop smallest while sum of squares stays
-    below the threshold, renormalise if anything was dropped."""
+    """Aer reduce_zeros in the default ("aer") reading -- chop sigma^2 <= 1e-16, cap at max chi, drop the smallest while
+    the sum of squares stays below the threshold (count unchanged if that loop runs out), renormalise only if the
+    count dropped below the chopped count -- and in the round-1 ("sigma") reading.  More cases: tests/test_chop_rule.py."""
     S = np.array([0.9, 0.4, 0.1, 1e-5, 1e-9, 1e-17])
-    k, kept = mo.reduce_zeros(S, None, 1e-16)
-    assert k == 4 and abs(np.sum(kept ** 2) - 1) < 1e-15          # 1e-17 chopped, (1e-9)^2 < 1e-16 dropped
-    k, kept = mo.reduce_zeros(S, None, 1e-8)
-    assert k == 3                                                   # 1e-18 + 1e-10 < 1e-8, + 1e-2 is not
-    k, kept = mo.reduce_zeros(S, 2, 1e-16)
-    assert k == 2 and abs(np.sum(kept ** 2) - 1) < 1e-15
-    k, kept = mo.reduce_zeros(np.array([1.0, 0.5]), None, 10.0)
-    assert k == 1                                                   # the largest value is always kept
+    try:
+        mo.set_chop_rule("aer")
+        k, kept = mo.reduce_zeros(S, None, 1e-16)
+        assert k == 4                                                   # 1e-9 and 1e-17 chopped (sigma^2 <= 1e-16) ...
+        np.testing.assert_array_equal(kept, S[:4])                      # ... which does not renormalise
+        k, kept = mo.reduce_zeros(S, None, 1e-8)
+        assert k == 3 and abs(np.sum(kept ** 2) - 1) < 1e-15            # 1e-10 < 1e-8 dropped, + 1e-2 is not
+        k, kept = mo.reduce_zeros(S, 2, 1e-16)
+        assert k == 2 and abs(np.sum(kept ** 2) - 1) < 1e-15
+        k, kept = mo.reduce_zeros(np.array([1.0, 0.5]), None, 10.0)
+        assert k == 2                                                   # the drop loop ran out: count unchanged
+        mo.set_chop_rule("sigma")
+        k, kept = mo.reduce_zeros(S, None, 1e-16)
+        assert k == 4 and abs(np.sum(kept ** 2) - 1) < 1e-15            # 1e-17 chopped, (1e-9)^2 < 1e-16 dropped
+        k, kept = mo.reduce_zeros(np.array([1.0, 0.5]), None, 10.0)
+        assert k == 1
+    finally:
+        mo.set_chop_rule("aer")
     k, kept = mo.reduce_zeros(np.array([0.8, 0.6]), None, 1e-16)
     np.testing.assert_array_equal(kept, [0.8, 0.6])                 # nothing dropped -> no renormalisation
 

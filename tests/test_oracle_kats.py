@@ -7,9 +7,9 @@ simulator written here (full 2^n x 2^n unitaries via kron) for random circuits.
 import numpy as np
 import pytest
 
-from adapt_aqc_b200 import measures as em
-from adapt_aqc_b200.circuit import Circuit
-from adapt_aqc_b200.compiler import AdaptCompiler
+from harness import measures as em
+from harness.circuit import Circuit
+from harness.compiler import AdaptCompiler
 from oracle import sv_oracle as orc
 from oracle.oracle_backends import OracleSVBackend, circuit_to_gates
 
@@ -23,7 +23,7 @@ def dense_unitary(n, gate):
     if name in ("mat1", "mat2"):
         m = np.asarray(params, dtype=np.complex128)
     else:
-        from adapt_aqc_b200.circuit import Gate
+        from harness.circuit import Gate
         m = Gate(name, params).to_matrix()
     k = len(qubits)
     dim = 1 << n
