@@ -48,6 +48,15 @@ def circuit_from_gates(n, gates):
     return c
 
 
+def golden_seeds():
+    """Seeds of every committed paper/random_mps fixture (all 54 of the reference's targets)."""
+    import glob
+    import os
+    import re
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(int(re.search(r"seed_(\d+)", f).group(1)) for f in glob.glob(os.path.join(here, "random_mps_seed_*.npz")))
+
+
 def load_golden_mps(seed):
     """tests/golden/random_mps_seed_<seed>.npz -> QiskitMPS tuple (constants.py:17)."""
     import os

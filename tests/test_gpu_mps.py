@@ -15,7 +15,7 @@ from oracle import mps_oracle as mo
 from oracle import sv_oracle as orc
 from oracle.oracle_backends import OracleMPSBackend, OracleSVBackend, circuit_to_gates
 
-from helpers import circuit_from_gates, load_golden_mps, random_gates
+from helpers import circuit_from_gates, golden_seeds, load_golden_mps, random_gates
 
 pytestmark = pytest.mark.gpu
 
@@ -94,13 +94,28 @@ def test_inverse_round_trip_and_long_range_gates(ctx):
     m.close()
 
 
-def test_truncation_rule_matches_oracle(ctx):
+@pytest.fixture(params=["aer", "sigma"])
+def chop_rule(request):
+    """Both readings of Aer's reduce_zeros (include/b200aqc.h: B200_CHOP_AER default, B200_CHOP_SIGMA), product and
+    oracle switched together."""
+    from adapt_aqc_b200 import mps_engine as me
+    me.set_chop_rule(request.param); mo.set_chop_rule(request.param)
+    yield request.param
+    me.set_chop_rule("aer"); mo.set_chop_rule("aer")
+
+
+def test_truncation_rule_matches_oracle(ctx, chop_rule):
     n = 10
     c = _generic_circuit(n, 8, 5)
-    for thr, max_chi in [(1e-6, None), (1e-16, 6), (1e-3, 8)]:
+    # a weakly entangling tail: singular values between 1e-16 and 1e-8, where the two chop readings differ
+    weak = c.copy()
+    for q in range(0, n - 1, 2):
+        weak.ry(3e-9, q); weak.cx(q, q + 1); weak.ry(-2e-9, q + 1)
+    kept = {}
+    for circ, thr, max_chi in [(c, 1e-6, None), (c, 1e-16, 6), (c, 1e-3, 8), (weak, 1e-16, None), (weak, 1e-20, None)]:
         m = ctx.new_mps(n, thr, max_chi)
-        m.apply(GateStream.from_circuit(c))
-        ref = mo.mps_from_circuit(c.copy(), sim=mo.OracleMPSSimulator(thr, max_chi))
+        m.apply(GateStream.from_circuit(circ))
+        ref = mo.mps_from_circuit(circ.copy(), sim=mo.OracleMPSSimulator(thr, max_chi))
         assert m.bond_dims() == [len(l) for l in ref[1]]
         got = m.get()
         for la, lb in zip(got[1], ref[1]):
@@ -111,9 +126,10 @@ def test_truncation_rule_matches_oracle(ctx):
 
 # ---- set / get / read-outs ----------------------------------------------------------------------
 def test_golden_fixture_round_trip_and_readouts(ctx):
-    """Three of the reference's own 50-site chi=2 targets (tests/golden): set -> get is verbatim
+    """ALL 54 of the reference's own 50-site chi=2 targets (tests/golden): set -> get is verbatim
     (test_utilityfunctions.py:317-338), <psi|psi> = 1, <Z>, amplitudes and RDMs equal the oracle's."""
-    for seed in (1, 17, 100):
+    assert len(golden_seeds()) == 54
+    for seed in golden_seeds():
         mps = load_golden_mps(seed)
         m = ctx.new_mps(50)
         m.set(mps)
@@ -321,3 +337,73 @@ def test_prefix_checkpoints_reproduce_full_reruns_bit_for_bit():
             for la, lb in zip(got[1], ref[1]):
                 assert np.array_equal(la, lb)
         assert sim.ckpt_stats["svds_skipped"] > 0 and sim.ckpt_stats["resumed_gates"] > 0
+
+
+# ---- general-gradient heuristic from one batched read-out ---------------------------------------
+def _dense(circ):
+    from oracle import sv_oracle as orc
+    return orc.evaluate_circuit(circ.num_qubits, circuit_to_gates(circ))
+
+
+@pytest.mark.parametrize("n", [3, 6, 9])
+def test_pair_transfer_matches_dense_contraction(ctx, n):
+    """b200_mps_pair_transfer: T_p[i][j] = <s|(|i><j| on p)|psi> for all pairs from one left + one right sweep."""
+    a, b = _generic_circuit(n, 3, 60 + n), _generic_circuit(n, 4, 80 + n)
+    ma, mb = ctx.new_mps(n), ctx.new_mps(n)
+    ma.apply(GateStream.from_circuit(a)); mb.apply(GateStream.from_circuit(b))
+    va, vb = _dense(a), _dense(b)
+    pairs = [(i, j) for i in range(n) for j in range(n) if i != j]            # both orders, all distances
+    got = ma.pair_transfer(mb, pairs)
+    for T, (p, q) in zip(got, pairs):
+        A = np.moveaxis(va.reshape([2] * n), [n - 1 - q, n - 1 - p], [0, 1]).reshape(4, -1)
+        B = np.moveaxis(vb.reshape([2] * n), [n - 1 - q, n - 1 - p], [0, 1]).reshape(4, -1)
+        np.testing.assert_allclose(T, A.conj() @ B.T, atol=1e-12)
+    ma.close(); mb.close()
+
+
+@pytest.mark.parametrize("n,with_start,rotoselect", [(4, False, True), (6, True, True), (8, False, False), (10, True, False),
+                                                     (10, False, True)])
+def test_general_gradient_from_one_readout_equals_the_reference_chain(n, with_start, rotoselect):
+    """B200MPSBackend.general_grad_of_pairs (one simulation + one batched read-out) against the reference's chain -- one
+    simulator run + one mps_dot per (pair, generator), adaptaqc/utils/gradients.py:23-124 -- on the oracle backend AND on
+    the device backend, all-to-all map."""
+    from harness import gradients as gr
+    target = _generic_circuit(n, 3, 100 + n)
+    start = None
+    if with_start:
+        start = Circuit(n); start.x(0); start.h(n - 2); start.cx(n - 2, n - 1); start.ry(0.3, 1)
+    cfg = dict(method="general_gradient")
+    kw = dict(starting_circuit=start, use_rotoselect=rotoselect)
+    dev = AdaptCompiler(target, backend=B200MPSBackend(), adapt_config=AdaptConfig(**cfg), **kw)
+    ref = AdaptCompiler(target, backend=OracleMPSBackend(), adapt_config=AdaptConfig(**cfg), **kw)
+    got = dev._get_all_qubit_pair_gradients()                       # device: batched read-out
+    want = ref._get_all_qubit_pair_gradients()                      # oracle: the chain
+    np.testing.assert_allclose(got, want, atol=COST_TOL)
+    circuit = dev.full_circuit.copy()
+    if start is not None:
+        del circuit.data[len(circuit.data) - len(start.data):]
+    chain_on_device = gr.general_grad_of_pairs(circuit, dev.inverse_zero_ansatz, dev.generators, dev.degeneracies,
+                                               dev.coupling_map, start, dev.backend)
+    np.testing.assert_allclose(got, chain_on_device, atol=COST_TOL)
+    if rotoselect or with_start:
+        assert max(want) > 1e-4
+
+
+def test_general_gradient_analytic_value_and_zero_case():
+    """test/utils/test_gradients.py:39-73 (ansatz rx on qubit 0, ry on qubit 1: gradient norm
+    sqrt(Im(a* b)^2 + Re(a* c)^2) for psi = (a, b, c, d)) and :15-37 (no ansatz -> no gradient), through the device."""
+    from harness import gradients as gr
+    qc = _generic_circuit(2, 3, 5)
+    a, b, c, _ = _dense(qc)
+    expected = np.sqrt(np.imag(np.conj(a) * b) ** 2 + np.real(np.conj(a) * c) ** 2)
+    ansatz = Circuit(2); ansatz.rx(0, 0); ansatz.ry(0, 1)
+    gens, degs = gr.get_generators_and_degeneracies(ansatz, rotoselect=False, inverse=True)
+    backend = B200MPSBackend()
+    got = backend.general_grad_of_pairs(qc, ansatz.inverse(), gens, degs, [(0, 1)])[0]
+    assert abs(got - expected) < 1e-10
+    empty = Circuit(2)
+    gens0, degs0 = gr.get_generators_and_degeneracies(empty)
+    qc5 = _generic_circuit(5, 3, 6)
+    start = Circuit(5); start.ry(0.7, 2); start.cx(2, 3)
+    g0 = backend.general_grad_of_pairs(qc5, empty, gens0, degs0, [(0, 1), (1, 2), (2, 3), (3, 4)], start)
+    np.testing.assert_allclose(g0, 0, atol=1e-12)

@@ -13,18 +13,28 @@ from oracle import mps_oracle as mo
 from oracle import sv_oracle as orc
 from oracle.oracle_backends import circuit_to_gates
 
-from helpers import circuit_from_gates, load_golden_mps, random_gates
+from helpers import circuit_from_gates, golden_seeds, load_golden_mps, random_gates
 
 
 def test_golden_fixtures_are_normalised_and_canonical():
     """Gamma_i . lambda_i (right) gives <psi|psi> = 1 on the paper's targets; lambdas
     are descending with unit 2-norm (utilityfunctions.py:309-311)."""
-    for seed in (1, 17, 100):
+    assert len(golden_seeds()) == 54          # every target the reference ships (paper/random_mps)
+    for seed in golden_seeds():
         mps = load_golden_mps(seed)
         assert mo.check_mps(mps) and len(mps[0]) == 50
         assert abs(mo.mps_dot(mps, mps) - 1) < 1e-13
         for lam in mps[1]:
             assert np.all(np.diff(lam) <= 0) and abs(np.sum(lam ** 2) - 1) < 1e-13
+        # Vidal canonical form of genuine Aer outputs: pins which side each lambda multiplies (A.5)
+        for i, (a0, a1) in enumerate(mps[0]):
+            if i < 49:        # sum_s (Gamma_s lambda_i)(Gamma_s lambda_i)^+ weighted on the left by lambda_{i-1}^2 ...
+                lr = mps[1][i]
+                ll = mps[1][i - 1] if i > 0 else np.ones(1)
+                left = sum((ll[:, None] * a).conj().T @ (ll[:, None] * a) for a in (a0, a1))
+                np.testing.assert_allclose(left, np.eye(len(lr)), atol=1e-7)
+                right = sum((a * lr[None, :]) @ (a * lr[None, :]).conj().T for a in (a0, a1))
+                np.testing.assert_allclose(right, np.eye(len(ll)), atol=1e-7)
         pp = mo._preprocess_mps(mps)
         assert pp[0].shape == (2, 1, 2) and pp[-1].shape == (2, 2, 1)
         z = [mo.mps_expectation(pp, "Z", q, already_preprocessed=True) for q in (0, 24, 49)]
