@@ -144,7 +144,7 @@ class DeviceStatevector:
         """4x4 RDMs for all `pairs` ((a,b) tuples); computed in one batched device call."""
         need = [p for p in {tuple(sorted(p)) for p in pairs} if p not in self._rdm]
         if need:
-            rho = self._engine().pair_rdm(SLOT_WORK, need)
+            rho = self._owner._pair_rdm(self._engine(), SLOT_WORK, need)
             for p, r in zip(need, rho):
                 self._rdm[p] = r
         return [self._rdm[tuple(sorted(p))] for p in pairs]
@@ -196,8 +196,13 @@ class B200StatevectorSimulator:
 class B200SVBackend(_SVBase):
     kind = "sv"  # what isinstance(backend, AerSVBackend) decides in the reference
 
-    def __init__(self, device=0, simulator=None):
+    def __init__(self, device=0, simulator=None, pair_comm=None):
+        """pair_comm (optional, dist_sv.TorchComm-shaped: .rank, .world, .allreduce_sum): ranks that run the SAME compile
+        on replicas of the state divide the pair-RDM read passes of the ISL heuristic among themselves
+        (adapt_compiler.py:955-976: one RDM per candidate pair per layer) and exchange the P x 16 complex results with
+        one small all-reduce -- SURVEY 8e row 1.  Every rank must make the same backend calls in the same order."""
         self.device = device
+        self.pair_comm = pair_comm
         self._engine = None
         self._compact = None
         self._evaluator = None
@@ -210,6 +215,16 @@ class B200SVBackend(_SVBase):
         self._wcache = None
         self._changed = None
         self.simulator = simulator if simulator is not None else B200StatevectorSimulator(self)
+
+    def _pair_rdm(self, engine, slot, pairs):
+        comm = self.pair_comm
+        if comm is None or comm.world == 1 or not len(pairs):
+            return engine.pair_rdm(slot, pairs)
+        # this rank's share of the read passes; pairs owned by other ranks come back as zeros, so the sum over the
+        # ranks is bit-identical to the undivided call (b200_sv_pair_rdm_part): same chosen pairs on any number of GPUs
+        part = engine.pair_rdm(slot, pairs, part=comm.rank, n_parts=comm.world)
+        flat = comm.allreduce_sum(np.ascontiguousarray(part).view(np.float64).reshape(-1))
+        return np.asarray(flat).view(np.complex128).reshape(-1, 4, 4)
 
     # checkpointing pickles the whole compiler, backend included (adapt_compiler.py:484-497)
     def __getstate__(self):

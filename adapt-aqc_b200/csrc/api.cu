@@ -601,8 +601,17 @@ int b200_sv_expz(b200_ctx* ctx, int slot, double* out) {
 }
 
 int b200_sv_pair_rdm(b200_ctx* ctx, int slot, const int32_t* pairs, int n_pairs, double* out) {
+    return b200_sv_pair_rdm_part(ctx, slot, pairs, n_pairs, 0, 1, out);
+}
+
+// The same pass list as b200_sv_pair_rdm (it depends only on the requested pairs), of which only the passes
+// k = part (mod n_parts) are launched: a pair owned by a pass of another part comes back as zeros, so that the SUM over
+// the parts (one all-reduce of 32 * n_pairs doubles between ranks holding replicas of the state) is, bit for bit, the
+// result of the undivided call.
+int b200_sv_pair_rdm_part(b200_ctx* ctx, int slot, const int32_t* pairs, int n_pairs, int part, int n_parts, double* out) {
     if (check_slot(ctx, slot)) return -1;
     if (n_pairs < 0 || (n_pairs > 0 && (!pairs || !out))) return set_error("null pointer");
+    if (n_parts < 1 || part < 0 || part >= n_parts) return set_error("pair_rdm_part: part out of range");
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int n = ctx->nq;
     const double2* psi = (const double2*)ctx->slots[slot];
@@ -624,13 +633,15 @@ int b200_sv_pair_rdm(b200_ctx* ctx, int slot, const int32_t* pairs, int n_pairs,
     struct Pending { int off, npairs; int pl[6][2]; };
     std::vector<Pending> pending;
     int out_off = 0;
+    int pass_index = 0;
     auto flush = [&]() -> int {
         if (pending.empty()) return 0;
         std::vector<double> r(out_off);
         if (fetch_out(ctx, r.data(), out_off)) return -1;
         for (const Pending& pd : pending)
             for (int t = 0; t < pd.npairs; ++t)
-                std::memcpy(&acc[(size_t)(pd.pl[t][0] * n + pd.pl[t][1]) * 16], r.data() + pd.off + 16 * t, 16 * sizeof(double));
+                if (pd.pl[t][0] >= 0)
+                    std::memcpy(&acc[(size_t)(pd.pl[t][0] * n + pd.pl[t][1]) * 16], r.data() + pd.off + 16 * t, 16 * sizeof(double));
         pending.clear();
         out_off = 0;
         return 0;
@@ -654,6 +665,17 @@ int b200_sv_pair_rdm(b200_ctx* ctx, int slot, const int32_t* pairs, int n_pairs,
             if (g4 > g3 && g4 >= 3) { q[2] = c4a; q[3] = c4b; nq = 4; }      // a quad pass costs ~1.2 triple passes
             else if (g3 >= 2) { q[2] = c3; nq = 3; }
             std::sort(q, q + nq);
+            // a pair belongs to the FIRST pass that covers it (a later quadruple may contain it again)
+            Pending pd;
+            pd.npairs = 0;
+            for (int i = 0; i < nq; ++i)
+                for (int j = i + 1; j < nq; ++j) {
+                    pd.pl[pd.npairs][0] = have[q[i] * n + q[j]] ? -1 : q[i];
+                    pd.pl[pd.npairs][1] = q[j];
+                    have[q[i] * n + q[j]] = 1;
+                    ++pd.npairs;
+                }
+            if ((pass_index++ % n_parts) != part) continue;       // another rank's pass
             const int width = nq == 4 ? RDM4_WIDTH : (nq == 3 ? RDM3_WIDTH : 16);
             if (out_off + width > (int)OUT_DOUBLES && flush()) return -1;
             const int grid = red_grid(ctx, 1ull << (n - nq));
@@ -670,14 +692,7 @@ int b200_sv_pair_rdm(b200_ctx* ctx, int slot, const int32_t* pairs, int n_pairs,
             }
             CUDA_TRY(cudaGetLastError());
             ctx->counters[3] += 16ull << n;
-            Pending pd;
-            pd.off = out_off; pd.npairs = 0;
-            for (int i = 0; i < nq; ++i)
-                for (int j = i + 1; j < nq; ++j) {
-                    pd.pl[pd.npairs][0] = q[i]; pd.pl[pd.npairs][1] = q[j];
-                    have[q[i] * n + q[j]] = 1;
-                    ++pd.npairs;
-                }
+            pd.off = out_off;
             pending.push_back(pd);
             out_off += width;
         }

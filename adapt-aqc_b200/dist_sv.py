@@ -426,7 +426,7 @@ class _CudaAlias:
         self.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
-def make_gpu_sharded(num_qubits, n_slots=2, staging_bytes=1 << 30, local_rank=0, exchange=None):
+def make_gpu_sharded(num_qubits, n_slots=2, staging_bytes=1 << 30, local_rank=0, exchange=None, engine=None):
     """Builds a ShardedStatevector over the default process group (NCCL), one rank per GPU.
 
     exchange: "peer" (default) = the slots are opened on every rank through CUDA IPC and global qubits are
@@ -441,7 +441,11 @@ def make_gpu_sharded(num_qubits, n_slots=2, staging_bytes=1 << 30, local_rank=0,
     g = int(np.log2(comm.world))
     nl = num_qubits - g
     exchange = os.environ.get("B200AQC_EXCHANGE", exchange or "peer")
-    eng = SVEngine(nl, device=local_rank, n_slots=n_slots)
+    # engine: a pre-allocated local engine (lets the caller agree on the allocation collectively before any rank enters
+    # the collectives below)
+    eng = engine if engine is not None else SVEngine(nl, device=local_rank, n_slots=n_slots)
+    if eng.num_qubits != nl or eng.n_slots < n_slots:
+        raise ValueError("pre-allocated engine does not match the sharding")
     tensors = [torch.as_tensor(_CudaAlias(eng.device_ptr(s), 2 << nl), device=dev) for s in range(n_slots)]
     staging = None
     peer_ptrs = None

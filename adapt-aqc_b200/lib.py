@@ -19,7 +19,7 @@ SYMBOLS = [
     "b200_ctx_profile_read", "b200_ctx_profile_sweeps", "b200_sv_alloc", "b200_sv_reserve_slots", "b200_sv_attach", "b200_sv_device_ptr",
     "b200_sv_ipc_export", "b200_sv_ipc_open", "b200_sv_ipc_close", "b200_sv_peer_swap",
     "b200_sv_num_qubits", "b200_sv_init_zero", "b200_sv_copy", "b200_sv_run",
-    "b200_sv_run_inverse", "b200_sv_amp", "b200_sv_expz", "b200_sv_pair_rdm", "b200_sv_inner", "b200_sv_inner2", "b200_sv_inner2_gather", "b200_sv_gather", "b200_sv_scatter", "b200_sv_gather_ranked",
+    "b200_sv_run_inverse", "b200_sv_amp", "b200_sv_expz", "b200_sv_pair_rdm", "b200_sv_pair_rdm_part", "b200_sv_inner", "b200_sv_inner2", "b200_sv_inner2_gather", "b200_sv_gather", "b200_sv_scatter", "b200_sv_gather_ranked",
     "b200_sv_download", "b200_sv_upload", "b200_sv_plan_stats", "b200_sv_plan_detail",
     "b200_mps_create", "b200_mps_destroy", "b200_mps_set_truncation", "b200_mps_num_qubits",
     "b200_mps_init_zero", "b200_mps_set", "b200_mps_bond_dims", "b200_mps_get", "b200_mps_copy",
@@ -81,6 +81,7 @@ def load():
     L.b200_sv_amp.argtypes = [vp, ci, cu64, dp]
     L.b200_sv_expz.argtypes = [vp, ci, dp]
     L.b200_sv_pair_rdm.argtypes = [vp, ci, vp, ci, dp]
+    L.b200_sv_pair_rdm_part.argtypes = [vp, ci, vp, ci, ci, ci, dp]
     L.b200_sv_inner.argtypes = [vp, ci, ci, ci, dp]
     L.b200_sv_inner2.argtypes = [vp, ci, ci, ci, ci, dp]
     L.b200_sv_inner2_gather.argtypes = [vp, ci, vp, ci, vp, ci, ci, dp]

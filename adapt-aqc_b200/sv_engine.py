@@ -113,11 +113,14 @@ class SVEngine:
         check(self._lib.b200_sv_expz(self._ctx, slot, dptr(out)))
         return out[:-1], float(out[-1])
 
-    def pair_rdm(self, slot, pairs):
+    def pair_rdm(self, slot, pairs, part=0, n_parts=1):
+        """4x4 RDMs of `pairs`.  n_parts > 1: only this share of the read passes is launched (pairs owned by other
+        shares come back as zeros; the sum over the shares is bit-identical to the undivided call)."""
         pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
         out = np.zeros((len(pairs), 16), dtype=np.complex128)
         if len(pairs):
-            check(self._lib.b200_sv_pair_rdm(self._ctx, slot, pairs.ctypes.data, len(pairs), dptr(out.view(np.float64))))
+            check(self._lib.b200_sv_pair_rdm_part(self._ctx, slot, pairs.ctypes.data, len(pairs), int(part), int(n_parts),
+                                                  dptr(out.view(np.float64))))
         return out.reshape(-1, 4, 4)
 
     def inner(self, l_slot, r_slot, q=-1):

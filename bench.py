@@ -129,33 +129,129 @@ def measured_traffic(n):
     return None
 
 
-def cpu_baseline_sample(n, target, ansatz, budget_s=20.0):
-    """CPU restatement of the reference path, bounded sample: the reference re-simulates ALL G
-    gates of full_circuit from |0..0> for every evaluation; time the first k gates at full size
-    (k chosen to fit the budget) and scale to G."""
-    from oracle import sv_oracle as orc
-    from oracle.oracle_backends import circuit_to_gates
-    gates = circuit_to_gates(target) + circuit_to_gates(ansatz)
-    G = len(gates)
-    cores = orc.num_threads()
-    # calibrate on 4 gates, then size the sample
-    psi = np.zeros(1 << n, dtype=np.complex128); psi[0] = 1
-    rec, mats = orc.pack_gates(gates[:4])
-    t0 = time.perf_counter()
-    orc.lib().orc_sv_apply(n, psi.view(np.float64).ctypes.data_as(orc.ctypes.POINTER(orc.ctypes.c_double)),
-                           rec.ctypes.data, len(rec), mats.ctypes.data_as(orc.ctypes.POINTER(orc.ctypes.c_double)))
-    per_gate = (time.perf_counter() - t0) / 4
-    k = int(max(8, min(G - 4, budget_s / max(per_gate, 1e-9))))
-    rec, mats = orc.pack_gates(gates[4:4 + k])
-    t0 = time.perf_counter()
-    orc.lib().orc_sv_apply(n, psi.view(np.float64).ctypes.data_as(orc.ctypes.POINTER(orc.ctypes.c_double)),
-                           rec.ctypes.data, len(rec), mats.ctypes.data_as(orc.ctypes.POINTER(orc.ctypes.c_double)))
-    dt = time.perf_counter() - t0
-    per_gate = dt / k
-    evals_per_s = 1.0 / (per_gate * G)
-    sample = (f"{k} of the {G} gates of one full re-simulation at n={n} ({dt:.1f} s), scaled x{G}/{k}; "
-              f"per-gate sweeps, no gate fusion")
-    return {"value": evals_per_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def fuse_two_qubit_blocks(n, gates):
+    """Greedy 2-qubit block fusion of an oracle gate list [(name, qubits, params)] -> list of mat2 / mat1 gates with the
+    same product: 1-qubit gates are absorbed into the neighbouring 2-qubit gate on their qubit, consecutive 2-qubit gates
+    on the same pair are multiplied together.  qiskit-aer fuses gates before applying them (fusion is on by default from
+    14 qubits up), so timing one sweep per ORIGINAL gate would overstate the reference's cost; this is the baseline's
+    stand-in for that pass (brickwork C3: 404 gates -> 124 dense 4x4 sweeps)."""
+    from oracle.mps_oracle import gate_matrix
+    pending = [None] * n            # 2x2 waiting for a 2-qubit gate on that qubit
+    block_of = [None] * n           # index into `out` of the open 2-qubit block whose LAST op on this qubit it is
+    out = []                        # [qubits(a, b), 4x4] with index bit(a) + 2 bit(b)
+
+    def kron_on(m, pos):            # 2x2 on bit `pos` of a 2-qubit index
+        return np.kron(np.eye(2), m) if pos == 0 else np.kron(m, np.eye(2))
+
+    for name, qubits, params in gates:
+        m = np.asarray(params, dtype=np.complex128).reshape(2 ** len(qubits), -1) if name in ("mat1", "mat2") \
+            else gate_matrix(name, params)
+        if len(qubits) == 1:
+            q = qubits[0]
+            b = block_of[q]
+            if b is not None:
+                pos = out[b][0].index(q)
+                out[b][1] = kron_on(m, pos) @ out[b][1]
+            else:
+                pending[q] = m if pending[q] is None else m @ pending[q]
+            continue
+        a, c = qubits
+        ba, bc = block_of[a], block_of[c]
+        if ba is not None and ba == bc:                       # same open block on the same pair: multiply in
+            qa, _ = out[ba][0]
+            mm = m if qa == a else m[np.ix_([0, 2, 1, 3], [0, 2, 1, 3])]
+            out[ba][1] = mm @ out[ba][1]
+            continue
+        pre = np.eye(4, dtype=np.complex128)
+        for q, pos in ((a, 0), (c, 1)):
+            if pending[q] is not None:
+                pre = kron_on(pending[q], pos) @ pre
+                pending[q] = None
+        out.append([(a, c), m @ pre])
+        block_of[a] = block_of[c] = len(out) - 1
+    fused = [("mat2", list(q), mat) for q, mat in out]
+    fused += [("mat1", [q], pending[q]) for q in range(n) if pending[q] is not None]
+    return fused
+
+
+class CpuReference:
+    """CPU restatement of the reference statevector path (oracle/sv_oracle.c): every cost evaluation re-simulates ALL
+    G gates of full_circuit from |0..0>, one sweep over the 2^n amplitudes per gate, no gate fusion
+    (aer_sv_backend.py:37-47 asks Aer for exactly that; Aer's own fusion pass would merge some neighbouring gates).
+    The thread count is set explicitly (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+
+    def __init__(self, n, target, ansatz, fused=True):
+        from oracle import sv_oracle as orc
+        from oracle.oracle_backends import circuit_to_gates
+        self.orc, self.n = orc, n
+        self.gates = circuit_to_gates(target) + circuit_to_gates(ansatz)
+        self.circuit_gates = len(self.gates)
+        self.fused = fused
+        if fused:
+            self.gates = fuse_two_qubit_blocks(n, self.gates)
+        self.G = len(self.gates)
+        self.threads = host_threads()
+        orc.lib().orc_set_num_threads(self.threads)
+        self.cores = orc.num_threads()
+        self.psi = np.zeros(1 << n, dtype=np.complex128)
+        self.pos = 0                 # gates of the current evaluation already applied
+        self.evaluations = []        # cost of every COMPLETED evaluation
+
+    def _apply(self, lo, hi):
+        orc = self.orc
+        rec, mats = orc.pack_gates(self.gates[lo:hi])
+        dp = orc.ctypes.POINTER(orc.ctypes.c_double)
+        rc = orc.lib().orc_sv_apply(self.n, self.psi.view(np.float64).ctypes.data_as(dp), rec.ctypes.data, len(rec),
+                                    mats.ctypes.data_as(dp))
+        assert rc == 0
+
+    def chunk(self, n_gates):
+        """Apply the next n_gates gates of the evaluation stream (|0..0> is re-initialised when an evaluation starts,
+        inside the timed region like in the reference); returns seconds."""
+        t0 = time.perf_counter()
+        left = n_gates
+        while left > 0:
+            if self.pos == 0:
+                self.psi[:] = 0
+                self.psi[0] = 1
+            k = min(left, self.G - self.pos)
+            self._apply(self.pos, self.pos + k)
+            self.pos += k
+            left -= k
+            if self.pos == self.G:
+                self.evaluations.append(float(1 - abs(self.psi[0]) ** 2))
+                self.pos = 0
+        return time.perf_counter() - t0
+
+    def restart(self):
+        self.pos = 0
+
+
+def cpu_baseline_sample(n, target, ansatz, unfused_too=True):
+    """cpu_baseline of the main arm: ONE complete evaluation, timed (404 gates at n = 28: ~25 s on 16 host threads)."""
+    ref = CpuReference(n, target, ansatz, fused=True)
+    ref.chunk(4)                     # page in the 4 GiB state, spin up the thread pool
+    ref.restart()
+    dt = ref.chunk(ref.G)
+    out = {"value": 1.0 / dt, "unit": UNIT, "cores": ref.cores, "kind": "port", "extrapolated": False,
+           "gate_fusion": "2-qubit blocks",
+           "sample": f"1 complete evaluation of full_circuit from |0..0> at n={n}: {ref.circuit_gates} gates fused into {ref.G} "
+                     f"dense 2-qubit sweeps (stand-in for Aer's fusion pass), {dt:.1f} s, timed, not extrapolated; cost "
+                     f"{ref.evaluations[-1]:.12f}"}
+    if unfused_too:
+        raw = CpuReference(n, target, ansatz, fused=False)
+        k = min(raw.G, 60)
+        dt_raw = raw.chunk(k) * raw.G / k
+        out["unfused"] = {"value": 1.0 / dt_raw, "unit": UNIT, "extrapolated": k < raw.G,
+                          "sample": f"{k} of {raw.G} gates, one sweep per original gate (round-1 baseline)"}
+    return out
 
 
 # ---- config C4: 50-qubit random MPS at bond dimension 256 ----------------------------------------
@@ -237,6 +333,82 @@ def bench_mps(args, device, with_cpu=True):
 
 
 # ---- compile wall-time (BASELINE metric, second half): a whole ADAPT-AQC compile of C3 -----------
+def bench_compile_converging(args, device, pair_comm=None):
+    """Compile WALL-TIME on a target ADAPT-AQC actually compiles (harness.workloads.compilable_target): the run ends by
+    reaching the reference's sufficient cost 1e-2 (adapt_compiler.py:368-393), default AdaptConfig, default all-to-all
+    coupling map (P = 378 pair RDMs per layer).  pair_comm: divide the pair-RDM passes over the ranks."""
+    from adapt_aqc_b200.backends import B200SVBackend
+    from harness.compiler import AdaptCompiler, AdaptConfig
+    from harness.workloads import compilable_target
+    n = args.qubits
+    target = compilable_target(n, args.converging_layers)
+    backend = B200SVBackend(device=device, pair_comm=pair_comm)
+    comp = AdaptCompiler(target, backend=backend, adapt_config=AdaptConfig(max_layers=args.converging_max_layers))
+    comp.evaluate_cost()
+    eng = backend._engine
+    eng.sync()
+    l0 = sum(e.counters()["launches"] for e in backend.engines())
+    eng.profile(True)
+    t0 = time.perf_counter()
+    res = comp.compile()
+    eng.sync()
+    wall = time.perf_counter() - t0
+    prof = eng.profile_read()
+    eng.profile(False)
+    l1 = sum(e.counters()["launches"] for e in backend.engines())
+    out = {"workload": f"{n}-qubit compilable target (ry layer + {args.converging_layers} thin layers, seed 1234), default AdaptConfig, "
+                       f"all-to-all coupling map (P={n * (n - 1) // 2})" + (f", pair-RDM passes divided over {pair_comm.world} ranks" if pair_comm else ""),
+           "wall_s": wall, "layers": len(res.qubit_pair_history), "cost_evaluations": int(comp.cost_evaluation_counter),
+           "final_global_cost": float(res.global_cost_history[-1]), "overlap": float(res.overlap),
+           "exact_overlap": float(res.exact_overlap), "converged": bool(res.global_cost_history[-1] < comp.adapt_config.sufficient_cost),
+           "evals_per_s": comp.cost_evaluation_counter / wall, "gpu_launches": int(l1 - l0),
+           "kernel_ms": {k: round(v[0], 2) for k, v in prof.items() if v[1]},
+           "kernel_launches": {k: int(v[1]) for k, v in prof.items() if v[1]},
+           "pair_history_head": [list(p) for p in res.qubit_pair_history[:8]]}
+    for e in backend.engines():
+        e.close()
+    return out
+
+
+def bench_compile_split(args, local_rank, world):
+    """N > 1: the C3 all-to-all compile with every rank running the same compiler on a replica of U|0> and the ISL
+    pair-RDM read passes divided over the ranks (b200_sv_pair_rdm_part + one all-reduce of P x 16 complex per layer)."""
+    import torch
+    import torch.distributed as dist
+    from adapt_aqc_b200.backends import B200SVBackend
+    from adapt_aqc_b200.dist_sv import TorchComm
+    from harness.compiler import AdaptCompiler, AdaptConfig
+    n = args.qubits
+    target, _ = build_workload(n, args.depth, 0)
+    out = {}
+    for name, comm in (("divided", TorchComm(torch.device("cuda", local_rank))), ("undivided", None)):
+        backend = B200SVBackend(device=local_rank, pair_comm=comm)
+        comp = AdaptCompiler(target, backend=backend, adapt_config=AdaptConfig(max_layers=args.compile_layers, method="ISL"))
+        comp.evaluate_cost()
+        eng = backend._engine
+        eng.sync()
+        dist.barrier()
+        eng.profile(True)
+        t0 = time.perf_counter()
+        res = comp.compile()
+        eng.sync()
+        dist.barrier()
+        wall = time.perf_counter() - t0
+        prof = eng.profile_read()
+        eng.profile(False)
+        t = torch.tensor([wall, prof["rdm"][0]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = {"wall_s": float(t[0]), "rdm_kernel_ms_max_over_ranks": float(t[1]), "rdm_launches_this_rank": int(prof["rdm"][1]),
+                     "layers": len(res.qubit_pair_history), "cost_evaluations": int(comp.cost_evaluation_counter),
+                     "pair_history": [list(p) for p in res.qubit_pair_history]}
+        for e in backend.engines():
+            e.close()
+    out["same_pairs"] = out["divided"]["pair_history"] == out["undivided"]["pair_history"]
+    out["workload"] = (f"C3 compile, {n}-qubit brickwork(depth={args.depth}) target, AdaptConfig(max_layers={args.compile_layers}, "
+                       f"method='ISL'), all-to-all coupling map (P={n * (n - 1) // 2}); every rank runs the same compile on a replica")
+    return out
+
+
 def bench_compile(args, device, cpu_evals_per_s=None):
     """AdaptCompiler.compile() (adapt_compiler.py:246) on the C3 target: ISL pair selection from pair
     RDMs on a linear coupling map (P = n - 1 pairs), Rotoselect on each new layer, Rotosolve over the
@@ -296,11 +468,32 @@ def bench_sharded(args, local_rank, world):
     import torch.distributed as dist
     from adapt_aqc_b200.dist_sv import make_gpu_sharded
     from adapt_aqc_b200.gates import canonical_window
+    from adapt_aqc_b200.lib import B200Error
+    from adapt_aqc_b200.sv_engine import SVEngine
     g = int(np.log2(world))
-    n = args.sharded_local_qubits + g
+    # BASELINE config 5: 34 qubits at 2 / 4 / 8 GPUs = 128 / 64 / 32 GiB per GPU (one slot, exchanged in place over
+    # NVLink peer memory).  The allocation is agreed on collectively: if any rank cannot hold its slice, all fall back
+    # to one qubit less (reported in "qubits").
+    n = args.sharded_qubits if args.sharded_local_qubits is None else args.sharded_local_qubits + g
+    sv = None
+    while sv is None:
+        try:
+            local_engine = SVEngine(n - g, device=local_rank, n_slots=1)
+            ok = 1.0
+        except B200Error:
+            local_engine, ok = None, 0.0
+        flag = torch.tensor([ok], device="cuda", dtype=torch.float64)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag[0]) > 0:
+            sv = make_gpu_sharded(n, n_slots=1, local_rank=local_rank, engine=local_engine)
+        else:
+            if local_engine is not None:
+                local_engine.close()
+            n -= 1
+            if n - g < 26:
+                raise RuntimeError("no sharded register size fits")
     target, ansatz = build_workload(n, args.sharded_depth, args.sharded_layers)
     window = canonical_window(target) + canonical_window(ansatz)
-    sv = make_gpu_sharded(n, n_slots=1, local_rank=local_rank)
     eng, comm = sv.eng, sv.comm
     sv.run(0, -1, window)                       # warm-up (also JIT of NCCL channels)
     sv.amp(0, 0)
@@ -343,7 +536,8 @@ def bench_sharded(args, local_rank, world):
     del sv
     torch.cuda.empty_cache()
     if not args.no_compile:
-        out["compile"] = bench_sharded_compile(args, local_rank, n)
+        # the compile keeps 4 sharded slots (WORK, BASE, L, R): 34 qubits at 8 GPUs (4 x 32 GiB), 33 at 4, 32 at 2
+        out["compile"] = bench_sharded_compile(args, local_rank, min(n, 31 + g))
     return out
 
 
@@ -381,28 +575,41 @@ def bench_sharded_compile(args, local_rank, n):
 
 
 def run_reference(args, rank, world):
+    """`--impl reference`: the reference's CPU algorithm for the path (full re-simulation per evaluation) on the host
+    cores, as TIMED work: the K timed steps are consecutive chunks of ceil(G/K) gates of real evaluations, so that
+    together they cover at least one complete G-gate evaluation; value = evaluations completed per second of timed
+    work (fractions count by gates), nothing is extrapolated unless K * chunk < G (reported)."""
     if rank != 0:
         return
     n = args.qubits
     target, ansatz = build_workload(n, args.depth, args.layers)
-    vals = []
-    total = args.warmup + args.steps
-    budget = max(3.0, min(20.0, 150.0 / max(1, total)))
-    base = None
     t_all = time.perf_counter()
-    for i in range(total):
-        base = cpu_baseline_sample(n, target, ansatz, budget_s=budget)
-        if i >= args.warmup:
-            vals.append(base["value"])
-    v = float(np.mean(vals))
-    base["value"] = v
+    ref = CpuReference(n, target, ansatz)
+    per_step = max(1, -(-ref.G // max(1, args.steps)))
+    for _ in range(args.warmup):
+        ref.chunk(min(per_step, 8))              # warm-up: page in the state, spin up the threads
+    ref.restart()
+    ref.evaluations.clear()
+    times = [ref.chunk(per_step) for _ in range(args.steps)]
+    total = float(sum(times))
+    gates_done = per_step * args.steps
+    v = gates_done / ref.G / total
+    extrapolated = gates_done < ref.G
+    base = {"value": v, "unit": UNIT, "cores": ref.cores, "kind": "port", "extrapolated": extrapolated,
+            "extrapolation_factor": ref.G / gates_done if extrapolated else 1.0,
+            "evaluations_timed": gates_done / ref.G, "gate_fusion": "2-qubit blocks" if ref.fused else "none",
+            "sample": f"{args.steps} timed steps x {per_step} fused gates = {gates_done / ref.G:.2f} complete evaluations of "
+                      f"full_circuit ({ref.circuit_gates} gates fused into {ref.G} dense 2-qubit sweeps, the stand-in for Aer's "
+                      f"fusion pass) at n={n} ({total:.1f} s of timed work); completed-evaluation costs "
+                      f"{[round(c, 12) for c in ref.evaluations[:3]]}"}
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * 220 / v, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
         "config": workload_config(args), "cpu_baseline": base,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
+        "step_definition": f"one step = {per_step} consecutive gates of a full re-simulation ({per_step / ref.G:.4f} evaluations)",
     }
     print(json.dumps(line), file=RESULT_OUT, flush=True)
 
@@ -428,12 +635,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mps", action="store_true", help="skip the secondary C4 (MPS) measurement")
     ap.add_argument("--mps-only", action="store_true", help="run only the C4 (MPS) measurement and print it")
-    ap.add_argument("--sharded-local-qubits", type=int, default=30, help="qubits per rank of the sharded C5 leg (N > 1)")
+    ap.add_argument("--sharded-qubits", type=int, default=34, help="register size of the sharded C5 leg (N > 1)")
+    ap.add_argument("--sharded-local-qubits", type=int, default=None, help="override: qubits per rank of the sharded C5 leg")
     ap.add_argument("--sharded-depth", type=int, default=4)
     ap.add_argument("--sharded-layers", type=int, default=4)
     ap.add_argument("--no-sharded", action="store_true")
     ap.add_argument("--no-compile", action="store_true", help="skip the compile wall-time leg")
     ap.add_argument("--compile-layers", type=int, default=6)
+    ap.add_argument("--converging-layers", type=int, default=12, help="thin layers of the compilable target")
+    ap.add_argument("--converging-max-layers", type=int, default=400)
+    ap.add_argument("--no-converging", action="store_true", help="skip the converging compile leg")
     ap.add_argument("--sharded-compile-layers", type=int, default=4)
     ap.add_argument("--mps-qubits", type=int, default=50)
     ap.add_argument("--mps-chi", type=int, default=256)
@@ -566,7 +777,7 @@ def main():
         "evaluator_stats": dict(backend._evaluator.stats),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_sample(n, target, ansatz, budget_s=15.0)
+        line["cpu_baseline"] = cpu_baseline_sample(n, target, ansatz)
     if rank == 0 and world == 1 and not args.no_compile:
         backend._engine.close()
         try:
@@ -574,6 +785,11 @@ def main():
             line["compile_c3"] = bench_compile(args, local_rank, cpu_rate)
         except Exception as exc:  # noqa: BLE001
             line["compile_c3"] = {"error": repr(exc)}
+    if rank == 0 and world == 1 and not args.no_compile and not args.no_converging:
+        try:
+            line["compile_converging"] = bench_compile_converging(args, local_rank)
+        except Exception as exc:  # noqa: BLE001
+            line["compile_converging"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_mps:
         if backend._engine is not None:
             backend._engine.close()          # free the 16 GiB of statevector slots first
@@ -581,8 +797,16 @@ def main():
             line["mps_c4"] = bench_mps(args, local_rank, with_cpu=not args.no_cpu_baseline)
         except Exception as exc:  # noqa: BLE001 - the secondary measurement must not hide the main line
             line["mps_c4"] = {"error": repr(exc)}
+    if dist is not None and not args.no_compile:
+        for e in backend.engines():
+            e.close()
+        try:
+            line["compile_c3_pairs_divided"] = bench_compile_split(args, local_rank, world)
+        except Exception as exc:  # noqa: BLE001
+            line["compile_c3_pairs_divided"] = {"error": repr(exc)}
     if dist is not None and not args.no_sharded:
-        backend._engine.close()          # free the replica's statevector slots first
+        for e in backend.engines():
+            e.close()                    # free the replica's statevector slots first
         try:
             sharded = bench_sharded(args, local_rank, world)
         except Exception as exc:  # noqa: BLE001

@@ -86,6 +86,19 @@ def build_workload(n, depth, layers, seed=1234):
     return target, thin_ansatz(n, layers, rng)
 
 
+def compilable_target(n, layers, seed=1234):
+    """A target ADAPT-AQC actually compiles to the reference's sufficient cost (1e-2): a dense product layer ry(theta_q)
+    followed by `layers` thinly dressed CNOT layers in brickwall order.  (The random brickwork target of C3 is what the
+    gate kernels are timed on, but no optimiser gets a 28-qubit depth-8 random circuit below cost 0.99 in a few layers;
+    compile WALL-TIME needs a run that converges.)"""
+    rng = np.random.default_rng(seed)
+    c = Circuit(n)
+    for q in range(n):
+        c.ry(float(rng.uniform(0.5, 2.5)), q)
+    c.data.extend(thin_ansatz(n, layers, rng).data)
+    return c
+
+
 def build_mps_workload(n, chi, layers, seed=1):
     """C4: (random Vidal MPS target at bond dimension chi, `layers` un-absorbed thin layers around the middle bond)."""
     target = random_vidal_mps(n, chi, seed)

@@ -147,6 +147,13 @@ int b200_sv_expz(b200_ctx *ctx, int slot, double *out /* n+1 */);
  * All pairs from a few read passes instead of one re-simulation + host trace per pair
  * (adaptaqc/compilers/adapt/adapt_compiler.py:964-975). */
 int b200_sv_pair_rdm(b200_ctx *ctx, int slot, const int32_t *pairs, int n_pairs, double *out);
+/* One share of the same work, for ranks that hold REPLICAS of the state ("pair-RDM kernel: split the
+ * pair list across GPUs, allgather"): the pass list is the one b200_sv_pair_rdm builds for `pairs`, only the passes
+ * k = part (mod n_parts) are launched, pairs owned by other parts are returned as zeros.  Summing `out` over the parts
+ * (one small all-reduce) reproduces the undivided call bit for bit, so the pair chosen by
+ * adaptaqc/compilers/adapt/adapt_compiler.py:858-921 does not depend on the number of GPUs. */
+int b200_sv_pair_rdm_part(b200_ctx *ctx, int slot, const int32_t *pairs, int n_pairs, int part, int n_parts,
+                          double *out);
 /* out = 2x2 complex M[i][j] = sum_rest conj(L[i,rest]) R[j,rest] for qubit q (row-major,
  * 8 doubles).  <L|G_q|R> = sum_ij G[i][j] M[i][j] then gives the cost for ANY 1-qubit gate G
  * on q, i.e. all Rotosolve / Rotoselect shift evaluations of one gate

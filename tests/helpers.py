@@ -118,9 +118,11 @@ class FakeEngine:
         psi = self.slots[slot]
         return np.array(orc.measure_qubit_expectation_values(psi)), float(np.vdot(psi, psi).real)
 
-    def pair_rdm(self, slot, pairs):
+    def pair_rdm(self, slot, pairs, part=0, n_parts=1):
+        """part / n_parts: emulates b200_sv_pair_rdm_part with one "pass" per pair -- pairs of other parts are zeros."""
         from oracle import sv_oracle as orc
-        return np.array([orc.partial_trace(self.slots[slot], a, b) for a, b in pairs]).reshape(-1, 4, 4)
+        return np.array([orc.partial_trace(self.slots[slot], a, b) if i % n_parts == part else np.zeros((4, 4), dtype=np.complex128)
+                         for i, (a, b) in enumerate(pairs)]).reshape(-1, 4, 4)
 
     def inner(self, l_slot, r_slot, q=-1):
         self.inners += 1

@@ -33,3 +33,16 @@ def test_compile_on_a_sharded_register_matches_oracle(emu, world, n, port):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "dist compile ok" in res.stdout
+
+
+@pytest.mark.parametrize("world,n,port", [(2, 6, 29615), (4, 7, 29616)])
+def test_pair_rdm_passes_divided_over_replicas_make_the_same_decisions(emu, world, n, port):
+    """ranks holding replicas of the state divide the ISL pair-RDM passes and all-reduce the P x 16
+    complex results (B200SVBackend(pair_comm=...)); pair history, EM values and costs equal the undivided compile."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"),
+           str(n), "cpu", "pairsplit"]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "dist pairsplit ok" in res.stdout

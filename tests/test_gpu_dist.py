@@ -46,3 +46,17 @@ def test_compile_on_a_sharded_register(world, n, port):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "dist compile ok" in res.stdout
+
+
+@pytest.mark.parametrize("world,n,port", [(2, 18, 29641), (8, 20, 29642)])
+def test_pair_rdm_passes_divided_over_replicas(world, n, port):
+    """B200SVBackend(pair_comm=...) on real GPUs: b200_sv_pair_rdm_part shares + NCCL all-reduce give, bit for bit, the
+    entanglement measures and therefore the pair history of the single-GPU compile."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"),
+           str(n), "gpu", "pairsplit"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "dist pairsplit ok" in res.stdout

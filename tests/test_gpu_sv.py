@@ -491,3 +491,33 @@ def test_gather_and_scatter_match_numpy(n, K):
     ref[x] = psi[x]
     np.testing.assert_array_equal(big.download(1), ref)
     big.close(); small.close()
+
+
+def test_pair_rdm_parts_sum_to_the_undivided_call_bit_for_bit():
+    """b200_sv_pair_rdm_part: the shares of 2 / 3 / 8 ranks sum, bit for bit, to b200_sv_pair_rdm, every
+    pair is produced by exactly one share, and each share launches its fraction of the read passes."""
+    n = 14
+    rng = np.random.default_rng(9)
+    eng = SVEngine(n, n_slots=1)
+    eng.run(0, -1, GateStream.from_gates(random_gates(n, 150, rng)))
+    pairs = [(a, b) for a in range(n) for b in range(a + 1, n)]                # all-to-all: 91 pairs
+    l0 = eng.counters()["launches"]
+    whole = eng.pair_rdm(0, pairs)
+    whole_launches = eng.counters()["launches"] - l0
+    for n_parts in (2, 3, 8):
+        acc = np.zeros_like(whole)
+        owners = np.zeros(len(pairs), dtype=int)
+        launches = []
+        for part in range(n_parts):
+            l0 = eng.counters()["launches"]
+            share = eng.pair_rdm(0, pairs, part=part, n_parts=n_parts)
+            launches.append(eng.counters()["launches"] - l0)
+            owners += np.any(share.reshape(len(pairs), -1) != 0, axis=1)
+            acc += share
+        assert np.array_equal(acc, whole)
+        assert np.all(owners == 1)
+        assert sum(launches) == whole_launches and max(launches) <= whole_launches / n_parts + 2
+    ref = orc.evaluate_circuit(n, random_gates(n, 150, np.random.default_rng(9)))
+    for r, (a, b) in zip(whole, pairs):
+        np.testing.assert_allclose(r, orc.partial_trace(ref, a, b), atol=AMP_TOL)
+    eng.close()
