@@ -214,14 +214,14 @@ int run_plan(b200_ctx* ctx, int dst_slot, int src_slot, const Plan& plan) {
 }
 
 int make_plan(int nq, const b200_gate* gates, int n_gates, const double* mats, int n_mats, bool inverse,
-              Plan& plan) {
+              Plan& plan, bool fold_perm = true) {
     if (n_gates < 0 || (n_gates > 0 && !gates)) return set_error("null gate array");
     std::vector<COp> ops;
     const std::string err = canonicalize(nq, gates, n_gates, mats, n_mats, inverse, ops);
     if (!err.empty()) return set_error(err);
     fuse_single_qubit_runs(ops);
     fuse_diagonals(ops);
-    build_plan(nq, ops, plan);
+    build_plan(nq, ops, plan, fold_perm);
     plan.n_gates_in = n_gates;
     return 0;
 }
@@ -232,7 +232,8 @@ int sv_run_impl(b200_ctx* ctx, int dst_slot, int src_slot, const b200_gate* gate
     if (src_slot >= 0 && check_slot(ctx, src_slot)) return -1;
     CUDA_TRY(cudaSetDevice(ctx->device));
     Plan plan;
-    if (make_plan(ctx->nq, gates, n_gates, mats, n_mats, inverse, plan)) return -1;
+    // the pipelined (bulk-copy) variant lands / picks up tiles in a linear layout and keeps executing X-type ops
+    if (make_plan(ctx->nq, gates, n_gates, mats, n_mats, inverse, plan, ctx->sweep_mode == 0)) return -1;
     ctx->counters[6] += 1;
     return run_plan(ctx, dst_slot, src_slot, plan);
 }

@@ -235,53 +235,62 @@ B200_HD void round_index(const SweepProg& sp, const PRound& rd, const uint64_t t
     for (int i = c; i < TILE_BITS; ++i) g |= (uint64_t)((tl >> i) & 1u) << sp.tileq[i];
 }
 
+// Per-thread address masks of the X-type ops folded into a round's load / store (sv_plan.h, PFold): the control is a
+// bit of the thread's base index g (or absent).  Uniform loop, uniform constant-bank loads, <= MAX_FOLD iterations.
+B200_HD uint32_t fold_smask(const PFold* f, const int n, const uint64_t g) {
+    uint32_t m = 0;
+    for (int i = 0; i < n; ++i) {
+        const bool ctl = f[i].cq < 0 || ((g >> f[i].cq) & 1ull);
+        m ^= ctl ? f[i].smask : 0u;
+    }
+    return m;
+}
+B200_HD uint64_t fold_gmask(const PFold* f, const int n, const uint64_t g) {
+    uint64_t m = 0;
+    for (int i = 0; i < n; ++i) {
+        const bool ctl = f[i].cq < 0 || ((g >> f[i].cq) & 1ull);
+        m ^= ctl ? f[i].gmask : 0ull;
+    }
+    return m;
+}
+
 // src == nullptr: the source is |0..0> (no read pass, no separate fill pass)
 template <int R>
 B200_HD void round_load_hbm(double2 (&a)[1 << R], const double2* __restrict__ src, const SweepProg& sp,
                             const PRound& rd, const uint64_t g) {
+    const uint64_t gm = g ^ fold_gmask(rd.lead, rd.n_lead, g);     // (register positions are zero in g: ^ == |)
     if (src == nullptr) {
 #pragma unroll
-        for (int j = 0; j < (1 << R); ++j) a[j] = make_double2(0.0, 0.0);
-        if (g == 0) a[0].x = 1.0;
+        for (int j = 0; j < (1 << R); ++j) a[j] = make_double2(gm == rd.goff_ld[j] ? 1.0 : 0.0, 0.0);
         return;
     }
-    uint64_t gs[R];
 #pragma unroll
-    for (int k = 0; k < R; ++k) gs[k] = 1ull << sp.tileq[rd.regpos[k]];
-#pragma unroll
-    for (int j = 0; j < (1 << R); ++j) {
-        uint64_t off = 0;
-#pragma unroll
-        for (int k = 0; k < R; ++k) if (j >> k & 1) off += gs[k];
-        a[j] = src[g + off];
-    }
+    for (int j = 0; j < (1 << R); ++j) a[j] = src[gm ^ rd.goff_ld[j]];
 }
 
 template <int R>
 B200_HD void round_store_hbm(const double2 (&a)[1 << R], double2* __restrict__ dst, const SweepProg& sp,
                              const PRound& rd, const uint64_t g) {
-    uint64_t gs[R];
+    const uint64_t gm = g ^ fold_gmask(rd.trail, rd.n_trail, g);
 #pragma unroll
-    for (int k = 0; k < R; ++k) gs[k] = 1ull << sp.tileq[rd.regpos[k]];
+    for (int j = 0; j < (1 << R); ++j) dst[gm ^ rd.goff_st[j]] = a[j];
+}
+
+// tls: the thread's swizzled tile index (zeros at the register positions) -- the folded flips are applied here
+template <int R>
+B200_HD void round_load_smem(double2 (&a)[1 << R], const double2* tile_smem, const PRound& rd, const uint32_t tls,
+                             const uint64_t g) {
+    const uint32_t t = tls ^ fold_smask(rd.lead, rd.n_lead, g);
 #pragma unroll
-    for (int j = 0; j < (1 << R); ++j) {
-        uint64_t off = 0;
-#pragma unroll
-        for (int k = 0; k < R; ++k) if (j >> k & 1) off += gs[k];
-        dst[g + off] = a[j];
-    }
+    for (int j = 0; j < (1 << R); ++j) a[j] = tile_smem[t ^ (uint32_t)rd.soff[j]];
 }
 
 template <int R>
-B200_HD void round_load_smem(double2 (&a)[1 << R], const double2* tile_smem, const PRound& rd, const uint32_t tls) {
+B200_HD void round_store_smem(const double2 (&a)[1 << R], double2* tile_smem, const PRound& rd, const uint32_t tls,
+                              const uint64_t g) {
+    const uint32_t t = tls ^ fold_smask(rd.trail, rd.n_trail, g);
 #pragma unroll
-    for (int j = 0; j < (1 << R); ++j) a[j] = tile_smem[tls ^ (uint32_t)rd.soff[j]];
-}
-
-template <int R>
-B200_HD void round_store_smem(const double2 (&a)[1 << R], double2* tile_smem, const PRound& rd, const uint32_t tls) {
-#pragma unroll
-    for (int j = 0; j < (1 << R); ++j) tile_smem[tls ^ (uint32_t)rd.soff[j]] = a[j];
+    for (int j = 0; j < (1 << R); ++j) tile_smem[t ^ (uint32_t)rd.soff_st[j]] = a[j];
 }
 
 // Linear (unswizzled) tile access: the layout the bulk copies of the pipelined kernel land / pick up.
@@ -469,10 +478,10 @@ sv_sweep_kernel(const double2* __restrict__ src, double2* __restrict__ dst, cons
             const uint32_t tls = swz(tl);
             double2 a[1 << R];
             if (r == 0) round_load_hbm<R>(a, src, sp, rd, g);
-            else round_load_smem<R>(a, tile_smem, rd, tls);
+            else round_load_smem<R>(a, tile_smem, rd, tls, g);
             round_ops<R, false>(a, sp, rd, g, lane, ex);
             if (r == nr - 1) round_store_hbm<R>(a, dst, sp, rd, g);
-            else { round_store_smem<R>(a, tile_smem, rd, tls); __syncthreads(); }
+            else { round_store_smem<R>(a, tile_smem, rd, tls, g); __syncthreads(); }
         }
         if (nr > 1) __syncthreads();
     }
@@ -591,12 +600,12 @@ sv_sweep_pipe_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
             const bool lin_in = r == 0, lin_out = r == nr - 1;
             double2 a[1 << R];
             if (lin_in) round_load_lin<R>(a, buf, rd, tl);
-            else round_load_smem<R>(a, buf, rd, tls);
+            else round_load_smem<R>(a, buf, rd, tls, g);
             round_ops<R, true>(a, sp, rd, g, lane, ex);
             // a round that changes the layout in place must have finished all its reads before any write
             if (lin_in != lin_out) compute_bar();
             if (lin_out) round_store_lin<R>(a, buf, rd, tl);
-            else { round_store_smem<R>(a, buf, rd, tls); compute_bar(); }
+            else { round_store_smem<R>(a, buf, rd, tls, g); compute_bar(); }
         }
         fence_proxy_async();             // generic-proxy writes -> visible to the bulk copy engine
         compute_bar();

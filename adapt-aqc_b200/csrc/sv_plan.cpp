@@ -425,7 +425,21 @@ void fill_tiled_op(const COp& o, const int* reg_of, SweepProg& sp, POp& d) {
 
 }  // namespace
 
-void build_plan(int nq, const std::vector<COp>& ops, Plan& plan) {
+namespace {
+
+// does the X-type op `x` (target t, optional control c) commute with `o`?
+bool x_commutes_with(const COp& x, const COp& o) {
+    const int t = x.t0, c = x.c;
+    if (o.kind == K_DIAG) return o.d0 != t && o.d1 != t;            // a diagonal may sit on the control
+    if (o.kind == K_X) return t != o.c && o.t0 != c;                // targets may coincide
+    for (int q : {o.t0, o.t1, o.c, o.d0, o.d1})
+        if (q >= 0 && (q == t || q == c)) return false;
+    return true;
+}
+
+}  // namespace
+
+void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm) {
     plan = Plan();
     plan.num_qubits = nq;
     if (nq <= SMALL_MAX_QUBITS) {
@@ -531,14 +545,71 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan) {
             int k = 0;
             for (int i = 0; i < TILE_BITS; ++i)
                 if (regs >> sp.tileq[i] & 1) { dr.regpos[k] = i; reg_of[sp.tileq[i]] = k; ++k; }
-            for (int j = 0; j < (1 << REG_BITS); ++j) {
-                uint32_t off = 0;
-                for (int b = 0; b < REG_BITS; ++b) if (j >> b & 1) off |= 1u << dr.regpos[b];
-                dr.soff[j] = (int32_t)swz(off);
+            // ---- X-type ops that commute to the front / back of the round are folded into its addressing ----
+            std::vector<int> lead, trail, middle;
+            {
+                auto foldable = [&](const COp& o) { return fold_perm && o.kind == K_X && reg_of[o.t0] >= 0; };
+                std::vector<char> is_lead(rt.ops.size(), 0), is_trail(rt.ops.size(), 0);
+                std::vector<int> before;
+                for (size_t i = 0; i < rt.ops.size(); ++i) {
+                    const COp& o = ops[rt.ops[i]];
+                    bool ok = foldable(o) && (int)lead.size() < MAX_FOLD;
+                    for (size_t b = 0; ok && b < before.size(); ++b) ok = x_commutes_with(o, ops[before[b]]);
+                    if (ok) { is_lead[i] = 1; lead.push_back(rt.ops[i]); }
+                    else before.push_back(rt.ops[i]);
+                }
+                std::vector<int> after;
+                for (size_t i = rt.ops.size(); i-- > 0;) {
+                    if (is_lead[i]) continue;
+                    const COp& o = ops[rt.ops[i]];
+                    bool ok = foldable(o) && (int)trail.size() < MAX_FOLD;
+                    for (size_t b = 0; ok && b < after.size(); ++b) ok = x_commutes_with(o, ops[after[b]]);
+                    if (ok) { is_trail[i] = 1; trail.push_back(rt.ops[i]); }
+                    else after.push_back(rt.ops[i]);
+                }
+                std::reverse(trail.begin(), trail.end());
+                for (size_t i = 0; i < rt.ops.size(); ++i)
+                    if (!is_lead[i] && !is_trail[i]) middle.push_back(rt.ops[i]);
+            }
+            auto expand = [&](uint32_t v) { uint32_t off = 0; for (int b = 0; b < REG_BITS; ++b) if (v >> b & 1) off |= 1u << dr.regpos[b]; return off; };
+            auto gexpand = [&](uint32_t v) { uint64_t off = 0; for (int b = 0; b < REG_BITS; ++b) if (v >> b & 1) off |= 1ull << sp.tileq[dr.regpos[b]]; return off; };
+            // index-space action of a folded op on the register index j: CX between registers is linear (j ^= j_rc << rt);
+            // anything else is a (conditional) flip of bit rt, kept as a per-thread mask
+            auto is_linear = [&](const COp& o) { return o.c >= 0 && reg_of[o.c] >= 0; };
+            auto lin_apply = [&](const COp& o, uint32_t j) { return j ^ (((j >> reg_of[o.c]) & 1u) << reg_of[o.t0]); };
+            {   // load side: register k receives the amplitude that sat at A^-1 k (^ the thread's flips, pulled in front of A)
+                uint32_t fwd[1 << REG_BITS], inv[1 << REG_BITS];
+                for (uint32_t j = 0; j < (1u << REG_BITS); ++j) fwd[j] = j;
+                dr.n_lead = 0;
+                for (int idx : lead) {
+                    const COp& o = ops[idx];
+                    if (is_linear(o)) { for (uint32_t j = 0; j < (1u << REG_BITS); ++j) fwd[j] = lin_apply(o, fwd[j]); continue; }
+                    // flip of e_b applied AFTER the linear ops so far (fwd = B): pulled to the front it flips B^-1 e_b
+                    uint32_t u = 0;
+                    for (uint32_t j = 0; j < (1u << REG_BITS); ++j) if (fwd[j] == (1u << reg_of[o.t0])) u = j;
+                    PFold& f = dr.lead[dr.n_lead++];
+                    f.cq = o.c; f.smask = swz(expand(u)); f.gmask = gexpand(u);
+                }
+                for (uint32_t j = 0; j < (1u << REG_BITS); ++j) inv[fwd[j]] = j;
+                for (uint32_t k = 0; k < (1u << REG_BITS); ++k) { dr.soff[k] = (int32_t)swz(expand(inv[k])); dr.goff_ld[k] = gexpand(inv[k]); }
+            }
+            {   // store side: register j goes to A j (^ the thread's flips, pushed behind A)
+                uint32_t fwd[1 << REG_BITS];
+                for (uint32_t j = 0; j < (1u << REG_BITS); ++j) fwd[j] = j;
+                dr.n_trail = 0;
+                for (size_t i = 0; i < trail.size(); ++i) {
+                    const COp& o = ops[trail[i]];
+                    if (is_linear(o)) { for (uint32_t j = 0; j < (1u << REG_BITS); ++j) fwd[j] = lin_apply(o, fwd[j]); continue; }
+                    uint32_t w = 1u << reg_of[o.t0];               // pushed through the linear ops that follow
+                    for (size_t l = i + 1; l < trail.size(); ++l) if (is_linear(ops[trail[l]])) w = lin_apply(ops[trail[l]], w);
+                    PFold& f = dr.trail[dr.n_trail++];
+                    f.cq = o.c; f.smask = swz(expand(w)); f.gmask = gexpand(w);
+                }
+                for (uint32_t j = 0; j < (1u << REG_BITS); ++j) { dr.soff_st[j] = (int32_t)swz(expand(fwd[j])); dr.goff_st[j] = gexpand(fwd[j]); }
             }
             dr.op_begin = sp.nops;
             bool pending = false;
-            for (int idx : rt.ops) {
+            for (int idx : middle) {
                 POp& po = sp.ops[sp.nops++];
                 fill_tiled_op(ops[idx], reg_of, sp, po);
                 if (po.kind == P_PEND || po.kind == P_DIAG1 || po.kind == P_DIAG2) { dr.has_pend = 1; pending = true; }

@@ -125,11 +125,32 @@ constexpr int MAX_SWEEP_MAT2 = 16;
 constexpr int MAX_LANE_OPS = 2;   // shuffle-served ops per HBM round before a shared-memory round is cheaper
                                   // (64 SHFL per thread each vs 32 LDS/STS.128 + barrier for a round trip)
 
+// An X / CX whose target is a register qubit only PERMUTES the thread's 2^R amplitudes.  When it commutes its way to the
+// front (back) of its round it is not executed at all: it is folded into WHERE the round loads (stores) --
+//   * control = another register qubit, or none with a fixed pattern: a GF(2)-linear relabelling of the register
+//     index j, resolved on the host into the round's load / store offset tables;
+//   * control = any other qubit (a bit of the thread's base index g), or an unconditional X: a per-thread XOR mask on
+//     the address (shared-memory index and global index are both XOR-linear in the register index).
+// ncu (profiles/prof_direct_r02x.txt): executed as in-place register exchanges these ops were ~29 % of the instructions
+// of a thin-layer sweep (96 register moves per conditional X).
+constexpr int MAX_FOLD = 8;
+struct PFold {
+    int32_t cq;        // control qubit read from the thread's base index g; -1: unconditional
+    uint32_t smask;    // XOR mask on the swizzled shared-memory index
+    uint64_t gmask;    // XOR mask on the global amplitude index
+};
+static_assert(sizeof(PFold) == 16, "PFold layout");
+
 struct PRound {
     int32_t op_begin, op_end;
     int32_t regpos[REG_BITS];        // tile-local bit positions of the register qubits, ascending
-    int32_t soff[1 << REG_BITS];     // swizzled shared-memory offset of register amplitude j (swz is XOR-linear)
+    int32_t soff[1 << REG_BITS];     // LOAD: swizzled shared-memory offset register amplitude j comes from (swz is XOR-linear)
     int32_t has_pend, pad;           // some op of the round multiplies into the per-thread pending phase
+    int32_t soff_st[1 << REG_BITS];  // STORE: swizzled shared-memory offset register amplitude j goes to
+    uint64_t goff_ld[1 << REG_BITS]; // the same for rounds that load from / store to HBM: offsets in the global index
+    uint64_t goff_st[1 << REG_BITS];
+    int32_t n_lead, n_trail;         // folded X-type ops with a per-thread condition (see PFold)
+    PFold lead[MAX_FOLD], trail[MAX_FOLD];
 };
 
 struct alignas(16) SweepProg {
@@ -160,6 +181,8 @@ void fuse_single_qubit_runs(std::vector<COp>& ops);
 // Pushes 1-/2-qubit diagonals forward through the CX gates they meet and merges them: a thinly dressed
 // CNOT layer (rz rz cx rz rz) becomes ONE cx + ONE two-qubit diagonal.
 void fuse_diagonals(std::vector<COp>& ops);
-void build_plan(int num_qubits, const std::vector<COp>& ops, Plan& plan);
+// fold_perm: fold leading / trailing X-type ops of every round into its load / store addressing (the direct sweep
+// kernel; the pipelined variant keeps executing them).
+void build_plan(int num_qubits, const std::vector<COp>& ops, Plan& plan, bool fold_perm = true);
 
 }  // namespace b200

@@ -30,7 +30,7 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
     fuse_single_qubit_runs(ops);
     fuse_diagonals(ops);
     Plan plan;
-    build_plan(nq, ops, plan);
+    build_plan(nq, ops, plan, /*fold_perm=*/g_variant == 0);
     double2* psi = reinterpret_cast<double2*>(state_ri);
     const uint64_t dim = 1ull << nq;
     if (src_is_zero) {
@@ -78,8 +78,12 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
             }
         }
     }
+    bool first_sweep = true;
     for (const SweepProg& sp : plan.sweeps) {
         const int nr = sp.nrounds;
+        // the direct kernel takes |0..0> as an IMPLICIT source (src == nullptr) in its first sweep
+        const double2* hbm_src = (first_sweep && src_is_zero && g_variant == 0) ? nullptr : psi;
+        first_sweep = false;
         for (uint32_t tile = 0; tile < ntiles; ++tile) {
             const uint64_t base = sweep_tile_base(sp, tile);
             const uint32_t rows = 1u << (TILE_BITS - sp.c), row_len = 1u << sp.c;
@@ -94,8 +98,8 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
                     tls[tid] = swz(tl);
                     tlin[tid] = tl;
                     if (r == 0 && g_variant == 1) round_load_lin<REG_BITS>(regs[tid].a, smem.data(), rd, tl);
-                    else if (r == 0) round_load_hbm<REG_BITS>(regs[tid].a, psi, sp, rd, gidx[tid]);
-                    else round_load_smem<REG_BITS>(regs[tid].a, smem.data(), rd, tls[tid]);
+                    else if (r == 0) round_load_hbm<REG_BITS>(regs[tid].a, hbm_src, sp, rd, gidx[tid]);
+                    else round_load_smem<REG_BITS>(regs[tid].a, smem.data(), rd, tls[tid], gidx[tid]);
                     pend[tid] = make_double2(1.0, 0.0);
                 }
                 for (int o = rd.op_begin; o < rd.op_end; ++o) {
@@ -121,7 +125,7 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
                     if (rd.has_pend) apply_pend<REG_BITS>(regs[tid].a, pend[tid]);
                     if (r == nr - 1 && g_variant == 1) round_store_lin<REG_BITS>(regs[tid].a, smem.data(), rd, tlin[tid]);
                     else if (r == nr - 1) round_store_hbm<REG_BITS>(regs[tid].a, psi, sp, rd, gidx[tid]);
-                    else round_store_smem<REG_BITS>(regs[tid].a, smem.data(), rd, tls[tid]);
+                    else round_store_smem<REG_BITS>(regs[tid].a, smem.data(), rd, tls[tid], gidx[tid]);
                 }
             }
             if (g_variant == 1)
