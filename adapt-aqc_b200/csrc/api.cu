@@ -515,6 +515,46 @@ int b200_sv_peer_swap(b200_ctx* ctx, int slot, void* const* peer_ptrs, int world
     return 0;
 }
 
+int b200_sv_peer_swap_strided(b200_ctx* ctx, int slot, void* const* peer_ptrs, int world, int rank, const int32_t* positions) {
+    if (check_slot(ctx, slot)) return -1;
+    if (!peer_ptrs || !positions) return set_error("null pointer");
+    if (world < 2 || world > PEER_MAX_WORLD || (world & (world - 1))) return set_error("peer_swap: world must be a power of two in [2,16]");
+    if (rank < 0 || rank >= world) return set_error("peer_swap: rank out of range");
+    int g = 0;
+    while ((1 << g) < world) ++g;
+    if (ctx->nq - g < 1) return set_error("peer_swap: slice too small for this world size");
+    PeerStride ps;
+    ps.g = g;
+    for (int j = 0; j < g; ++j) {
+        if (positions[j] < 0 || positions[j] >= ctx->nq) return set_error("peer_swap_strided: position out of range");
+        for (int k = 0; k < j; ++k)
+            if (positions[k] == positions[j]) return set_error("peer_swap_strided: positions must differ");
+        ps.pos_sorted[j] = positions[j];
+    }
+    std::sort(ps.pos_sorted, ps.pos_sorted + g);
+    for (int r = 0; r < PEER_MAX_WORLD; ++r) {
+        ps.pattern[r] = 0;
+        for (int j = 0; j < g; ++j) ps.pattern[r] |= (uint64_t)((r >> j) & 1) << positions[j];
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    PeerTable pt;
+    for (int p = 0; p < PEER_MAX_WORLD; ++p) pt.p[p] = nullptr;
+    for (int p = 0; p < world; ++p) {
+        if (p != rank && !peer_ptrs[p]) return set_error("peer_swap: missing peer pointer");
+        pt.p[p] = (double2*)peer_ptrs[p];
+    }
+    const uint64_t sub = (1ull << ctx->nq) >> g;
+    Timer tm(ctx);
+    {
+        KScope ks(ctx, B200_PROF_FILL);
+        sv_peer_swap_strided_kernel<<<ctx->num_sms * 4, 512, 0, ctx->stream>>>((double2*)ctx->slots[slot], pt, world, rank, sub, ps);
+    }
+    CUDA_TRY(cudaGetLastError());
+    ctx->counters[6] += 1;
+    tm.stop();
+    return 0;
+}
+
 int b200_sv_num_qubits(b200_ctx* ctx, int* out) {
     if (!ctx || !out) return set_error("null pointer");
     *out = ctx->nq;

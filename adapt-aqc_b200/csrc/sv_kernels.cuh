@@ -656,6 +656,45 @@ sv_peer_swap_kernel(double2* __restrict__ local, const PeerTable peers, const in
             if (mine[u]) { *mine[u] = b[u]; __stcg(theirs[u], a[u]); }
     }
 }
+// The same exchange without first moving the outgoing qubits to the top of the local index: "chunk p" is the set of
+// amplitudes whose bits at the g victim positions spell p (a strided set), traded with the peer's set that spells this
+// rank.  Saves the SWAP-localisation sweep (one full read+write pass over the slice) that used to precede every
+// exchange.  `sub` = amplitudes per chunk = 2^(nl - g); pos_sorted: victim positions ascending (for the zero
+// insertion); pattern[r]: the bits of rank r deposited at the victim positions (rank bit j -> the j-th victim).
+struct PeerStride { int32_t g; int32_t pos_sorted[4]; uint64_t pattern[PEER_MAX_WORLD]; };
+
+__global__ void __launch_bounds__(512)
+sv_peer_swap_strided_kernel(double2* __restrict__ local, const PeerTable peers, const int world, const int rank,
+                            const uint64_t sub, const PeerStride ps) {
+    const uint64_t half = sub >> 1;
+    const uint64_t total = (uint64_t)(world - 1) * half;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    constexpr int U = 4;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += stride * U) {
+        double2 a[U], b[U];
+        double2* mine[U];
+        double2* theirs[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t idx = base + (uint64_t)u * stride;
+            mine[u] = nullptr;
+            if (idx < total) {
+                const int s = (int)(idx / half) + 1;
+                const int peer = rank ^ s;
+                uint64_t i = idx % half + (rank < peer ? 0 : half);
+                for (int k = 0; k < ps.g; ++k) i = ins0_64(i, ps.pos_sorted[k]);
+                mine[u] = local + (i | ps.pattern[peer]);
+                theirs[u] = peers.p[peer] + (i | ps.pattern[rank]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (mine[u]) { a[u] = *mine[u]; b[u] = __ldcg(theirs[u]); }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (mine[u]) { *mine[u] = b[u]; __stcg(theirs[u], a[u]); }
+    }
+}
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------------------------------------

@@ -548,7 +548,21 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm)
             // ---- X-type ops that commute to the front / back of the round are folded into its addressing ----
             std::vector<int> lead, trail, middle;
             {
-                auto foldable = [&](const COp& o) { return fold_perm && o.kind == K_X && reg_of[o.t0] >= 0; };
+                // An X-type op on a LANE qubit (0..COAL_BITS-1, served by warp shuffles in HBM rounds: 64 SHFL + 64 selects,
+                // the hottest spot of a thin-layer sweep in profiles/r2d_sweep_ansatz.md) folds into the GLOBAL address of
+                // the round that loads from (lead) / stores to (trail) HBM: the thread simply loads its partner's
+                // amplitude -- same 128 B lines per warp access.  Its control must be a plain thread bit, and no X-type op
+                // of the round may be controlled by the flipped qubit (the controls of folded ops are read from the
+                // thread's own index).
+                uint64_t x_controls = 0;
+                for (int idx : rt.ops) if (ops[idx].kind == K_X && ops[idx].c >= 0) x_controls |= 1ull << ops[idx].c;
+                const bool loads_hbm = r == 0, stores_hbm = r + 1 == rounds.size();
+                auto foldable_side = [&](const COp& o, bool hbm_side) {
+                    if (!fold_perm || o.kind != K_X) return false;
+                    if (reg_of[o.t0] >= 0) return true;
+                    return hbm_side && o.t0 < COAL_BITS && (o.c < 0 || reg_of[o.c] < 0) && !((x_controls >> o.t0) & 1ull);
+                };
+                auto foldable = [&](const COp& o) { return foldable_side(o, loads_hbm); };
                 std::vector<char> is_lead(rt.ops.size(), 0), is_trail(rt.ops.size(), 0);
                 std::vector<int> before;
                 for (size_t i = 0; i < rt.ops.size(); ++i) {
@@ -562,7 +576,7 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm)
                 for (size_t i = rt.ops.size(); i-- > 0;) {
                     if (is_lead[i]) continue;
                     const COp& o = ops[rt.ops[i]];
-                    bool ok = foldable(o) && (int)trail.size() < MAX_FOLD;
+                    bool ok = foldable_side(o, stores_hbm) && (int)trail.size() < MAX_FOLD;
                     for (size_t b = 0; ok && b < after.size(); ++b) ok = x_commutes_with(o, ops[after[b]]);
                     if (ok) { is_trail[i] = 1; trail.push_back(rt.ops[i]); }
                     else after.push_back(rt.ops[i]);
@@ -575,7 +589,8 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm)
             auto gexpand = [&](uint32_t v) { uint64_t off = 0; for (int b = 0; b < REG_BITS; ++b) if (v >> b & 1) off |= 1ull << sp.tileq[dr.regpos[b]]; return off; };
             // index-space action of a folded op on the register index j: CX between registers is linear (j ^= j_rc << rt);
             // anything else is a (conditional) flip of bit rt, kept as a per-thread mask
-            auto is_linear = [&](const COp& o) { return o.c >= 0 && reg_of[o.c] >= 0; };
+            auto is_linear = [&](const COp& o) { return o.c >= 0 && reg_of[o.c] >= 0; };     // (never true for a lane target)
+            auto is_lane = [&](const COp& o) { return reg_of[o.t0] < 0; };
             auto lin_apply = [&](const COp& o, uint32_t j) { return j ^ (((j >> reg_of[o.c]) & 1u) << reg_of[o.t0]); };
             {   // load side: register k receives the amplitude that sat at A^-1 k (^ the thread's flips, pulled in front of A)
                 uint32_t fwd[1 << REG_BITS], inv[1 << REG_BITS];
@@ -584,10 +599,11 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm)
                 for (int idx : lead) {
                     const COp& o = ops[idx];
                     if (is_linear(o)) { for (uint32_t j = 0; j < (1u << REG_BITS); ++j) fwd[j] = lin_apply(o, fwd[j]); continue; }
+                    PFold& f = dr.lead[dr.n_lead++];
+                    if (is_lane(o)) { f.cq = o.c; f.smask = 0; f.gmask = 1ull << o.t0; continue; }   // HBM round: lane bit = qubit
                     // flip of e_b applied AFTER the linear ops so far (fwd = B): pulled to the front it flips B^-1 e_b
                     uint32_t u = 0;
                     for (uint32_t j = 0; j < (1u << REG_BITS); ++j) if (fwd[j] == (1u << reg_of[o.t0])) u = j;
-                    PFold& f = dr.lead[dr.n_lead++];
                     f.cq = o.c; f.smask = swz(expand(u)); f.gmask = gexpand(u);
                 }
                 for (uint32_t j = 0; j < (1u << REG_BITS); ++j) inv[fwd[j]] = j;
@@ -600,9 +616,10 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm)
                 for (size_t i = 0; i < trail.size(); ++i) {
                     const COp& o = ops[trail[i]];
                     if (is_linear(o)) { for (uint32_t j = 0; j < (1u << REG_BITS); ++j) fwd[j] = lin_apply(o, fwd[j]); continue; }
+                    PFold& f = dr.trail[dr.n_trail++];
+                    if (is_lane(o)) { f.cq = o.c; f.smask = 0; f.gmask = 1ull << o.t0; continue; }
                     uint32_t w = 1u << reg_of[o.t0];               // pushed through the linear ops that follow
                     for (size_t l = i + 1; l < trail.size(); ++l) if (is_linear(ops[trail[l]])) w = lin_apply(ops[trail[l]], w);
-                    PFold& f = dr.trail[dr.n_trail++];
                     f.cq = o.c; f.smask = swz(expand(w)); f.gmask = gexpand(w);
                 }
                 for (uint32_t j = 0; j < (1u << REG_BITS); ++j) { dr.soff_st[j] = (int32_t)swz(expand(fwd[j])); dr.goff_st[j] = gexpand(fwd[j]); }

@@ -142,6 +142,8 @@ class ShardedStatevector:
         self.perm = [list(range(self.n)) for _ in slot_tensors]
         self.stats = {"exchanges": 0, "local_runs": 0}
         self.peer_ptrs = None      # [slot][rank] -> device pointer into that rank's slot (CUDA IPC), or None: NCCL path
+        self.strided_exchange = True    # peer path: exchange the victims in place (no SWAP-localisation sweep)
+        self.reorder = True        # run(): commutation-aware scheduling that postpones gates on global qubits
 
     def close(self):
         """Collective: every rank unmaps its peers' slots (CUDA IPC) before any rank frees its own."""
@@ -167,8 +169,20 @@ class ShardedStatevector:
         """Swap the g global qubits with the local logical qubits `victims` (len g)."""
         perm = self.perm[slot]
         nl, g = self.nl, self.g
-        # 1. move the victims to the top-g local physical positions with local swap gates
         inv = {p: l for l, p in enumerate(perm)}
+        if self.peer_ptrs is not None and self.strided_exchange:
+            # peer-memory path: the victims stay where they are -- chunk p is the strided set of amplitudes whose bits
+            # at the victims' positions spell p (b200_sv_peer_swap_strided): no SWAP-localisation sweep
+            positions = [perm[v] for v in victims]
+            self._sync()
+            self._peer_exchange(slot, positions)
+            self._sync()
+            for j, v in enumerate(victims):
+                glob = inv[nl + j]
+                perm[glob], perm[v] = positions[j], nl + j
+            self.stats["exchanges"] += 1
+            return
+        # 1. move the victims to the top-g local physical positions with local swap gates
         swaps = []
         for j, v in enumerate(victims):
             want = nl - g + j
@@ -181,6 +195,7 @@ class ShardedStatevector:
         if swaps:
             self.eng.run(slot, slot, G.GateStream.from_window(swaps))
             self.stats["local_runs"] += 1
+            self.stats["localisation_sweeps"] = self.stats.get("localisation_sweeps", 0) + 1
         # 2. all-to-all: chunk index (top-g local bits) <-> rank bits
         self._sync()
         if self.peer_ptrs is not None:
@@ -193,14 +208,14 @@ class ShardedStatevector:
             perm[a], perm[b] = nl + j, nl - g + j
         self.stats["exchanges"] += 1
 
-    def _peer_exchange(self, slot):
-        """One fused kernel per rank over NVLink peer memory (b200_sv_peer_swap): no staging, no copy-back.
+    def _peer_exchange(self, slot, positions=None):
+        """One fused kernel per rank over NVLink peer memory (b200_sv_peer_swap[_strided]): no staging, no copy-back.
         Ranks meet before (every slice is final) and after (every remote store has landed)."""
         import time
         comm = self.comm
         comm.dist.barrier()
         t0 = time.perf_counter()
-        self.eng.peer_swap(slot, self.peer_ptrs[slot], comm.rank)
+        self.eng.peer_swap(slot, self.peer_ptrs[slot], comm.rank, positions)
         self.eng.sync()
         comm.exchange_ms += 1e3 * (time.perf_counter() - t0)
         comm.dist.barrier()
@@ -215,6 +230,12 @@ class ShardedStatevector:
         cands = [l for l in range(self.n) if perm[l] < self.nl and l not in needed]
         if len(cands) < self.g:
             raise ValueError("too many qubits must be local at once for this sharding")
+        if self.peer_ptrs is not None and self.strided_exchange:
+            # strided exchange: a victim at bit position p leaves runs of 2^p contiguous amplitudes (16 B each);
+            # keep the runs >= 1 KB when there is a choice
+            high = [l for l in cands if perm[l] >= 6]
+            if len(high) >= self.g:
+                cands = high
         cands.sort(key=lambda l: (-(next_use[l] if next_use is not None else 0), -perm[l]))
         self._exchange(slot, cands[:self.g])
 
@@ -267,6 +288,48 @@ class ShardedStatevector:
         elif src != dst:
             eng.copy(dst, src)
             self.perm[dst] = list(self.perm[src])
+        if not self.reorder:
+            return self._run_in_order(dst, window)
+        # Commutation-aware scheduling.  Gates are taken in circuit order whenever all their mixing qubits are local; a
+        # gate that mixes a GLOBAL qubit is postponed, and later gates may overtake the postponed ones only if they
+        # commute with them (no postponed gate touches their mixing qubits; no postponed gate mixes a qubit they touch
+        # at all).  When nothing more can be taken, ONE exchange brings the global qubits in -- the victims are the local
+        # qubits whose next pending use is furthest away -- and the scan restarts.  On a brickwork target this applies
+        # every gate outside the light cone of the global qubits, through all layers, before the first exchange.
+        pending = list(window)
+        mix = [mixing_qubits(e) for e in pending]
+        touch = [tuple(q for q in (e[1], e[2]) if q >= 0) for e in pending]
+        while pending:
+            batch, rest, rest_mix, rest_touch = [], [], [], []
+            blocked_any, blocked_mix = set(), set()
+            for e, m, t in zip(pending, mix, touch):
+                free = not (set(m) & blocked_any) and not (set(t) & blocked_mix)
+                if free and not any(self._is_global(dst, q) for q in m):
+                    batch.extend(self._localise(dst, e))
+                else:
+                    rest.append(e); rest_mix.append(m); rest_touch.append(t)
+                    blocked_any.update(t); blocked_mix.update(m)
+            if batch:
+                eng.run(dst, dst, G.GateStream.from_window(batch))
+                self.stats["local_runs"] += 1
+            pending, mix, touch = rest, rest_mix, rest_touch
+            if not pending:
+                break
+            # every remaining gate waits (directly or through a postponed gate) on a global qubit: exchange.
+            INF = len(pending) + 1
+            nxt = [INF] * self.n
+            for i in range(len(pending) - 1, -1, -1):
+                for q in mix[i]:
+                    nxt[q] = i
+            needed = {q for q in range(self.n) if self._is_global(dst, q) and nxt[q] < INF}
+            if not needed:       # cannot happen: a postponed gate mixes a global qubit
+                raise AssertionError("sharded scheduler is stuck without a pending global qubit")
+            # the first postponed gate must be executable after the exchange: its local qubits are not victims
+            self.ensure_local(dst, needed | set(mix[0]), nxt)
+
+    def _run_in_order(self, dst, window):
+        """Circuit order (round-1 behaviour, reorder = False): exchange as soon as a gate mixes a global qubit."""
+        eng = self.eng
         mix = [mixing_qubits(e) for e in window]
         # next use (as a mixing target) of every logical qubit, scanning from the back
         INF = len(window) + 1

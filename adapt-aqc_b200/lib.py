@@ -17,7 +17,7 @@ SYMBOLS = [
     "b200_ctx_destroy", "b200_ctx_sync", "b200_ctx_counters", "b200_ctx_last_ms",
     "b200_ctx_set_timing", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_ctx_profile",
     "b200_ctx_profile_read", "b200_ctx_profile_sweeps", "b200_sv_alloc", "b200_sv_reserve_slots", "b200_sv_attach", "b200_sv_device_ptr",
-    "b200_sv_ipc_export", "b200_sv_ipc_open", "b200_sv_ipc_close", "b200_sv_peer_swap",
+    "b200_sv_ipc_export", "b200_sv_ipc_open", "b200_sv_ipc_close", "b200_sv_peer_swap", "b200_sv_peer_swap_strided",
     "b200_sv_num_qubits", "b200_sv_init_zero", "b200_sv_copy", "b200_sv_run",
     "b200_sv_run_inverse", "b200_sv_amp", "b200_sv_expz", "b200_sv_pair_rdm", "b200_sv_pair_rdm_part", "b200_sv_inner", "b200_sv_inner2", "b200_sv_inner2_gather", "b200_sv_gather", "b200_sv_scatter", "b200_sv_gather_ranked",
     "b200_sv_download", "b200_sv_upload", "b200_sv_plan_stats", "b200_sv_plan_detail",
@@ -73,6 +73,7 @@ def load():
     L.b200_sv_ipc_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
     L.b200_sv_ipc_close.argtypes = [vp, vp]
     L.b200_sv_peer_swap.argtypes = [vp, ci, ctypes.POINTER(vp), ci, ci]
+    L.b200_sv_peer_swap_strided.argtypes = [vp, ci, ctypes.POINTER(vp), ci, ci, vp]
     L.b200_sv_num_qubits.argtypes = [vp, ctypes.POINTER(ci)]
     L.b200_sv_init_zero.argtypes = [vp, ci]
     L.b200_sv_copy.argtypes = [vp, ci, ci]

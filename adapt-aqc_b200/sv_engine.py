@@ -70,10 +70,15 @@ class SVEngine:
     def ipc_close(self, ptr):
         check(self._lib.b200_sv_ipc_close(self._ctx, ctypes.c_void_p(ptr)))
 
-    def peer_swap(self, slot, peer_ptrs, rank):
-        """In-place exchange of chunk[p] with rank p's chunk[rank] for all p (one kernel over NVLink)."""
+    def peer_swap(self, slot, peer_ptrs, rank, positions=None):
+        """In-place exchange of chunk[p] with rank p's chunk[rank] for all p (one kernel over NVLink).  positions: local
+        bit positions that trade places with the rank bits (default: the top log2(world) local bits = contiguous chunks)."""
         arr = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(p or 0) for p in peer_ptrs])
-        check(self._lib.b200_sv_peer_swap(self._ctx, int(slot), arr, len(peer_ptrs), int(rank)))
+        if positions is None:
+            check(self._lib.b200_sv_peer_swap(self._ctx, int(slot), arr, len(peer_ptrs), int(rank)))
+        else:
+            pos = np.ascontiguousarray(np.asarray(positions, dtype=np.int32))
+            check(self._lib.b200_sv_peer_swap_strided(self._ctx, int(slot), arr, len(peer_ptrs), int(rank), pos.ctypes.data))
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:

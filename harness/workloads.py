@@ -86,15 +86,17 @@ def build_workload(n, depth, layers, seed=1234):
     return target, thin_ansatz(n, layers, rng)
 
 
-def compilable_target(n, layers, seed=1234):
-    """A target ADAPT-AQC actually compiles to the reference's sufficient cost (1e-2): a dense product layer ry(theta_q)
-    followed by `layers` thinly dressed CNOT layers in brickwall order.  (The random brickwork target of C3 is what the
-    gate kernels are timed on, but no optimiser gets a 28-qubit depth-8 random circuit below cost 0.99 in a few layers;
-    compile WALL-TIME needs a run that converges.)"""
+def compilable_target(n, layers, seed=1234, lo=0.15, hi=0.45):
+    """A target ADAPT-AQC actually compiles to the reference's sufficient cost (1e-2) at 28 qubits: a product layer
+    ry(theta_q), theta_q in [lo, hi], followed by `layers` thinly dressed CNOT layers in brickwall order.  The global
+    cost 1 - |<0|psi>|^2 of a GENERIC 28-qubit state is 1 - O(2^-28): the reference's stopping rule
+    (has_stopped_improving on the last 10 layers, adapt_compiler.py:368-393) then ends the run before any progress is
+    visible -- measured on the C3 brickwork target and on large-angle product layers.  Small angles keep the initial
+    overlap at O(1) (prod cos^2(theta_q / 2) ~ 0.5), so the run CONVERGES and compile wall-time means something."""
     rng = np.random.default_rng(seed)
     c = Circuit(n)
     for q in range(n):
-        c.ry(float(rng.uniform(0.5, 2.5)), q)
+        c.ry(float(rng.uniform(lo, hi)), q)
     c.data.extend(thin_ansatz(n, layers, rng).data)
     return c
 

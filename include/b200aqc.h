@@ -118,6 +118,12 @@ int b200_sv_ipc_export(b200_ctx *ctx, int slot, unsigned char handle[64]);
 int b200_sv_ipc_open(b200_ctx *ctx, const unsigned char handle[64], void **peer_ptr);
 int b200_sv_ipc_close(b200_ctx *ctx, void *peer_ptr);
 int b200_sv_peer_swap(b200_ctx *ctx, int slot, void *const *peer_ptrs, int world, int rank);
+/* The same exchange for outgoing qubits that sit ANYWHERE in the local index: positions[j] (j < log2(world)) is the
+ * local bit position that trades places with rank bit j.  Chunk p is then the strided set of amplitudes whose bits at
+ * those positions spell p.  Saves the SWAP-localisation sweep (one read+write pass over the slice) that must otherwise
+ * precede every exchange to bring the outgoing qubits to the top of the local index. */
+int b200_sv_peer_swap_strided(b200_ctx *ctx, int slot, void *const *peer_ptrs, int world, int rank,
+                              const int32_t *positions);
 int b200_sv_num_qubits(b200_ctx *ctx, int *out);
 
 /* slot <- |0...0> */

@@ -79,7 +79,10 @@ def emu_run(emu, n, gates, psi0=None, inverse=False):
                             int(inverse), stats)
         assert rc == 0, emu.emu_last_error()
         outs.append(st)
-    assert np.array_equal(outs[0], outs[1]), "direct and pipelined sweep bodies disagree"
+    # Same arithmetic up to where pending phases are flushed: the direct body folds X-type ops on lane qubits into its
+    # addressing, the pipelined body executes them as shuffles (which flush the pending phase first), so a product of two
+    # phases may be rounded once instead of twice -- a few ulp, never more.
+    assert np.allclose(outs[0], outs[1], rtol=0, atol=1e-14), "direct and pipelined sweep bodies disagree"
     return st, tuple(stats)
 
 

@@ -521,3 +521,38 @@ def test_pair_rdm_parts_sum_to_the_undivided_call_bit_for_bit():
     for r, (a, b) in zip(whole, pairs):
         np.testing.assert_allclose(r, orc.partial_trace(ref, a, b), atol=AMP_TOL)
     eng.close()
+
+
+@pytest.mark.parametrize("world,positions", [(2, [9]), (4, [11, 6]), (8, [7, 12, 10]), (4, None)])
+def test_peer_swap_kernels_on_one_gpu(world, positions):
+    """b200_sv_peer_swap / b200_sv_peer_swap_strided: the `world` slots of one engine stand in for the ranks' slices
+    (every amplitude pair is owned by exactly one rank's kernel, so running the ranks' kernels one after the other on one
+    GPU gives what the concurrent launches give over NVLink).  positions = None: contiguous chunks (top local bits)."""
+    nl = 13
+    g = int(np.log2(world))
+    rng = np.random.default_rng(world)
+    eng = SVEngine(nl, n_slots=world)
+    before = [rng.normal(size=1 << nl) + 1j * rng.normal(size=1 << nl) for _ in range(world)]
+    for r in range(world):
+        eng.upload(r, before[r])
+    ptrs = [eng.device_ptr(r) for r in range(world)]
+    for r in range(world):
+        eng.peer_swap(r, [None if p == r else ptrs[p] for p in range(world)], r, positions)
+    eng.sync()
+    pos = positions if positions is not None else [nl - g + j for j in range(g)]
+    idx = np.arange(1 << nl)
+    chunk_of = np.zeros_like(idx)
+    for j, p in enumerate(pos):
+        chunk_of |= ((idx >> p) & 1) << j
+    for r in range(world):
+        got = eng.download(r)
+        want = np.empty_like(got)
+        for p in range(world):
+            # the amplitudes of rank r whose victim bits spell p come from rank p's set that spells r (same other bits)
+            sel = chunk_of == p
+            src_idx = idx[sel]
+            for j, b in enumerate(pos):
+                src_idx = (src_idx & ~(1 << b)) | (((r >> j) & 1) << b)
+            want[sel] = before[p][src_idx]
+        np.testing.assert_array_equal(got, want)
+    eng.close()
