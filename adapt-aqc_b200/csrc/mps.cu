@@ -52,7 +52,7 @@ struct b200_mps {
     std::vector<int> chi;            // chi[i] = bond to the right of site i (chi[n-1] = 1)
     std::vector<DevBuf> gam;         // [2][chi_l][chi_r] double2
     std::vector<DevBuf> lam;         // chi[i] doubles, i < n-1
-    uint64_t svd_count = 0, svd_sweeps = 0;
+    uint64_t svd_count = 0, svd_sweeps = 0, svd_flops = 0;
     int chiL(int i) const { return i == 0 ? 1 : chi[i - 1]; }
 };
 
@@ -84,7 +84,8 @@ MpsState* state(b200_ctx* ctx) {
 struct MScope {  // counts + (in profile mode) times one MPS kernel launch, like KScope in api.cu
     b200_ctx* c;
     cudaEvent_t a = nullptr, b = nullptr;
-    explicit MScope(b200_ctx* ctx) : c(ctx) {
+    int cls;
+    explicit MScope(b200_ctx* ctx, int cls_ = B200_PROF_MPS) : c(ctx), cls(cls_) {
         c->counters[0] += 1;
         if (c->profiling) {
             auto get = [&]() { if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
@@ -94,7 +95,7 @@ struct MScope {  // counts + (in profile mode) times one MPS kernel launch, like
         }
     }
     ~MScope() {
-        if (a) { cudaEventRecord(b, c->stream); c->prof_recs.push_back({B200_PROF_MPS, a, b}); }
+        if (a) { cudaEventRecord(b, c->stream); c->prof_recs.push_back({cls, a, b}); }
     }
 };
 
@@ -107,11 +108,11 @@ int gemm(b200_ctx* ctx, const GemmArgs& g) {
     const long long tiles64 = (long long)((g.N + G2_TILE - 1) / G2_TILE) * ((g.M + G2_TILE - 1) / G2_TILE);
     if (tiles64 >= ctx->num_sms / 4 && g.K >= 2 * G2_K && !std::getenv("B200AQC_GEMM32")) {
         dim3 grid((g.N + G2_TILE - 1) / G2_TILE, (g.M + G2_TILE - 1) / G2_TILE);
-        MScope ms(ctx);
+        MScope ms(ctx, B200_PROF_GEMM);
         zgemm_dmma64_kernel<<<grid, 256, 0, ctx->stream>>>(g);
     } else {
         dim3 grid((g.N + GM_TILE - 1) / GM_TILE, (g.M + GM_TILE - 1) / GM_TILE);
-        MScope ms(ctx);
+        MScope ms(ctx, B200_PROF_GEMM);
         zgemm_dmma_kernel<<<grid, 128, 0, ctx->stream>>>(g);
     }
     CUDA_TRY(cudaGetLastError());
@@ -274,7 +275,7 @@ int apply_adjacent(b200_mps* m, int i, const cplx u4[16]) {
         const int pairs = ((q + 1) / 2);
         const int threads = std::min(1024, std::max(32, pairs * 32));
         {
-            MScope ms(ctx);
+            MScope ms(ctx, B200_PROF_SVD);
             jacobi_cta_kernel<<<1, threads, 0, s>>>((double2*)st->X.p, (double2*)st->W.p, p, q, max_sweeps, (int*)st->flag.p);
         }
         CUDA_TRY(cudaGetLastError());
@@ -302,7 +303,7 @@ int apply_adjacent(b200_mps* m, int i, const cplx u4[16]) {
                 const double* fr = fro2; int* ctrl = (int*)st->flag.p;
                 void* args[] = {&Xp, &Wp, &pp, &qq, &NN, &ms_, &fr, &ctrl};
                 {
-                    MScope ms(ctx);
+                    MScope ms(ctx, B200_PROF_SVD);
                     CUDA_TRY(cudaLaunchCooperativeKernel((const void*)jacobi_block_kernel<WB>, dim3(NB / 2), dim3(JB_GROUP * WB), args, jb_smem, s));
                 }
                 int done[3] = {0, 0, 0};
@@ -324,7 +325,7 @@ int apply_adjacent(b200_mps* m, int i, const cplx u4[16]) {
                 const double* fr = fro2; int* ctrl = (int*)st->flag.p;
                 void* args[] = {&Xp, &Wp, &pp, &qq, &NN, &ms_, &fr, &ctrl};
                 {
-                    MScope ms(ctx);
+                    MScope ms(ctx, B200_PROF_SVD);
                     CUDA_TRY(cudaLaunchCooperativeKernel((const void*)jacobi_coop_kernel, dim3(N / 2), dim3(128), args, 0, s));
                 }
                 int done[3] = {0, 0, 0};
@@ -338,7 +339,7 @@ int apply_adjacent(b200_mps* m, int i, const cplx u4[16]) {
         for (; !coop_done && sweeps < max_sweeps; ++sweeps) {
             CUDA_TRY(cudaMemsetAsync(st->flag.p, 0, sizeof(int), s));
             for (int r = 0; r < N - 1; ++r) {
-                MScope ms(ctx);
+                MScope ms(ctx, B200_PROF_SVD);
                 jacobi_round_kernel<<<N / 2, 128, 0, s>>>((double2*)st->X.p, (double2*)st->W.p, p, q, N, r, fro2, (int*)st->flag.p);
             }
             CUDA_TRY(cudaGetLastError());
@@ -368,6 +369,10 @@ int apply_adjacent(b200_mps* m, int i, const cplx u4[16]) {
     }
     m->svd_count += 1;
     m->svd_sweeps += sweeps;
+    // algorithmic flop model of one-sided Jacobi: per column pair and sweep, three length-p complex inner
+    // products (Gram entries: 2 + 2 + 8 flop per row) and the rotation of two columns of X (p rows) and of W (q rows),
+    // 28 flop per row -- (40 p + 28 q) flop per pair, q (q - 1) / 2 pairs per sweep
+    m->svd_flops += (uint64_t)sweeps * ((uint64_t)q * (q - 1) / 2) * (uint64_t)(40 * p + 28 * q);
 
     // ---- truncation (Aer reduce_zeros) ----
     std::vector<int> order(q);
@@ -851,7 +856,7 @@ int b200_mps_reduce_zeros(const double* s_desc, int n, int max_bond_dimension, d
 
 int b200_mps_stats(b200_mps* m, uint64_t out[4]) {
     if (check_mps(m) || !out) return set_error("null pointer");
-    out[0] = m->svd_count; out[1] = m->svd_sweeps; out[2] = (uint64_t)max_bond(m); out[3] = 0;
+    out[0] = m->svd_count; out[1] = m->svd_sweeps; out[2] = (uint64_t)max_bond(m); out[3] = m->svd_flops;
     return 0;
 }
 

@@ -112,10 +112,10 @@ class MPSContext:
         check(self._lib.b200_ctx_profile(self._ctx, 1 if enable else 0))
 
     def profile_read(self):
-        ms = (ctypes.c_double * 8)()
-        cnt = (ctypes.c_uint64 * 8)()
+        ms = (ctypes.c_double * 10)()
+        cnt = (ctypes.c_uint64 * 10)()
         check(self._lib.b200_ctx_profile_read(self._ctx, ms, cnt))
-        names = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps")
+        names = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps", "svd", "gemm")
         return {name: (ms[i], cnt[i]) for i, name in enumerate(names)}
 
 
@@ -232,7 +232,7 @@ class DeviceMPS:
     def stats(self):
         out = (ctypes.c_uint64 * 4)()
         check(self._lib.b200_mps_stats(self._h, out))
-        return {"svds": out[0], "jacobi_sweeps": out[1], "max_bond": out[2]}
+        return {"svds": out[0], "jacobi_sweeps": out[1], "max_bond": out[2], "svd_flops": out[3]}
 
 
 SLOT_WORK, SLOT_BASE, SLOT_L, SLOT_R = 0, 1, 2, 3

@@ -209,15 +209,15 @@ class SVEngine:
         check(self._lib.b200_ctx_elapsed_ms(self._ctx, ctypes.byref(ms)))
         return ms.value
 
-    PROF_CLASSES = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps")
+    PROF_CLASSES = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps", "svd", "gemm")
 
     def profile(self, enable=True):
         check(self._lib.b200_ctx_profile(self._ctx, 1 if enable else 0))
 
     def profile_read(self):
         """{class: (total_ms, launches)} of the kernels launched since profile(True)."""
-        ms = (ctypes.c_double * 8)()
-        cnt = (ctypes.c_uint64 * 8)()
+        ms = (ctypes.c_double * 10)()
+        cnt = (ctypes.c_uint64 * 10)()
         check(self._lib.b200_ctx_profile_read(self._ctx, ms, cnt))
         return {name: (ms[i], cnt[i]) for i, name in enumerate(self.PROF_CLASSES)}
 

@@ -255,6 +255,35 @@ def cpu_baseline_sample(n, target, ansatz, unfused_too=True):
 
 
 # ---- config C4: 50-qubit random MPS at bond dimension 256 ----------------------------------------
+FP64_FMA_PEAK_TFLOPS = 33.9     # measured on this pool with scripts/micro/sweep_probe.cu (profiles/probe_r01k.txt): 58.3 FMA/clk/SM
+
+
+def measure_zgemm_tflops(device, n=4096, reps=5):
+    """Denominator for the DMMA contractions: cuBLAS Zgemm n^3 through torch.matmul on complex128, best of
+    `reps`, CUDA events, 8 n^3 real flop.  Library call used ONLY as the roofline denominator."""
+    try:
+        import torch
+        dev = torch.device("cuda", device)
+        a = torch.randn(n, n, dtype=torch.complex128, device=dev)
+        b = torch.randn(n, n, dtype=torch.complex128, device=dev)
+        torch.matmul(a, b)
+        torch.cuda.synchronize(dev)
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        del a, b
+        torch.cuda.empty_cache()
+        return 8.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def mps_step(comp):
     lo, hi = comp.variational_circuit_range()
     comp.minimizer._reduce_cost(False, (lo, hi))
@@ -278,6 +307,9 @@ def bench_mps(args, device, with_cpu=True):
     gen_s = time.perf_counter() - t0
     out = {"workload": f"C4: {n}-qubit random Vidal MPS, chi={chi}, {layers} un-absorbed thinly-dressed CNOT layers; "
                        "step = one Rotosolve cycle over their rotations", "target_generation_s": gen_s}
+    zgemm_peak = measure_zgemm_tflops(device)
+    out["denominators"] = {"fp64_fma_tflops": FP64_FMA_PEAK_TFLOPS, "fp64_fma_source": "scripts/micro/sweep_probe.cu on this pool (profiles/probe_r01k.txt)",
+                           "cublas_zgemm_4096_tflops": zgemm_peak, "zgemm_source": "torch.matmul complex128 4096^3, best of 5, measured in this run"}
     for mode, cap in (("capped", chi), ("default", None)):
         sim = B200MPSSimulator(1e-16, max_chi=cap, device=device)
         backend = B200MPSBackend(sim)
@@ -289,6 +321,7 @@ def bench_mps(args, device, with_cpu=True):
             mps_step(comp)
         ctx.sync()
         c0, e0 = ctx.counters(), comp.cost_evaluation_counter
+        f0 = sum(m.stats()["svd_flops"] for m in ctx._live)
         ctx.profile(True)
         ctx.mark(0)
         steps = max(1, args.steps // 2) if mode == "capped" else max(2, args.steps)
@@ -305,11 +338,29 @@ def bench_mps(args, device, with_cpu=True):
             "evaluation": "reference contraction order" if mode == "capped" else "block transfer matrices",
             "value": evals / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "evals_per_step": evals // steps,
             "gpu_launches": int(c1["launches"] - c0["launches"]),
-            "kernel_ms": prof["mps"][0], "kernel_launches": int(prof["mps"][1]),
+            "kernel_ms": prof["mps"][0] + prof["svd"][0] + prof["gemm"][0],
+            "kernel_launches": int(prof["mps"][1] + prof["svd"][1] + prof["gemm"][1]),
+            "kernel_ms_by_class": {"jacobi_svd": prof["svd"][0], "dmma_gemm": prof["gemm"][0], "other": prof["mps"][0]},
             "dmma_flops": int(c1["tensor_flops"] - c0["tensor_flops"]),
             "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / steps,
             "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / steps,
         }
+        svd_flops = sum(m.stats()["svd_flops"] for m in ctx._live) - f0
+        svd_ms, gemm_ms = prof["svd"][0], prof["gemm"][0]
+        # the dominant kernel of this mode and the roof that bounds it (FP64 FMA pipe for the Jacobi SVD, FP64 tensor
+        # cores for the contractions; both against measured denominators)
+        rl_svd = {"bound": "fp64", "kernel": "jacobi_block_kernel / jacobi_cta_kernel", "unit": "TFLOP/s",
+                  "achieved": svd_flops / (svd_ms * 1e-3) / 1e12 if svd_ms > 0 else None, "peak": FP64_FMA_PEAK_TFLOPS,
+                  "flop_model": "(40 p + 28 q) flop per column pair per sweep, counted by the library", "launches": int(prof["svd"][1]),
+                  "share_of_kernel_time": svd_ms / max(1e-9, res["kernel_ms"])}
+        rl_svd["frac"] = rl_svd["achieved"] / rl_svd["peak"] if rl_svd["achieved"] else None
+        rl_gemm = {"bound": "tensor", "kernel": "zgemm_dmma_kernel / zgemm_dmma64_kernel", "unit": "TFLOP/s",
+                   "achieved": res["dmma_flops"] / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None, "peak": zgemm_peak,
+                   "peak_kind": "measured cuBLAS Zgemm 4096^3", "launches": int(prof["gemm"][1]),
+                   "share_of_kernel_time": gemm_ms / max(1e-9, res["kernel_ms"])}
+        rl_gemm["frac"] = rl_gemm["achieved"] / zgemm_peak if (rl_gemm["achieved"] and zgemm_peak) else None
+        res["roofline"] = rl_svd if svd_ms >= gemm_ms else rl_gemm
+        res["roofline_other"] = rl_gemm if svd_ms >= gemm_ms else rl_svd
         if backend._engine is not None:
             res["max_bond"] = max(max(m.bond_dims()) for m in backend._engine.slots)
             res["svd"] = {k: int(sum(m.stats()[k] for m in backend._engine.slots)) for k in ("svds", "jacobi_sweeps")}

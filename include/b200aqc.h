@@ -77,7 +77,7 @@ int b200_ctx_elapsed_ms(b200_ctx *ctx, double *ms);
 /* Per-kernel-class device times: while enabled, every kernel launch is bracketed by its own CUDA
  * event pair on the context's stream.  enable != 0 also resets the accumulators.  profile_read
  * synchronises the stream and returns, per class, the summed milliseconds and launch count. */
-#define B200_PROF_CLASSES 8
+#define B200_PROF_CLASSES 10
 enum {
     B200_PROF_SWEEP = 0,  /* sv_sweep_kernel (fused gate sweep, tiled path)  */
     B200_PROF_SMALL = 1,  /* sv_small_kernel (n <= 11, one CTA)              */
@@ -86,7 +86,9 @@ enum {
     B200_PROF_INNER = 4,  /* <L|.|R> transfer-matrix pass                    */
     B200_PROF_FILL = 5,   /* |0..0> fill / device copies                     */
     B200_PROF_REDUCE = 6, /* final fixed-order reductions                    */
-    B200_PROF_MPS = 7     /* MPS kernels                                     */
+    B200_PROF_MPS = 7,    /* MPS kernels other than the two below            */
+    B200_PROF_SVD = 8,    /* on-device Jacobi SVD (jacobi_*_kernel)          */
+    B200_PROF_GEMM = 9    /* complex GEMM on the FP64 tensor cores (DMMA)    */
 };
 int b200_ctx_profile(b200_ctx *ctx, int enable);
 int b200_ctx_profile_read(b200_ctx *ctx, double ms[B200_PROF_CLASSES], uint64_t launches[B200_PROF_CLASSES]);
@@ -272,7 +274,8 @@ int b200_mps_pair_transfer(b200_mps *a, b200_mps *b, const int32_t *pairs, int n
 int b200_mps_set_chop_rule(int rule);
 int b200_mps_reduce_zeros(const double *s_desc, int n, int max_bond_dimension, double truncation_threshold,
                           int *n_kept, double *kept_out);
-/* out = {SVDs run, Jacobi sweeps run, current max bond dimension, 0}. */
+/* out = {SVDs run, Jacobi sweeps run, current max bond dimension, algorithmic flop of those sweeps:
+ * (40 p + 28 q) flop per column pair per sweep of a p x q matrix}. */
 int b200_mps_stats(b200_mps *mps, uint64_t out[4]);
 
 /* Planner introspection (no GPU needed): how many sweeps / rounds / fused ops the gate stream
