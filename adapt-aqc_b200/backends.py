@@ -14,6 +14,7 @@ because the reference calls it directly, bypassing the backend, once per candida
 Everything is evaluated on the GPU through libb200aqc.so; there is no CPU path.
 """
 import abc
+import operator
 import os
 import weakref
 
@@ -57,6 +58,10 @@ COMPACT_MIN_QUBITS = 12
 # Projected tail (SVCostEvaluator): K-qubit engines (4 slots each; 1 GiB in total at K = 24) on which the blocks of the
 # window are optimised once the remaining gates touch at most K qubits.  B200AQC_PROJECT=0 disables.
 PROJECT_QUBITS = (16, 20, 24)
+
+
+_is = operator.is_
+_params_of = operator.attrgetter("operation.params")
 
 
 def _fingerprint(inst, qmap):
@@ -339,24 +344,45 @@ class B200SVBackend(_SVBase):
                 self._wcache = None
                 return window, None
             qmap = G.qubit_indices(circuit)
-            self._wcache = (key, [_fingerprint(inst, qmap) for inst in (data[lhs:] if lhs else data)], window, qmap)
+            fps = [_fingerprint(inst, qmap) for inst in (data[lhs:] if lhs else data)]
+            self._wcache = (key, fps, window, qmap)
+            self._wlists = ([f[0] for f in fps], [f[1] for f in fps])      # parallel lists for the C-level scans
             return window, None
         _, fps, window, qmap = wc
-        # value comparison (name, params, qubits); `is` only short-cuts it: qiskit >= 1.0 hands out a fresh
-        # CircuitInstruction per data[i] access, so identity alone would flag every gate on every call
-        cur = data[lhs:] if lhs else data
-        try:        # (identity test inlined: this line runs once per gate per cost evaluation)
-            changed = [i for i, (inst, f) in enumerate(zip(cur, fps))
-                       if not (inst is f[0] and inst.operation.params == f[1]) and not _same_instruction(inst, f, qmap)]
-        except ValueError:          # array-valued parameters
-            changed = [i for i, (inst, f) in enumerate(zip(cur, fps)) if not _same_instruction(inst, f, qmap)]
+        # Which instructions changed since the previous call?  Compared by VALUE (name, params, qubits); object identity
+        # only short-cuts it (qiskit >= 1.0 hands out a fresh CircuitInstruction per data[i] access).  The scan over the
+        # window runs once per cost evaluation, so the common case -- same objects, one of them replaced by the optimiser
+        # (circuit_operations_basic.py:70-99) -- is kept in C-level loops: identity flags, then the parameter lists of the
+        # untouched objects (an in-place edit of .params must not go unnoticed).
+        cur = data[lhs:] if lhs else list(data)
+        insts, params = wc_lists = self._wlists
+        flags = list(map(_is, cur, insts))
+        suspects = [] if all(flags) else [i for i, f in enumerate(flags) if not f]
+        if len(suspects) * 4 > m:                      # fresh objects everywhere (qiskit): value comparison of every entry
+            suspects = range(m)
+        else:
+            try:
+                plist = list(map(_params_of, cur))
+                for i in suspects:
+                    plist[i] = params[i]
+                if plist != params:
+                    suspects = sorted(set(suspects) | {i for i, (a, b) in enumerate(zip(plist, params)) if a != b})
+            except ValueError:                         # array-valued parameters
+                suspects = range(m)
+        changed = []
+        for i in suspects:
+            inst = cur[i]
+            if not _same_instruction(inst, fps[i], qmap):
+                changed.append(i)
+            insts[i] = fps[i][0]                       # (refreshed by _same_instruction on a value match)
         for i in changed:
             ent = G.canonical_window(circuit, lhs + i, lhs + i + 1, qmap)
             if len(ent) != 1:
                 self._wcache = None
                 return G.canonical_window(circuit, lhs, None), None
             window[i] = ent[0]
-            fps[i] = _fingerprint(data[lhs + i], qmap)
+            fps[i] = _fingerprint(cur[i], qmap)
+            insts[i], params[i] = fps[i][0], fps[i][1]
         return window, changed
 
     # ---- the four backend methods ----

@@ -225,6 +225,29 @@ def one_qubit_matrix(name, theta):
     return m
 
 
+_CTUPLE_CACHE = {}
+
+
+def complex_tuple(m):
+    """(m00, m01, m10, m11) as Python complex of a 2x2 array; cached for the read-only rotation matrices of
+    one_qubit_matrix (the optimiser's shift candidates)."""
+    if not m.flags.writeable:
+        t = _CTUPLE_CACHE.get(id(m))
+        if t is not None and t[0] is m:
+            return t[1]
+        v = tuple(complex(x) for x in m.ravel())
+        if len(_CTUPLE_CACHE) > 16384:
+            _CTUPLE_CACHE.clear()
+        _CTUPLE_CACHE[id(m)] = (m, v)
+        return v
+    return tuple(complex(x) for x in np.asarray(m).ravel())
+
+
+def matrix_of_entry_complex(ent):
+    """complex_tuple of a canonical 1-qubit window entry."""
+    return complex_tuple(matrix_of_entry(ent))
+
+
 _R2 = 1 / np.sqrt(2)
 
 

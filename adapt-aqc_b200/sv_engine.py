@@ -396,6 +396,7 @@ class SVCostEvaluator:
         self.cut = None
         self.pair = None
         self.T = None
+        self._gw = None
         self.rwin = None
         self.lwin = None
         self.lkey = None
@@ -654,6 +655,7 @@ class SVCostEvaluator:
             # T is still valid for this block (slot L may already hold the prefetched bra of the next one)
             self.cut, self.pair = (b0, b1), pair
             self.window = list(window)
+            self._gw = None
             return
         qmap = self._compact_map(window[b1:], pair)
         if qmap is not None:
@@ -674,13 +676,49 @@ class SVCostEvaluator:
                 self.stats["t_passes"] += 1
             self._tkey = tkey
             self._t_sfx = list(window[b1:])
+            self._gw = None
             if mode == "dense" and self.prefetch_L:
                 self._prefetch_next_L(window, b1)
         self.cut, self.pair = (b0, b1), pair
         self.window = list(window)
+        self._gw = None
 
     _tkey = None
     _t_sfx = None
+    _gw = None          # (k, w): gate-context cache of the open block, see _gate_context
+
+    def _gate_context(self, window, k):
+        """(w00, w01, w10, w11), Python complex, such that for ANY 2x2 matrix m placed at window position k of the open
+        block  <0|psi> = sum_ab m[a][b] w_ab.  With pre / post = the products of the block's other gates before / after
+        position k:  <0|psi> = sum_ij (post E(m) pre)_ij T_ij = tr(E(m) . pre T^T post), so w is the partial trace of
+        W = pre T^T post over the block's other qubit.  The optimiser asks for 3-7 values of the SAME gate in a row
+        (cost_minimiser.py:318-368): they all share w, and each costs four complex multiplications on the host.
+        Cached until T, or another gate of the block, changes."""
+        gw = self._gw
+        if gw is not None and gw[0] == k:
+            return gw[1]
+        b0, b1 = self.cut
+        pair = self.pair
+        pre = post = None
+        for i in range(b0, k):
+            mm = embed_entry(window[i], pair)
+            pre = mm if pre is None else mm @ pre
+        for i in range(k + 1, b1):
+            mm = embed_entry(window[i], pair)
+            post = mm if post is None else mm @ post
+        W = self.T.T
+        if pre is not None:
+            W = pre @ W
+        if post is not None:
+            W = W @ post
+        if len(pair) == 1:
+            w = (complex(W[0, 0]), complex(W[1, 0]), complex(W[0, 1]), complex(W[1, 1]))
+        elif window[k][1] == pair[0]:       # the gate's qubit is the low index bit: idx(a, o) = a + 2 o
+            w = tuple(complex(W[b, a] + W[b + 2, a + 2]) for a in (0, 1) for b in (0, 1))
+        else:                               # high index bit: idx(a, o) = o + 2 a
+            w = tuple(complex(W[2 * b, 2 * a] + W[2 * b + 1, 2 * a + 1]) for a in (0, 1) for b in (0, 1))
+        self._gw = (k, w)
+        return w
 
     def _operator(self, window, override_index=None, override=None):
         b0, b1 = self.cut
@@ -722,8 +760,30 @@ class SVCostEvaluator:
                         and window[i][2] == self.window[i][2] for i in changed)):
             for i in changed:
                 self.window[i] = window[i]
+            # pivot = the gate the optimiser is working on (the last one it touched): all 3-7 values it asks for in a
+            # row are then computed with the SAME arithmetic (one gate context w, four multiplications each), exactly
+            # like the batched front end -- Rotoselect's exact ties between axes break the same way in both
+            gw = self._gw
+            k = max(changed) if changed else (gw[0] if gw is not None else None)
+            if k is not None and window[k][2] < 0:
+                if gw is not None and (gw[0] != k or len(changed) > 1):
+                    self._gw = None            # another gate of the block changed: its context is stale
+                self.stats["host_evals"] += 1
+                w = self._gate_context(window, k)
+                m = G.matrix_of_entry_complex(window[k])
+                return m[0] * w[0] + m[1] * w[1] + m[2] * w[2] + m[3] * w[3]
+            self._gw = None
         else:
             self._prepare_block(window, self._select_block(window, focus, changed))
+            # same arithmetic as the fast path / the batched front end whenever a pivot gate is known
+            b0, b1 = self.cut
+            inside = [i for i in (changed or ()) if b0 <= i < b1]
+            k = max(inside) if inside else None
+            if k is not None and window[k][2] < 0:
+                self.stats["host_evals"] += 1
+                w = self._gate_context(window, k)
+                m = G.matrix_of_entry_complex(window[k])
+                return m[0] * w[0] + m[1] * w[1] + m[2] * w[2] + m[3] * w[3]
         self.stats["host_evals"] += 1
         return complex(np.sum(self._operator(window) * self.T))
 
@@ -750,20 +810,12 @@ class SVCostEvaluator:
                 break
         self.stats["evals"] += len(candidates)
         self.stats["host_evals"] += len(candidates)
-        # The product of the block's gates in front of position k is the same for every candidate: fold it
-        # once.  Same association order as _operator (later gates multiply from the left), so every candidate
-        # gets bit-identical arithmetic.
-        b0, b1 = self.cut
-        pre = None
-        for i in range(b0, k):
-            m = embed_entry(window[i], self.pair)
-            pre = m if pre is None else m @ pre
-        post = [embed_entry(window[i], self.pair) for i in range(k + 1, b1)]
+        # Every candidate shares the gate context w of position k (_gate_context): the same four complex multiplications
+        # per value as the one-scalar-at-a-time path (amp0), so both front ends produce bit-identical costs.
+        self._gw = None if (self._gw is not None and self._gw[0] != k) else self._gw
+        w = self._gate_context(window, k)
         out = []
         for c in candidates:
-            m = embed_entry(window[k], self.pair, c)
-            op = m if pre is None else m @ pre
-            for pm in post:
-                op = pm @ op
-            out.append(complex(np.sum(op * self.T)))
+            m = G.complex_tuple(c)
+            out.append(m[0] * w[0] + m[1] * w[1] + m[2] * w[2] + m[3] * w[3])
         return out
