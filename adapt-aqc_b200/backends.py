@@ -55,9 +55,20 @@ except Exception:  # noqa: BLE001
 # COMPACT_MIN_QUBITS qubits are cheap enough to always use the dense path.
 COMPACT_QUBITS = (12, 19, 26)
 COMPACT_MIN_QUBITS = 12
-# Projected tail (SVCostEvaluator): K-qubit engines (4 slots each; 1 GiB in total at K = 24) on which the blocks of the
-# window are optimised once the remaining gates touch at most K qubits.  B200AQC_PROJECT=0 disables.
-PROJECT_QUBITS = (16, 20, 24)
+# Projected tail (SVCostEvaluator): K-qubit engines (4 slots each) on which the blocks of the window are optimised once
+# the remaining gates touch at most K qubits -- nested: the evaluator of a K-qubit engine projects ITS tail onto the next
+# smaller one.  Sizes: n-1, n-2, then every second size down to 12 (each thin layer adds at most two qubits to the support
+# of the gates behind it), at most 28 qubits (4 x 4 GiB).  B200AQC_PROJECT=0 disables.
+PROJECT_QUBITS = (16, 20, 24)          # the sizes round 1 used (kept for the sharded backend's replicated engines)
+PROJECT_MAX_QUBITS = 28
+
+
+def project_sizes(num_qubits, limit=None):
+    """Engine sizes of the nested projection levels below a `num_qubits` register, ascending."""
+    top = min(num_qubits - 1, PROJECT_MAX_QUBITS, limit if limit is not None else num_qubits)
+    sizes = {k for k in (top, top - 1) if k >= COMPACT_MIN_QUBITS}
+    sizes.update(range(top - 3, COMPACT_MIN_QUBITS - 1, -2))
+    return sorted(sizes)
 
 
 _is = operator.is_
@@ -258,8 +269,7 @@ class B200SVBackend(_SVBase):
                 c.close()
             self._projected = []
             if num_qubits > COMPACT_MIN_QUBITS and os.environ.get("B200AQC_PROJECT", "1") != "0":
-                self._projected = [SVEngine(k, device=self.device, n_slots=4) for k in PROJECT_QUBITS
-                                   if COMPACT_MIN_QUBITS <= k <= num_qubits - SVCostEvaluator.PROJECT_MIN_SAVING]
+                self._projected = [SVEngine(k, device=self.device, n_slots=4) for k in project_sizes(num_qubits)]
             self._evaluator = SVCostEvaluator(self._engine, self._compact, self._projected)
             self._state_version += 1
             self._last_run_key = None

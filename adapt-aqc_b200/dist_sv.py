@@ -545,7 +545,7 @@ def make_gpu_sharded(num_qubits, n_slots=2, staging_bytes=1 << 30, local_rank=0,
 
 
 def _sharded_backend_class():
-    from .backends import PROJECT_QUBITS, B200SVBackend
+    from .backends import B200SVBackend, project_sizes
     from .sv_engine import SVCostEvaluator, SVEngine
 
     class B200ShardedSVBackend(B200SVBackend):
@@ -570,7 +570,7 @@ def _sharded_backend_class():
             """(ShardedEngine, [compact-bra engines, 2 slots], [projected engines, 4 slots]) -- overridden by the CPU tests."""
             from .backends import COMPACT_QUBITS
             sv = make_gpu_sharded(num_qubits, n_slots=4, local_rank=self.device, exchange=self.exchange)
-            sizes = [k for k in PROJECT_QUBITS if 12 <= k <= min(num_qubits - SVCostEvaluator.PROJECT_MIN_SAVING, sv.nl)]
+            sizes = project_sizes(num_qubits, limit=min(sv.nl, 26))     # replicated per rank: 4 slots of at most 1 GiB
             csizes = sorted({min(k, sv.nl) for k in COMPACT_QUBITS})
             return (ShardedEngine(sv), [SVEngine(k, device=self.device, n_slots=2) for k in csizes],
                     [SVEngine(k, device=self.device, n_slots=4) for k in sizes])

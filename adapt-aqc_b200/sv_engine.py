@@ -336,23 +336,28 @@ class SVCostEvaluator:
     """
 
     REFRESH_MOVES = 256  # rebuild R / dense L from scratch after this many incremental moves
-    PROJECT_MIN_SAVING = 3  # project only onto engines at least this many qubits smaller than the register
+    PROJECT_MIN_SAVING = 3  # project only onto engines at least this many qubits smaller than the register ...
+    LARGE_QUBITS = 20       # ... or at least ONE qubit smaller once the register has this many qubits (see min_saving)
 
-    def __init__(self, engine, compact=None, projected=None):
+    def __init__(self, engine, compact=None, projected=None, registry=None):
         """projected: optional K-qubit engines (4 slots each, same device) for the PROJECTED TAIL: once the
         gates of window[m:] act on at most K qubits S, <0|W|base> = <0_S| W[m:] |phi> with
         |phi> = <0_rest| W[:m] |base> (a gather of 2^K amplitudes of R, ``gather``), so every evaluation
         of the blocks in window[m:] -- R/L moves, transfer passes -- runs on the 2^K-amplitude engine
         through a nested evaluator, and no sweep over the 2^n register is needed while the optimiser
-        stays in the tail."""
+        stays in the tail.  The nested evaluator projects its own tail onto the next smaller engine, and so on: every
+        thin layer adds at most two qubits to the support of the gates behind it, so each level keeps one or two
+        blocks and the passes over 2^n, 2^(n-1), 2^(n-2), 2^(n-4) ... amplitudes add up to a geometric series.
+        registry: {id(engine): evaluator} shared by all levels -- ONE evaluator per engine, whoever projects into it."""
         self.eng = engine
         # False (sharded registers, dist_sv.ShardedEngine): no dense bra / transfer passes over the register --
         # blocks outside the projected tail are evaluated by re-simulating the window from the base state
         self.dense_blocks = True
         self.prefetch_L = True        # see _prefetch_next_L
         self.projected = sorted(projected or [], key=lambda e: e.num_qubits)
-        self._sub = {}                # id(projected engine) -> nested SVCostEvaluator
-        self._proj_state = None       # (engine id, m, qmap) of the phi currently held by that engine
+        self._registry = registry if registry is not None else {}
+        self._registry.setdefault(id(engine), self)
+        self._proj_state = None       # (engine id, m, qmap, base key, token) of the phi currently held by that engine
         self._split_key, self._split = None, None
         self._split_info = None       # (split, (engine, qmap, position of each qubit, nested evaluator) | None)
         self._tail_cache = None       # (proj key, remapped tail window)
@@ -387,11 +392,14 @@ class SVCostEvaluator:
         self.base_key = key
         self.invalidate()
 
+    def min_saving(self):
+        """Project only onto engines at least this many qubits smaller than the register: halving a pass over >= 2^20
+        amplitudes pays for the gather; small registers are launch-latency bound anyway."""
+        return 1 if self.eng.num_qubits >= self.LARGE_QUBITS else self.PROJECT_MIN_SAVING
+
     def invalidate(self):
-        self._proj_state = None
-        for sub in self._sub.values():
-            sub.base_key = None
-            sub.invalidate()
+        self._proj_state = None       # (a nested evaluator is re-based, with a fresh token, by the next projection)
+        self._hot, self._hot_dirty = None, False
         self.window = None
         self.cut = None
         self.pair = None
@@ -450,7 +458,7 @@ class SVCostEvaluator:
                 if len(new) > kmax:
                     break
                 supp, m = new, s0
-            ok = m < len(window) and len(supp) + self.PROJECT_MIN_SAVING <= self.eng.num_qubits
+            ok = m < len(window) and len(supp) + self.min_saving() <= self.eng.num_qubits
             self._split_key, self._split = self._part_key, ((m, sorted(supp)) if ok else None)
         return self._split
 
@@ -460,7 +468,7 @@ class SVCostEvaluator:
         info = self._split_info
         if info is None or info[0] is not split:
             fits = [e for e in self.projected if e.num_qubits >= len(supp) and
-                    e.num_qubits + self.PROJECT_MIN_SAVING <= self.eng.num_qubits]
+                    e.num_qubits + self.min_saving() <= self.eng.num_qubits]
             if not fits:
                 info = self._split_info = (split, None)
                 return info
@@ -468,13 +476,45 @@ class SVCostEvaluator:
             used = set(supp)
             free = [q for q in range(self.eng.num_qubits) if q not in used]
             qmap = supp + free[:peng.num_qubits - len(supp)]     # padded qubits carry no gate: <0| projects them out
-            sub = self._sub.get(id(peng))
-            if sub is None:
-                # (no compact-bra engines for the nested evaluator: they are owned by this one, and a pass over
-                # 2^K amplitudes is cheap anyway)
-                sub = self._sub[id(peng)] = SVCostEvaluator(peng)
+            sub = self._sub_for(peng)
             info = self._split_info = (split, (peng, tuple(qmap), {q: c for c, q in enumerate(qmap)}, sub))
         return info
+
+    def _sub_for(self, peng):
+        """The evaluator of a projected engine: one per engine, shared by every level that may project into it; its own
+        projected tail goes to the smaller engines (no compact-bra engines: they belong to the top level)."""
+        sub = self._registry.get(id(peng))
+        if sub is None:
+            sub = SVCostEvaluator(peng, None, [e for e in self.projected if e.num_qubits < peng.num_qubits],
+                                  registry=self._registry)
+        return sub
+
+    def _bra_into(self, slot, window):
+        """slot <- window^+ |0..0> on this engine.  The longest tail of `window` that fits a smaller engine is built THERE
+        (recursively) and embedded with one write pass (``scatter``); only the remaining head gates run at this size."""
+        eng, stream = self.eng, G.GateStream.from_window
+        if self.projected and hasattr(eng, "scatter") and len(window):
+            kmax = max((e.num_qubits for e in self.projected if e.num_qubits + self.min_saving() <= eng.num_qubits), default=0)
+            supp, m = set(), len(window)
+            for (s0, _, sp) in reversed(partition_blocks(window)):
+                new = supp | set(sp)
+                if len(new) > kmax:
+                    break
+                supp, m = new, s0
+            if m < len(window):
+                peng = [e for e in self.projected if e.num_qubits >= len(supp)][0]
+                supp = sorted(supp)
+                used = set(supp)
+                qmap = supp + [q for q in range(eng.num_qubits) if q not in used][:peng.num_qubits - len(supp)]
+                pos = {q: c for c, q in enumerate(qmap)}
+                tail = [(e[0], pos[e[1]], pos[e[2]] if e[2] >= 0 else -1) + tuple(e[3:]) for e in window[m:]]
+                self._sub_for(peng)._bra_into(SLOT_WORK, tail)
+                eng.scatter(slot, list(qmap), peng, SLOT_WORK)
+                if m > 0:
+                    eng.run(slot, slot, stream(window[:m]), inverse=True)
+                self.stats["scattered_L"] = self.stats.get("scattered_L", 0) + 1
+                return
+        eng.run(slot, -1, stream(window), inverse=True)
 
     def _projected(self, window, target, changed):
         """If window[target] lies in the projected tail: (nested evaluator, tail window in the engine's qubit
@@ -487,17 +527,21 @@ class SVCostEvaluator:
         if info[1] is None:
             return None
         peng, qmap, pos, sub = info[1]
-        if (m > 0 and changed is not None and self._proj_state is not None and self._proj_state[1] == m
+        ps = self._proj_state
+        if ps is not None and sub.base_key is not ps[4]:
+            ps = self._proj_state = None      # another level has projected into that engine since
+        if (m > 0 and changed is not None and ps is not None and ps[1] == m
                 and self.rwin is not None and len(self.rwin) == m and all(i >= m for i in changed)):
             r_changed = False        # only tail gates changed since phi was gathered from this R
         else:
             r_changed = self._update_R(window, m) if m > 0 else False
         state = (id(peng), m, qmap, self.base_key)
-        if r_changed or state != self._proj_state:
+        if r_changed or ps is None or state != ps[:4]:
             self.eng.gather(self.r_slot if m > 0 else SLOT_BASE, list(qmap), peng, SLOT_BASE)
-            sub.base_key = ("projected", self.stats["projections"])
+            token = ("projected", id(self), self.stats["projections"])
+            sub.base_key = token
             sub.invalidate()
-            self._proj_state = state
+            self._proj_state = state + (token,)
             self.stats["projections"] += 1
             self._tail_cache = None
         # the dense evaluator's T / window no longer describe the circuit once the tail is edited here
@@ -505,6 +549,7 @@ class SVCostEvaluator:
         self.window = None
         tc = self._tail_cache
         sub_changed = None
+        state = self._proj_state
         if (tc is not None and tc[0] == state and len(tc[1]) == len(window) - m and changed is not None
                 and all(i >= m for i in changed)):
             tail = tc[1]
@@ -564,20 +609,10 @@ class SVCostEvaluator:
                 eng.run(SLOT_L, SLOT_L, stream(sfx[:sn - so]), inverse=True)
                 self.lwin = list(sfx); self.l_moves += 1; self.stats["moves_L"] += 1
                 return True
-        # rebuild.  When the suffix contains the whole projected tail, tail^+ |0> is supported on the tail's K
-        # qubits: build it on the K-qubit engine (cheap sweeps), embed it into the register (one write pass)
-        # and apply only the remaining head gates with sweeps over 2^n
-        split = self._tail_split(new) if (self.projected and self.dense_blocks) else None
-        info = self._proj_info(split)[1] if split is not None else None
-        if info is not None and b1 <= split[0] < len(new) and hasattr(eng, "scatter"):
-            m = split[0]
-            peng, qmap, pos, _ = info
-            tail = [(e[0], pos[e[1]], pos[e[2]] if e[2] >= 0 else -1) + tuple(e[3:]) for e in new[m:]]
-            peng.run(SLOT_WORK, -1, stream(tail), inverse=True)
-            eng.scatter(SLOT_L, list(qmap), peng, SLOT_WORK)
-            if b1 < m:
-                eng.run(SLOT_L, SLOT_L, stream(new[b1:m]), inverse=True)
-            self.stats["scattered_L"] = self.stats.get("scattered_L", 0) + 1
+        # rebuild: suffix^+ |0> is supported on the qubits the suffix touches -- built on the smaller engines as far as it
+        # fits them (cheap sweeps), embedded level by level, only the remaining head gates are applied at this size
+        if self.dense_blocks:
+            self._bra_into(SLOT_L, sfx)
         else:
             eng.run(SLOT_L, -1, stream(sfx), inverse=True)
         self.lwin = list(sfx)
@@ -686,6 +721,8 @@ class SVCostEvaluator:
     _tkey = None
     _t_sfx = None
     _gw = None          # (k, w): gate-context cache of the open block, see _gate_context
+    _hot = None         # (k, w, window length, qubit): the gate the optimiser is working on, see amp0
+    _hot_dirty = False  # a hot-path value was served: the nested levels have not seen that gate's latest entry
 
     def _gate_context(self, window, k):
         """(w00, w01, w10, w11), Python complex, such that for ANY 2x2 matrix m placed at window position k of the open
@@ -735,6 +772,23 @@ class SVCostEvaluator:
         structure changed).  `changed`: indices at which `window` differs from the previous call's
         window (None = unknown), so that edits inside the open block skip all bookkeeping."""
         self.stats["evals"] += 1
+        # HOT PATH: the optimiser asks for another value of the gate it has just been given a value for
+        # (cost_minimiser.py:356-363: theta = 0, pi/2, -pi/2 of ONE gate; 7 values in Rotoselect) and nothing else
+        # changed: the gate context w computed by whichever nested level owns that gate still holds, the value is four
+        # complex multiplications -- no block bookkeeping, no descent through the projection levels.  The levels below
+        # have then not seen the latest entry of that gate: it is added to `changed` when the hot path is left.
+        hot = self._hot
+        if hot is not None:
+            if (changed is not None and len(changed) == 1 and changed[0] == hot[0] and len(window) == hot[2]
+                    and window[hot[0]][2] < 0 and window[hot[0]][1] == hot[3]):
+                self._hot_dirty = True
+                self.stats["hot_evals"] = self.stats.get("hot_evals", 0) + 1
+                w = hot[1]
+                m = G.matrix_of_entry_complex(window[hot[0]])
+                return m[0] * w[0] + m[1] * w[1] + m[2] * w[2] + m[3] * w[3]
+            if self._hot_dirty and changed is not None:
+                changed = sorted(set(changed) | {hot[0]})
+            self._hot, self._hot_dirty = None, False
         if len(window) == 0:
             self.invalidate()
             return self.eng.amp(SLOT_BASE, 0)
@@ -744,7 +798,13 @@ class SVCostEvaluator:
             if pj is not None:
                 sub, tail, sub_changed, m = pj
                 self.stats["projected_evals"] += 1
-                return sub.amp0(tail, focus=None if focus is None else max(focus - m, 0), changed=sub_changed)
+                out = sub.amp0(tail, focus=None if focus is None else max(focus - m, 0), changed=sub_changed)
+                sh = sub._hot
+                if sh is not None and not sub._hot_dirty:
+                    e = window[sh[0] + m]
+                    self._hot = (sh[0] + m, sh[1], len(window), e[1])      # the same context, in this level's numbering
+                    sub._hot = None                                          # (only the top level takes the hot path)
+                return out
         if not self.dense_blocks and not self._open_block_ok(window, changed) \
                 and not self._compact_ok(window, self._select_block(window, focus, changed)):
             self.stats["resimulations"] = self.stats.get("resimulations", 0) + 1
@@ -770,6 +830,7 @@ class SVCostEvaluator:
                     self._gw = None            # another gate of the block changed: its context is stale
                 self.stats["host_evals"] += 1
                 w = self._gate_context(window, k)
+                self._hot = (k, w, len(window), window[k][1])
                 m = G.matrix_of_entry_complex(window[k])
                 return m[0] * w[0] + m[1] * w[1] + m[2] * w[2] + m[3] * w[3]
             self._gw = None
@@ -782,6 +843,7 @@ class SVCostEvaluator:
             if k is not None and window[k][2] < 0:
                 self.stats["host_evals"] += 1
                 w = self._gate_context(window, k)
+                self._hot = (k, w, len(window), window[k][1])
                 m = G.matrix_of_entry_complex(window[k])
                 return m[0] * w[0] + m[1] * w[1] + m[2] * w[2] + m[3] * w[3]
         self.stats["host_evals"] += 1
@@ -790,6 +852,10 @@ class SVCostEvaluator:
     # ---- batched API (K6): every shift value of one gate from one transfer pass ----
     def shift_amplitudes(self, window, k, candidates, changed=None):
         """<0|psi> for each replacement 2x2 matrix in `candidates` at window position k.  `changed`: as in amp0."""
+        if self._hot is not None:
+            if self._hot_dirty and changed is not None:
+                changed = sorted(set(changed) | {self._hot[0]})
+            self._hot, self._hot_dirty = None, False
         if self.projected:
             pj = self._projected(window, k, changed)
             if pj is not None:

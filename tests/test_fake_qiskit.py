@@ -66,7 +66,9 @@ def test_fresh_instruction_objects_keep_the_incremental_fast_path(fake_engine_ba
         stats[kind]["engine_runs"] = runs
     np.testing.assert_allclose(costs["fresh"], costs["identity"], rtol=0, atol=1e-13)
     assert stats["fresh"] == stats["identity"], (stats["fresh"], stats["identity"])
-    assert stats["fresh"]["host_evals"] > 10 * (stats["fresh"]["t_passes"] + stats["fresh"]["t_gathers"])
+    served_on_host = stats["fresh"]["host_evals"] + stats["fresh"].get("hot_evals", 0)
+    assert served_on_host > 10 * (stats["fresh"]["t_passes"] + stats["fresh"]["t_gathers"])
+    assert stats["fresh"].get("hot_evals", 0) > 0          # repeated values of one gate: four multiplications each
     # and the values are right
     ocomp = AdaptCompiler(target, backend=OracleSVBackend())
     ocomp.full_circuit.data.extend(ansatz.copy().data)

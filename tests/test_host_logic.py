@@ -27,7 +27,9 @@ def fake_backend(emu, monkeypatch, request):
             if compact_k is not None and num_qubits > compact_k:
                 compact = FakeEngine(emu, compact_k, n_slots=1)
             projected = None
-            if proj_k is not None and num_qubits >= proj_k + SVCostEvaluator.PROJECT_MIN_SAVING:
+            if isinstance(proj_k, (list, tuple)):      # nested projection levels
+                projected = [FakeEngine(emu, k, n_slots=4) for k in proj_k if k < num_qubits]
+            elif proj_k is not None and num_qubits >= proj_k + SVCostEvaluator.PROJECT_MIN_SAVING:
                 projected = [FakeEngine(emu, proj_k, n_slots=4)]
             self._evaluator = SVCostEvaluator(self._engine, compact, projected)
             self._state_version += 1
@@ -35,6 +37,49 @@ def fake_backend(emu, monkeypatch, request):
         return self._engine
     monkeypatch.setattr(B200SVBackend, "_get_engine", _get_engine)
     return B200SVBackend()
+
+
+@pytest.fixture
+def nested_levels(monkeypatch):
+    """Registers of >= 8 qubits project onto engines ONE qubit smaller (production: >= 20 qubits), so that the small
+    CPU stand-in engines exercise the multi-level nesting of the 28-qubit runs."""
+    monkeypatch.setattr(SVCostEvaluator, "LARGE_QUBITS", 8)
+
+
+@pytest.mark.parametrize("fake_backend", [(None, (6, 8, 10, 11)), (5, (7, 9, 11))], indirect=True)
+def test_nested_projection_levels_equal_full_resimulation(fake_backend, nested_levels):
+    """The evaluator of a K-qubit projected engine projects its own tail onto the next smaller engine (one evaluator per
+    engine, shared through the registry); edits walk across all levels and back; every cost equals the oracle's full
+    re-simulation."""
+    n = 12
+    rng = np.random.default_rng(7)
+    target, trng = brickwork(n, 3, seed=5)
+    ansatz = thin_ansatz(n, 9, trng)
+    comp = AdaptCompiler(target, backend=fake_backend)
+    comp.full_circuit.data.extend(ansatz.data)
+    ocomp = AdaptCompiler(target, backend=OracleSVBackend())
+    ocomp.full_circuit.data.extend(ansatz.copy().data)
+    rot = [i for i in range(*comp.variational_circuit_range())
+           if comp.full_circuit.data[i].operation.name in ("rx", "ry", "rz")]
+    order = rot + rot[::-1] + [rot[int(rng.integers(len(rot)))] for _ in range(30)]
+    for step, idx in enumerate(order):
+        for rep in range(1 + step % 2):
+            name = ["rx", "ry", "rz"][int(rng.integers(3))]
+            theta = float(rng.uniform(-np.pi, np.pi))
+            for c in (comp, ocomp):
+                replace_1q_gate(c.full_circuit, idx, name, theta)
+            assert abs(comp.evaluate_cost() - ocomp.evaluate_cost()) < 1e-10, (step, idx)
+    ev = fake_backend._evaluator
+    levels = [e for e in ev._registry.values() if e is not ev and e.stats["evals"] > 0]
+    assert len(levels) >= 3, [e.eng.num_qubits for e in levels]          # at least three nested levels did work
+    assert sum(e.stats["projections"] for e in levels) > 0                # ... and projected further down themselves
+    # the Rotosolve / Rotoselect stream of the bench step through the same levels
+    lo, hi = comp.variational_circuit_range()
+    olo, ohi = ocomp.variational_circuit_range()
+    a = comp.minimizer._reduce_cost(True, (hi - 5, hi)); b = ocomp.minimizer._reduce_cost(True, (ohi - 5, ohi))
+    assert abs(a - b) < 1e-9
+    a = comp.minimizer._reduce_cost(False, (lo, hi)); b = ocomp.minimizer._reduce_cost(False, (olo, ohi))
+    assert abs(a - b) < 1e-9
 
 
 @pytest.mark.parametrize("fake_backend", [None, 6, (None, 8), (4, 8)], indirect=True)
