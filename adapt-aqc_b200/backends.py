@@ -56,18 +56,21 @@ except Exception:  # noqa: BLE001
 COMPACT_QUBITS = (12, 19, 26)
 COMPACT_MIN_QUBITS = 12
 # Projected tail (SVCostEvaluator): K-qubit engines (4 slots each) on which the blocks of the window are optimised once
-# the remaining gates touch at most K qubits -- nested: the evaluator of a K-qubit engine projects ITS tail onto the next
-# smaller one.  Sizes: n-1, n-2, then every second size down to 12 (each thin layer adds at most two qubits to the support
-# of the gates behind it), at most 28 qubits (4 x 4 GiB).  B200AQC_PROJECT=0 disables.
-PROJECT_QUBITS = (16, 20, 24)          # the sizes round 1 used (kept for the sharded backend's replicated engines)
+# the remaining gates touch at most K qubits.  Sizes 16 / 20 / 24 as in round 1, plus every second size from 26 up to
+# n - 2: the evaluators of those LARGE engines project their own tail one level further down (nesting), so that a block
+# whose suffix touches 26 of 28 qubits costs passes over 2^26 amplitudes instead of 2^28.  Nesting all the way down
+# (n-1, n-2, n-4, ... 12) was measured and is SLOWER (profiles/r2h_hostprof.txt: 8404 vs 9746 evals/s): every level pays a
+# gather, two stream synchronisations and its own bra rebuild per optimiser cycle, which only the passes over >= 2^26
+# amplitudes win back.  B200AQC_PROJECT=0 disables.
+PROJECT_QUBITS = (16, 20, 24)
 PROJECT_MAX_QUBITS = 28
 
 
 def project_sizes(num_qubits, limit=None):
-    """Engine sizes of the nested projection levels below a `num_qubits` register, ascending."""
-    top = min(num_qubits - 1, PROJECT_MAX_QUBITS, limit if limit is not None else num_qubits)
-    sizes = {k for k in (top, top - 1) if k >= COMPACT_MIN_QUBITS}
-    sizes.update(range(top - 3, COMPACT_MIN_QUBITS - 1, -2))
+    """Engine sizes of the projection levels below a `num_qubits` register, ascending."""
+    top = min(num_qubits - 2, PROJECT_MAX_QUBITS, limit if limit is not None else num_qubits)
+    sizes = {k for k in PROJECT_QUBITS if COMPACT_MIN_QUBITS <= k <= min(top, num_qubits - SVCostEvaluator.PROJECT_MIN_SAVING)}
+    sizes.update(range(26, top + 1, 2))
     return sorted(sizes)
 
 

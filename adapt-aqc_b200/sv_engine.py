@@ -338,6 +338,7 @@ class SVCostEvaluator:
     REFRESH_MOVES = 256  # rebuild R / dense L from scratch after this many incremental moves
     PROJECT_MIN_SAVING = 3  # project only onto engines at least this many qubits smaller than the register ...
     LARGE_QUBITS = 20       # ... or at least ONE qubit smaller once the register has this many qubits (see min_saving)
+    NEST_MIN_QUBITS = 26    # the evaluator of a projected engine of at least this size projects its own tail further down
 
     def __init__(self, engine, compact=None, projected=None, registry=None):
         """projected: optional K-qubit engines (4 slots each, same device) for the PROJECTED TAIL: once the
@@ -485,8 +486,8 @@ class SVCostEvaluator:
         projected tail goes to the smaller engines (no compact-bra engines: they belong to the top level)."""
         sub = self._registry.get(id(peng))
         if sub is None:
-            sub = SVCostEvaluator(peng, None, [e for e in self.projected if e.num_qubits < peng.num_qubits],
-                                  registry=self._registry)
+            nested = [e for e in self.projected if e.num_qubits < peng.num_qubits] if peng.num_qubits >= self.NEST_MIN_QUBITS else []
+            sub = SVCostEvaluator(peng, None, nested, registry=self._registry)
         return sub
 
     def _bra_into(self, slot, window):

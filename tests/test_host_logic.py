@@ -44,6 +44,7 @@ def nested_levels(monkeypatch):
     """Registers of >= 8 qubits project onto engines ONE qubit smaller (production: >= 20 qubits), so that the small
     CPU stand-in engines exercise the multi-level nesting of the 28-qubit runs."""
     monkeypatch.setattr(SVCostEvaluator, "LARGE_QUBITS", 8)
+    monkeypatch.setattr(SVCostEvaluator, "NEST_MIN_QUBITS", 6)
 
 
 @pytest.mark.parametrize("fake_backend", [(None, (6, 8, 10, 11)), (5, (7, 9, 11))], indirect=True)
