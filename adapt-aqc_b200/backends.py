@@ -55,13 +55,13 @@ except Exception:  # noqa: BLE001
 # COMPACT_MIN_QUBITS qubits are cheap enough to always use the dense path.
 COMPACT_QUBITS = (12, 19, 26)
 COMPACT_MIN_QUBITS = 12
-# Projected tail (SVCostEvaluator): K-qubit engines (4 slots each) on which the blocks of the window are optimised once
-# the remaining gates touch at most K qubits.  Sizes 16 / 20 / 24 as in round 1, plus every second size from 26 up to
-# n - 2: the evaluators of those LARGE engines project their own tail one level further down (nesting), so that a block
-# whose suffix touches 26 of 28 qubits costs passes over 2^26 amplitudes instead of 2^28.  Nesting all the way down
-# (n-1, n-2, n-4, ... 12) was measured and is SLOWER (profiles/r2h_hostprof.txt: 8404 vs 9746 evals/s): every level pays a
-# gather, two stream synchronisations and its own bra rebuild per optimiser cycle, which only the passes over >= 2^26
-# amplitudes win back.  B200AQC_PROJECT=0 disables.
+# Projected tail (SVCostEvaluator): K-qubit engines (4 slots each; 1 GiB in total at K = 24) on which the blocks of the
+# window are optimised once the remaining gates touch at most K qubits.  B200AQC_PROJECT=0 disables.
+# The evaluator supports NESTED levels (the evaluator of a large projected engine projects its own tail further down:
+# sizes 26, 28, ... with B200AQC_NEST=1).  Measured on C3 (profiles/r2_hostprof.md) nesting is SLOWER -- 9746 evals/s flat,
+# 9027 with one nested level (28 -> 26 -> 24), 8404 nested all the way down: every level pays a gather, two stream
+# synchronisations and its own bra rebuild per optimiser cycle, and blocks that had a compact bra (gather-based transfer
+# matrix) fall back to dense passes -- so it stays off by default.
 PROJECT_QUBITS = (16, 20, 24)
 PROJECT_MAX_QUBITS = 28
 
@@ -70,7 +70,8 @@ def project_sizes(num_qubits, limit=None):
     """Engine sizes of the projection levels below a `num_qubits` register, ascending."""
     top = min(num_qubits - 2, PROJECT_MAX_QUBITS, limit if limit is not None else num_qubits)
     sizes = {k for k in PROJECT_QUBITS if COMPACT_MIN_QUBITS <= k <= min(top, num_qubits - SVCostEvaluator.PROJECT_MIN_SAVING)}
-    sizes.update(range(26, top + 1, 2))
+    if os.environ.get("B200AQC_NEST", "0") == "1":
+        sizes.update(range(26, top + 1, 2))
     return sorted(sizes)
 
 
