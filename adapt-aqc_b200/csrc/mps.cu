@@ -293,9 +293,14 @@ int apply_adjacent(b200_mps* m, int i, const cplx u4[16]) {
         const size_t jb_smem = (size_t)2 * WB * (p + q) * sizeof(double2);
         if (ctx->coop_ok && jb_smem <= 200 * 1024 && !std::getenv("B200AQC_JACOBI_SCALAR")) {
             const int NB = (((q + WB - 1) / WB) + 1) & ~1;
-            CUDA_TRY(cudaFuncSetAttribute(jacobi_block_kernel<WB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            // default: block Jacobi through the Gram matrix of the block pair (jacobi_gram_kernel); B200AQC_JACOBI=rot keeps
+            // the round-1 body (one plane rotation per cross pair per round) as the measured alternative
+            const char* jmode = std::getenv("B200AQC_JACOBI");
+            const void* jkernel = (jmode && std::strcmp(jmode, "rot") == 0) ? (const void*)jacobi_block_kernel<WB>
+                                                                             : (const void*)jacobi_gram_kernel<WB>;
+            CUDA_TRY(cudaFuncSetAttribute(jkernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_block_kernel<WB>, JB_GROUP * WB, jb_smem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jkernel, JB_GROUP * WB, jb_smem));
             if ((long long)per_sm * ctx->num_sms >= NB / 2) {
                 CUDA_TRY(cudaMemsetAsync(st->flag.p, 0, 4 * sizeof(int), s));
                 double2* Xp = (double2*)st->X.p; double2* Wp = (double2*)st->W.p;
@@ -304,7 +309,7 @@ int apply_adjacent(b200_mps* m, int i, const cplx u4[16]) {
                 void* args[] = {&Xp, &Wp, &pp, &qq, &NN, &ms_, &fr, &ctrl};
                 {
                     MScope ms(ctx, B200_PROF_SVD);
-                    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)jacobi_block_kernel<WB>, dim3(NB / 2), dim3(JB_GROUP * WB), args, jb_smem, s));
+                    CUDA_TRY(cudaLaunchCooperativeKernel(jkernel, dim3(NB / 2), dim3(JB_GROUP * WB), args, jb_smem, s));
                 }
                 int done[3] = {0, 0, 0};
                 CUDA_TRY(cudaMemcpyAsync(done, st->flag.p, sizeof done, cudaMemcpyDeviceToHost, s));
