@@ -293,11 +293,10 @@ int apply_adjacent(b200_mps* m, int i, const cplx u4[16]) {
         const size_t jb_smem = (size_t)2 * WB * (p + q) * sizeof(double2);
         if (ctx->coop_ok && jb_smem <= 200 * 1024 && !std::getenv("B200AQC_JACOBI_SCALAR")) {
             const int NB = (((q + WB - 1) / WB) + 1) & ~1;
-            // default: block Jacobi through the Gram matrix of the block pair (jacobi_gram_kernel); B200AQC_JACOBI=rot keeps
-            // the round-1 body (one plane rotation per cross pair per round) as the measured alternative
-            const char* jmode = std::getenv("B200AQC_JACOBI");
-            const void* jkernel = (jmode && std::strcmp(jmode, "rot") == 0) ? (const void*)jacobi_block_kernel<WB>
-                                                                             : (const void*)jacobi_gram_kernel<WB>;
+            // (A variant that orthogonalises the whole block pair per round through its 8x8 Gram matrix -- one warp
+            // diagonalises it, one pass applies the accumulated unitary -- was built and measured in round 2: same sweep
+            // count, 73.9 ms instead of 40.0 ms per 512x512 SVD: profiles/r2j_svd_gram_negative.txt.  Removed.)
+            const void* jkernel = (const void*)jacobi_block_kernel<WB>;
             CUDA_TRY(cudaFuncSetAttribute(jkernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             int per_sm = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jkernel, JB_GROUP * WB, jb_smem));

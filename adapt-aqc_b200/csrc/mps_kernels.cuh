@@ -628,180 +628,6 @@ jacobi_block_kernel(double2* __restrict__ X, double2* __restrict__ W, const int 
     if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[2] = sweep;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Block Jacobi through the Gram matrix of the block pair (round 2).  Same tournament over block pairs, same grid
-// barrier per outer round, but inside a round the 2*WB columns held in shared memory are orthogonalised COMPLETELY:
-//   1. G = Xb^H Xb (2WB x 2WB Hermitian): every entry is one warp's length-p inner product, no cross-warp reduction;
-//   2. one warp diagonalises G by cyclic Jacobi (WB disjoint pairs per step, column phase then row phase), accumulating
-//      the unitary V; rotation criterion and formulas are those of jacobi_rotate (|g_ij| <= tol sqrt(g_ii g_jj) skips);
-//   3. [Xb; Wb] <- [Xb; Wb] V in ONE pass over the rows (each thread: its rows x 2WB columns, V broadcast from smem).
-// A round therefore costs two block-wide barriers instead of 2*WB (the old body: inner product -> barrier -> rotation
-// -> barrier per local step, latency-bound: ncu stall barrier 2.0 / short_scoreboard 2.6 per issue), and it removes ALL
-// 2WB(2WB-1)/2 couplings of the pair, not only the WB^2 cross pairs once -- fewer outer sweeps.  Whether a sweep
-// "rotated" is still decided on inner products of the actual columns (step 1), so the stopping rule is unchanged.
-template <int WB>
-__global__ void __launch_bounds__(JB_GROUP * WB, 1)
-jacobi_gram_kernel(double2* __restrict__ X, double2* __restrict__ W, const int p, const int q, const int NB,
-                   const int max_sweeps, const double* __restrict__ fro2, int* __restrict__ ctrl) {
-    extern __shared__ __align__(16) double2 jb_smem[];
-    constexpr int C = 2 * WB;
-    constexpr int NT = JB_GROUP * WB;
-    __shared__ double2 Gs[C][C + 1];
-    __shared__ double2 Vs[C][C + 1];
-    __shared__ int s_rot;
-    static_assert(WB * C <= 32, "one warp diagonalises the Gram matrix: WB pairs x 2WB lanes");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int NW = NT / 32;
-    const int ld = p + q;
-    const double tiny2 = 1e-34 * (*fro2);
-    const double tol = jacobi_tol(p);
-    unsigned* bar = (unsigned*)(ctrl + 3);
-    unsigned epoch = 0;
-    int sweep = 0;
-    for (; sweep < max_sweeps; ++sweep) {
-        int* flag = ctrl + (sweep & 1);
-        int mine = 0;
-        for (int r = 0; r < NB - 1; ++r) {
-            int A, B;
-            rr_pair(NB, r, blockIdx.x, A, B);
-            jb_copy<WB, NT, true>(jb_smem, X, p, q, 0, ld, A, B);
-            jb_copy<WB, NT, true>(jb_smem, W, q, q, p, ld, A, B);
-            for (int cc = 0; cc < C; ++cc) {      // padding columns (beyond q) count as zero columns
-                const int col = cc < WB ? A * WB + cc : B * WB + (cc - WB);
-                if (col >= q)
-                    for (int k = threadIdx.x; k < ld; k += NT) jb_smem[(size_t)cc * ld + k] = make_double2(0.0, 0.0);
-            }
-            if (threadIdx.x == 0) s_rot = 0;
-            __syncthreads();
-            // ---- 1. Gram matrix of the 2WB columns (X rows only) ----
-            for (int e = warp; e < C * (C + 1) / 2; e += NW) {
-                int i = 0, rem = e;
-                while (rem >= C - i) { rem -= C - i; ++i; }
-                const int j = i + rem;
-                const int ci = i < WB ? A * WB + i : B * WB + (i - WB);
-                const int cj = j < WB ? A * WB + j : B * WB + (j - WB);
-                double gr = 0, gi = 0;
-                if (ci < q && cj < q) {
-                    const double2* ca = jb_smem + (size_t)i * ld;
-                    const double2* cb = jb_smem + (size_t)j * ld;
-#pragma unroll 4
-                    for (int k = lane; k < p; k += 32) {
-                        const double2 u = ca[k], v = cb[k];
-                        gr = fma(u.x, v.x, fma(u.y, v.y, gr));      // conj(u) * v
-                        gi = fma(u.x, v.y, fma(-u.y, v.x, gi));
-                    }
-                }
-                gr = warp_sum_d(gr); gi = warp_sum_d(gi);
-                if (lane == 0) {
-                    Gs[i][j] = make_double2(gr, i == j ? 0.0 : gi);
-                    if (i != j) Gs[j][i] = make_double2(gr, -gi);
-                }
-            }
-            for (int e = threadIdx.x; e < C * C; e += NT) Vs[e / C][e % C] = make_double2(e / C == e % C ? 1.0 : 0.0, 0.0);
-            __syncthreads();
-            // ---- 2. warp 0: cyclic Jacobi on G, V accumulated ----
-            if (warp == 0) {
-                const int pr = lane / C, rr = lane % C;      // pair slot of the step (WB pairs x C lanes = 32 lanes for WB = 4)
-                int any_outer = 0;
-                for (int isweep = 0; isweep < 12; ++isweep) {
-                    int rotated = 0;
-                    for (int t = 0; t < C - 1; ++t) {
-                        int i = 0, j = 0;
-                        bool act = pr < WB;
-                        if (act) rr_pair(C, t, pr, i, j);
-                        const int ci = i < WB ? A * WB + i : B * WB + (i - WB);
-                        const int cj = j < WB ? A * WB + j : B * WB + (j - WB);
-                        double c = 1.0;
-                        double2 sm = make_double2(0.0, 0.0), sp = make_double2(0.0, 0.0);
-                        bool rot = false;
-                        if (act && ci < q && cj < q) {
-                            const double al = Gs[i][i].x, be = Gs[j][j].x;
-                            const double2 gij = Gs[i][j];
-                            const double g = sqrt(gij.x * gij.x + gij.y * gij.y);
-                            if (!(g == 0.0 || g <= tol * sqrt(al * be) || al <= tiny2 || be <= tiny2)) {
-                                const double zeta = (be - al) / (2.0 * g);
-                                const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                                c = 1.0 / sqrt(1.0 + tt * tt);
-                                const double sn = c * tt;
-                                const double2 ph = make_double2(gij.x / g, gij.y / g);
-                                sm = make_double2(-sn * ph.x, sn * ph.y);
-                                sp = make_double2(sn * ph.x, sn * ph.y);
-                                rot = true;
-                            }
-                        }
-                        __syncwarp();
-                        if (rot) {      // column phase: G <- G J, V <- V J  (row rr of columns i, j)
-                            const double2 u = Gs[rr][i], v = Gs[rr][j];
-                            double2 nu = z_mul(sm, v); nu.x = fma(c, u.x, nu.x); nu.y = fma(c, u.y, nu.y);
-                            double2 nv = z_mul(sp, u); nv.x = fma(c, v.x, nv.x); nv.y = fma(c, v.y, nv.y);
-                            Gs[rr][i] = nu; Gs[rr][j] = nv;
-                            const double2 a = Vs[rr][i], b = Vs[rr][j];
-                            double2 na = z_mul(sm, b); na.x = fma(c, a.x, na.x); na.y = fma(c, a.y, na.y);
-                            double2 nb = z_mul(sp, a); nb.x = fma(c, b.x, nb.x); nb.y = fma(c, b.y, nb.y);
-                            Vs[rr][i] = na; Vs[rr][j] = nb;
-                        }
-                        __syncwarp();
-                        if (rot) {      // row phase: G <- J^H G  (column rr of rows i, j)
-                            const double2 u = Gs[i][rr], v = Gs[j][rr];
-                            const double2 smc = make_double2(sm.x, -sm.y), spc = make_double2(sp.x, -sp.y);
-                            double2 nu = z_mul(smc, v); nu.x = fma(c, u.x, nu.x); nu.y = fma(c, u.y, nu.y);
-                            double2 nv = z_mul(spc, u); nv.x = fma(c, v.x, nv.x); nv.y = fma(c, v.y, nv.y);
-                            Gs[i][rr] = nu; Gs[j][rr] = nv;
-                        }
-                        __syncwarp();
-                        if (rot && rr == 0) {   // the rotated 2x2 block is diagonal and real on the diagonal: make it exact
-                            Gs[i][j] = make_double2(0.0, 0.0); Gs[j][i] = make_double2(0.0, 0.0);
-                            Gs[i][i].y = 0.0; Gs[j][j].y = 0.0;
-                        }
-                        __syncwarp();
-                        rotated |= __any_sync(0xffffffffu, rot) ? 1 : 0;
-                    }
-                    any_outer |= rotated;
-                    if (!rotated) break;
-                }
-                if (lane == 0) { s_rot = any_outer; }
-            }
-            __syncthreads();
-            // ---- 3. [Xb; Wb] <- [Xb; Wb] V (skipped when nothing rotated) ----
-            if (s_rot) {
-                mine = 1;
-                // (V is read from shared memory inside the row loop -- broadcast loads; hoisted into registers its
-                // 2WB x 2WB complex entries spill)
-                const volatile double* Vv = reinterpret_cast<const volatile double*>(&Vs[0][0]);
-#pragma unroll 1
-                for (int k = threadIdx.x; k < ld; k += NT) {
-                    double2 x[C], y[C];
-#pragma unroll
-                    for (int cc = 0; cc < C; ++cc) x[cc] = jb_smem[(size_t)cc * ld + k];
-#pragma unroll
-                    for (int cc = 0; cc < C; ++cc) {
-                        double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-                        for (int d = 0; d < C; ++d) {
-                            const double2 v = make_double2(Vv[2 * (d * (C + 1) + cc)], Vv[2 * (d * (C + 1) + cc) + 1]);
-                            acc.x = fma(x[d].x, v.x, fma(-x[d].y, v.y, acc.x));
-                            acc.y = fma(x[d].x, v.y, fma(x[d].y, v.x, acc.y));
-                        }
-                        y[cc] = acc;
-                    }
-#pragma unroll
-                    for (int cc = 0; cc < C; ++cc) jb_smem[(size_t)cc * ld + k] = y[cc];
-                }
-                __syncthreads();
-                jb_copy<WB, NT, false>(jb_smem, X, p, q, 0, ld, A, B);
-                jb_copy<WB, NT, false>(jb_smem, W, q, q, p, ld, A, B);
-            }
-            jacobi_grid_barrier(bar, ++epoch * gridDim.x);
-        }
-        if (__syncthreads_or(mine) && threadIdx.x == 0) atomicOr(flag, 1);
-        if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[(sweep + 1) & 1] = 0;   // next sweep's flag
-        jacobi_grid_barrier(bar, ++epoch * gridDim.x);
-        const int any = *((volatile int*)flag);
-        if (!any) { ++sweep; break; }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[2] = sweep;
-}
-
 // fro2[0] = |X|_F^2 (one CTA)
 __global__ void __launch_bounds__(256)
 jacobi_fro_kernel(const double2* __restrict__ X, const size_t nelem, double* __restrict__ fro2) {
