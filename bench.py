@@ -693,7 +693,7 @@ def main():
     ap.add_argument("--no-sharded", action="store_true")
     ap.add_argument("--no-compile", action="store_true", help="skip the compile wall-time leg")
     ap.add_argument("--compile-layers", type=int, default=6)
-    ap.add_argument("--converging-layers", type=int, default=12, help="thin layers of the compilable target")
+    ap.add_argument("--converging-layers", type=int, default=6, help="thin layers of the compilable target")
     ap.add_argument("--converging-max-layers", type=int, default=400)
     ap.add_argument("--no-converging", action="store_true", help="skip the converging compile leg")
     ap.add_argument("--sharded-compile-layers", type=int, default=4)
