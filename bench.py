@@ -70,7 +70,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -863,6 +863,18 @@ def main():
         except Exception as exc:  # noqa: BLE001
             sharded = {"error": repr(exc)}
         line["sharded_c5"] = sharded
+    if dist is not None:
+        # the paths that actually USE several GPUs for one problem, side by side (the headline `value` of an N > 1 line is
+        # N independent replicas of the C3 stream: throughput, not scaling)
+        sh, pd = line.get("sharded_c5") or {}, line.get("compile_c3_pairs_divided") or {}
+        line["multi_gpu_paths"] = {
+            "c5_qubits": sh.get("qubits"), "c5_s_per_eval": sh.get("s_per_eval"), "c5_sweeps_per_eval": sh.get("sweeps_per_eval"),
+            "c5_exchanges_per_eval": sh.get("exchanges_per_eval"), "c5_nvlink_GBps_per_direction": sh.get("nvlink_GBps_per_direction"),
+            "c5_compile_wall_s": (sh.get("compile") or {}).get("wall_s"), "c5_compile_qubits": (sh.get("compile") or {}).get("workload", "")[:8],
+            "c3_all_to_all_compile_wall_s": {k: (pd.get(k) or {}).get("wall_s") for k in ("divided", "undivided")},
+            "c3_rdm_kernel_ms_max_over_ranks": {k: (pd.get(k) or {}).get("rdm_kernel_ms_max_over_ranks") for k in ("divided", "undivided")},
+            "c3_same_pairs": pd.get("same_pairs"),
+        }
     if rank == 0:
         print(json.dumps(line), file=RESULT_OUT, flush=True)
     if dist is not None:
