@@ -384,7 +384,7 @@ def bench_mps(args, device, with_cpu=True):
 
 
 # ---- compile wall-time (BASELINE metric, second half): a whole ADAPT-AQC compile of C3 -----------
-def bench_compile_converging(args, device, pair_comm=None):
+def bench_compile_converging(args, device, pair_comm=None, cpu_s_per_fused_sweep=None):
     """Compile WALL-TIME on a target ADAPT-AQC actually compiles (harness.workloads.compilable_target): the run ends by
     reaching the reference's sufficient cost 1e-2 (adapt_compiler.py:368-393), default AdaptConfig, default all-to-all
     coupling map (P = 378 pair RDMs per layer).  pair_comm: divide the pair-RDM passes over the ranks."""
@@ -416,6 +416,18 @@ def bench_compile_converging(args, device, pair_comm=None):
            "kernel_ms": {k: round(v[0], 2) for k, v in prof.items() if v[1]},
            "kernel_launches": {k: int(v[1]) for k, v in prof.items() if v[1]},
            "pair_history_head": [list(p) for p in res.qubit_pair_history[:8]]}
+    if cpu_s_per_fused_sweep:
+        # what the reference's algorithm would cost on the host cores: one full re-simulation per evaluation and one per
+        # candidate pair per layer (adapt_compiler.py:964-975), each = the fused 2-qubit sweeps of the circuit at that point
+        from oracle.oracle_backends import circuit_to_gates
+        layers = len(res.qubit_pair_history)
+        n_target = len(fuse_two_qubit_blocks(n, circuit_to_gates(target)))
+        sims = int(comp.cost_evaluation_counter) + layers * len(comp.coupling_map)
+        avg_sweeps = n_target + layers / 2.0                     # the ansatz grows by one fused block per layer
+        out["cpu_estimate_s"] = sims * avg_sweeps * cpu_s_per_fused_sweep
+        out["cpu_estimate_note"] = (f"ESTIMATE, not timed: {sims} full re-simulations (evaluations + one per candidate pair per layer) x "
+                                    f"~{avg_sweeps:.0f} fused 2-qubit sweeps x {cpu_s_per_fused_sweep * 1e3:.0f} ms per sweep measured on this box "
+                                    "(cpu_baseline)")
     for e in backend.engines():
         e.close()
     return out
@@ -838,7 +850,9 @@ def main():
             line["compile_c3"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_compile and not args.no_converging:
         try:
-            line["compile_converging"] = bench_compile_converging(args, local_rank)
+            cb = line.get("cpu_baseline") or {}
+            per_sweep = (1.0 / cb["value"] / 124.0) if (cb.get("value") and args.qubits == 28 and args.depth == 8 and args.layers == 16) else None
+            line["compile_converging"] = bench_compile_converging(args, local_rank, cpu_s_per_fused_sweep=per_sweep)
         except Exception as exc:  # noqa: BLE001
             line["compile_converging"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_mps:
