@@ -245,20 +245,26 @@ B200_HD uint32_t fold_smask(const PFold* f, const int n, const uint64_t g) {
     }
     return m;
 }
-B200_HD uint64_t fold_gmask(const PFold* f, const int n, const uint64_t g) {
-    uint64_t m = 0;
-    for (int i = 0; i < n; ++i) {
-        const bool ctl = f[i].cq < 0 || ((g >> f[i].cq) & 1ull);
-        m ^= ctl ? f[i].gmask : 0ull;
+// HBM rounds: returns the thread's base index WITH the flips applied.  A folded op may flip a lane qubit that a
+// neighbouring folded op is controlled by, so the ops are evaluated one after the other on the running index: the source
+// index of a load is f_1(f_2(...f_m(y))) (every X-type op is its own inverse: REVERSE order), the destination of a store is
+// f_m(...f_1(y)) (forward order).
+template <bool REVERSE>
+B200_HD uint64_t fold_gindex(const PFold* f, const int n, const uint64_t g) {
+    uint64_t x = g;
+    for (int k = 0; k < n; ++k) {
+        const int i = REVERSE ? n - 1 - k : k;
+        const bool ctl = f[i].cq < 0 || ((x >> f[i].cq) & 1ull);
+        x ^= ctl ? f[i].gmask : 0ull;
     }
-    return m;
+    return x;
 }
 
 // src == nullptr: the source is |0..0> (no read pass, no separate fill pass)
 template <int R>
 B200_HD void round_load_hbm(double2 (&a)[1 << R], const double2* __restrict__ src, const SweepProg& sp,
                             const PRound& rd, const uint64_t g) {
-    const uint64_t gm = g ^ fold_gmask(rd.lead, rd.n_lead, g);     // (register positions are zero in g: ^ == |)
+    const uint64_t gm = fold_gindex<true>(rd.lead, rd.n_lead, g);     // (register positions are zero in g: ^ == |)
     if (src == nullptr) {
 #pragma unroll
         for (int j = 0; j < (1 << R); ++j) a[j] = make_double2(gm == rd.goff_ld[j] ? 1.0 : 0.0, 0.0);
@@ -271,7 +277,7 @@ B200_HD void round_load_hbm(double2 (&a)[1 << R], const double2* __restrict__ sr
 template <int R>
 B200_HD void round_store_hbm(const double2 (&a)[1 << R], double2* __restrict__ dst, const SweepProg& sp,
                              const PRound& rd, const uint64_t g) {
-    const uint64_t gm = g ^ fold_gmask(rd.trail, rd.n_trail, g);
+    const uint64_t gm = fold_gindex<false>(rd.trail, rd.n_trail, g);
 #pragma unroll
     for (int j = 0; j < (1 << R); ++j) dst[gm ^ rd.goff_st[j]] = a[j];
 }

@@ -551,16 +551,14 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm)
                 // An X-type op on a LANE qubit (0..COAL_BITS-1, served by warp shuffles in HBM rounds: 64 SHFL + 64 selects,
                 // the hottest spot of a thin-layer sweep in profiles/r2d_sweep_ansatz.md) folds into the GLOBAL address of
                 // the round that loads from (lead) / stores to (trail) HBM: the thread simply loads its partner's
-                // amplitude -- same 128 B lines per warp access.  Its control must be a plain thread bit, and no X-type op
-                // of the round may be controlled by the flipped qubit (the controls of folded ops are read from the
-                // thread's own index).
-                uint64_t x_controls = 0;
-                for (int idx : rt.ops) if (ops[idx].kind == K_X && ops[idx].c >= 0) x_controls |= 1ull << ops[idx].c;
+                // amplitude -- same 128 B lines per warp access.  Its control must be a plain thread bit (the kernel
+                // evaluates the folded ops of an HBM round one after the other on the running index, so a folded op may
+                // be controlled by a lane qubit that another folded op flips: fold_gindex).
                 const bool loads_hbm = r == 0, stores_hbm = r + 1 == rounds.size();
                 auto foldable_side = [&](const COp& o, bool hbm_side) {
                     if (!fold_perm || o.kind != K_X) return false;
                     if (reg_of[o.t0] >= 0) return true;
-                    return hbm_side && o.t0 < COAL_BITS && (o.c < 0 || reg_of[o.c] < 0) && !((x_controls >> o.t0) & 1ull);
+                    return hbm_side && o.t0 < COAL_BITS && (o.c < 0 || reg_of[o.c] < 0);
                 };
                 auto foldable = [&](const COp& o) { return foldable_side(o, loads_hbm); };
                 std::vector<char> is_lead(rt.ops.size(), 0), is_trail(rt.ops.size(), 0);
