@@ -161,51 +161,6 @@ B200_HD void op_diag2(double2 (&a)[1 << R], const double2 r10, const double2 r01
     }
 }
 
-// A merged run of phase ops (P_DIAGSET): `sub` points at the n_sub records that follow the header (P_PEND: one phase
-// per thread; P_DIAG1: base + ratio of register bit r0, selected by a thread-level bit), tab = 16-entry table of the
-// register-only phases or nullptr.  Collects ONE pending phase and ONE ratio per register bit, then walks the 2^R
-// amplitudes in Gray-code order, two independent chains (register bit 3 clear / set): 2 complex multiplications per
-// amplitude whatever the run length (the ratios are unit-modulus: leaving a bit multiplies by the conjugate).
-template <int R>
-B200_HD void op_diagset(double2 (&a)[1 << R], const POp* __restrict__ sub, const int n_sub, const double* __restrict__ tab,
-                        const uint64_t g, double2& pend) {
-    static_assert(R == 4, "Gray-code walk written out for 16 amplitudes");
-    if (n_sub > 0) {
-        double2 rho0 = make_double2(1.0, 0.0), rho1 = rho0, rho2 = rho0, rho3 = rho0;
-        for (int s = 0; s < n_sub; ++s) {
-            const POp& e = sub[s];
-            if (e.kind == P_PEND) {
-                const int u0 = e.dq0 >= 0 ? (int)((g >> e.dq0) & 1ull) : 0;
-                const int u1 = e.dq1 >= 0 ? (int)((g >> e.dq1) & 1ull) : 0;
-                pend = cmul(pend, sel4(e.m, u0, u1));
-            } else {
-                const int u = (int)((g >> e.dq1) & 1ull);
-                pend = cmul(pend, sel2(e.m, 0, u));
-                const double2 rt = sel2(e.m, 2, u);
-                if (e.r0 == 0) rho0 = cmul(rho0, rt);
-                else if (e.r0 == 1) rho1 = cmul(rho1, rt);
-                else if (e.r0 == 2) rho2 = cmul(rho2, rt);
-                else rho3 = cmul(rho3, rt);
-            }
-        }
-        const double2 c0 = make_double2(rho0.x, -rho0.y), c1 = make_double2(rho1.x, -rho1.y);
-        double2 p = pend, q = cmul(pend, rho3);
-        a[0] = cmul(a[0], p);   a[8] = cmul(a[8], q);
-        p = cmul(p, rho0); q = cmul(q, rho0);   a[1] = cmul(a[1], p);   a[9] = cmul(a[9], q);      // 0001
-        p = cmul(p, rho1); q = cmul(q, rho1);   a[3] = cmul(a[3], p);   a[11] = cmul(a[11], q);    // 0011
-        p = cmul(p, c0);   q = cmul(q, c0);     a[2] = cmul(a[2], p);   a[10] = cmul(a[10], q);    // 0010
-        p = cmul(p, rho2); q = cmul(q, rho2);   a[6] = cmul(a[6], p);   a[14] = cmul(a[14], q);    // 0110
-        p = cmul(p, rho0); q = cmul(q, rho0);   a[7] = cmul(a[7], p);   a[15] = cmul(a[15], q);    // 0111
-        p = cmul(p, c1);   q = cmul(q, c1);     a[5] = cmul(a[5], p);   a[13] = cmul(a[13], q);    // 0101
-        p = cmul(p, c0);   q = cmul(q, c0);     a[4] = cmul(a[4], p);   a[12] = cmul(a[12], q);    // 0100
-        pend = make_double2(1.0, 0.0);
-    }
-    if (tab != nullptr) {
-#pragma unroll
-        for (int j = 0; j < (1 << R); ++j) a[j] = cmul(a[j], ld_c(tab, j));
-    }
-}
-
 // generic diagonal (non-unitary input with a zero phase entry): phase index = bit(q0) + 2 bit(q1), each
 // bit either a register bit (r >= 0) or a bit of the thread's base index g
 template <int R, class OP>
@@ -386,13 +341,11 @@ B200_HD void apply_pend(double2 (&a)[1 << R], const double2 pend) {
 struct OpHead {
     int32_t code, flush, r0, r1, cq, dq0, dq1, mat2;
     double m[8];
-    const POp* self;
 };
 B200_HD OpHead load_head(const POp& op) {
     OpHead h;
     h.code = (op.flush >> 8) & 0xff; h.flush = op.flush & 1;
     h.r0 = op.r0; h.r1 = op.r1; h.cq = op.cq; h.dq0 = op.dq0; h.dq1 = op.dq1; h.mat2 = op.mat2;
-    h.self = &op;
 #pragma unroll
     for (int k = 0; k < 8; ++k) h.m[k] = op.m[k];
     return h;
@@ -404,10 +357,9 @@ struct OpRef {
     int32_t code, flush;
     const int32_t &r0, &r1, &cq, &dq0, &dq1, &mat2;
     const double (&m)[8];
-    const POp* self;
     B200_HD explicit OpRef(const POp& op)
         : code((op.flush >> 8) & 0xff), flush(op.flush & 1), r0(op.r0), r1(op.r1), cq(op.cq), dq0(op.dq0),
-          dq1(op.dq1), mat2(op.mat2), m(op.m), self(&op) {}
+          dq1(op.dq1), mat2(op.mat2), m(op.m) {}
 };
 
 // One op of a round on the thread's registers.  `pend` collects the phases that multiply all 2^R
@@ -472,12 +424,9 @@ B200_HD void apply_decoded(double2 (&a)[1 << R], const SweepProg& sp, const HEAD
         op_xlane<R>(a, h.r0, h.r1, ctl, ex);
         break;
     }
-    case 39:   // dense 2x2 on a lane qubit
+    default:   // 39: dense 2x2 on a lane qubit
         if (h.flush) { apply_pend<R>(a, pend); pend = make_double2(1.0, 0.0); }
         op_mat1lane<R>(a, h.m, h.r0, lane, ex);
-        break;
-    default:   // 40: merged run of phase ops; its h.r0 sub-records follow in ops[] (the caller skips them)
-        op_diagset<R>(a, h.self + 1, h.r0, h.mat2 >= 0 ? sp.mat2[h.mat2] : nullptr, g, pend);
         break;
     }
 #undef B200_DIAG1
@@ -486,9 +435,6 @@ B200_HD void apply_decoded(double2 (&a)[1 << R], const SweepProg& sp, const HEAD
 }
 
 // emulator entry: one op, decoded on the spot
-// slots of ops[] an op occupies: a P_DIAGSET header is followed by its sub-records
-B200_HD int op_slots(const POp& op) { return op.kind == P_DIAGSET ? 1 + op.r0 : 1; }
-
 template <int R, class EX>
 B200_HD void apply_op(double2 (&a)[1 << R], const SweepProg& sp, const POp& op, const uint64_t g,
                       const uint32_t lane, double2& pend, const EX& ex) {
@@ -505,8 +451,8 @@ B200_HD void round_ops(double2 (&a)[1 << R], const SweepProg& sp, const PRound& 
     int o = rd.op_begin;
     const int oe = rd.op_end;
     if (!PREFETCH) {
-        for (; o < oe; o += op_slots(sp.ops[o])) apply_op<R>(a, sp, sp.ops[o], g, lane, pend, ex);
-    } else if (o < oe) {      // (plans of the pipelined kernel contain no P_DIAGSET: build_plan(fold_perm = false))
+        for (; o < oe; ++o) apply_op<R>(a, sp, sp.ops[o], g, lane, pend, ex);
+    } else if (o < oe) {
         OpHead h = load_head(sp.ops[o]);
         for (; o < oe; ++o) {
             const OpHead nh = load_head(sp.ops[o + 1]);   // ops[] has one slot of slack

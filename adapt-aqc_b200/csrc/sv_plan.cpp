@@ -533,8 +533,6 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm)
         n_taken += (int)sw_ops.size() - left;
 
         sp.nrounds = (int32_t)rounds.size();
-        int canon_left = 0;              // canonical ops of this sweep not yet emitted (each needs at most one ops[] slot)
-        for (const auto& rt : rounds) canon_left += (int)rt.ops.size();
         for (size_t r = 0; r < rounds.size(); ++r) {
             RoundTmp& rt = rounds[r];
             // pad the register set with the highest free tile positions >= LANE_BITS
@@ -626,7 +624,9 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm)
             }
             dr.op_begin = sp.nops;
             bool pending = false;
-            auto emit = [&](POp& po) {
+            for (int idx : middle) {
+                POp& po = sp.ops[sp.nops++];
+                fill_tiled_op(ops[idx], reg_of, sp, po);
                 if (po.kind == P_PEND || po.kind == P_DIAG1 || po.kind == P_DIAG2) { dr.has_pend = 1; pending = true; }
                 if (po.kind == P_XLANE || po.kind == P_MAT1LANE) { po.flush = pending ? 1 : 0; pending = false; }
                 int code = 0;
@@ -640,79 +640,10 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm)
                 case P_MAT1: code = 28 + po.r0; break;
                 case P_MAT2: code = 32 + pair_index(po.r0, po.r1); break;
                 case P_XLANE: code = 38; break;
-                case P_MAT1LANE: code = 39; break;
-                default: code = 40; break;
+                default: code = 39; break;
                 }
                 po.flush |= code << 8;
-            };
-            auto unit = [](double re, double im) { return std::abs(std::hypot(re, im) - 1.0) < 1e-12; };
-            for (size_t mi = 0; mi < middle.size();) {
-                // ---- a maximal run of consecutive unitary phase ops (they commute with each other) ----
-                size_t me = mi;
-                std::vector<POp> run;
-                int nmat2_before = sp.nmat2;
-                while (fold_perm && me < middle.size() && ops[middle[me]].kind == K_DIAG) {
-                    POp t;
-                    fill_tiled_op(ops[middle[me]], reg_of, sp, t);
-                    bool ok = t.kind == P_PEND || t.kind == P_DIAG1 || t.kind == P_DIAG2;
-                    for (int k = 0; ok && k < 4; ++k) ok = unit(t.m[2 * k], t.m[2 * k + 1]);
-                    if (!ok) break;
-                    run.push_back(t);
-                    ++me;
-                }
-                sp.nmat2 = nmat2_before;      // (diagonal ops never allocate mat2 slots; defensive)
-                // cost model in DP instructions per thread: separate ops = 36 per DIAG1, 48 per DIAG2, 4 per PEND + one
-                // 64-DP pending-phase multiply; merged = 8 per thread-dependent sub-record + 124 for the walk + 64 for the table
-                int n_sub = 0, n_tab = 0, separate = 64;
-                for (const POp& t : run) {
-                    const bool thread_dep = t.kind == P_PEND || (t.kind == P_DIAG1 && t.dq1 >= 0);
-                    if (thread_dep) ++n_sub; else ++n_tab;
-                    separate += t.kind == P_PEND ? 4 : (t.kind == P_DIAG1 ? 36 : 48);
-                }
-                const int merged = (n_sub ? 8 * n_sub + 124 : 0) + (n_tab ? 64 : 0);
-                // (the header is the only slot a merged run adds: never run past ops[] whatever the rest of the sweep emits)
-                const bool room = sp.nops + 1 + canon_left <= MAX_SWEEP_OPS + MAX_SWEEP_HEADERS && (n_tab == 0 || sp.nmat2 < MAX_SWEEP_MAT2);
-                if (run.size() >= 2 && merged < separate && room) {
-                    POp& head = sp.ops[sp.nops++];
-                    std::memset(&head, 0, sizeof head);
-                    head.kind = P_DIAGSET;
-                    head.r0 = n_sub; head.r1 = head.cq = head.dq0 = head.dq1 = -1;
-                    head.mat2 = -1;
-                    if (n_tab) {
-                        head.mat2 = sp.nmat2++;
-                        cplx tab[1 << REG_BITS];
-                        for (int j = 0; j < (1 << REG_BITS); ++j) tab[j] = cplx(1.0, 0.0);
-                        for (const POp& t : run) {
-                            if (t.kind == P_DIAG2) {
-                                const cplx p00(t.m[0], t.m[1]), r10(t.m[2], t.m[3]), r01(t.m[4], t.m[5]), r11(t.m[6], t.m[7]);
-                                for (int j = 0; j < (1 << REG_BITS); ++j) {
-                                    const bool b0 = j >> t.r0 & 1, b1 = j >> t.r1 & 1;
-                                    tab[j] *= p00 * (b0 && b1 ? r11 : (b0 ? r10 : (b1 ? r01 : cplx(1.0, 0.0))));
-                                }
-                            } else if (t.kind == P_DIAG1 && t.dq1 < 0) {
-                                const cplx base(t.m[0], t.m[1]), ratio(t.m[4], t.m[5]);
-                                for (int j = 0; j < (1 << REG_BITS); ++j) tab[j] *= base * ((j >> t.r0 & 1) ? ratio : cplx(1.0, 0.0));
-                            }
-                        }
-                        for (int j = 0; j < (1 << REG_BITS); ++j) put(sp.mat2[head.mat2], j, tab[j]);
-                    }
-                    emit(head);
-                    head.flush &= ~0xff;           // a DIAGSET applies (and clears) the pending phase itself
-                    for (const POp& t : run)
-                        if (t.kind == P_PEND || (t.kind == P_DIAG1 && t.dq1 >= 0)) sp.ops[sp.nops++] = t;
-                    pending = false;
-                    canon_left -= (int)run.size();
-                    mi = me;
-                    continue;
-                }
-                // ---- not merged: one op ----
-                POp& po = sp.ops[sp.nops++];
-                fill_tiled_op(ops[middle[mi]], reg_of, sp, po);
-                emit(po);
-                --canon_left;
-                ++mi;
             }
-            canon_left -= (int)(lead.size() + trail.size());
             dr.op_end = sp.nops;
         }
     }

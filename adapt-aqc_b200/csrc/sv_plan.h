@@ -94,16 +94,11 @@ enum PKind : int32_t {
     P_MAT2 = 7,      // dense 4x4 on registers r0 < r1 (matrix index `mat2`)
     P_XLANE = 8,     // X on lane bit r0, control: none / thread-level cq / register r1
     P_MAT1LANE = 9,  // dense 2x2 on lane bit r0
-    P_DIAGSET = 10,  // a run of consecutive phase ops of the round merged into ONE body: r0 = number of sub-records that
-                     // follow in ops[] (P_PEND / P_DIAG1 entries, thread-dependent phases), mat2 = index of a 16-entry
-                     // table in SweepProg::mat2 holding the product of the register-only phases (-1: none).  The kernel
-                     // collects one pending phase and one ratio per register bit from the sub-records, then walks the
-                     // 16 amplitudes in Gray-code order: 2 complex multiplications per amplitude whatever the run length.
 };
 
 // Dispatch code of a tiled op: kind and register selectors folded into ONE warp-uniform switch index.
 //   0 PEND | 1..4 DIAG1(r0) | 5..10 DIAG2(r0<r1) | 11 DIAGRAW | 12..15 XREG(r0) | 16..27 CXREG(t=r0,c=r1)
-//   28..31 MAT1(r0) | 32..37 MAT2(r0<r1) | 38 XLANE | 39 MAT1LANE | 40 DIAGSET
+//   28..31 MAT1(r0) | 32..37 MAT2(r0<r1) | 38 XLANE | 39 MAT1LANE
 inline int pair_index(int r0, int r1) {   // r0 < r1 < 4 -> 0..5 in the order 01 02 03 12 13 23
     return r0 == 0 ? r1 - 1 : (r0 == 1 ? r1 + 1 : 5);
 }
@@ -127,7 +122,6 @@ static_assert(sizeof(POp) == 96, "POp layout");
 constexpr int MAX_SWEEP_ROUNDS = 16;
 constexpr int MAX_SWEEP_OPS = 96;
 constexpr int MAX_SWEEP_MAT2 = 16;
-constexpr int MAX_SWEEP_HEADERS = 32;   // extra ops[] slots for the headers of merged phase runs (P_DIAGSET)
 constexpr int MAX_LANE_OPS = 2;   // shuffle-served ops per HBM round before a shared-memory round is cheaper
                                   // (64 SHFL per thread each vs 32 LDS/STS.128 + barrier for a round trip)
 
@@ -164,7 +158,7 @@ struct alignas(16) SweepProg {
     int32_t c;                  // number of leading contiguous low qubits in tileq
     int32_t tileq[TILE_BITS];   // global qubit of each tile-local bit, ascending
     PRound rounds[MAX_SWEEP_ROUNDS];
-    POp ops[MAX_SWEEP_OPS + 1 + MAX_SWEEP_HEADERS];   // +1: the kernel prefetches one op ahead; DIAGSET headers
+    POp ops[MAX_SWEEP_OPS + 1];   // +1: the kernel prefetches one op ahead
     double mat2[MAX_SWEEP_MAT2][32];
 };
 static_assert(sizeof(SweepProg) <= 32000, "SweepProg must fit the 32 KB kernel-parameter space");

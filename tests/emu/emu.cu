@@ -102,9 +102,8 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
                     else round_load_smem<REG_BITS>(regs[tid].a, smem.data(), rd, tls[tid], gidx[tid]);
                     pend[tid] = make_double2(1.0, 0.0);
                 }
-                for (int o = rd.op_begin; o < rd.op_end; o += op_slots(sp.ops[o])) {
-                    const POp& op_ref = sp.ops[o];
-                    POp op = op_ref;
+                for (int o = rd.op_begin; o < rd.op_end; ++o) {
+                    POp op = sp.ops[o];
                     const bool lane_op = op.kind == P_XLANE || op.kind == P_MAT1LANE;
                     if (lane_op) {
                         if (r != 0 && r != nr - 1) { g_err = "lane op scheduled in a shared-memory round"; return -1; }
@@ -119,9 +118,7 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
                     }
                     for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid) {
                         const SnapExchange ex{snap.data(), tid};
-                        // (a P_DIAGSET reads the records that follow it in ops[]: pass the op in place unless its flush bit
-                        // was cleared in the local copy above)
-                        apply_op<REG_BITS>(regs[tid].a, sp, lane_op ? op : op_ref, gidx[tid], tid & 31u, pend[tid], ex);
+                        apply_op<REG_BITS>(regs[tid].a, sp, op, gidx[tid], tid & 31u, pend[tid], ex);
                     }
                 }
                 for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid) {
