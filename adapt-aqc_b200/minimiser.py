@@ -37,7 +37,7 @@ def make_b200_minimiser(base_cls, replace_1q_gate, minimum_of_sinusoidal, suppor
             c = self.compiler
             if not hasattr(c.backend, "shift_costs") or c.optimise_local_cost or c.soften_global_cost:
                 return False
-            supports = getattr(c.backend, "_use_incremental", None)
+            supports = getattr(c.backend, "supports_shift_costs", None) or getattr(c.backend, "_use_incremental", None)
             return True if supports is None else bool(supports(c))
 
         def _shift(self, gate_index, candidates):

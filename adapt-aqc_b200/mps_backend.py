@@ -68,6 +68,25 @@ class DeviceMPSView:
             pass
 
 
+class _Op:
+    def __init__(self, name, params):
+        self.name, self.params, self.label = name, params, name
+
+
+class _Inst:
+    def __init__(self, operation, qubits):
+        self.operation, self.qubits, self.clbits = operation, qubits, ()
+
+
+class _CircuitView:
+    """full_circuit with ONE instruction replaced (a shift candidate), without copying or touching the circuit."""
+
+    def __init__(self, circuit, data, index, inst):
+        self.num_qubits = circuit.num_qubits
+        self.qubits = circuit.qubits
+        self.data = data[:index] + [inst] + data[index + 1:]
+
+
 class _Options:
     def __init__(self, thr, max_chi):
         self.matrix_product_state_truncation_threshold = thr
@@ -414,7 +433,7 @@ class B200MPSBackend(_MPSBase):
         self._engine = None
         self._evaluator = None
 
-    def __getstate__(self):
+    def __getstate__(self):          # (the worker simulators and their thread pool are rebuilt on demand)
         return {"simulator": self.simulator, "incremental": self.incremental}
 
     def __setstate__(self, st):
@@ -564,9 +583,56 @@ class B200MPSBackend(_MPSBase):
         return gradients
 
     # ---- batched extension (B200CostMinimiser) ----
+    SHIFT_WORKERS = 2       # concurrent candidate simulations (the blocked Jacobi SVD occupies 64 of the 148 SMs)
+
+    def supports_shift_costs(self, compiler):
+        return not (compiler.soften_global_cost or getattr(compiler, "optimise_local_cost", False))
+
+    def _shift_costs_truncating(self, compiler, gate_index, candidates):
+        """Reference contraction order (real truncation: bond cap or a threshold above roundoff).  The candidates are
+        INDEPENDENT simulations that share every gate before `gate_index`; each worker simulator has its own device
+        context (own stream, own scratch, own prefix checkpoints) and is driven by its own thread -- ctypes releases the
+        GIL, so the SVDs of different candidates overlap on the GPU.  Every candidate's value is what the one-scalar
+        path computes for that circuit: same gates, same order, same truncation rule."""
+        import concurrent.futures
+        o = self.simulator.options
+        if getattr(self, "_shift_pool", None) is None:
+            self._shift_pool = concurrent.futures.ThreadPoolExecutor(max_workers=self.SHIFT_WORKERS)
+            self._shift_sims = []
+        key = (o.matrix_product_state_truncation_threshold, o.matrix_product_state_max_bond_dimension)
+        if getattr(self, "_shift_key", None) != key:
+            self._shift_sims = [B200MPSSimulator(key[0], key[1], device=self.simulator.device) for _ in range(self.SHIFT_WORKERS)]
+            self._shift_key = key
+        circuit = compiler.full_circuit
+        data = list(circuit.data)
+        if data[gate_index].operation.name not in G.ROTATIONS and getattr(data[gate_index].operation, "label", None) not in G.ROTATIONS:
+            raise ValueError(f"full_circuit index {gate_index} is not a rotation gate")
+        qubits = data[gate_index].qubits
+
+        def one(worker, jobs):
+            sim = self._shift_sims[worker]
+            out = []
+            for j in jobs:
+                name, theta = candidates[j]
+                view = _CircuitView(circuit, data, gate_index, _Inst(_Op(name, [float(theta)]), qubits))
+                handle = sim.simulate(view)
+                out.append((j, 1 - np.absolute(handle.amps([0])[0]) ** 2))
+                sim._recycle(handle)
+            return out
+
+        jobs = [list(range(w, len(candidates), self.SHIFT_WORKERS)) for w in range(self.SHIFT_WORKERS)]
+        futures = [self._shift_pool.submit(one, w, jb) for w, jb in enumerate(jobs) if jb]
+        costs = [None] * len(candidates)
+        for f in futures:
+            for j, c in f.result():
+                costs[j] = c
+        return costs
+
     def shift_costs(self, compiler, gate_index, candidates):
         if not self._use_incremental(compiler):
-            raise NotImplementedError("batched shifts need roundoff-level truncation (see _use_incremental)")
+            if not self.supports_shift_costs(compiler):
+                raise NotImplementedError("batched shifts are not defined for the softened / local cost")
+            return self._shift_costs_truncating(compiler, gate_index, candidates)
         ev, window, start = self.amp0(compiler, with_start=True)
         # the window starts right after the set_matrix_product_state instruction (index 1), or at 0 for a circuit
         # target that was not converted -- not necessarily at lhs_gate_count

@@ -8,7 +8,7 @@ from harness import measures as em
 from harness.circuit import Circuit
 from harness.compiler import CMAP_LINEAR, AdaptCompiler, AdaptConfig, generate_coupling_map
 from adapt_aqc_b200.gates import GateStream
-from harness.minimiser import B200CostMinimiser
+from harness.minimiser import B200CostMinimiser, replace_1q_gate
 from adapt_aqc_b200.mps_backend import B200MPSBackend, B200MPSSimulator, DeviceMPSView
 from adapt_aqc_b200.mps_engine import MPSContext
 from oracle import mps_oracle as mo
@@ -407,3 +407,37 @@ def test_general_gradient_analytic_value_and_zero_case():
     start = Circuit(5); start.ry(0.7, 2); start.cx(2, 3)
     g0 = backend.general_grad_of_pairs(qc5, empty, gens0, degs0, [(0, 1), (1, 2), (2, 3), (3, 4)], start)
     np.testing.assert_allclose(g0, 0, atol=1e-12)
+
+
+def test_batched_shift_costs_under_truncation_equal_the_one_scalar_path():
+    """B200MPSBackend.shift_costs with REAL truncation (bond cap): the candidates are independent simulations run
+    concurrently on worker contexts (own stream, own prefix checkpoints, one thread each); every value must be what the
+    one-scalar-at-a-time path computes for the same circuit, and a Rotosolve cycle through the batched front end must
+    leave the same circuit behind."""
+    from harness.workloads import build_mps_workload
+    n, chi = 16, 16
+    target, ansatz = build_mps_workload(n, chi, 3)
+    runs = {}
+    for batched in (False, True):
+        backend = B200MPSBackend(B200MPSSimulator(1e-16, max_chi=chi))
+        comp = AdaptCompiler(target, backend=backend, minimiser_cls=B200CostMinimiser if batched else None)
+        comp.full_circuit.data.extend(ansatz.copy().data)
+        assert not backend._use_incremental(comp)
+        lo, hi = comp.variational_circuit_range()
+        rot = [i for i in range(lo, hi) if comp.full_circuit.data[i].operation.name == "rz"]
+        if batched:
+            cands = [("rx", 0.0), ("rx", np.pi / 2), ("ry", -np.pi / 2), ("rz", 0.7), ("ry", 1.1)]
+            got = backend.shift_costs(comp, rot[2], cands)
+            ref = []
+            saved = comp.full_circuit.data[rot[2]]
+            for name, th in cands:
+                replace_1q_gate(comp.full_circuit, rot[2], name, th)
+                ref.append(comp.evaluate_cost())
+            comp.full_circuit.data[rot[2]] = saved
+            np.testing.assert_allclose(got, ref, rtol=0, atol=1e-13)
+        c = comp.minimizer._reduce_cost(False, (lo, hi))
+        runs[batched] = (c, [(comp.full_circuit.data[i].operation.name, comp.full_circuit.data[i].operation.params[0]) for i in rot],
+                         comp.cost_evaluation_counter)
+    assert abs(runs[True][0] - runs[False][0]) < 1e-12
+    for (na, ta), (nb, tb) in zip(runs[True][1], runs[False][1]):
+        assert na == nb and abs(ta - tb) < 1e-9
