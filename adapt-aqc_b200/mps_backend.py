@@ -585,8 +585,16 @@ class B200MPSBackend(_MPSBase):
     # ---- batched extension (B200CostMinimiser) ----
     SHIFT_WORKERS = 2       # concurrent candidate simulations (the blocked Jacobi SVD occupies 64 of the 148 SMs)
 
+    # Under real truncation the shift values of a gate can be simulated concurrently (_shift_costs_truncating).  Measured
+    # on C4 (profiles/bench_r2n_mps.json) that is SLOWER than one scalar at a time -- 49.2 vs 58.4 evals/s: only 9 of the 24
+    # evaluations of a Rotosolve cycle need an SVD at all (prefix checkpoints), two cooperative Jacobi launches do not
+    # overlap enough to pay for the second context's checkpoint misses -- so the batched front end uses it only on request.
+    batch_truncating = False
+
     def supports_shift_costs(self, compiler):
-        return not (compiler.soften_global_cost or getattr(compiler, "optimise_local_cost", False))
+        if compiler.soften_global_cost or getattr(compiler, "optimise_local_cost", False):
+            return False
+        return self._use_incremental(compiler) or self.batch_truncating
 
     def _shift_costs_truncating(self, compiler, gate_index, candidates):
         """Reference contraction order (real truncation: bond cap or a threshold above roundoff).  The candidates are

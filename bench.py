@@ -314,6 +314,7 @@ def bench_mps(args, device, with_cpu=True):
     for mode, cap in (("capped", chi), ("capped_batched", chi), ("default", None)):
         sim = B200MPSSimulator(1e-16, max_chi=cap, device=device)
         backend = B200MPSBackend(sim)
+        backend.batch_truncating = mode == "capped_batched"      # (off by default: measured slower, see mps_backend.py)
         # capped_batched: the batched front end under real truncation -- the 3 shift values of a gate are independent
         # simulations run concurrently on worker contexts (B200MPSBackend._shift_costs_truncating)
         comp = AdaptCompiler(target, backend=backend, minimiser_cls=B200CostMinimiser if mode == "capped_batched" else None)

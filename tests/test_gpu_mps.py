@@ -420,6 +420,7 @@ def test_batched_shift_costs_under_truncation_equal_the_one_scalar_path():
     runs = {}
     for batched in (False, True):
         backend = B200MPSBackend(B200MPSSimulator(1e-16, max_chi=chi))
+        backend.batch_truncating = True          # opt-in (measured slower than one scalar at a time on C4)
         comp = AdaptCompiler(target, backend=backend, minimiser_cls=B200CostMinimiser if batched else None)
         comp.full_circuit.data.extend(ansatz.copy().data)
         assert not backend._use_incremental(comp)
