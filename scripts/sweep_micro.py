@@ -18,7 +18,7 @@ eng = SVEngine(n, n_slots=2)
 streams = {"target": GateStream.from_circuit(target), "ansatz": GateStream.from_circuit(ansatz),
            "layer(13,14)": GateStream.from_window(canonical_window(ansatz)[30:35]),
            "layer(0,1)": GateStream.from_window(canonical_window(ansatz)[0:5])}
-only = sys.argv[3].split(",") if len(sys.argv) > 3 else None      # e.g. "ansatz" (for ncu captures)
+only = sys.argv[3].split(";") if len(sys.argv) > 3 else None      # e.g. "ansatz" or "layer(13,14);layer(0,1)" (for ncu captures)
 if only:
     eng.run(0, -1, streams["layer(13,14)"])      # any normalised state will do for timing
     streams = {k: v for k, v in streams.items() if k in only}
