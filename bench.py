@@ -488,6 +488,48 @@ def bench_compile_split(args, local_rank, world):
     return out
 
 
+def bench_readme_configs(args, device, with_cpu=True):
+    """BASELINE configs C1 (README 3-qubit statevector example) and C2 (README 50-qubit MPS example): whole
+    AdaptCompiler.compile() runs with the reference's defaults, TIMED on the B200 backends and -- same harness, same
+    circuits -- on the CPU oracle backends (the restatement of the Aer path).  These are the parity configs: launch-latency
+    bound, the GPU is not expected to win; pair histories and final costs must agree."""
+    from adapt_aqc_b200.backends import B200SVBackend
+    from adapt_aqc_b200.mps_backend import B200MPSBackend
+    from harness.circuit import Circuit
+    from harness.compiler import AdaptCompiler
+    c1 = Circuit(3)
+    c1.rx(1.23, 0); c1.cx(0, 1); c1.ry(2.5, 1); c1.rx(-1.6, 2); c1.ccx(2, 1, 0)
+    n = 50
+    c2 = Circuit(n)
+    c2.h(0); c2.cx(0, 1); c2.h(2); c2.cx(2, 3); c2.h(list(range(4, n)))
+    out = {}
+    for name, qc, make_gpu, make_cpu in (
+            ("c1_readme_3q_sv", c1, lambda: B200SVBackend(device=device), "sv"),
+            ("c2_readme_50q_mps", c2, lambda: B200MPSBackend(device=device), "mps")):
+        r = {}
+        backends = [("b200", make_gpu)]
+        if with_cpu:
+            from oracle.oracle_backends import OracleMPSBackend, OracleSVBackend
+            backends.append(("cpu_oracle", OracleSVBackend if make_cpu == "sv" else OracleMPSBackend))
+        hist = {}
+        for tag, mk in backends:
+            comp = AdaptCompiler(qc, backend=mk())
+            t0 = time.perf_counter()
+            res = comp.compile()
+            wall = time.perf_counter() - t0
+            r[tag] = {"wall_s": wall, "layers": len(res.qubit_pair_history), "cost_evaluations": int(res.cost_evaluations),
+                      "final_global_cost": float(res.global_cost_history[-1]), "evals_per_s": res.cost_evaluations / wall}
+            hist[tag] = (res.qubit_pair_history, res.global_cost_history)
+        if with_cpu:
+            r["same_pairs"] = hist["b200"][0] == hist["cpu_oracle"][0]
+            r["max_cost_difference"] = float(max(abs(a - b) for a, b in zip(hist["b200"][1], hist["cpu_oracle"][1])))
+            r["cpu_cores"] = host_threads()
+        out[name] = r
+    out["note"] = ("whole compiles with default AdaptConfig and the default all-to-all coupling map; cpu_oracle = the same compile loop on "
+                   "the CPU restatement of the Aer path (oracle/), timed on this box")
+    return out
+
+
 def bench_compile(args, device, cpu_evals_per_s=None):
     """AdaptCompiler.compile() (adapt_compiler.py:246) on the C3 target: ISL pair selection from pair
     RDMs on a linear coupling map (P = n - 1 pairs), Rotoselect on each new layer, Rotosolve over the
@@ -724,6 +766,7 @@ def main():
     ap.add_argument("--converging-layers", type=int, default=6, help="thin layers of the compilable target")
     ap.add_argument("--converging-max-layers", type=int, default=400)
     ap.add_argument("--no-converging", action="store_true", help="skip the converging compile leg")
+    ap.add_argument("--no-readme", action="store_true", help="skip the C1 / C2 README compile legs")
     ap.add_argument("--sharded-compile-layers", type=int, default=4)
     ap.add_argument("--mps-qubits", type=int, default=50)
     ap.add_argument("--mps-chi", type=int, default=256)
@@ -871,6 +914,11 @@ def main():
             line["compile_converging"] = bench_compile_converging(args, local_rank, cpu_s_per_fused_sweep=per_sweep)
         except Exception as exc:  # noqa: BLE001
             line["compile_converging"] = {"error": repr(exc)}
+    if rank == 0 and world == 1 and not args.no_compile and not args.no_readme:
+        try:
+            line["compile_c1_c2"] = bench_readme_configs(args, local_rank, with_cpu=not args.no_cpu_baseline)
+        except Exception as exc:  # noqa: BLE001
+            line["compile_c1_c2"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_mps:
         if backend._engine is not None:
             backend._engine.close()          # free the 16 GiB of statevector slots first
