@@ -22,6 +22,7 @@ call:
     (two fused gate sweeps + one transfer pass) or the circuit structure changes.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -596,8 +597,14 @@ class SVCostEvaluator:
 
     # ---- L: suffix^+ applied to |0..0> ----
     def _update_L_dense(self, new, b1):
+        return self._update_L_to(new[b1:])
+
+    MIDDLE_MAX_GATES = 24
+
+    def _update_L_to(self, sfx):
+        """Make slot L hold sfx^+ |0..0> (sfx: gate list applied in order to a ket).  Returns True if the slot changed."""
         eng, stream = self.eng, G.GateStream.from_window
-        old, sfx = self.lwin, new[b1:]
+        old = self.lwin
         if old is not None and old == sfx:
             return False
         if old is not None and self.l_moves < self.REFRESH_MOVES:
@@ -610,6 +617,25 @@ class SVCostEvaluator:
                 eng.run(SLOT_L, SLOT_L, stream(sfx[:sn - so]), inverse=True)
                 self.lwin = list(sfx); self.l_moves += 1; self.stats["moves_L"] += 1
                 return True
+            # middle replacement: old = P + X + S, new = P + Y + S  =>  L_new = P^+ Y^+ X P L_old = Y^+ X L_old when the
+            # gates of P act on none of the qubits of X and Y (front mode: one block leaves the bra, its neighbour enters)
+            p = 0
+            lim = min(so, sn)
+            while p < lim and old[p] == sfx[p]:
+                p += 1
+            q = 0
+            while q < lim - p and old[so - 1 - q] == sfx[sn - 1 - q]:
+                q += 1
+            X, Y = old[p:so - q], sfx[p:sn - q]
+            if 0 < len(X) + len(Y) <= self.MIDDLE_MAX_GATES:
+                xy = set()
+                for e in X + Y:
+                    xy.update(_support(e))
+                if all(xy.isdisjoint(_support(e)) for e in old[:p]):
+                    eng.run(SLOT_L, SLOT_L, stream(list(X) + G.invert_window(Y)))
+                    self.lwin = list(sfx); self.l_moves += 1
+                    self.stats["middle_L"] = self.stats.get("middle_L", 0) + 1
+                    return True
         # rebuild: suffix^+ |0> is supported on the qubits the suffix touches -- built on the smaller engines as far as it
         # fits them (cheap sweeps), embedded level by level, only the remaining head gates are applied at this size
         if self.dense_blocks:
@@ -660,6 +686,19 @@ class SVCostEvaluator:
         b0, b1, supp = block
         return len(supp) == 2 and self._compact_map(window[b1:], tuple(supp)) is not None
 
+    front_mode = os.environ.get("B200AQC_FRONT", "1") != "0"       # see _prepare_block
+    FRONT_MAX_PREFIX = 96   # gates
+
+    def _front_ok(self, window, b0, pair):
+        """The block at [b0, ...) on `pair` commutes to the front of the window: every gate before it avoids its qubits."""
+        if not (self.front_mode and self.dense_blocks) or len(pair) != 2 or not 0 < b0 <= self.FRONT_MAX_PREFIX:
+            return False
+        a, b = pair
+        for e in window[:b0]:
+            if e[1] == a or e[1] == b or e[2] == a or e[2] == b:
+                return False
+        return True
+
     def _prefetch_next_L(self, window, b1):
         """T of the open block has been read back, so slot L is free: enqueue (asynchronously) the bra of the
         NEXT block -- Rotosolve walks the blocks in order (cost_minimiser.py:267-316) -- while the host
@@ -669,6 +708,8 @@ class SVCostEvaluator:
         if nxt is None or self.lwin is None or self.l_moves >= self.REFRESH_MOVES:
             return
         n0, n1, supp = nxt
+        if len(supp) == 2 and self._front_ok(window, n0, tuple(supp)):
+            return          # the next block commutes to the front: its bra is one middle replacement away from this one
         if len(supp) == 2 and self._compact_map(window[n1:], tuple(supp)) is not None:
             return          # the next block will use a compact bra
         split = self._tail_split(window)
@@ -685,6 +726,27 @@ class SVCostEvaluator:
         b0, b1, supp = block
         n = eng.num_qubits
         pair = tuple(supp) if (len(supp) == 2 or n == 1) else (supp[0], (supp[0] + 1) % n)
+        if self._front_ok(window, b0, pair):
+            # FRONT MODE: every gate in front of the block acts on other qubits, so the block commutes to the front of the
+            # window:  <0| W[b1:] B W[:b0] |base> = <0| W[b1:] W[:b0] B |base>.  The ket side is the base state itself (no
+            # R move); the bra carries W[:b0] + W[b1:], and going from one such block to the next replaces ONE block in
+            # the middle of that list (_update_L_to): one sweep per block instead of an R move plus a bra move.
+            sfx = list(window[:b0]) + list(window[b1:])
+            tkey = (b0, b1, pair, "front")
+            if self.T is not None and self._tkey == tkey and self._t_sfx == sfx:
+                self.cut, self.pair = (b0, b1), pair
+                self.window = list(window)
+                self._gw = None
+                return
+            self._update_L_to(sfx)
+            self.T = eng.inner2(SLOT_L, SLOT_BASE, *pair)
+            self.stats["t_passes"] += 1
+            self.stats["front_blocks"] = self.stats.get("front_blocks", 0) + 1
+            self._tkey, self._t_sfx = tkey, sfx
+            self.cut, self.pair = (b0, b1), pair
+            self.window = list(window)
+            self._gw = None
+            return
         r_changed = self._update_R(window, b0)
         if (not r_changed and self.T is not None and self._tkey is not None and self._tkey[:3] == (b0, b1, pair)
                 and self._t_sfx == window[b1:]):

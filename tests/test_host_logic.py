@@ -85,7 +85,9 @@ def test_nested_projection_levels_equal_full_resimulation(fake_backend, nested_l
 
 @pytest.mark.parametrize("fake_backend", [None, 6, (None, 8), (4, 8)], indirect=True)
 @pytest.mark.parametrize("n", [4, 12])
-def test_incremental_evaluator_equals_full_resimulation(fake_backend, n):
+@pytest.mark.parametrize("front", [True, False])
+def test_incremental_evaluator_equals_full_resimulation(fake_backend, n, front, monkeypatch):
+    monkeypatch.setattr(SVCostEvaluator, "front_mode", front)
     rng = np.random.default_rng(50 + n)
     target, trng = brickwork(n, 3, seed=n)
     ansatz = thin_ansatz(n, 5, trng)
@@ -104,8 +106,10 @@ def test_incremental_evaluator_equals_full_resimulation(fake_backend, n):
                 replace_1q_gate(c.full_circuit, idx, name, theta)
             assert abs(comp.evaluate_cost() - ocomp.evaluate_cost()) < 1e-10
     st = fake_backend._evaluator.stats
-    assert st["moves_R"] + st["rebuild_R"] > 0 and st["t_passes"] + st["t_gathers"] < st["evals"]
-    if fake_backend._evaluator.compact is not None and not fake_backend._evaluator.projected:
+    assert st["moves_R"] + st["rebuild_R"] + st.get("front_blocks", 0) > 0 and st["t_passes"] + st["t_gathers"] < st["evals"]
+    if front and not fake_backend._evaluator.projected:
+        assert st.get("front_blocks", 0) > 0
+    elif fake_backend._evaluator.compact is not None and not fake_backend._evaluator.projected:
         assert st["t_gathers"] > 0 and st["compact_L"] > 0
     if fake_backend._evaluator.projected:
         assert st["projected_evals"] > 0 and st["projections"] > 0
