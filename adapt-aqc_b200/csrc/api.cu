@@ -146,7 +146,9 @@ int upload_plan(b200_ctx* ctx, const Plan& plan, const DevOp** d_ops, const doub
     return 0;
 }
 
-int run_plan(b200_ctx* ctx, int dst_slot, int src_slot, const Plan& plan) {
+const EmbedSrc kNoEmbed = {};
+
+int run_plan(b200_ctx* ctx, int dst_slot, int src_slot, const Plan& plan, const EmbedSrc* es = nullptr) {
     const int n = ctx->nq;
     const uint64_t dim = 1ull << n;
     double2* dst = (double2*)ctx->slots[dst_slot];
@@ -200,7 +202,10 @@ int run_plan(b200_ctx* ctx, int dst_slot, int src_slot, const Plan& plan) {
             // a sweep from the implicit |0..0> only writes (16 * 2^n bytes): accounted with the fills, so
             // that the SWEEP class holds read+write passes only (roofline accounting, bench.py)
             KScope ks(ctx, src == nullptr ? B200_PROF_FILL : B200_PROF_SWEEP);
-            sv_sweep_kernel<REG_BITS><<<grid, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles);
+            if (es != nullptr && src == nullptr)
+                sv_sweep_kernel<REG_BITS, true><<<grid, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles, *es);
+            else
+                sv_sweep_kernel<REG_BITS><<<grid, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles, kNoEmbed);
         }
         CUDA_TRY(cudaGetLastError());
         ctx->counters[1] += 1; ctx->counters[3] += (src == nullptr ? 16 : 32) * dim;
@@ -302,6 +307,15 @@ int b200_ctx_create(int device, b200_ctx** out) {
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sweep_occ_nosmem, sv_sweep_kernel<REG_BITS>,
                                                            SWEEP_THREADS, 0));
     if (ctx->sweep_occ_smem < 1 || ctx->sweep_occ_nosmem < 1) { delete ctx; return set_error("sweep kernel does not fit on an SM"); }
+    CUDA_TRY(cudaFuncSetAttribute(sv_sweep_inner2_kernel<REG_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)FUSED_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(sv_sweep_inner2_kernel<REG_BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)FUSED_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(sv_sweep_kernel<REG_BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tile_bytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->fused_occ, sv_sweep_inner2_kernel<REG_BITS>,
+                                                           SWEEP_THREADS, FUSED_SMEM_BYTES));
+    if (ctx->fused_occ < 1) { delete ctx; return set_error("fused sweep kernel does not fit on an SM"); }
     if (const char* e = std::getenv("B200AQC_GRID_MULT")) ctx->grid_mult = std::max(1, std::atoi(e));
     if (ensure_scratch(ctx)) { delete ctx; return -1; }
     *out = ctx;
@@ -818,6 +832,136 @@ int b200_sv_inner2(b200_ctx* ctx, int l_slot, int r_slot, int qa, int qb, double
             }
     }
     return 0;
+}
+
+// shared body of b200_sv_run_inner2 / b200_sv_run_embedded_inner2 (es != nullptr: the source is the embedded state)
+static int run_inner2_impl(b200_ctx* ctx, int dst_slot, int src_slot, const EmbedSrc* es, const b200_gate* gates, int n_gates,
+                           const double* mats, int n_mats, int inverse, int other_slot, int qa, int qb, double out[32]) {
+    const int n = ctx->nq;
+    if (qa < 0 || qb < 0 || qa >= n || qb >= n || qa == qb) return set_error("run_inner2: qubits out of range");
+    if (!out) return set_error("null pointer");
+    if (other_slot == dst_slot) return set_error("run_inner2: `other` must not be the destination");
+    if (n <= SMALL_MAX_QUBITS) return set_error("run_inner2: register too small for the tiled path (use b200_sv_run + b200_sv_inner2)");
+    if (n_gates < 0 || (n_gates > 0 && !gates)) return set_error("null gate array");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Plan plan;
+    {
+        std::vector<COp> ops;
+        const std::string err = canonicalize(n, gates, n_gates, mats, n_mats, inverse != 0, ops);
+        if (!err.empty()) return set_error(err);
+        fuse_single_qubit_runs(ops);
+        fuse_diagonals(ops);
+        build_plan(n, ops, plan, true, qa, qb);
+        plan.n_gates_in = n_gates;
+    }
+    EpiProg ep;
+    if (plan.sweeps.empty() || !make_epilogue(plan.sweeps.back(), qa, qb, ep)) return set_error("run_inner2: planner did not place the pair in the last tile");
+    ctx->counters[6] += 2;
+    const uint64_t dim = 1ull << n;
+    const uint32_t ntiles = (uint32_t)(dim >> TILE_BITS);
+    const double2* src = es != nullptr ? nullptr : (const double2*)ctx->slots[src_slot];
+    double2* dst = (double2*)ctx->slots[dst_slot];
+    const size_t tile_bytes = ((size_t)1 << TILE_BITS) * sizeof(double2);
+    Timer tm(ctx);
+    uint32_t grid = 1;
+    for (size_t k = 0; k < plan.sweeps.size(); ++k) {
+        const SweepProg& sw = plan.sweeps[k];
+        const bool embed = es != nullptr && k == 0;
+        if (k + 1 < plan.sweeps.size()) {
+            const size_t smem = sw.nrounds > 1 ? tile_bytes : 0;
+            const int per_sm = sw.nrounds > 1 ? ctx->sweep_occ_smem : ctx->sweep_occ_nosmem;
+            const uint32_t g = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * per_sm * ctx->grid_mult);
+            KScope ks(ctx, embed ? B200_PROF_FILL : B200_PROF_SWEEP);
+            if (embed) sv_sweep_kernel<REG_BITS, true><<<g, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles, *es);
+            else sv_sweep_kernel<REG_BITS><<<g, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles, kNoEmbed);
+            ctx->counters[3] += (embed ? 16 : 32) * dim;
+        } else {
+            grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * ctx->fused_occ);
+            // from an embedded source the pass reads `other` and writes dst only (32 B per amplitude): its own class, so
+            // that the FUSED class holds 48-byte passes only (roofline accounting, bench.py)
+            KScope ks(ctx, embed ? B200_PROF_FUSED_EMBED : B200_PROF_FUSED);
+            if (embed)
+                sv_sweep_inner2_kernel<REG_BITS, true><<<grid, SWEEP_THREADS, FUSED_SMEM_BYTES, ctx->stream>>>(
+                    src, dst, (const double2*)ctx->slots[other_slot], sw, ep, ntiles, ctx->d_partial, *es);
+            else
+                sv_sweep_inner2_kernel<REG_BITS><<<grid, SWEEP_THREADS, FUSED_SMEM_BYTES, ctx->stream>>>(
+                    src, dst, (const double2*)ctx->slots[other_slot], sw, ep, ntiles, ctx->d_partial, kNoEmbed);
+            ctx->counters[3] += (embed ? 32 : 48) * dim;
+        }
+        CUDA_TRY(cudaGetLastError());
+        ctx->counters[1] += 1;
+        ctx->counters[4] += offsetof(SweepProg, ops) + (size_t)sw.nops * sizeof(POp) + (size_t)sw.nmat2 * 32 * sizeof(double);
+        src = dst;
+    }
+    {
+        KScope ks(ctx, B200_PROF_REDUCE);
+        reduce_partials_kernel<<<INNER2_WIDTH, 32, 0, ctx->stream>>>(ctx->d_partial, (int)grid, INNER2_WIDTH, ctx->d_out);
+    }
+    CUDA_TRY(cudaGetLastError());
+    ctx->counters[2] += n_gates;
+    tm.stop();
+    double t[32];
+    if (fetch_out(ctx, t, 32)) return -1;
+    if (qa < qb) {
+        std::memcpy(out, t, sizeof t);
+    } else {
+        auto sw2 = [](int i) { return ((i & 1) << 1) | (i >> 1); };
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                out[2 * (4 * sw2(i) + sw2(j))] = t[2 * (4 * i + j)];
+                out[2 * (4 * sw2(i) + sw2(j)) + 1] = t[2 * (4 * i + j) + 1];
+            }
+    }
+    return 0;
+}
+
+int b200_sv_run_inner2(b200_ctx* ctx, int dst_slot, int src_slot, const b200_gate* gates, int n_gates, const double* mats,
+                       int n_mats, int inverse, int other_slot, int qa, int qb, double out[32]) {
+    if (check_slot(ctx, dst_slot) || check_slot(ctx, src_slot) || check_slot(ctx, other_slot)) return -1;
+    return run_inner2_impl(ctx, dst_slot, src_slot, nullptr, gates, n_gates, mats, n_mats, inverse, other_slot, qa, qb, out);
+}
+
+// fills `es` from the caller's (compact_state, K, qmap)
+static int make_embed(b200_ctx* ctx, const void* compact_state, int K, const int32_t* qmap, EmbedSrc& es) {
+    if (!qmap || !compact_state) return set_error("null pointer");
+    const int n = ctx->nq;
+    if (K < 1 || K > n || K > 40) return set_error("embedded source: K out of range");
+    std::memset(&es, 0, sizeof es);
+    uint64_t inside = 0;
+    for (int b = 0; b < K; ++b) {
+        if (qmap[b] < 0 || qmap[b] >= n || (inside >> qmap[b] & 1)) return set_error("embedded source: qmap must hold distinct qubits of the register");
+        inside |= 1ull << qmap[b];
+        es.q[b] = qmap[b];
+    }
+    es.phi = (const double2*)compact_state;
+    es.K = K;
+    es.outside = ~inside & ((1ull << n) - 1ull);
+    return 0;
+}
+
+int b200_sv_run_embedded(b200_ctx* ctx, int dst_slot, const void* compact_state, int K, const int32_t* qmap,
+                         const b200_gate* gates, int n_gates, const double* mats, int n_mats, int inverse) {
+    if (check_slot(ctx, dst_slot)) return -1;
+    EmbedSrc es;
+    if (make_embed(ctx, compact_state, K, qmap, es)) return -1;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Plan plan;
+    if (make_plan(ctx->nq, gates, n_gates, mats, n_mats, inverse != 0, plan, true)) return -1;
+    ctx->counters[6] += 1;
+    if (plan.small || plan.sweeps.empty() || ctx->sweep_mode == 1) {     // no sweep to ride on: embed first, then the program
+        if (b200_sv_scatter(ctx, dst_slot, qmap, K, compact_state)) return -1;
+        return run_plan(ctx, dst_slot, dst_slot, plan);
+    }
+    return run_plan(ctx, dst_slot, -1, plan, &es);
+}
+
+int b200_sv_run_embedded_inner2(b200_ctx* ctx, int dst_slot, const void* compact_state, int K, const int32_t* qmap,
+                                const b200_gate* gates, int n_gates, const double* mats, int n_mats, int inverse,
+                                int other_slot, int qa, int qb, double out[32]) {
+    if (check_slot(ctx, dst_slot) || check_slot(ctx, other_slot)) return -1;
+    EmbedSrc es;
+    if (make_embed(ctx, compact_state, K, qmap, es)) return -1;
+    return run_inner2_impl(ctx, dst_slot, -1, &es, gates, n_gates, mats, n_mats, inverse, other_slot, qa, qb, out);
 }
 
 int b200_sv_inner2_gather(b200_ctx* ctx, int r_slot, const void* compact_state, int K, const int32_t* qmap, int qa,

@@ -52,7 +52,7 @@ struct b200_ctx {
     size_t h_plan_cap = 0;
 
     // launch geometry of the sweep kernel
-    int sweep_occ_smem = 1, sweep_occ_nosmem = 1;
+    int sweep_occ_smem = 1, sweep_occ_nosmem = 1, fused_occ = 1;
     int grid_mult = 1;
     int sweep_mode = 0;   // 0 = direct-load kernel (default), 1 = pipelined bulk-copy kernel (B200AQC_SWEEP=pipe)
 

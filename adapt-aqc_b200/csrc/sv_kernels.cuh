@@ -26,6 +26,7 @@
 namespace b200 {
 
 constexpr int SWEEP_THREADS = 1 << (TILE_BITS - REG_BITS);  // 256
+constexpr size_t FUSED_SMEM_BYTES = (((size_t)1 << TILE_BITS) + 4 * SWEEP_THREADS) * 16;   // tile + 4 accumulators per thread
 constexpr int RED_THREADS = 256;
 constexpr int EXPZ_WIDTH = 32;   // doubles per block partial
 constexpr int RDM3_WIDTH = 48;
@@ -260,11 +261,32 @@ B200_HD uint64_t fold_gindex(const PFold* f, const int n, const uint64_t g) {
     return x;
 }
 
-// src == nullptr: the source is |0..0> (no read pass, no separate fill pass)
+// An EMBEDDED source: the state is phi (2^K amplitudes, a smaller engine's slot) on the qubits q[0..K) and |0> on every
+// other qubit -- amplitude x is phi[extract(x)] when x has no bit outside those qubits, else 0.  A sweep that starts from
+// it has no read pass over the register (and needs no zero fill + scatter pass before it): 16 * 2^n bytes instead of 48.
+struct EmbedSrc {
+    const double2* phi;
+    uint64_t outside;     // bits of the global index that must be zero
+    int32_t K, pad;
+    int32_t q[40];
+};
+B200_HD double2 embed_load(const EmbedSrc& es, const uint64_t x) {
+    if (x & es.outside) return make_double2(0.0, 0.0);
+    uint64_t c = 0;
+    for (int b = 0; b < es.K; ++b) c |= ((x >> es.q[b]) & 1ull) << b;
+    return es.phi[c];
+}
+
+// src == nullptr: the source is |0..0> (no read pass, no separate fill pass), or the embedded state `es` if given
 template <int R>
 B200_HD void round_load_hbm(double2 (&a)[1 << R], const double2* __restrict__ src, const SweepProg& sp,
-                            const PRound& rd, const uint64_t g) {
+                            const PRound& rd, const uint64_t g, const EmbedSrc* es = nullptr) {
     const uint64_t gm = fold_gindex<true>(rd.lead, rd.n_lead, g);     // (register positions are zero in g: ^ == |)
+    if (es != nullptr) {
+#pragma unroll
+        for (int j = 0; j < (1 << R); ++j) a[j] = embed_load(*es, gm ^ rd.goff_ld[j]);
+        return;
+    }
     if (src == nullptr) {
 #pragma unroll
         for (int j = 0; j < (1 << R); ++j) a[j] = make_double2(gm == rd.goff_ld[j] ? 1.0 : 0.0, 0.0);
@@ -463,13 +485,68 @@ B200_HD void round_ops(double2 (&a)[1 << R], const SweepProg& sp, const PRound& 
     if (rd.has_pend) apply_pend<R>(a, pend);
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1 + K6b fused: epilogue of a sweep whose result is contracted straight away with a second state into the 4x4
+// transfer matrix of an open pair,  T[i][j] = sum_rest conj(S[i,rest]) O[j,rest]  (S = the swept state, O = `other`).
+// The last round leaves the tile in shared memory; thread `tid` then owns the 16 amplitudes EpiProg assigns to it: it
+// loads them from O (coalesced: thread bits 0..4 are qubits 0..4), reads the 4 pair-partners of each from the tile, stores
+// its own amplitude of S (optional), and accumulates column j = its own pair value.  Algorithmic bytes: read S, read O,
+// write S = 48 * 2^n, against 64 * 2^n for the sweep followed by the separate transfer pass (sv_inner2_kernel).
+// ---------------------------------------------------------------------------------------------
+struct EpiIdx {
+    uint32_t ls[4];   // swizzled tile index of pair value i with the thread's other bits (amplitude bits zero)
+    uint64_t g0;      // global index offset of the thread's bits (amplitude bits zero)
+    int j;            // the thread's pair value = column of T
+};
+
+B200_HD EpiIdx epi_index(const SweepProg& sp, const EpiProg& ep, const uint32_t tid) {
+    uint32_t tl = 0;
+    for (int b = 0; b < TILE_BITS - REG_BITS; ++b) tl |= ((tid >> b) & 1u) << ep.tpos[b];
+    EpiIdx ix;
+    ix.j = (int)(((tid >> ep.ja) & 1u) | (((tid >> ep.jb) & 1u) << 1));
+    const uint32_t rest = tl & ~((1u << ep.pa) | (1u << ep.pb));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ix.ls[i] = swz(rest | ((uint32_t)(i & 1) << ep.pa) | ((uint32_t)(i >> 1) << ep.pb));
+    uint64_t g = 0;
+    for (int i = 0; i < TILE_BITS; ++i) g |= (uint64_t)((tl >> i) & 1u) << sp.tileq[i];
+    ix.g0 = g;
+    return ix;
+}
+
+template <int R>
+B200_HD void epi_tile(const double2* tile_smem, const double2* __restrict__ other, double2* __restrict__ dst,
+                      const EpiProg& ep, const EpiIdx& ix, const uint64_t tile_base, double2 (&t)[4]) {
+    const uint64_t G = tile_base | ix.g0;
+    constexpr int NB = 2, HALF = (1 << R) / NB;   // batches of 8 loads in flight (all 16 at once spill at the 128-register cap)
+#pragma unroll
+    for (int h = 0; h < NB; ++h) {
+        double2 r[HALF];
+#pragma unroll
+        for (int m = 0; m < HALF; ++m) r[m] = other[G | ep.moff_g[h * HALF + m]];
+#pragma unroll
+        for (int m = 0; m < HALF; ++m) {
+            const uint32_t mo = ep.moff_sw[h * HALF + m];
+            const double2 l0 = tile_smem[ix.ls[0] ^ mo], l1 = tile_smem[ix.ls[1] ^ mo], l2 = tile_smem[ix.ls[2] ^ mo],
+                          l3 = tile_smem[ix.ls[3] ^ mo];
+            if (dst != nullptr) {
+                const double2 lo = (ix.j & 1) ? l1 : l0, hi = (ix.j & 1) ? l3 : l2;
+                dst[G | ep.moff_g[h * HALF + m]] = (ix.j & 2) ? hi : lo;
+            }
+            t[0] = cjfma(l0, r[m], t[0]);
+            t[1] = cjfma(l1, r[m], t[1]);
+            t[2] = cjfma(l2, r[m], t[2]);
+            t[3] = cjfma(l3, r[m], t[3]);
+        }
+    }
+}
+
 #ifdef __CUDACC__
 // The whole program of the sweep is a kernel parameter: op decode is uniform constant-bank loads and
 // uniform branches.  One CTA owns one tile at a time (persistent grid-stride over tiles).
-template <int R>
+template <int R, bool EMBED = false>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2)
 sv_sweep_kernel(const double2* __restrict__ src, double2* __restrict__ dst, const __grid_constant__ SweepProg sp,
-                const uint32_t ntiles) {
+                const uint32_t ntiles, const __grid_constant__ EmbedSrc es) {
     extern __shared__ __align__(16) double2 tile_smem[];
     static_assert(R == REG_BITS, "register bits");
     const int nr = sp.nrounds;
@@ -483,13 +560,64 @@ sv_sweep_kernel(const double2* __restrict__ src, double2* __restrict__ dst, cons
             round_index<R>(sp, rd, tile_base, tid, tl, g);
             const uint32_t tls = swz(tl);
             double2 a[1 << R];
-            if (r == 0) round_load_hbm<R>(a, src, sp, rd, g);
+            if (r == 0) round_load_hbm<R>(a, src, sp, rd, g, EMBED ? &es : nullptr);
             else round_load_smem<R>(a, tile_smem, rd, tls, g);
             round_ops<R, false>(a, sp, rd, g, lane, ex);
             if (r == nr - 1) round_store_hbm<R>(a, dst, sp, rd, g);
             else { round_store_smem<R>(a, tile_smem, rd, tls, g); __syncthreads(); }
         }
         if (nr > 1) __syncthreads();
+    }
+}
+
+// Fused sweep + transfer pass.  partial[blockIdx.x * 32 + 2 * (4 * i + j) + {0, 1}] = this CTA's share of T[i][j].
+template <int R, bool EMBED = false>
+__global__ void __launch_bounds__(SWEEP_THREADS, 2)
+sv_sweep_inner2_kernel(const double2* __restrict__ src, double2* __restrict__ dst, const double2* __restrict__ other,
+                       const __grid_constant__ SweepProg sp, const __grid_constant__ EpiProg ep, const uint32_t ntiles,
+                       double* __restrict__ partial, const __grid_constant__ EmbedSrc es) {
+    extern __shared__ __align__(16) double2 tile_smem[];
+    static_assert(R == REG_BITS, "register bits");
+    const int nr = sp.nrounds;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const ShflExchange ex;
+    // the thread's 4 accumulators wait in shared memory while the rounds of the next tile need every register
+    double2* acc = tile_smem + ((size_t)1 << TILE_BITS);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i * SWEEP_THREADS + tid] = make_double2(0.0, 0.0);
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t tile_base = sweep_tile_base(sp, tile);
+        for (int r = 0; r < nr; ++r) {
+            const PRound& rd = sp.rounds[r];
+            uint32_t tl; uint64_t g;
+            round_index<R>(sp, rd, tile_base, tid, tl, g);
+            const uint32_t tls = swz(tl);
+            double2 a[1 << R];
+            if (r == 0) round_load_hbm<R>(a, src, sp, rd, g, EMBED ? &es : nullptr);
+            else round_load_smem<R>(a, tile_smem, rd, tls, g);
+            round_ops<R, false>(a, sp, rd, g, lane, ex);
+            round_store_smem<R>(a, tile_smem, rd, tls, g);
+            __syncthreads();
+        }
+        const EpiIdx ix = epi_index(sp, ep, tid);
+        double2 t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = acc[i * SWEEP_THREADS + tid];
+        epi_tile<R>(tile_smem, other, dst, ep, ix, tile_base, t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i * SWEEP_THREADS + tid] = t[i];
+        __syncthreads();                              // the tile has been read: the next one may land
+    }
+    // ---- CTA reduction: 64 threads per column j, fixed order ----
+    if (tid < 32) {
+        const int k = (int)tid >> 1, part = (int)tid & 1, i = k >> 2, j = k & 3;
+        const double* sh = reinterpret_cast<const double*>(acc + i * SWEEP_THREADS);
+        double s = 0.0;
+        for (uint32_t u = 0; u < (uint32_t)SWEEP_THREADS; ++u) {
+            const int ju = (int)(((u >> ep.ja) & 1u) | (((u >> ep.jb) & 1u) << 1));
+            if (ju == j) s += sh[2 * u + part];
+        }
+        partial[(size_t)blockIdx.x * INNER2_WIDTH + tid] = s;
     }
 }
 

@@ -439,7 +439,39 @@ bool x_commutes_with(const COp& x, const COp& o) {
 
 }  // namespace
 
-void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm) {
+bool make_epilogue(const SweepProg& sp, int qa, int qb, EpiProg& ep) {
+    std::memset(&ep, 0, sizeof ep);
+    int pa = -1, pb = -1;
+    for (int i = 0; i < TILE_BITS; ++i) {
+        if (sp.tileq[i] == qa) pa = i;
+        if (sp.tileq[i] == qb) pb = i;
+    }
+    if (pa < 0 || pb < 0 || pa == pb) return false;
+    if (pa > pb) std::swap(pa, pb);
+    ep.pa = pa; ep.pb = pb;
+    // amplitude bits: the REG_BITS highest tile positions that are not the pair; thread bits: the rest, ascending
+    uint32_t mmask = 0;
+    for (int i = TILE_BITS - 1, k = 0; i >= 0 && k < REG_BITS; --i)
+        if (i != pa && i != pb) { mmask |= 1u << i; ++k; }
+    int mpos[REG_BITS];
+    for (int i = 0, k = 0, b = 0; i < TILE_BITS; ++i) {
+        if (mmask >> i & 1) { mpos[k++] = i; continue; }
+        if (i == pa) ep.ja = b;
+        if (i == pb) ep.jb = b;
+        ep.tpos[b++] = i;
+    }
+    for (uint32_t m = 0; m < (1u << REG_BITS); ++m) {
+        uint32_t off = 0;
+        uint64_t g = 0;
+        for (int k = 0; k < REG_BITS; ++k)
+            if (m >> k & 1) { off |= 1u << mpos[k]; g |= 1ull << sp.tileq[mpos[k]]; }
+        ep.moff_sw[m] = swz(off);
+        ep.moff_g[m] = g;
+    }
+    return true;
+}
+
+void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm, int pair_a, int pair_b) {
     plan = Plan();
     plan.num_qubits = nq;
     if (nq <= SMALL_MAX_QUBITS) {
@@ -457,9 +489,15 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm)
     const uint64_t low_mask = (1ull << LANE_BITS) - 1;
     const uint64_t coal_mask = (1ull << COAL_BITS) - 1;
 
-    while (n_taken < nops) {
+    const bool fused = pair_a >= 0 && pair_b >= 0;
+    uint64_t H_forced = 0;
+    if (fused) H_forced = ((1ull << pair_a) | (1ull << pair_b)) & ~low_mask;
+    bool need_one = fused && nops == 0;
+
+    while (n_taken < nops || need_one) {
+        need_one = false;
         // ---- choose the ops of this sweep and its set H of high mixing qubits ----
-        uint64_t H = 0;
+        uint64_t H = H_forced;
         int n_sw = 0, n_m2 = 0;
         std::vector<int> sw_ops = greedy_pick(ops, all, taken, [&](const COp& o) {
             if (n_sw >= MAX_SWEEP_OPS || (o.kind == K_MAT2 && n_m2 >= MAX_SWEEP_MAT2)) return false;
@@ -531,6 +569,7 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm)
         // was scheduled ahead of them, see greedy_pick)
         for (int idx : sw_ops) if (!rtaken[idx]) taken[idx] = 0;
         n_taken += (int)sw_ops.size() - left;
+        const bool tail_in_smem = fused && n_taken == nops;   // the fused epilogue picks the tile up from shared memory
 
         sp.nrounds = (int32_t)rounds.size();
         for (size_t r = 0; r < rounds.size(); ++r) {
@@ -554,7 +593,7 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm)
                 // amplitude -- same 128 B lines per warp access.  Its control must be a plain thread bit (the kernel
                 // evaluates the folded ops of an HBM round one after the other on the running index, so a folded op may
                 // be controlled by a lane qubit that another folded op flips: fold_gindex).
-                const bool loads_hbm = r == 0, stores_hbm = r + 1 == rounds.size();
+                const bool loads_hbm = r == 0, stores_hbm = r + 1 == rounds.size() && !tail_in_smem;
                 auto foldable_side = [&](const COp& o, bool hbm_side) {
                     if (!fold_perm || o.kind != K_X) return false;
                     if (reg_of[o.t0] >= 0) return true;

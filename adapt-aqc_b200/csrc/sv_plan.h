@@ -163,6 +163,18 @@ struct alignas(16) SweepProg {
 };
 static_assert(sizeof(SweepProg) <= 32000, "SweepProg must fit the 32 KB kernel-parameter space");
 
+// Epilogue of a FUSED sweep + transfer pass (sv_sweep_inner2_kernel): after the last round of the sweep the tile sits in
+// shared memory; every thread then owns 16 amplitudes of the tile -- thread bit b at tile position tpos[b], amplitude
+// m at the 4 tile positions outside tpos -- chosen so that the values of the open pair (qa, qb) are THREAD bits: a thread
+// sees one fixed column j of the 4x4 transfer matrix and keeps only 4 complex accumulators.
+struct EpiProg {
+    int32_t pa, pb;          // tile-local positions of the open pair (pa < pb)
+    int32_t ja, jb;          // thread bits that sit at pa / pb
+    int32_t tpos[TILE_BITS - REG_BITS];
+    uint32_t moff_sw[1 << REG_BITS];   // amplitude m of a thread: swizzled tile offset ...
+    uint64_t moff_g[1 << REG_BITS];    // ... and offset in the global index
+};
+
 struct Plan {
     int num_qubits = 0;
     bool small = false;              // single-CTA shared-memory path
@@ -183,6 +195,12 @@ void fuse_single_qubit_runs(std::vector<COp>& ops);
 void fuse_diagonals(std::vector<COp>& ops);
 // fold_perm: fold leading / trailing X-type ops of every round into its load / store addressing (the direct sweep
 // kernel; the pipelined variant keeps executing them).
-void build_plan(int num_qubits, const std::vector<COp>& ops, Plan& plan, bool fold_perm = true);
+// pair_a / pair_b >= 0: plan for the fused sweep + transfer pass -- both qubits are tile qubits of EVERY sweep (so of the
+// last one), there is at least one sweep, and the last round of the last sweep stores to shared memory (no lane-qubit
+// folds on its store side).
+void build_plan(int num_qubits, const std::vector<COp>& ops, Plan& plan, bool fold_perm = true, int pair_a = -1,
+                int pair_b = -1);
+// Epilogue tables for the pair (qa, qb) on the tile of `sp`; false if one of them is not a tile qubit.
+bool make_epilogue(const SweepProg& sp, int qa, int qb, EpiProg& ep);
 
 }  // namespace b200

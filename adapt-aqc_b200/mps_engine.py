@@ -112,10 +112,11 @@ class MPSContext:
         check(self._lib.b200_ctx_profile(self._ctx, 1 if enable else 0))
 
     def profile_read(self):
-        ms = (ctypes.c_double * 10)()
-        cnt = (ctypes.c_uint64 * 10)()
+        from .sv_engine import SVEngine
+        names = SVEngine.PROF_CLASSES          # one table for both engines: B200_PROF_CLASSES entries (include/b200aqc.h)
+        ms = (ctypes.c_double * len(names))()
+        cnt = (ctypes.c_uint64 * len(names))()
         check(self._lib.b200_ctx_profile_read(self._ctx, ms, cnt))
-        names = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps", "svd", "gemm")
         return {name: (ms[i], cnt[i]) for i, name in enumerate(names)}
 
 

@@ -141,6 +141,32 @@ class SVEngine:
         check(self._lib.b200_sv_inner2(self._ctx, l_slot, r_slot, int(qa), int(qb), dptr(out)))
         return out.view(np.complex128).reshape(4, 4).copy()
 
+    FUSED_MIN_QUBITS = 12
+
+    def run_inner2(self, dst, src, stream, other, qa, qb, inverse=False):
+        """run(dst, src, stream) and inner2(dst, other, qa, qb) in one pass over the register (b200_sv_run_inner2)."""
+        out = np.zeros(32)
+        check(self._lib.b200_sv_run_inner2(self._ctx, dst, src, stream.rec_ptr(), len(stream.rec), stream.mats_ptr(),
+                                           len(stream.mats), 1 if inverse else 0, int(other), int(qa), int(qb), dptr(out)))
+        return out.view(np.complex128).reshape(4, 4).copy()
+
+    def run_embedded(self, dst, qmap, src_engine, src_slot, stream, inverse=False, fuse=None):
+        """dst <- stream applied to the embedded state (slot `src_slot` of `src_engine` on the qubits qmap, |0> elsewhere):
+        scatter + run without the zero fill and the read pass.  fuse = (other slot, qa, qb): also returns the transfer
+        matrix of (dst, other) from the same pass (b200_sv_run_embedded_inner2)."""
+        qm = np.ascontiguousarray(np.asarray(qmap, dtype=np.int32))
+        src_engine.sync()
+        ptr = ctypes.c_void_p(src_engine.device_ptr(src_slot))
+        if fuse is None:
+            check(self._lib.b200_sv_run_embedded(self._ctx, int(dst), ptr, len(qm), qm.ctypes.data, stream.rec_ptr(), len(stream.rec),
+                                                 stream.mats_ptr(), len(stream.mats), 1 if inverse else 0))
+            return None
+        out = np.zeros(32)
+        check(self._lib.b200_sv_run_embedded_inner2(self._ctx, int(dst), ptr, len(qm), qm.ctypes.data, stream.rec_ptr(),
+                                                    len(stream.rec), stream.mats_ptr(), len(stream.mats), 1 if inverse else 0,
+                                                    int(fuse[0]), int(fuse[1]), int(fuse[2]), dptr(out)))
+        return out.view(np.complex128).reshape(4, 4).copy()
+
     def inner2_gather(self, r_slot, compact_engine, compact_slot, qmap, qa, qb):
         """Same T with the bra given compactly: slot `compact_slot` of `compact_engine` (K qubits,
         same device) holds L on the qubits qmap[0..K)."""
@@ -210,15 +236,15 @@ class SVEngine:
         check(self._lib.b200_ctx_elapsed_ms(self._ctx, ctypes.byref(ms)))
         return ms.value
 
-    PROF_CLASSES = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps", "svd", "gemm")
+    PROF_CLASSES = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps", "svd", "gemm", "fused", "fused_embed")
 
     def profile(self, enable=True):
         check(self._lib.b200_ctx_profile(self._ctx, 1 if enable else 0))
 
     def profile_read(self):
         """{class: (total_ms, launches)} of the kernels launched since profile(True)."""
-        ms = (ctypes.c_double * 10)()
-        cnt = (ctypes.c_uint64 * 10)()
+        ms = (ctypes.c_double * len(self.PROF_CLASSES))()
+        cnt = (ctypes.c_uint64 * len(self.PROF_CLASSES))()
         check(self._lib.b200_ctx_profile_read(self._ctx, ms, cnt))
         return {name: (ms[i], cnt[i]) for i, name in enumerate(self.PROF_CLASSES)}
 
@@ -491,9 +517,11 @@ class SVCostEvaluator:
             sub = SVCostEvaluator(peng, None, nested, registry=self._registry)
         return sub
 
-    def _bra_into(self, slot, window):
+    def _bra_into(self, slot, window, fuse=None):
         """slot <- window^+ |0..0> on this engine.  The longest tail of `window` that fits a smaller engine is built THERE
-        (recursively) and embedded with one write pass (``scatter``); only the remaining head gates run at this size."""
+        (recursively); the head gates run at this size in a sweep that reads its tiles straight from the small engine's
+        slot (b200_sv_run_embedded: no zero fill, no scatter pass, no read pass).  fuse = (other slot, qa, qb): the
+        transfer matrix of (slot, other) comes out of that same sweep and is returned (else None)."""
         eng, stream = self.eng, G.GateStream.from_window
         if self.projected and hasattr(eng, "scatter") and len(window):
             kmax = max((e.num_qubits for e in self.projected if e.num_qubits + self.min_saving() <= eng.num_qubits), default=0)
@@ -511,12 +539,21 @@ class SVCostEvaluator:
                 pos = {q: c for c, q in enumerate(qmap)}
                 tail = [(e[0], pos[e[1]], pos[e[2]] if e[2] >= 0 else -1) + tuple(e[3:]) for e in window[m:]]
                 self._sub_for(peng)._bra_into(SLOT_WORK, tail)
+                self.stats["scattered_L"] = self.stats.get("scattered_L", 0) + 1
+                T = None
+                if self.fused_passes and hasattr(eng, "run_embedded") and eng.num_qubits >= getattr(eng, "FUSED_MIN_QUBITS", 1 << 30) \
+                        and (m > 0 or fuse is not None):
+                    T = eng.run_embedded(slot, list(qmap), peng, SLOT_WORK, stream(window[:m]), inverse=True, fuse=fuse)
+                    self.stats["embedded_L"] = self.stats.get("embedded_L", 0) + 1
+                    if T is not None:
+                        self.stats["fused_T"] = self.stats.get("fused_T", 0) + 1
+                    return T
                 eng.scatter(slot, list(qmap), peng, SLOT_WORK)
                 if m > 0:
                     eng.run(slot, slot, stream(window[:m]), inverse=True)
-                self.stats["scattered_L"] = self.stats.get("scattered_L", 0) + 1
-                return
+                return None
         eng.run(slot, -1, stream(window), inverse=True)
+        return None
 
     def _projected(self, window, target, changed):
         """If window[target] lies in the projected tail: (nested evaluator, tail window in the engine's qubit
@@ -601,20 +638,34 @@ class SVCostEvaluator:
 
     MIDDLE_MAX_GATES = 24
 
-    def _update_L_to(self, sfx):
-        """Make slot L hold sfx^+ |0..0> (sfx: gate list applied in order to a ket).  Returns True if the slot changed."""
+    fused_passes = os.environ.get("B200AQC_FUSED", "1") != "0"
+
+    def _move_L(self, gate_stream, inverse, fuse):
+        """One in-place sweep of slot L; fuse = (other slot, qa, qb): the transfer matrix against that slot is taken in the
+        same pass over the register (b200_sv_run_inner2) and left in self._fused_T."""
+        eng = self.eng
+        if fuse is not None and self.fused_passes and eng.num_qubits >= getattr(eng, "FUSED_MIN_QUBITS", 1 << 30):
+            self._fused_T = eng.run_inner2(SLOT_L, SLOT_L, gate_stream, fuse[0], fuse[1], fuse[2], inverse=inverse)
+            self.stats["fused_T"] = self.stats.get("fused_T", 0) + 1
+        else:
+            eng.run(SLOT_L, SLOT_L, gate_stream, inverse=inverse)
+
+    def _update_L_to(self, sfx, fuse=None):
+        """Make slot L hold sfx^+ |0..0> (sfx: gate list applied in order to a ket).  Returns True if the slot changed.
+        fuse: see _move_L (self._fused_T is None afterwards unless the update was one fused sweep)."""
         eng, stream = self.eng, G.GateStream.from_window
         old = self.lwin
+        self._fused_T = None
         if old is not None and old == sfx:
             return False
         if old is not None and self.l_moves < self.REFRESH_MOVES:
             so, sn = len(old), len(sfx)
             if sn <= so and so - sn <= sn and old[so - sn:] == sfx:
-                eng.run(SLOT_L, SLOT_L, stream(old[:so - sn]))
+                self._move_L(stream(old[:so - sn]), False, fuse)
                 self.lwin = list(sfx); self.l_moves += 1; self.stats["moves_L"] += 1
                 return True
             if sn > so and sn - so <= sn and sfx[sn - so:] == old:
-                eng.run(SLOT_L, SLOT_L, stream(sfx[:sn - so]), inverse=True)
+                self._move_L(stream(sfx[:sn - so]), True, fuse)
                 self.lwin = list(sfx); self.l_moves += 1; self.stats["moves_L"] += 1
                 return True
             # middle replacement: old = P + X + S, new = P + Y + S  =>  L_new = P^+ Y^+ X P L_old = Y^+ X L_old when the
@@ -632,14 +683,14 @@ class SVCostEvaluator:
                 for e in X + Y:
                     xy.update(_support(e))
                 if all(xy.isdisjoint(_support(e)) for e in old[:p]):
-                    eng.run(SLOT_L, SLOT_L, stream(list(X) + G.invert_window(Y)))
+                    self._move_L(stream(list(X) + G.invert_window(Y)), False, fuse)
                     self.lwin = list(sfx); self.l_moves += 1
                     self.stats["middle_L"] = self.stats.get("middle_L", 0) + 1
                     return True
         # rebuild: suffix^+ |0> is supported on the qubits the suffix touches -- built on the smaller engines as far as it
         # fits them (cheap sweeps), embedded level by level, only the remaining head gates are applied at this size
         if self.dense_blocks:
-            self._bra_into(SLOT_L, sfx)
+            self._fused_T = self._bra_into(SLOT_L, sfx, fuse=fuse)
         else:
             eng.run(SLOT_L, -1, stream(sfx), inverse=True)
         self.lwin = list(sfx)
@@ -738,8 +789,9 @@ class SVCostEvaluator:
                 self.window = list(window)
                 self._gw = None
                 return
-            self._update_L_to(sfx)
-            self.T = eng.inner2(SLOT_L, SLOT_BASE, *pair)
+            self._update_L_to(sfx, fuse=(SLOT_BASE, pair[0], pair[1]))
+            self.T = self._fused_T if self._fused_T is not None else eng.inner2(SLOT_L, SLOT_BASE, *pair)
+            self._fused_T = None
             self.stats["t_passes"] += 1
             self.stats["front_blocks"] = self.stats.get("front_blocks", 0) + 1
             self._tkey, self._t_sfx = tkey, sfx
@@ -760,10 +812,19 @@ class SVCostEvaluator:
             l_changed = self._update_L_compact(window, b1, qmap)
             mode = "compact"
         else:
-            l_changed = self._update_L_dense(window, b1)
+            self._fused_T = None
+            l_changed = self._update_L_to(window[b1:], fuse=(self.r_slot, pair[0], pair[1]) if len(pair) == 2 else None)
             mode = "dense"
         tkey = (b0, b1, pair, mode)
-        if r_changed or l_changed or self.T is None or tkey != self._tkey:
+        if mode == "dense" and self._fused_T is not None:
+            self.T, self._fused_T = self._fused_T, None       # the bra moved in one sweep: T came out of the same pass
+            self.stats["t_passes"] += 1
+            self._tkey = tkey
+            self._t_sfx = list(window[b1:])
+            self._gw = None
+            if self.prefetch_L:
+                self._prefetch_next_L(window, b1)
+        elif r_changed or l_changed or self.T is None or tkey != self._tkey:
             if mode == "compact":
                 self.compact.sync()
                 self.T = eng.inner2_gather(self.r_slot, self.compact, 0, qmap, *pair)

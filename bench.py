@@ -116,13 +116,16 @@ def measured_peak_hbm():
     return 6650.0, "fallback"
 
 
-def measured_traffic(n):
-    """DRAM bytes per launch of the sweep kernel from the committed `ncu --set full` capture
-    (profiles/sweep_traffic.json, taken at n = 28); None for other sizes."""
+def measured_traffic(n, kernel="sv_sweep_kernel"):
+    """DRAM bytes per launch of the sweep kernel (or of the fused sweep + transfer pass) from the committed
+    `ncu --set full` capture (profiles/sweep_traffic.json, taken at n = 28); None for other sizes / no capture."""
     p = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     try:
         t = json.load(open(p))
-        if int(t["algorithmic_bytes_per_launch"]) == 32 * (1 << n):
+        if kernel != "sv_sweep_kernel":
+            t = t[kernel]
+        per_amp = 32 if kernel == "sv_sweep_kernel" else 48
+        if int(t["algorithmic_bytes_per_launch"]) == per_amp * (1 << n):
             return float(t["traffic_bytes_per_launch"])
     except Exception:  # noqa: BLE001
         pass
@@ -875,16 +878,25 @@ def main():
     value = evals / (dev_ms * 1e-3)
     e2e_value = e2e_evals / (e2e_ms * 1e-3)
 
-    sweep_ms, sweep_n = prof["sweep"]
     peak, peak_kind = measured_peak_hbm()
-    alg_bytes = 32.0 * (1 << n)
-    achieved = alg_bytes / (sweep_ms / max(1, sweep_n) * 1e-3) / 1e9 if sweep_n else None
-    roofline = {"bound": "hbm", "kernel": "sv_sweep_kernel", "achieved": achieved, "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                "traffic": measured_traffic(n), "bytes_per_launch": alg_bytes, "launches": int(sweep_n),
-                "avg_launch_ms": sweep_ms / max(1, sweep_n),
-                "share_of_step": sweep_ms / dev_ms if world == 1 else None,
-                "other_kernels_ms": {k: round(v[0], 3) for k, v in prof.items() if k != "sweep" and v[1]}}
+
+    def hbm_roofline(cls, kernel, bytes_per_amp):
+        ms, cnt = prof[cls]
+        alg = float(bytes_per_amp) * (1 << n)
+        ach = alg / (ms / max(1, cnt) * 1e-3) / 1e9 if cnt else None
+        return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": ach / peak if ach else None, "traffic": measured_traffic(n, kernel), "bytes_per_launch": alg,
+                "launches": int(cnt), "avg_launch_ms": ms / max(1, cnt), "share_of_step": ms / dev_ms if world == 1 else None}
+
+    # the two register-sized kernels of the step: the gate sweep (read + write: 32 B per amplitude) and the fused
+    # sweep + transfer pass (read two states, write one: 48 B per amplitude); the one with more device time leads
+    r_sweep = hbm_roofline("sweep", "sv_sweep_kernel", 32)
+    r_fused = hbm_roofline("fused", "sv_sweep_inner2_kernel", 48)
+    roofline, other = (r_fused, r_sweep) if prof["fused"][0] > prof["sweep"][0] else (r_sweep, r_fused)
+    roofline = dict(roofline)
+    if other["launches"]:
+        roofline["also"] = other
+    roofline["other_kernels_ms"] = {k: round(v[0], 3) for k, v in prof.items() if k not in ("sweep", "fused") and v[1]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,

@@ -77,7 +77,7 @@ int b200_ctx_elapsed_ms(b200_ctx *ctx, double *ms);
 /* Per-kernel-class device times: while enabled, every kernel launch is bracketed by its own CUDA
  * event pair on the context's stream.  enable != 0 also resets the accumulators.  profile_read
  * synchronises the stream and returns, per class, the summed milliseconds and launch count. */
-#define B200_PROF_CLASSES 10
+#define B200_PROF_CLASSES 12
 enum {
     B200_PROF_SWEEP = 0,  /* sv_sweep_kernel (fused gate sweep, tiled path)  */
     B200_PROF_SMALL = 1,  /* sv_small_kernel (n <= 11, one CTA)              */
@@ -88,7 +88,9 @@ enum {
     B200_PROF_REDUCE = 6, /* final fixed-order reductions                    */
     B200_PROF_MPS = 7,    /* MPS kernels other than the two below            */
     B200_PROF_SVD = 8,    /* on-device Jacobi SVD (jacobi_*_kernel)          */
-    B200_PROF_GEMM = 9    /* complex GEMM on the FP64 tensor cores (DMMA)    */
+    B200_PROF_GEMM = 9,   /* complex GEMM on the FP64 tensor cores (DMMA)    */
+    B200_PROF_FUSED = 10, /* sv_sweep_inner2_kernel (sweep + transfer pass)  */
+    B200_PROF_FUSED_EMBED = 11 /* the same from an embedded source (no read of the swept state) */
 };
 int b200_ctx_profile(b200_ctx *ctx, int enable);
 int b200_ctx_profile_read(b200_ctx *ctx, double ms[B200_PROF_CLASSES], uint64_t launches[B200_PROF_CLASSES]);
@@ -175,6 +177,29 @@ int b200_sv_inner(b200_ctx *ctx, int l_slot, int r_slot, int q, double out[8]);
  * one read pass over L and R serves every Rotoselect / Rotosolve evaluation of that layer
  * (adaptaqc/utils/cost_minimiser.py:267-368), for any number of optimiser cycles. */
 int b200_sv_inner2(b200_ctx *ctx, int l_slot, int r_slot, int qa, int qb, double out[32]);
+
+/* b200_sv_run (or b200_sv_run_inverse: `inverse` != 0) followed by b200_sv_inner2 with the swept state as the bra, in ONE
+ * pass: dst <- gates applied to src, out = T[i][j] = sum_rest conj(dst[i,rest]) other[j,rest].  The last sweep of the
+ * program keeps each tile in shared memory and contracts it with `other` before storing it, so the pair costs
+ * 48 * 2^n bytes of HBM traffic instead of 64 * 2^n.  The optimiser's walk from one ansatz block to the next
+ * (adaptaqc/utils/cost_minimiser.py:267-316: one small edit of the bra, then a fresh transfer matrix) is exactly this
+ * pair.  dst may equal src; `other` must differ from dst.  Registers of fewer than 12 qubits: error (call the two
+ * functions). */
+int b200_sv_run_inner2(b200_ctx *ctx, int dst_slot, int src_slot, const b200_gate *gates, int n_gates, const double *mats,
+                       int n_mats, int inverse, int other_slot, int qa, int qb, double out[32]);
+
+/* dst <- gates applied to the EMBEDDED state: compact_state (2^K amplitudes on the device, e.g. a slot of a K-qubit context
+ * that the caller has synchronised) on the qubits qmap[0..K), |0> on every other qubit.  Equivalent to b200_sv_scatter
+ * followed by b200_sv_run, without the zero-fill pass and without the sweep's read pass: the first sweep reads its tiles
+ * from the compact array (16 * 2^n bytes instead of 16 + 32).  The bra (suffix)^+ |0..0> of the optimiser's walk
+ * (adaptaqc/utils/cost_minimiser.py:267-316) is such a state: its tail is built on a small register and only the head gates
+ * run at full size.  b200_sv_run_embedded_inner2: the same followed by the transfer pass of b200_sv_run_inner2, in one pass
+ * (read `other`, write dst: 32 * 2^n bytes against 16 + 32 + 32). */
+int b200_sv_run_embedded(b200_ctx *ctx, int dst_slot, const void *compact_state, int K, const int32_t *qmap,
+                         const b200_gate *gates, int n_gates, const double *mats, int n_mats, int inverse);
+int b200_sv_run_embedded_inner2(b200_ctx *ctx, int dst_slot, const void *compact_state, int K, const int32_t *qmap,
+                                const b200_gate *gates, int n_gates, const double *mats, int n_mats, int inverse,
+                                int other_slot, int qa, int qb, double out[32]);
 
 /* Same T as b200_sv_inner2, for a bra that is given COMPACTLY: <L| = (suffix)^+ <0..0| is supported
  * only on the K qubits the suffix touches, so it is stored as a 2^K-amplitude device array

@@ -22,15 +22,21 @@ extern "C" const char* emu_last_error() { return g_err.c_str(); }
 extern "C" void emu_set_variant(int v) { g_variant = v; }
 
 // state: 2^nq complex128 (host), updated in place.  src_is_zero: start from |0..0>.
-extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_gate* gates, int n_gates,
-                          const double* mats, int n_mats, int inverse, int32_t stats[4]) {
+// fused (qa >= 0): the last sweep keeps its tiles in "shared memory" and runs the epilogue of
+// sv_sweep_inner2_kernel against `other`; T (32 doubles, bit0 = lower qubit) comes back in t_out.
+static int emu_run_impl(int nq, double* state_ri, int src_is_zero, const b200_gate* gates, int n_gates,
+                        const double* mats, int n_mats, int inverse, int32_t stats[4], int qa, int qb,
+                        const double* other_ri, int write_back, double* t_out, const EmbedSrc* es = nullptr) {
+    const bool fused = qa >= 0;
     std::vector<COp> ops;
     g_err = canonicalize(nq, gates, n_gates, mats, n_mats, inverse != 0, ops);
     if (!g_err.empty()) return -1;
     fuse_single_qubit_runs(ops);
     fuse_diagonals(ops);
     Plan plan;
-    build_plan(nq, ops, plan, /*fold_perm=*/g_variant == 0);
+    build_plan(nq, ops, plan, /*fold_perm=*/g_variant == 0 || fused, fused ? qa : -1, fused ? qb : -1);
+    if (fused && (plan.small || g_variant != 0)) { g_err = "fused path: tiled direct kernel only"; return -1; }
+    if (es != nullptr && (plan.small || plan.sweeps.empty() || g_variant != 0)) { g_err = "embedded source: needs a tiled sweep to ride on"; return -1; }
     double2* psi = reinterpret_cast<double2*>(state_ri);
     const uint64_t dim = 1ull << nq;
     if (src_is_zero) {
@@ -79,7 +85,13 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
         }
     }
     bool first_sweep = true;
-    for (const SweepProg& sp : plan.sweeps) {
+    EpiProg ep;
+    std::vector<double2> tacc((size_t)SWEEP_THREADS * 4, make_double2(0.0, 0.0));
+    const double2* other = reinterpret_cast<const double2*>(other_ri);
+    if (fused && !make_epilogue(plan.sweeps.back(), qa, qb, ep)) { g_err = "pair not in the last tile"; return -1; }
+    for (size_t si = 0; si < plan.sweeps.size(); ++si) {
+        const SweepProg& sp = plan.sweeps[si];
+        const bool tail = fused && si + 1 == plan.sweeps.size();
         const int nr = sp.nrounds;
         // the direct kernel takes |0..0> as an IMPLICIT source (src == nullptr) in its first sweep
         const double2* hbm_src = (first_sweep && src_is_zero && g_variant == 0) ? nullptr : psi;
@@ -98,15 +110,19 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
                     tls[tid] = swz(tl);
                     tlin[tid] = tl;
                     if (r == 0 && g_variant == 1) round_load_lin<REG_BITS>(regs[tid].a, smem.data(), rd, tl);
-                    else if (r == 0) round_load_hbm<REG_BITS>(regs[tid].a, hbm_src, sp, rd, gidx[tid]);
+                    else if (r == 0) round_load_hbm<REG_BITS>(regs[tid].a, hbm_src, sp, rd, gidx[tid], (es != nullptr && si == 0) ? es : nullptr);
                     else round_load_smem<REG_BITS>(regs[tid].a, smem.data(), rd, tls[tid], gidx[tid]);
                     pend[tid] = make_double2(1.0, 0.0);
                 }
+                if (tail && r == nr - 1)
+                    for (int f = 0; f < rd.n_trail; ++f)
+                        if (rd.trail[f].smask == 0) { g_err = "lane fold on the store side of a fused tail"; return -1; }
                 for (int o = rd.op_begin; o < rd.op_end; ++o) {
                     POp op = sp.ops[o];
                     const bool lane_op = op.kind == P_XLANE || op.kind == P_MAT1LANE;
                     if (lane_op) {
                         if (r != 0 && r != nr - 1) { g_err = "lane op scheduled in a shared-memory round"; return -1; }
+
                         if (op.flush & 1) {   // every lane applies its pending phase before the exchange
                             for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid) {
                                 apply_pend<REG_BITS>(regs[tid].a, pend[tid]);
@@ -124,14 +140,71 @@ extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_
                 for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid) {
                     if (rd.has_pend) apply_pend<REG_BITS>(regs[tid].a, pend[tid]);
                     if (r == nr - 1 && g_variant == 1) round_store_lin<REG_BITS>(regs[tid].a, smem.data(), rd, tlin[tid]);
-                    else if (r == nr - 1) round_store_hbm<REG_BITS>(regs[tid].a, psi, sp, rd, gidx[tid]);
+                    else if (r == nr - 1 && !tail) round_store_hbm<REG_BITS>(regs[tid].a, psi, sp, rd, gidx[tid]);
                     else round_store_smem<REG_BITS>(regs[tid].a, smem.data(), rd, tls[tid], gidx[tid]);
                 }
             }
             if (g_variant == 1)
                 for (uint32_t row = 0; row < rows; ++row)
                     std::memcpy(psi + sweep_row_index(sp, base, row), smem.data() + ((size_t)row << sp.c), row_len * sizeof(double2));
+            if (tail)
+                for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid) {
+                    const EpiIdx ix = epi_index(sp, ep, tid);
+                    double2 t[4];
+                    for (int i = 0; i < 4; ++i) t[i] = tacc[(size_t)i * SWEEP_THREADS + tid];
+                    epi_tile<REG_BITS>(smem.data(), other, write_back ? psi : nullptr, ep, ix, base, t);
+                    for (int i = 0; i < 4; ++i) tacc[(size_t)i * SWEEP_THREADS + tid] = t[i];
+                }
+        }
+    }
+    if (fused) {   // the kernel's CTA reduction
+        for (int x = 0; x < 32; ++x) {
+            const int k = x >> 1, part = x & 1, i = k >> 2, j = k & 3;
+            double sum = 0.0;
+            for (uint32_t u = 0; u < (uint32_t)SWEEP_THREADS; ++u) {
+                const int ju = (int)(((u >> ep.ja) & 1u) | (((u >> ep.jb) & 1u) << 1));
+                const double2 v = tacc[(size_t)i * SWEEP_THREADS + u];
+                if (ju == j) sum += part ? v.y : v.x;
+            }
+            t_out[x] = sum;
         }
     }
     return 0;
+}
+
+extern "C" int emu_sv_run(int nq, double* state_ri, int src_is_zero, const b200_gate* gates, int n_gates,
+                          const double* mats, int n_mats, int inverse, int32_t stats[4]) {
+    return emu_run_impl(nq, state_ri, src_is_zero, gates, n_gates, mats, n_mats, inverse, stats, -1, -1, nullptr, 0, nullptr);
+}
+
+// state <- gates applied to state (write_back != 0), t_out = T[i][j] = sum conj(state'[i,rest]) other[j,rest], index bit 0 = the
+// LOWER of (qa, qb) (b200_sv_run_inner2 reorders for the caller; the test does the same)
+extern "C" int emu_sv_run_inner2(int nq, double* state_ri, const double* other_ri, const b200_gate* gates, int n_gates,
+                                 const double* mats, int n_mats, int inverse, int qa, int qb, int write_back, double* t_out,
+                                 int32_t stats[4]) {
+    const int saved = g_variant;
+    g_variant = 0;
+    const int rc = emu_run_impl(nq, state_ri, 0, gates, n_gates, mats, n_mats, inverse, stats, qa, qb, other_ri, write_back, t_out);
+    g_variant = saved;
+    return rc;
+}
+
+
+// state <- gates applied to the embedded state (phi on the qubits qmap[0..K), |0> elsewhere); qa >= 0: also the fused
+// transfer pass against `other` (see emu_sv_run_inner2).  rc 1: no tiled sweep to ride on (the product scatters first).
+extern "C" int emu_sv_run_embedded(int nq, double* state_ri, const double* phi_ri, int K, const int32_t* qmap,
+                                   const b200_gate* gates, int n_gates, const double* mats, int n_mats, int inverse, int qa,
+                                   int qb, const double* other_ri, double* t_out, int32_t stats[4]) {
+    EmbedSrc es;
+    std::memset(&es, 0, sizeof es);
+    uint64_t inside = 0;
+    for (int b = 0; b < K; ++b) { es.q[b] = qmap[b]; inside |= 1ull << qmap[b]; }
+    es.phi = reinterpret_cast<const double2*>(phi_ri);
+    es.K = K;
+    es.outside = ~inside & ((1ull << nq) - 1ull);
+    const int saved = g_variant;
+    g_variant = 0;
+    const int rc = emu_run_impl(nq, state_ri, 0, gates, n_gates, mats, n_mats, inverse, stats, qa, qb, other_ri, 1, t_out, &es);
+    g_variant = saved;
+    return rc;
 }

@@ -86,6 +86,59 @@ def emu_run(emu, n, gates, psi0=None, inverse=False):
     return st, tuple(stats)
 
 
+def emu_run_inner2(emu, n, gates, psi0, other, qa, qb, inverse=False, write_back=True):
+    """CPU execution of the fused sweep + transfer-pass kernel bodies: (swept state, T[i][j] with index = bit(qa) + 2 bit(qb),
+    planner stats)."""
+    gs = gates if isinstance(gates, GateStream) else GateStream.from_gates(gates)
+    st = np.array(psi0, dtype=np.complex128)
+    oth = np.ascontiguousarray(other, dtype=np.complex128)
+    t = np.zeros(32)
+    stats = (ctypes.c_int32 * 4)()
+    dp = ctypes.POINTER(ctypes.c_double)
+    rc = emu.emu_sv_run_inner2(n, st.view(np.float64).ctypes.data_as(dp), oth.view(np.float64).ctypes.data_as(dp),
+                               gs.rec_ptr(), len(gs), gs.mats_ptr(), len(gs.mats), int(inverse), int(qa), int(qb),
+                               1 if write_back else 0, t.ctypes.data_as(dp), stats)
+    assert rc == 0, emu.emu_last_error()
+    T = t.view(np.complex128).reshape(4, 4)
+    if qa > qb:     # kernel index: bit 0 = the lower qubit
+        sw = [0, 2, 1, 3]
+        T = T[np.ix_(sw, sw)]
+    return st, T.copy(), tuple(stats)
+
+
+def emu_run_embedded(emu, n, gates, phi, qmap, inverse=False, fuse=None, other=None):
+    """CPU execution of the embedded-source sweep (and of its fused variant): (state, T or None).  Falls back to the
+    product's scatter + run order when there is no tiled sweep to ride on (small register, empty program)."""
+    gs = gates if isinstance(gates, GateStream) else GateStream.from_gates(gates)
+    qm = np.ascontiguousarray(np.asarray(qmap, dtype=np.int32))
+    phi = np.ascontiguousarray(phi, dtype=np.complex128)
+    dp = ctypes.POINTER(ctypes.c_double)
+    if n <= 11 or (len(gs) == 0 and fuse is None):
+        c = np.arange(len(phi))
+        x = np.zeros_like(c)
+        for b, q in enumerate(qm):
+            x |= ((c >> b) & 1) << int(q)
+        psi = np.zeros(1 << n, dtype=np.complex128); psi[x] = phi
+        out, _ = emu_run(emu, n, gs, psi0=psi, inverse=inverse)
+        return out, None
+    st = np.zeros(1 << n, dtype=np.complex128)
+    t = np.zeros(32)
+    stats = (ctypes.c_int32 * 4)()
+    oth = np.ascontiguousarray(other, dtype=np.complex128) if fuse is not None else np.zeros(1, dtype=np.complex128)
+    qa, qb = (int(fuse[0]), int(fuse[1])) if fuse is not None else (-1, -1)
+    rc = emu.emu_sv_run_embedded(n, st.view(np.float64).ctypes.data_as(dp), phi.view(np.float64).ctypes.data_as(dp), len(qm),
+                                 qm.ctypes.data, gs.rec_ptr(), len(gs), gs.mats_ptr(), len(gs.mats), int(inverse), qa, qb,
+                                 oth.view(np.float64).ctypes.data_as(dp), t.ctypes.data_as(dp), stats)
+    assert rc == 0, emu.emu_last_error()
+    if fuse is None:
+        return st, None
+    T = t.view(np.complex128).reshape(4, 4)
+    if qa > qb:
+        sw = [0, 2, 1, 3]
+        T = T[np.ix_(sw, sw)]
+    return st, T.copy()
+
+
 class FakeEngine:
     """CPU stand-in for SVEngine used by the `not gpu` host-logic tests: gate application goes
     through the product planner + kernel thread bodies (tests/emu), read-outs through the oracle.
@@ -106,6 +159,23 @@ class FakeEngine:
         out, _ = emu_run(self.emu, self.num_qubits, stream, psi0=psi0, inverse=inverse)
         self.slots[dst][...] = out          # in place: the sharded tests alias slot memory with torch tensors
         self.runs += 1
+
+    FUSED_MIN_QUBITS = 12
+
+    def run_inner2(self, dst, src, stream, other, qa, qb, inverse=False):
+        out, T, _ = emu_run_inner2(self.emu, self.num_qubits, stream, self.slots[src], self.slots[other], qa, qb, inverse=inverse)
+        self.slots[dst][...] = out
+        self.runs += 1
+        self.inners += 1
+        return T
+
+    def run_embedded(self, dst, qmap, src_engine, src_slot, stream, inverse=False, fuse=None):
+        other = self.slots[fuse[0]] if fuse is not None else None
+        out, T = emu_run_embedded(self.emu, self.num_qubits, stream, src_engine.slots[src_slot], qmap, inverse=inverse,
+                                  fuse=None if fuse is None else (fuse[1], fuse[2]), other=other)
+        self.slots[dst][...] = out
+        self.runs += 1
+        return T
 
     def copy(self, dst, src):
         self.slots[dst][...] = self.slots[src]

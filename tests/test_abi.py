@@ -30,6 +30,17 @@ def test_library_exports_every_declared_symbol():
     assert L.b200_abi_version() == 1
 
 
+def test_profile_class_table_matches_header():
+    """b200_ctx_profile_read fills B200_PROF_CLASSES entries: the host-side table (shared by both engines) has the same length
+    and order as the header's enum."""
+    from adapt_aqc_b200.sv_engine import SVEngine
+    text = open(os.path.join(ROOT, "include", "b200aqc.h")).read()
+    count = int(re.search(r"#define\s+B200_PROF_CLASSES\s+(\d+)", text).group(1))
+    enum = sorted((int(v), k.lower()) for k, v in re.findall(r"B200_PROF_([A-Z0-9_]+)\s*=\s*(\d+)", text))
+    assert [v for v, _ in enum] == list(range(count))
+    assert tuple(k for _, k in enum) == SVEngine.PROF_CLASSES
+
+
 def test_gate_record_layout_matches_header():
     assert GATE_DTYPE.itemsize == 40
     assert [GATE_DTYPE.fields[k][1] for k in ("op", "q0", "q1", "aux", "p")] == [0, 4, 8, 12, 16]

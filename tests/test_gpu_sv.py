@@ -177,6 +177,86 @@ def test_inner2_gather_matches_dense_transfer():
     eng.close(); small.close()
 
 
+@pytest.mark.parametrize("n", [12, 14, 17, 22])
+def test_fused_sweep_and_transfer_pass_equals_the_two_calls(n):
+    """b200_sv_run_inner2 = b200_sv_run followed by b200_sv_inner2 (bra = the swept state): the swept state is bit-identical
+    to the plain sweep's up to the folded-permutation rounding (1e-14), T matches the separate transfer pass and the oracle's
+    numpy restatement, for pairs on lane / register / padding / untouched qubits, forward and inverse, empty, thin-layer and
+    multi-sweep programs, in place and out of place."""
+    rng = np.random.default_rng(8800 + n)
+    dim = 1 << n
+    eng = SVEngine(n, n_slots=4)
+    for trial in range(8):
+        psi0 = rng.normal(size=dim) + 1j * rng.normal(size=dim); psi0 /= np.linalg.norm(psi0)
+        other = rng.normal(size=dim) + 1j * rng.normal(size=dim); other /= np.linalg.norm(other)
+        if trial == 0:
+            gates = []
+        elif trial == 1:
+            _, trng = brickwork(n, 1, seed=trial)
+            gates = circuit_to_gates(thin_ansatz(n, 6, trng))
+        else:
+            gates = random_gates(n, int(rng.integers(1, 120 if trial < 6 else 400)), rng)
+        qa, qb = [int(q) for q in rng.choice(n, size=2, replace=False)]
+        if trial == 2:
+            qa, qb = 0, 1
+        if trial == 3:
+            qa, qb = n - 1, 2
+        inverse = bool(trial % 2)
+        gs = GateStream.from_gates(gates)
+        eng.upload(0, psi0); eng.upload(1, other)
+        eng.run(2, 0, gs, inverse=inverse)
+        ref_state = eng.download(2)
+        ref_T = eng.inner2(2, 1, qa, qb)
+        dst = 0 if trial % 3 == 0 else 3                 # in place / out of place
+        T = eng.run_inner2(dst, 0, gs, 1, qa, qb, inverse=inverse)
+        np.testing.assert_allclose(eng.download(dst), ref_state, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(T, ref_T, rtol=0, atol=1e-13)
+        if n <= 17:
+            Lt = np.moveaxis(ref_state.reshape([2] * n), [n - 1 - qb, n - 1 - qa], [0, 1]).reshape(4, -1)
+            Rt = np.moveaxis(other.reshape([2] * n), [n - 1 - qb, n - 1 - qa], [0, 1]).reshape(4, -1)
+            np.testing.assert_allclose(T, Lt.conj() @ Rt.T, rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(eng.download(1), other)     # `other` is only read
+    with pytest.raises(blib.B200Error, match="destination"):
+        eng.run_inner2(1, 0, GateStream.from_gates([]), 1, 0, 1)
+    eng.close()
+    small = SVEngine(8, n_slots=3)
+    with pytest.raises(blib.B200Error, match="too small"):
+        small.run_inner2(0, 0, GateStream.from_gates([]), 1, 0, 1)
+    small.close()
+
+
+@pytest.mark.parametrize("n", [12, 15, 22])
+def test_embedded_source_sweep_equals_scatter_then_run(n):
+    """b200_sv_run_embedded / b200_sv_run_embedded_inner2 = b200_sv_scatter + b200_sv_run (+ b200_sv_inner2): sorted and
+    permuted qmaps, K from 2 to n, forward and inverse, empty program for the fused variant."""
+    rng = np.random.default_rng(8900 + n)
+    dim = 1 << n
+    eng = SVEngine(n, n_slots=3)
+    for trial in range(6):
+        K = [2, 5, n - 1, n, 7, 9][trial]
+        qmap = [int(q) for q in (rng.permutation(n)[:K] if trial % 2 else np.sort(rng.permutation(n)[:K]))]
+        small = SVEngine(K, n_slots=1)
+        phi = rng.normal(size=1 << K) + 1j * rng.normal(size=1 << K); phi /= np.linalg.norm(phi)
+        other = rng.normal(size=dim) + 1j * rng.normal(size=dim); other /= np.linalg.norm(other)
+        small.upload(0, phi); eng.upload(1, other)
+        gates = random_gates(n, int(rng.integers(1, 100)), rng) if trial else []
+        gs = GateStream.from_gates(gates)
+        inverse = bool(trial % 2)
+        eng.scatter(2, qmap, small, 0)
+        eng.run(2, 2, gs, inverse=inverse)
+        ref = eng.download(2)
+        qa, qb = [int(q) for q in rng.choice(n, size=2, replace=False)]
+        ref_T = eng.inner2(2, 1, qa, qb)
+        assert eng.run_embedded(0, qmap, small, 0, gs, inverse=inverse) is None
+        np.testing.assert_allclose(eng.download(0), ref, rtol=0, atol=1e-14)
+        eng.init_zero(0)
+        T = eng.run_embedded(0, qmap, small, 0, gs, inverse=inverse, fuse=(1, qa, qb))
+        np.testing.assert_allclose(eng.download(0), ref, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(T, ref_T, rtol=0, atol=1e-13)
+        small.close()
+    eng.close()
+
+
 # ---- error behaviour ----------------------------------------------------------------------------
 def test_errors_are_raised_not_swallowed():
     eng = SVEngine(4, n_slots=2)
@@ -278,7 +358,7 @@ def test_evaluator_tracks_rotosolve_edits(n):
             replace_1q_gate(c.full_circuit, idx, name, theta)
         assert abs(comp.evaluate_cost() - oracle_comp.evaluate_cost()) < COST_TOL
     st = backend._evaluator.stats
-    assert st["moves_R"] > 0 and st["t_passes"] + st["t_gathers"] < st["evals"]
+    assert st["moves_R"] + st.get("front_blocks", 0) > 0 and st["t_passes"] + st["t_gathers"] < st["evals"]
 
 
 def test_shift_costs_equal_individual_evaluations(backend):

@@ -109,10 +109,14 @@ def test_incremental_evaluator_equals_full_resimulation(fake_backend, n, front, 
     assert st["moves_R"] + st["rebuild_R"] + st.get("front_blocks", 0) > 0 and st["t_passes"] + st["t_gathers"] < st["evals"]
     if front and not fake_backend._evaluator.projected:
         assert st.get("front_blocks", 0) > 0
+        if n >= 12:      # the bra's move and the transfer matrix came out of ONE pass (b200_sv_run_inner2)
+            assert st.get("fused_T", 0) > 0
     elif fake_backend._evaluator.compact is not None and not fake_backend._evaluator.projected:
         assert st["t_gathers"] > 0 and st["compact_L"] > 0
     if fake_backend._evaluator.projected:
         assert st["projected_evals"] > 0 and st["projections"] > 0
+        if n >= 12:      # bras whose tail was built on a smaller engine entered the register through an embedded-source sweep
+            assert st.get("embedded_L", 0) == st.get("scattered_L", 0)
 
 
 @pytest.mark.parametrize("fake_backend", [None, 5], indirect=True)

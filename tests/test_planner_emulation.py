@@ -204,3 +204,75 @@ def test_phase_heavy_rounds_match_oracle(emu, n):
         ref = orc.evaluate_circuit(n, gates)
         got, _ = emu_run(emu, n, gates)
         np.testing.assert_allclose(got, ref, atol=TOL)
+
+
+def _transfer(L, R, n, qa, qb):
+    """T[i][j] = sum_rest conj(L[i,rest]) R[j,rest], index = bit(qa) + 2 bit(qb) (numpy restatement of b200_sv_inner2)."""
+    Lt = np.moveaxis(L.reshape([2] * n), [n - 1 - qb, n - 1 - qa], [0, 1]).reshape(4, -1)
+    Rt = np.moveaxis(R.reshape([2] * n), [n - 1 - qb, n - 1 - qa], [0, 1]).reshape(4, -1)
+    return Lt.conj() @ Rt.T
+
+
+@pytest.mark.parametrize("n", [12, 13, 15])
+def test_fused_sweep_and_transfer_pass_matches_the_two_separate_steps(emu, n):
+    """sv_sweep_inner2_kernel's bodies on the CPU: the swept state equals the plain sweep's, T equals the transfer matrix of
+    (swept state, other) -- for pairs on lane qubits, register qubits, tile padding and qubits the gates never touch, for
+    empty programs, multi-sweep programs and X-heavy rounds whose trailing folds must not leak into the stored tile."""
+    from helpers import emu_run_inner2
+    rng = np.random.default_rng(4200 + n)
+    dim = 1 << n
+    for trial in range(8):
+        psi0 = rng.normal(size=dim) + 1j * rng.normal(size=dim); psi0 /= np.linalg.norm(psi0)
+        other = rng.normal(size=dim) + 1j * rng.normal(size=dim); other /= np.linalg.norm(other)
+        if trial == 0:
+            gates = []
+        elif trial == 1:      # thin layers: cx + rz (folded permutations and lane-qubit X)
+            _, trng = brickwork(n, 1, seed=trial)
+            gates = circuit_to_gates(thin_ansatz(n, 6, trng))
+        else:
+            gates = random_gates(n, int(rng.integers(1, 120 if trial < 6 else 400)), rng)
+        qa, qb = [int(q) for q in rng.choice(n, size=2, replace=False)]
+        if trial == 2:
+            qa, qb = 0, 1
+        if trial == 3:
+            qa, qb = n - 1, 2
+        inverse = bool(trial % 2)
+        ref, _ = emu_run(emu, n, gates, psi0=psi0, inverse=inverse)
+        got, T, stats = emu_run_inner2(emu, n, gates, psi0, other, qa, qb, inverse=inverse)
+        np.testing.assert_allclose(got, ref, atol=1e-13)
+        np.testing.assert_allclose(T, _transfer(ref, other, n, qa, qb), atol=1e-12)
+        # without the write-back the state stays as it was when the program is a single sweep
+        if stats[0] == 1:
+            keep, T2, _ = emu_run_inner2(emu, n, gates, psi0, other, qa, qb, inverse=inverse, write_back=False)
+            np.testing.assert_array_equal(keep, psi0)
+            np.testing.assert_array_equal(T2, T)
+
+
+@pytest.mark.parametrize("n", [12, 14])
+def test_embedded_source_sweep_matches_scatter_then_run(emu, n):
+    """The first sweep reads its tiles from a compact 2^K-amplitude array (b200_sv_run_embedded): same state as embedding
+    first and sweeping afterwards, same T from the fused variant -- for sorted and permuted qmaps, K from 2 to n."""
+    from helpers import emu_run_embedded
+    rng = np.random.default_rng(4300 + n)
+    dim = 1 << n
+    for trial in range(6):
+        K = [2, 5, n - 1, n, 7, 9][trial]
+        qmap = [int(q) for q in (rng.permutation(n)[:K] if trial % 2 else np.sort(rng.permutation(n)[:K]))]
+        phi = rng.normal(size=1 << K) + 1j * rng.normal(size=1 << K); phi /= np.linalg.norm(phi)
+        other = rng.normal(size=dim) + 1j * rng.normal(size=dim); other /= np.linalg.norm(other)
+        gates = random_gates(n, int(rng.integers(1, 100)), rng)
+        c = np.arange(1 << K)
+        x = np.zeros_like(c)
+        for b, q in enumerate(qmap):
+            x |= ((c >> b) & 1) << q
+        psi = np.zeros(dim, dtype=np.complex128); psi[x] = phi
+        inverse = bool(trial % 2)
+        ref, _ = emu_run(emu, n, gates, psi0=psi, inverse=inverse)
+        got, none = emu_run_embedded(emu, n, gates, phi, qmap, inverse=inverse)
+        assert none is None
+        np.testing.assert_allclose(got, ref, atol=1e-13)
+        qa, qb = [int(q) for q in rng.choice(n, size=2, replace=False)]
+        got2, T = emu_run_embedded(emu, n, gates if trial else [], phi, qmap, inverse=inverse, fuse=(qa, qb), other=other)
+        ref2 = ref if trial else psi
+        np.testing.assert_allclose(got2, ref2, atol=1e-13)
+        np.testing.assert_allclose(T, _transfer(ref2, other, n, qa, qb), atol=1e-12)
