@@ -149,7 +149,7 @@ int main(int argc, char** argv) {
         for (int nr : {1, 2, 3, 4}) {
             const SweepProg sp = empty_prog(n, c, nr);
             const float md = time_ms(st, [&] {
-                sv_sweep_kernel<REG_BITS><<<sms * 2, SWEEP_THREADS, nr > 1 ? TILE_BYTES : 0, st>>>(a, b, sp, ntiles); });
+                sv_sweep_kernel<REG_BITS><<<sms * 2, SWEEP_THREADS, nr > 1 ? TILE_BYTES : 0, st>>>(a, b, sp, ntiles, EmbedSrc{}); });
             const float mp = time_ms(st, [&] {
                 sv_sweep_pipe_kernel<REG_BITS><<<sms, PIPE_THREADS, PIPE_STAGES * TILE_BYTES, st>>>(a, b, sp, ntiles); });
             std::printf("empty sweep  c=%2d (row %5d B) rounds=%d  direct %.3f ms %6.0f GB/s | pipe %.3f ms %6.0f GB/s\n", c, 16 << c, nr,
