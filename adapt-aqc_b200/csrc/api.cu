@@ -202,8 +202,11 @@ int run_plan(b200_ctx* ctx, int dst_slot, int src_slot, const Plan& plan, const 
             // a sweep from the implicit |0..0> only writes (16 * 2^n bytes): accounted with the fills, so
             // that the SWEEP class holds read+write passes only (roofline accounting, bench.py)
             KScope ks(ctx, src == nullptr ? B200_PROF_FILL : B200_PROF_SWEEP);
-            if (es != nullptr && src == nullptr)
-                sv_sweep_kernel<REG_BITS, true><<<grid, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles, *es);
+            if (es != nullptr && src == nullptr) {
+                EmbedSrc e1 = *es;
+                embed_prepare(e1, sw);
+                sv_sweep_kernel<REG_BITS, true><<<grid, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles, e1);
+            }
             else
                 sv_sweep_kernel<REG_BITS><<<grid, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles, kNoEmbed);
         }
@@ -836,7 +839,8 @@ int b200_sv_inner2(b200_ctx* ctx, int l_slot, int r_slot, int qa, int qb, double
 
 // shared body of b200_sv_run_inner2 / b200_sv_run_embedded_inner2 (es != nullptr: the source is the embedded state)
 static int run_inner2_impl(b200_ctx* ctx, int dst_slot, int src_slot, const EmbedSrc* es, const b200_gate* gates, int n_gates,
-                           const double* mats, int n_mats, int inverse, int other_slot, int qa, int qb, double out[32]) {
+                           const double* mats, int n_mats, int inverse, int other_slot, int qa, int qb, double out[32],
+                           int* stored = nullptr) {
     const int n = ctx->nq;
     if (qa < 0 || qb < 0 || qa >= n || qb >= n || qa == qb) return set_error("run_inner2: qubits out of range");
     if (!out) return set_error("null pointer");
@@ -861,32 +865,38 @@ static int run_inner2_impl(b200_ctx* ctx, int dst_slot, int src_slot, const Embe
     const uint32_t ntiles = (uint32_t)(dim >> TILE_BITS);
     const double2* src = es != nullptr ? nullptr : (const double2*)ctx->slots[src_slot];
     double2* dst = (double2*)ctx->slots[dst_slot];
+    // *stored == 0 on entry: the caller only wants T -- the swept state is not written when ONE sweep does the whole
+    // program (32 bytes per amplitude instead of 48); a longer program needs dst for its intermediate state anyway
+    const bool keep = stored != nullptr && *stored == 0 && plan.sweeps.size() == 1 && es == nullptr;
+    if (stored != nullptr) *stored = keep ? 0 : 1;
     const size_t tile_bytes = ((size_t)1 << TILE_BITS) * sizeof(double2);
     Timer tm(ctx);
     uint32_t grid = 1;
     for (size_t k = 0; k < plan.sweeps.size(); ++k) {
         const SweepProg& sw = plan.sweeps[k];
         const bool embed = es != nullptr && k == 0;
+        EmbedSrc e1 = embed ? *es : kNoEmbed;
+        if (embed) embed_prepare(e1, sw);
         if (k + 1 < plan.sweeps.size()) {
             const size_t smem = sw.nrounds > 1 ? tile_bytes : 0;
             const int per_sm = sw.nrounds > 1 ? ctx->sweep_occ_smem : ctx->sweep_occ_nosmem;
             const uint32_t g = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * per_sm * ctx->grid_mult);
             KScope ks(ctx, embed ? B200_PROF_FILL : B200_PROF_SWEEP);
-            if (embed) sv_sweep_kernel<REG_BITS, true><<<g, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles, *es);
+            if (embed) sv_sweep_kernel<REG_BITS, true><<<g, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles, e1);
             else sv_sweep_kernel<REG_BITS><<<g, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles, kNoEmbed);
             ctx->counters[3] += (embed ? 16 : 32) * dim;
         } else {
             grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * ctx->fused_occ);
             // from an embedded source the pass reads `other` and writes dst only (32 B per amplitude): its own class, so
             // that the FUSED class holds 48-byte passes only (roofline accounting, bench.py)
-            KScope ks(ctx, embed ? B200_PROF_FUSED_EMBED : B200_PROF_FUSED);
+            KScope ks(ctx, (embed || keep) ? B200_PROF_FUSED_EMBED : B200_PROF_FUSED);
             if (embed)
                 sv_sweep_inner2_kernel<REG_BITS, true><<<grid, SWEEP_THREADS, FUSED_SMEM_BYTES, ctx->stream>>>(
-                    src, dst, (const double2*)ctx->slots[other_slot], sw, ep, ntiles, ctx->d_partial, *es);
+                    src, dst, (const double2*)ctx->slots[other_slot], sw, ep, ntiles, ctx->d_partial, e1);
             else
                 sv_sweep_inner2_kernel<REG_BITS><<<grid, SWEEP_THREADS, FUSED_SMEM_BYTES, ctx->stream>>>(
-                    src, dst, (const double2*)ctx->slots[other_slot], sw, ep, ntiles, ctx->d_partial, kNoEmbed);
-            ctx->counters[3] += (embed ? 32 : 48) * dim;
+                    src, keep ? nullptr : dst, (const double2*)ctx->slots[other_slot], sw, ep, ntiles, ctx->d_partial, kNoEmbed);
+            ctx->counters[3] += ((embed || keep) ? 32 : 48) * dim;
         }
         CUDA_TRY(cudaGetLastError());
         ctx->counters[1] += 1;
@@ -916,9 +926,9 @@ static int run_inner2_impl(b200_ctx* ctx, int dst_slot, int src_slot, const Embe
 }
 
 int b200_sv_run_inner2(b200_ctx* ctx, int dst_slot, int src_slot, const b200_gate* gates, int n_gates, const double* mats,
-                       int n_mats, int inverse, int other_slot, int qa, int qb, double out[32]) {
+                       int n_mats, int inverse, int other_slot, int qa, int qb, double out[32], int* stored) {
     if (check_slot(ctx, dst_slot) || check_slot(ctx, src_slot) || check_slot(ctx, other_slot)) return -1;
-    return run_inner2_impl(ctx, dst_slot, src_slot, nullptr, gates, n_gates, mats, n_mats, inverse, other_slot, qa, qb, out);
+    return run_inner2_impl(ctx, dst_slot, src_slot, nullptr, gates, n_gates, mats, n_mats, inverse, other_slot, qa, qb, out, stored);
 }
 
 // fills `es` from the caller's (compact_state, K, qmap)

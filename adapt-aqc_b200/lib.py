@@ -85,7 +85,7 @@ def load():
     L.b200_sv_pair_rdm_part.argtypes = [vp, ci, vp, ci, ci, ci, dp]
     L.b200_sv_inner.argtypes = [vp, ci, ci, ci, dp]
     L.b200_sv_inner2.argtypes = [vp, ci, ci, ci, ci, dp]
-    L.b200_sv_run_inner2.argtypes = [vp, ci, ci, vp, ci, vp, ci, ci, ci, ci, ci, dp]
+    L.b200_sv_run_inner2.argtypes = [vp, ci, ci, vp, ci, vp, ci, ci, ci, ci, ci, dp, ctypes.POINTER(ctypes.c_int)]
     L.b200_sv_run_embedded.argtypes = [vp, ci, vp, ci, vp, vp, ci, vp, ci, ci]
     L.b200_sv_run_embedded_inner2.argtypes = [vp, ci, vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, ci, dp]
     L.b200_sv_inner2_gather.argtypes = [vp, ci, vp, ci, vp, ci, ci, dp]

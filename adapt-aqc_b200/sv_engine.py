@@ -143,12 +143,16 @@ class SVEngine:
 
     FUSED_MIN_QUBITS = 12
 
-    def run_inner2(self, dst, src, stream, other, qa, qb, inverse=False):
-        """run(dst, src, stream) and inner2(dst, other, qa, qb) in one pass over the register (b200_sv_run_inner2)."""
+    def run_inner2(self, dst, src, stream, other, qa, qb, inverse=False, store=True):
+        """run(dst, src, stream) and inner2(dst, other, qa, qb) in one pass over the register (b200_sv_run_inner2).
+        store=False: only T is wanted -- returns (T, stored): dst is left alone when one sweep carries the program."""
         out = np.zeros(32)
+        stored = ctypes.c_int(1 if store else 0)
         check(self._lib.b200_sv_run_inner2(self._ctx, dst, src, stream.rec_ptr(), len(stream.rec), stream.mats_ptr(),
-                                           len(stream.mats), 1 if inverse else 0, int(other), int(qa), int(qb), dptr(out)))
-        return out.view(np.complex128).reshape(4, 4).copy()
+                                           len(stream.mats), 1 if inverse else 0, int(other), int(qa), int(qb), dptr(out),
+                                           ctypes.byref(stored)))
+        T = out.view(np.complex128).reshape(4, 4).copy()
+        return T if store else (T, bool(stored.value))
 
     def run_embedded(self, dst, qmap, src_engine, src_slot, stream, inverse=False, fuse=None):
         """dst <- stream applied to the embedded state (slot `src_slot` of `src_engine` on the qubits qmap, |0> elsewhere):
@@ -637,18 +641,26 @@ class SVCostEvaluator:
         return self._update_L_to(new[b1:])
 
     MIDDLE_MAX_GATES = 24
+    LAZY_MAX_GATES = 20
+    lazy_bra = os.environ.get("B200AQC_LAZY", "1") != "0"
 
     fused_passes = os.environ.get("B200AQC_FUSED", "1") != "0"
 
-    def _move_L(self, gate_stream, inverse, fuse):
+    def _move_L(self, gate_stream, inverse, fuse, store=True):
         """One in-place sweep of slot L; fuse = (other slot, qa, qb): the transfer matrix against that slot is taken in the
-        same pass over the register (b200_sv_run_inner2) and left in self._fused_T."""
+        same pass over the register (b200_sv_run_inner2) and left in self._fused_T.  store=False (fused only): T is all
+        that is wanted -- returns False if slot L was left as it was."""
         eng = self.eng
         if fuse is not None and self.fused_passes and eng.num_qubits >= getattr(eng, "FUSED_MIN_QUBITS", 1 << 30):
-            self._fused_T = eng.run_inner2(SLOT_L, SLOT_L, gate_stream, fuse[0], fuse[1], fuse[2], inverse=inverse)
             self.stats["fused_T"] = self.stats.get("fused_T", 0) + 1
-        else:
-            eng.run(SLOT_L, SLOT_L, gate_stream, inverse=inverse)
+            if store:
+                self._fused_T = eng.run_inner2(SLOT_L, SLOT_L, gate_stream, fuse[0], fuse[1], fuse[2], inverse=inverse)
+                return True
+            self._fused_T, stored = eng.run_inner2(SLOT_L, SLOT_L, gate_stream, fuse[0], fuse[1], fuse[2], inverse=inverse,
+                                                   store=False)
+            return stored
+        eng.run(SLOT_L, SLOT_L, gate_stream, inverse=inverse)
+        return True
 
     def _update_L_to(self, sfx, fuse=None):
         """Make slot L hold sfx^+ |0..0> (sfx: gate list applied in order to a ket).  Returns True if the slot changed.
@@ -683,9 +695,16 @@ class SVCostEvaluator:
                 for e in X + Y:
                     xy.update(_support(e))
                 if all(xy.isdisjoint(_support(e)) for e in old[:p]):
-                    self._move_L(stream(list(X) + G.invert_window(Y)), False, fuse)
-                    self.lwin = list(sfx); self.l_moves += 1
+                    # a short replacement whose T is all that is wanted leaves slot L where it is: the next block is
+                    # then reached from the same stored bra with a (longer) replacement of its own, and each block costs
+                    # two reads of the register instead of two reads and a write
+                    lazy = fuse is not None and self.lazy_bra and len(X) + len(Y) <= self.LAZY_MAX_GATES
+                    stored = self._move_L(stream(list(X) + G.invert_window(Y)), False, fuse, store=not lazy)
                     self.stats["middle_L"] = self.stats.get("middle_L", 0) + 1
+                    if stored:
+                        self.lwin = list(sfx); self.l_moves += 1
+                    else:
+                        self.stats["lazy_L"] = self.stats.get("lazy_L", 0) + 1
                     return True
         # rebuild: suffix^+ |0> is supported on the qubits the suffix touches -- built on the smaller engines as far as it
         # fits them (cheap sweeps), embedded level by level, only the remaining head gates are applied at this size
@@ -758,6 +777,8 @@ class SVCostEvaluator:
         nxt = next((b for b in self._blocks(window) if b[0] == b1), None)
         if nxt is None or self.lwin is None or self.l_moves >= self.REFRESH_MOVES:
             return
+        if self.lwin != list(window[b1:]):
+            return          # T came from a pass that left slot L at an earlier bra (lazy middle replacement)
         n0, n1, supp = nxt
         if len(supp) == 2 and self._front_ok(window, n0, tuple(supp)):
             return          # the next block commutes to the front: its bra is one middle replacement away from this one

@@ -90,7 +90,7 @@ enum {
     B200_PROF_SVD = 8,    /* on-device Jacobi SVD (jacobi_*_kernel)          */
     B200_PROF_GEMM = 9,   /* complex GEMM on the FP64 tensor cores (DMMA)    */
     B200_PROF_FUSED = 10, /* sv_sweep_inner2_kernel (sweep + transfer pass)  */
-    B200_PROF_FUSED_EMBED = 11 /* the same from an embedded source (no read of the swept state) */
+    B200_PROF_FUSED_EMBED = 11 /* the same with 32 bytes per amplitude: embedded source (no read of the swept state) or T only (no write) */
 };
 int b200_ctx_profile(b200_ctx *ctx, int enable);
 int b200_ctx_profile_read(b200_ctx *ctx, double ms[B200_PROF_CLASSES], uint64_t launches[B200_PROF_CLASSES]);
@@ -184,9 +184,11 @@ int b200_sv_inner2(b200_ctx *ctx, int l_slot, int r_slot, int qa, int qb, double
  * 48 * 2^n bytes of HBM traffic instead of 64 * 2^n.  The optimiser's walk from one ansatz block to the next
  * (adaptaqc/utils/cost_minimiser.py:267-316: one small edit of the bra, then a fresh transfer matrix) is exactly this
  * pair.  dst may equal src; `other` must differ from dst.  Registers of fewer than 12 qubits: error (call the two
- * functions). */
+ * functions).  `stored` (may be NULL = always store): *stored = 0 on entry asks for T only -- when one sweep carries the
+ * whole program the swept state is then NOT written (32 * 2^n bytes: the two reads) and dst keeps its contents; on return
+ * *stored says whether dst was written (a program of several sweeps needs dst for its intermediate states). */
 int b200_sv_run_inner2(b200_ctx *ctx, int dst_slot, int src_slot, const b200_gate *gates, int n_gates, const double *mats,
-                       int n_mats, int inverse, int other_slot, int qa, int qb, double out[32]);
+                       int n_mats, int inverse, int other_slot, int qa, int qb, double out[32], int *stored);
 
 /* dst <- gates applied to the EMBEDDED state: compact_state (2^K amplitudes on the device, e.g. a slot of a K-qubit context
  * that the caller has synchronised) on the qubits qmap[0..K), |0> on every other qubit.  Equivalent to b200_sv_scatter

@@ -52,4 +52,30 @@ for name, (gs, qa, qb) in cases.items():
     gb = 2.0 ** n / 1e9
     print(f"{name:18s} sweep {r[0]:6.3f} ms ({32 * gb / max(r[0], 1e-9) * 1e3:6.0f} GB/s)  transfer {r[1]:6.3f} ms ({32 * gb / max(r[1], 1e-9) * 1e3:6.0f} GB/s)  "
           f"separate total {r[0] + r[1] + r[2]:6.3f} ms | fused {r[3]:6.3f} ms ({48 * gb / max(r[3], 1e-9) * 1e3:6.0f} GB/s)  total {r[3] + r[4]:6.3f} ms")
+# the bra's rebuild: tail built on a 24-qubit engine, head gates at full size, T against the ket -- one pass
+if only is None and n >= 26:
+    K = 24
+    small = SVEngine(K, n_slots=1)
+    small.run(0, -1, GateStream.from_window([e for e in win if max(e[1], e[2]) < K][:40]))
+    small.sync()
+    for label, outside in (("outside = 4 highest qubits", list(range(n - 4, n))), ("outside = qubits 0, 5, 13, n-1", [0, 5, 13, n - 1])):
+        qmap = [q for q in range(n) if q not in outside]
+        gs = GateStream.from_window(win[30:40])
+        rows = []
+        for rep in range(reps):
+            eng.profile(True)
+            eng.scatter(2, qmap, small, 0)
+            eng.run(2, 2, gs, inverse=True)
+            T0 = eng.inner2(2, 1, 13, 14)
+            p = eng.profile_read(); eng.profile(False)
+            sep = p["sweep"][0] + p["fill"][0] + p["inner"][0] + p["reduce"][0]
+            eng.profile(True)
+            T1 = eng.run_embedded(2, qmap, small, 0, gs, inverse=True, fuse=(1, 13, 14))
+            p = eng.profile_read(); eng.profile(False)
+            rows.append((sep, p["fused_embed"][0]))
+        assert np.allclose(T0, T1, rtol=0, atol=1e-13)
+        r = np.median(np.array(rows), axis=0)
+        print(f"embedded bra ({label}): zero fill + scatter + sweep + transfer {r[0]:6.3f} ms | one pass {r[1]:6.3f} ms "
+              f"({32 * 2.0 ** n / 1e9 / r[1] * 1e3:6.0f} GB/s on read `other` + write)")
+    small.close()
 eng.close()

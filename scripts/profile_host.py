@@ -29,6 +29,21 @@ for batched in (False, True):
     backend._engine.sync()
     dt = time.perf_counter() - t0
     print(f"batched={batched}: {(comp.cost_evaluation_counter - e0) / dt:.0f} evals/s, {1e3 * dt / steps:.2f} ms/step (wall, unprofiled)")
+    # device time per engine and kernel class over the same steps (CUDA events around every launch)
+    for e in backend.engines():
+        e.profile(True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        bench.one_step(comp)
+    backend._engine.sync()
+    dt = time.perf_counter() - t0
+    tot = 0.0
+    for e in backend.engines():
+        p = e.profile_read(); e.profile(False)
+        used = {k: (round(v[0] / steps, 3), v[1] // steps) for k, v in p.items() if v[1]}
+        tot += sum(v[0] for v in p.values()) / steps
+        print(f"  engine {e.num_qubits:2d} qubits: (ms, launches) per step by class {used}")
+    print(f"  device total {tot:.2f} ms per step of {1e3 * dt / steps:.2f} ms wall (event-timed launches)")
     pr = cProfile.Profile()
     pr.enable()
     for _ in range(steps):

@@ -92,6 +92,8 @@ static int emu_run_impl(int nq, double* state_ri, int src_is_zero, const b200_ga
     for (size_t si = 0; si < plan.sweeps.size(); ++si) {
         const SweepProg& sp = plan.sweeps[si];
         const bool tail = fused && si + 1 == plan.sweeps.size();
+        EmbedSrc e1;
+        if (es != nullptr && si == 0) { e1 = *es; embed_prepare(e1, sp); }
         const int nr = sp.nrounds;
         // the direct kernel takes |0..0> as an IMPLICIT source (src == nullptr) in its first sweep
         const double2* hbm_src = (first_sweep && src_is_zero && g_variant == 0) ? nullptr : psi;
@@ -110,7 +112,7 @@ static int emu_run_impl(int nq, double* state_ri, int src_is_zero, const b200_ga
                     tls[tid] = swz(tl);
                     tlin[tid] = tl;
                     if (r == 0 && g_variant == 1) round_load_lin<REG_BITS>(regs[tid].a, smem.data(), rd, tl);
-                    else if (r == 0) round_load_hbm<REG_BITS>(regs[tid].a, hbm_src, sp, rd, gidx[tid], (es != nullptr && si == 0) ? es : nullptr);
+                    else if (r == 0) round_load_hbm<REG_BITS>(regs[tid].a, hbm_src, sp, rd, gidx[tid], (es != nullptr && si == 0) ? &e1 : nullptr);
                     else round_load_smem<REG_BITS>(regs[tid].a, smem.data(), rd, tls[tid], gidx[tid]);
                     pend[tid] = make_double2(1.0, 0.0);
                 }

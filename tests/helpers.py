@@ -162,12 +162,18 @@ class FakeEngine:
 
     FUSED_MIN_QUBITS = 12
 
-    def run_inner2(self, dst, src, stream, other, qa, qb, inverse=False):
-        out, T, _ = emu_run_inner2(self.emu, self.num_qubits, stream, self.slots[src], self.slots[other], qa, qb, inverse=inverse)
-        self.slots[dst][...] = out
+    def run_inner2(self, dst, src, stream, other, qa, qb, inverse=False, store=True):
+        out, T, stats = emu_run_inner2(self.emu, self.num_qubits, stream, self.slots[src], self.slots[other], qa, qb, inverse=inverse)
         self.runs += 1
         self.inners += 1
-        return T
+        stored = store or stats[0] != 1          # b200_sv_run_inner2: T only when one sweep carries the program
+        if stored:
+            self.slots[dst][...] = out
+        else:
+            keep, T2, _ = emu_run_inner2(self.emu, self.num_qubits, stream, self.slots[src], self.slots[other], qa, qb,
+                                         inverse=inverse, write_back=False)
+            assert np.array_equal(keep, self.slots[src]) and np.array_equal(T2, T)
+        return T if store else (T, stored)
 
     def run_embedded(self, dst, qmap, src_engine, src_slot, stream, inverse=False, fuse=None):
         other = self.slots[fuse[0]] if fuse is not None else None

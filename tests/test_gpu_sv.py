@@ -16,7 +16,7 @@ from harness.circuit import Circuit
 from harness.compiler import (CMAP_LINEAR, AdaptCompiler, AdaptConfig, generate_coupling_map)
 from adapt_aqc_b200.gates import GateStream
 from harness.minimiser import B200CostMinimiser
-from adapt_aqc_b200.sv_engine import SLOT_BASE, SLOT_L, SLOT_R, SLOT_WORK, SVCostEvaluator, SVEngine
+from adapt_aqc_b200.sv_engine import SLOT_BASE, SLOT_L, SLOT_R, SLOT_WORK, SVCostEvaluator, SVEngine, plan_detail
 from oracle import sv_oracle as orc
 from oracle.oracle_backends import OracleSVBackend, circuit_to_gates
 
@@ -216,6 +216,18 @@ def test_fused_sweep_and_transfer_pass_equals_the_two_calls(n):
             Rt = np.moveaxis(other.reshape([2] * n), [n - 1 - qb, n - 1 - qa], [0, 1]).reshape(4, -1)
             np.testing.assert_allclose(T, Lt.conj() @ Rt.T, rtol=0, atol=1e-12)
         np.testing.assert_array_equal(eng.download(1), other)     # `other` is only read
+        # T only: one-sweep programs leave the destination alone (and say so), longer ones store as before
+        eng.upload(0, psi0)
+        T2, stored = eng.run_inner2(0, 0, gs, 1, qa, qb, inverse=inverse, store=False)
+        np.testing.assert_allclose(T2, ref_T, rtol=0, atol=1e-13)
+        if stored:
+            np.testing.assert_allclose(eng.download(0), ref_state, rtol=0, atol=1e-14)
+        else:
+            np.testing.assert_array_equal(eng.download(0), psi0)
+        if not gates or len(gates) < 20:
+            assert not stored                      # short programs are one sweep
+        if len(plan_detail(n, gs)) > 1:
+            assert stored                          # (keeping the pair in every tile can only add sweeps)
     with pytest.raises(blib.B200Error, match="destination"):
         eng.run_inner2(1, 0, GateStream.from_gates([]), 1, 0, 1)
     eng.close()
