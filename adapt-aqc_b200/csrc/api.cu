@@ -889,7 +889,7 @@ static int run_inner2_impl(b200_ctx* ctx, int dst_slot, int src_slot, const Embe
             grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * ctx->fused_occ);
             // from an embedded source the pass reads `other` and writes dst only (32 B per amplitude): its own class, so
             // that the FUSED class holds 48-byte passes only (roofline accounting, bench.py)
-            KScope ks(ctx, (embed || keep) ? B200_PROF_FUSED_EMBED : B200_PROF_FUSED);
+            KScope ks(ctx, embed ? B200_PROF_FUSED_EMBED : (keep ? B200_PROF_FUSED_READ : B200_PROF_FUSED));
             if (embed)
                 sv_sweep_inner2_kernel<REG_BITS, true><<<grid, SWEEP_THREADS, FUSED_SMEM_BYTES, ctx->stream>>>(
                     src, dst, (const double2*)ctx->slots[other_slot], sw, ep, ntiles, ctx->d_partial, e1);

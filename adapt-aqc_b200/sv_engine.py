@@ -240,7 +240,7 @@ class SVEngine:
         check(self._lib.b200_ctx_elapsed_ms(self._ctx, ctypes.byref(ms)))
         return ms.value
 
-    PROF_CLASSES = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps", "svd", "gemm", "fused", "fused_embed")
+    PROF_CLASSES = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps", "svd", "gemm", "fused", "fused_embed", "fused_read")
 
     def profile(self, enable=True):
         check(self._lib.b200_ctx_profile(self._ctx, 1 if enable else 0))
@@ -640,8 +640,8 @@ class SVCostEvaluator:
     def _update_L_dense(self, new, b1):
         return self._update_L_to(new[b1:])
 
-    MIDDLE_MAX_GATES = 24
-    LAZY_MAX_GATES = 20
+    MIDDLE_MAX_GATES = int(os.environ.get("B200AQC_MIDDLE_MAX", "32"))
+    LAZY_MAX_GATES = int(os.environ.get("B200AQC_LAZY_MAX", "32"))
     lazy_bra = os.environ.get("B200AQC_LAZY", "1") != "0"
 
     fused_passes = os.environ.get("B200AQC_FUSED", "1") != "0"

@@ -124,7 +124,7 @@ def measured_traffic(n, kernel="sv_sweep_kernel"):
         t = json.load(open(p))
         if kernel != "sv_sweep_kernel":
             t = t[kernel]
-        per_amp = 32 if kernel == "sv_sweep_kernel" else 48
+        per_amp = 48 if kernel.endswith("(store)") else 32
         if int(t["algorithmic_bytes_per_launch"]) == per_amp * (1 << n):
             return float(t["traffic_bytes_per_launch"])
     except Exception:  # noqa: BLE001
@@ -888,15 +888,20 @@ def main():
                 "frac": ach / peak if ach else None, "traffic": measured_traffic(n, kernel), "bytes_per_launch": alg,
                 "launches": int(cnt), "avg_launch_ms": ms / max(1, cnt), "share_of_step": ms / dev_ms if world == 1 else None}
 
-    # the two register-sized kernels of the step: the gate sweep (read + write: 32 B per amplitude) and the fused
-    # sweep + transfer pass (read two states, write one: 48 B per amplitude); the one with more device time leads
-    r_sweep = hbm_roofline("sweep", "sv_sweep_kernel", 32)
-    r_fused = hbm_roofline("fused", "sv_sweep_inner2_kernel", 48)
-    roofline, other = (r_fused, r_sweep) if prof["fused"][0] > prof["sweep"][0] else (r_sweep, r_fused)
-    roofline = dict(roofline)
-    if other["launches"]:
-        roofline["also"] = other
-    roofline["other_kernels_ms"] = {k: round(v[0], 3) for k, v in prof.items() if k not in ("sweep", "fused") and v[1]}
+    # the register-sized kernels of the step: the gate sweep (read + write: 32 B per amplitude) and the fused sweep +
+    # transfer pass in its three forms (read two states, write one: 48 B; T only: two reads, 32 B; from an embedded source:
+    # one read, one write, 32 B).  The one with the most device time leads, the others follow under `also`.
+    cands = [hbm_roofline("sweep", "sv_sweep_kernel", 32),
+             hbm_roofline("fused", "sv_sweep_inner2_kernel (store)", 48),
+             hbm_roofline("fused_read", "sv_sweep_inner2_kernel (T only)", 32),
+             hbm_roofline("fused_embed", "sv_sweep_inner2_kernel (embedded source)", 32)]
+    cands = [c for c in cands if c["launches"]] or cands[:1]
+    cands.sort(key=lambda c: -(c["avg_launch_ms"] * c["launches"]))
+    roofline = dict(cands[0])
+    if len(cands) > 1:
+        roofline["also"] = cands[1:]
+    roofline["other_kernels_ms"] = {k: round(v[0], 3) for k, v in prof.items()
+                                    if k not in ("sweep", "fused", "fused_read", "fused_embed") and v[1]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,

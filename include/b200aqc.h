@@ -77,7 +77,7 @@ int b200_ctx_elapsed_ms(b200_ctx *ctx, double *ms);
 /* Per-kernel-class device times: while enabled, every kernel launch is bracketed by its own CUDA
  * event pair on the context's stream.  enable != 0 also resets the accumulators.  profile_read
  * synchronises the stream and returns, per class, the summed milliseconds and launch count. */
-#define B200_PROF_CLASSES 12
+#define B200_PROF_CLASSES 13
 enum {
     B200_PROF_SWEEP = 0,  /* sv_sweep_kernel (fused gate sweep, tiled path)  */
     B200_PROF_SMALL = 1,  /* sv_small_kernel (n <= 11, one CTA)              */
@@ -90,7 +90,8 @@ enum {
     B200_PROF_SVD = 8,    /* on-device Jacobi SVD (jacobi_*_kernel)          */
     B200_PROF_GEMM = 9,   /* complex GEMM on the FP64 tensor cores (DMMA)    */
     B200_PROF_FUSED = 10, /* sv_sweep_inner2_kernel (sweep + transfer pass)  */
-    B200_PROF_FUSED_EMBED = 11 /* the same with 32 bytes per amplitude: embedded source (no read of the swept state) or T only (no write) */
+    B200_PROF_FUSED_EMBED = 11, /* the same from an embedded source: read `other`, write dst (32 bytes per amplitude) */
+    B200_PROF_FUSED_READ = 12   /* the same, T only: read src and `other`, no write (32 bytes per amplitude) */
 };
 int b200_ctx_profile(b200_ctx *ctx, int enable);
 int b200_ctx_profile_read(b200_ctx *ctx, double ms[B200_PROF_CLASSES], uint64_t launches[B200_PROF_CLASSES]);
