@@ -14,7 +14,7 @@ from helpers import brickwork, thin_ansatz  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 28
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-only = sys.argv[3] if len(sys.argv) > 3 else None       # "fused" / "separate": one side only (ncu captures)
+only = sys.argv[3] if len(sys.argv) > 3 else None       # "fused" / "separate" / "read" (T only, no store): one side only (ncu captures)
 target, rng = brickwork(n, 8, 1234)
 ansatz = thin_ansatz(n, 16, rng)
 win = canonical_window(ansatz)
@@ -29,7 +29,15 @@ for name, (gs, qa, qb) in cases.items():
     if qa == qb:
         qb = (qa + 1) % n
     rows = []
+    T0 = T1 = None
     for rep in range(reps):
+        if only == "read":
+            eng.profile(True)
+            T1, stored = eng.run_inner2(2, 0, gs, 1, qa, qb, store=False)
+            assert not stored
+            p = eng.profile_read(); eng.profile(False)
+            rows.append((0.0, 0.0, 0.0, p["fused_read"][0], p["reduce"][0]))
+            continue
         if only != "fused":
             eng.profile(True)
             eng.run(2, 0, gs)
@@ -50,6 +58,9 @@ for name, (gs, qa, qb) in cases.items():
         assert np.allclose(T0, T1, rtol=0, atol=1e-13), abs(T0 - T1).max()
     r = np.median(np.array(rows), axis=0)
     gb = 2.0 ** n / 1e9
+    if only == "read":
+        print(f"{name:18s} T only (two reads, no store) {r[3]:6.3f} ms ({32 * gb / max(r[3], 1e-9) * 1e3:6.0f} GB/s)")
+        continue
     print(f"{name:18s} sweep {r[0]:6.3f} ms ({32 * gb / max(r[0], 1e-9) * 1e3:6.0f} GB/s)  transfer {r[1]:6.3f} ms ({32 * gb / max(r[1], 1e-9) * 1e3:6.0f} GB/s)  "
           f"separate total {r[0] + r[1] + r[2]:6.3f} ms | fused {r[3]:6.3f} ms ({48 * gb / max(r[3], 1e-9) * 1e3:6.0f} GB/s)  total {r[3] + r[4]:6.3f} ms")
 # the bra's rebuild: tail built on a 24-qubit engine, head gates at full size, T against the ket -- one pass
