@@ -316,6 +316,8 @@ int b200_ctx_create(int device, b200_ctx** out) {
                                   (int)FUSED_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(sv_sweep_kernel<REG_BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tile_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(sv_sweep_project_kernel<REG_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tile_bytes));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->fused_occ, sv_sweep_inner2_kernel<REG_BITS>,
                                                            SWEEP_THREADS, FUSED_SMEM_BYTES));
     if (ctx->fused_occ < 1) { delete ctx; return set_error("fused sweep kernel does not fit on an SM"); }
@@ -963,6 +965,64 @@ int b200_sv_run_embedded(b200_ctx* ctx, int dst_slot, const void* compact_state,
         return run_plan(ctx, dst_slot, dst_slot, plan);
     }
     return run_plan(ctx, dst_slot, -1, plan, &es);
+}
+
+int b200_sv_run_project(b200_ctx* ctx, int scratch_slot, int src_slot, const b200_gate* gates, int n_gates, const double* mats,
+                        int n_mats, int inverse, void* compact_dst, int K, const int32_t* qmap, int* scratch_used) {
+    if (check_slot(ctx, scratch_slot) || check_slot(ctx, src_slot)) return -1;
+    if (scratch_slot == src_slot) return set_error("run_project: the scratch slot must differ from the source");
+    EmbedSrc es;
+    if (make_embed(ctx, compact_dst, K, qmap, es)) return -1;
+    const int n = ctx->nq;
+    if (n <= SMALL_MAX_QUBITS) return set_error("run_project: register too small for the tiled path (use b200_sv_run + b200_sv_gather)");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Plan plan;
+    {
+        if (n_gates < 0 || (n_gates > 0 && !gates)) return set_error("null gate array");
+        std::vector<COp> ops;
+        const std::string err = canonicalize(n, gates, n_gates, mats, n_mats, inverse != 0, ops);
+        if (!err.empty()) return set_error(err);
+        fuse_single_qubit_runs(ops);
+        fuse_diagonals(ops);
+        build_plan(n, ops, plan, true, -2, -2);      // (-2: at least one sweep, nothing forced into the tile)
+        plan.n_gates_in = n_gates;
+    }
+    if (plan.sweeps.empty()) return set_error("run_project: empty plan");
+    ProjectDst pd;
+    std::memset(&pd, 0, sizeof pd);
+    pd.phi = (double2*)compact_dst; pd.outside = es.outside; pd.K = K;
+    for (int b = 0; b < K; ++b) pd.q[b] = es.q[b];
+    ctx->counters[6] += 1;
+    const uint64_t dim = 1ull << n;
+    const uint32_t ntiles = (uint32_t)(dim >> TILE_BITS);
+    const double2* src = (const double2*)ctx->slots[src_slot];
+    double2* scratch = (double2*)ctx->slots[scratch_slot];
+    const size_t tile_bytes = ((size_t)1 << TILE_BITS) * sizeof(double2);
+    if (scratch_used) *scratch_used = plan.sweeps.size() > 1 ? 1 : 0;
+    Timer tm(ctx);
+    for (size_t k = 0; k < plan.sweeps.size(); ++k) {
+        const SweepProg& sw = plan.sweeps[k];
+        const size_t smem = sw.nrounds > 1 ? tile_bytes : 0;
+        const int per_sm = sw.nrounds > 1 ? ctx->sweep_occ_smem : ctx->sweep_occ_nosmem;
+        const uint32_t g = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * per_sm * ctx->grid_mult);
+        if (k + 1 < plan.sweeps.size()) {
+            KScope ks(ctx, B200_PROF_SWEEP);
+            sv_sweep_kernel<REG_BITS><<<g, SWEEP_THREADS, smem, ctx->stream>>>(src, scratch, sw, ntiles, kNoEmbed);
+            ctx->counters[3] += 32 * dim;
+            src = scratch;
+        } else {
+            project_prepare(pd, sw);
+            KScope ks(ctx, B200_PROF_PROJECT);
+            sv_sweep_project_kernel<REG_BITS><<<g, SWEEP_THREADS, smem, ctx->stream>>>(src, sw, ntiles, pd);
+            ctx->counters[3] += 16 * dim + (16ull << K);
+        }
+        CUDA_TRY(cudaGetLastError());
+        ctx->counters[1] += 1;
+        ctx->counters[4] += offsetof(SweepProg, ops) + (size_t)sw.nops * sizeof(POp) + (size_t)sw.nmat2 * 32 * sizeof(double);
+    }
+    ctx->counters[2] += n_gates;
+    tm.stop();
+    return 0;
 }
 
 int b200_sv_run_embedded_inner2(b200_ctx* ctx, int dst_slot, const void* compact_state, int K, const int32_t* qmap,

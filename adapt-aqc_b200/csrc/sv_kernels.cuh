@@ -274,6 +274,16 @@ struct EmbedSrc {
     uint64_t coff[1 << REG_BITS];
     uint64_t regspan;     // OR of the first round's register offsets
 };
+// The mirror image on the STORE side: only the amplitudes with no bit outside q[0..K) are kept, phi[extract(x)] = value --
+// the projection of the swept state onto |0> of every other qubit (sv_gather_kernel) without writing the swept state.
+struct ProjectDst {
+    double2* phi;
+    uint64_t outside;
+    int32_t K, pad;
+    int32_t q[40];
+    uint64_t coff[1 << REG_BITS];   // extract(goff_st[j]) of the last round
+    uint64_t regspan;
+};
 B200_HD uint64_t embed_extract(const EmbedSrc& es, const uint64_t x) {
     uint64_t c = 0;
     for (int b = 0; b < es.K; ++b) c |= ((x >> es.q[b]) & 1ull) << b;
@@ -287,6 +297,28 @@ inline void embed_prepare(EmbedSrc& es, const SweepProg& sp) {
         es.regspan |= sp.rounds[0].goff_ld[j];
     }
 }
+inline void project_prepare(ProjectDst& pd, const SweepProg& sp) {
+    const PRound& rd = sp.rounds[sp.nrounds - 1];
+    pd.regspan = 0;
+    for (int j = 0; j < (1 << REG_BITS); ++j) {
+        uint64_t c = 0;
+        for (int b = 0; b < pd.K; ++b) c |= ((rd.goff_st[j] >> pd.q[b]) & 1ull) << b;
+        pd.coff[j] = c;
+        pd.regspan |= rd.goff_st[j];
+    }
+}
+template <int R>
+B200_HD void project_store(const double2 (&a)[1 << R], const ProjectDst& pd, const PRound& rd, const uint64_t gm) {
+    if (gm & pd.outside & ~pd.regspan) return;      // none of the thread's amplitudes survives the projection
+    uint64_t cg = 0;
+    for (int b = 0; b < pd.K; ++b) cg |= ((gm >> pd.q[b]) & 1ull) << b;
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) {
+        const uint64_t x = gm ^ rd.goff_st[j];
+        if (!(x & pd.outside)) pd.phi[cg ^ pd.coff[j]] = a[j];
+    }
+}
+
 template <int R>
 B200_HD void embed_load(double2 (&a)[1 << R], const EmbedSrc& es, const PRound& rd, const uint64_t gm) {
     if (gm & es.outside & ~es.regspan) {     // a bit outside the embedded qubits is set whatever j is: all zeros
@@ -319,8 +351,9 @@ B200_HD void round_load_hbm(double2 (&a)[1 << R], const double2* __restrict__ sr
 
 template <int R>
 B200_HD void round_store_hbm(const double2 (&a)[1 << R], double2* __restrict__ dst, const SweepProg& sp,
-                             const PRound& rd, const uint64_t g) {
+                             const PRound& rd, const uint64_t g, const ProjectDst* pd = nullptr) {
     const uint64_t gm = fold_gindex<false>(rd.trail, rd.n_trail, g);
+    if (pd != nullptr) { project_store<R>(a, *pd, rd, gm); return; }
 #pragma unroll
     for (int j = 0; j < (1 << R); ++j) dst[gm ^ rd.goff_st[j]] = a[j];
 }
@@ -564,6 +597,33 @@ B200_HD void epi_tile(const double2* tile_smem, const double2* __restrict__ othe
 #ifdef __CUDACC__
 // The whole program of the sweep is a kernel parameter: op decode is uniform constant-bank loads and
 // uniform branches.  One CTA owns one tile at a time (persistent grid-stride over tiles).
+// sv_sweep_project_kernel: the same sweep whose last round keeps only the projected amplitudes (ProjectDst).
+template <int R>
+__global__ void __launch_bounds__(SWEEP_THREADS, 2)
+sv_sweep_project_kernel(const double2* __restrict__ src, const __grid_constant__ SweepProg sp, const uint32_t ntiles,
+                        const __grid_constant__ ProjectDst pd) {
+    extern __shared__ __align__(16) double2 tile_smem[];
+    const int nr = sp.nrounds;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const ShflExchange ex;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t tile_base = sweep_tile_base(sp, tile);
+        for (int r = 0; r < nr; ++r) {
+            const PRound& rd = sp.rounds[r];
+            uint32_t tl; uint64_t g;
+            round_index<R>(sp, rd, tile_base, tid, tl, g);
+            const uint32_t tls = swz(tl);
+            double2 a[1 << R];
+            if (r == 0) round_load_hbm<R>(a, src, sp, rd, g);
+            else round_load_smem<R>(a, tile_smem, rd, tls, g);
+            round_ops<R, false>(a, sp, rd, g, lane, ex);
+            if (r == nr - 1) round_store_hbm<R>(a, nullptr, sp, rd, g, &pd);
+            else { round_store_smem<R>(a, tile_smem, rd, tls, g); __syncthreads(); }
+        }
+        if (nr > 1) __syncthreads();
+    }
+}
+
 template <int R, bool EMBED = false>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2)
 sv_sweep_kernel(const double2* __restrict__ src, double2* __restrict__ dst, const __grid_constant__ SweepProg sp,

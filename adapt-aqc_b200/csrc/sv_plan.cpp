@@ -492,7 +492,7 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm,
     const bool fused = pair_a >= 0 && pair_b >= 0;
     uint64_t H_forced = 0;
     if (fused) H_forced = ((1ull << pair_a) | (1ull << pair_b)) & ~low_mask;
-    bool need_one = fused && nops == 0;
+    bool need_one = (fused || (pair_a == -2 && pair_b == -2)) && nops == 0;    // (-2, -2): at least one (possibly empty) sweep
 
     while (n_taken < nops || need_one) {
         need_one = false;

@@ -20,7 +20,7 @@ SYMBOLS = [
     "b200_sv_ipc_export", "b200_sv_ipc_open", "b200_sv_ipc_close", "b200_sv_peer_swap", "b200_sv_peer_swap_strided",
     "b200_sv_num_qubits", "b200_sv_init_zero", "b200_sv_copy", "b200_sv_run",
     "b200_sv_run_inverse", "b200_sv_amp", "b200_sv_expz", "b200_sv_pair_rdm", "b200_sv_pair_rdm_part", "b200_sv_inner", "b200_sv_inner2", "b200_sv_inner2_gather", "b200_sv_gather", "b200_sv_scatter", "b200_sv_gather_ranked",
-    "b200_sv_run_inner2", "b200_sv_run_embedded", "b200_sv_run_embedded_inner2", "b200_sv_download", "b200_sv_upload", "b200_sv_plan_stats", "b200_sv_plan_detail",
+    "b200_sv_run_inner2", "b200_sv_run_embedded", "b200_sv_run_embedded_inner2", "b200_sv_run_project", "b200_sv_download", "b200_sv_upload", "b200_sv_plan_stats", "b200_sv_plan_detail",
     "b200_mps_create", "b200_mps_destroy", "b200_mps_set_truncation", "b200_mps_num_qubits",
     "b200_mps_init_zero", "b200_mps_set", "b200_mps_bond_dims", "b200_mps_get", "b200_mps_copy",
     "b200_mps_apply", "b200_mps_apply_inverse", "b200_mps_transfer", "b200_mps_amps", "b200_mps_dot",
@@ -86,6 +86,7 @@ def load():
     L.b200_sv_inner.argtypes = [vp, ci, ci, ci, dp]
     L.b200_sv_inner2.argtypes = [vp, ci, ci, ci, ci, dp]
     L.b200_sv_run_inner2.argtypes = [vp, ci, ci, vp, ci, vp, ci, ci, ci, ci, ci, dp, ctypes.POINTER(ctypes.c_int)]
+    L.b200_sv_run_project.argtypes = [vp, ci, ci, vp, ci, vp, ci, ci, vp, ci, vp, ctypes.POINTER(ctypes.c_int)]
     L.b200_sv_run_embedded.argtypes = [vp, ci, vp, ci, vp, vp, ci, vp, ci, ci]
     L.b200_sv_run_embedded_inner2.argtypes = [vp, ci, vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, ci, dp]
     L.b200_sv_inner2_gather.argtypes = [vp, ci, vp, ci, vp, ci, ci, dp]

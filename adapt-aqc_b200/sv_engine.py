@@ -154,6 +154,21 @@ class SVEngine:
         T = out.view(np.complex128).reshape(4, 4).copy()
         return T if store else (T, bool(stored.value))
 
+    def run_project(self, scratch, src, stream, qmap, dst_engine, dst_slot, inverse=False):
+        """run + gather without storing the swept state (b200_sv_run_project): slot `dst_slot` of `dst_engine` <- the
+        projection of (stream applied to slot src) onto |0> of every qubit outside qmap.  Synchronous like ``gather``.
+        Returns True if slot `scratch` was overwritten (programs of several sweeps)."""
+        qm = np.ascontiguousarray(np.asarray(qmap, dtype=np.int32))
+        if len(qm) != dst_engine.num_qubits:
+            raise ValueError("qmap must name one qubit per qubit of the destination engine")
+        dst_engine.sync()
+        used = ctypes.c_int(0)
+        check(self._lib.b200_sv_run_project(self._ctx, int(scratch), int(src), stream.rec_ptr(), len(stream.rec), stream.mats_ptr(),
+                                            len(stream.mats), 1 if inverse else 0, ctypes.c_void_p(dst_engine.device_ptr(dst_slot)),
+                                            len(qm), qm.ctypes.data, ctypes.byref(used)))
+        self.sync()
+        return bool(used.value)
+
     def run_embedded(self, dst, qmap, src_engine, src_slot, stream, inverse=False, fuse=None):
         """dst <- stream applied to the embedded state (slot `src_slot` of `src_engine` on the qubits qmap, |0> elsewhere):
         scatter + run without the zero fill and the read pass.  fuse = (other slot, qa, qb): also returns the transfer
@@ -240,7 +255,7 @@ class SVEngine:
         check(self._lib.b200_ctx_elapsed_ms(self._ctx, ctypes.byref(ms)))
         return ms.value
 
-    PROF_CLASSES = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps", "svd", "gemm", "fused", "fused_embed", "fused_read")
+    PROF_CLASSES = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps", "svd", "gemm", "fused", "fused_embed", "fused_read", "project")
 
     def profile(self, enable=True):
         check(self._lib.b200_ctx_profile(self._ctx, 1 if enable else 0))
@@ -573,14 +588,29 @@ class SVCostEvaluator:
         ps = self._proj_state
         if ps is not None and sub.base_key is not ps[4]:
             ps = self._proj_state = None      # another level has projected into that engine since
-        if (m > 0 and changed is not None and ps is not None and ps[1] == m
-                and self.rwin is not None and len(self.rwin) == m and all(i >= m for i in changed)):
-            r_changed = False        # only tail gates changed since phi was gathered from this R
-        else:
-            r_changed = self._update_R(window, m) if m > 0 else False
+        # phi is valid while it was projected from the same prefix of the same base into the same engine / qubit map
+        pwin = self._pwin            # the prefix phi was projected from (slot R itself need not hold it: see below)
         state = (id(peng), m, qmap, self.base_key)
-        if r_changed or ps is None or state != ps[:4]:
-            self.eng.gather(self.r_slot if m > 0 else SLOT_BASE, list(qmap), peng, SLOT_BASE)
+        # (compared by CONTENT: head blocks served in front mode never touch slot R, and a head edit that has already been
+        # evaluated is no longer in `changed` -- nothing else records it.  Unchanged entries are the same tuple objects, so
+        # the comparison is m identity checks.)
+        prefix_same = m == 0 or (pwin is not None and len(pwin) == m and pwin == window[:m])
+        if not (ps is not None and state == ps[:4] and prefix_same):
+            # Nothing but the projection needs prefix|base> here (front mode serves the head blocks from the base state):
+            # unless slot R already holds it, the sweep that would build it keeps only the projected amplitudes
+            # (b200_sv_run_project: half the traffic of sweep + gather; slot R stays as it is)
+            direct = (m > 0 and self.project_direct and self.front_mode and self.fused_passes and hasattr(self.eng, "run_project")
+                      and self.eng.num_qubits >= getattr(self.eng, "FUSED_MIN_QUBITS", 1 << 30)
+                      and not (self.rwin is not None and self.rwin == window[:m]))
+            if direct:
+                if self.eng.run_project(SLOT_R, SLOT_BASE, G.GateStream.from_window(window[:m]), list(qmap), peng, SLOT_BASE):
+                    self.rwin, self.r_slot, self.r_moves = None, SLOT_R, 0      # slot R served as scratch
+                self.stats["direct_projections"] = self.stats.get("direct_projections", 0) + 1
+            else:
+                if m > 0:
+                    self._update_R(window, m)
+                self.eng.gather(self.r_slot if m > 0 else SLOT_BASE, list(qmap), peng, SLOT_BASE)
+            self._pwin = list(window[:m])
             token = ("projected", id(self), self.stats["projections"])
             sub.base_key = token
             sub.invalidate()
@@ -863,6 +893,8 @@ class SVCostEvaluator:
         self.window = list(window)
         self._gw = None
 
+    _pwin = None
+    project_direct = os.environ.get("B200AQC_PROJECT_DIRECT", "1") != "0"
     _tkey = None
     _t_sfx = None
     _gw = None          # (k, w): gate-context cache of the open block, see _gate_context

@@ -77,7 +77,7 @@ int b200_ctx_elapsed_ms(b200_ctx *ctx, double *ms);
 /* Per-kernel-class device times: while enabled, every kernel launch is bracketed by its own CUDA
  * event pair on the context's stream.  enable != 0 also resets the accumulators.  profile_read
  * synchronises the stream and returns, per class, the summed milliseconds and launch count. */
-#define B200_PROF_CLASSES 13
+#define B200_PROF_CLASSES 14
 enum {
     B200_PROF_SWEEP = 0,  /* sv_sweep_kernel (fused gate sweep, tiled path)  */
     B200_PROF_SMALL = 1,  /* sv_small_kernel (n <= 11, one CTA)              */
@@ -91,7 +91,8 @@ enum {
     B200_PROF_GEMM = 9,   /* complex GEMM on the FP64 tensor cores (DMMA)    */
     B200_PROF_FUSED = 10, /* sv_sweep_inner2_kernel (sweep + transfer pass)  */
     B200_PROF_FUSED_EMBED = 11, /* the same from an embedded source: read `other`, write dst (32 bytes per amplitude) */
-    B200_PROF_FUSED_READ = 12   /* the same, T only: read src and `other`, no write (32 bytes per amplitude) */
+    B200_PROF_FUSED_READ = 12,  /* the same, T only: read src and `other`, no write (32 bytes per amplitude) */
+    B200_PROF_PROJECT = 13      /* sv_sweep_project_kernel: sweep that keeps only the projected amplitudes (16 bytes per amplitude) */
 };
 int b200_ctx_profile(b200_ctx *ctx, int enable);
 int b200_ctx_profile_read(b200_ctx *ctx, double ms[B200_PROF_CLASSES], uint64_t launches[B200_PROF_CLASSES]);
@@ -198,6 +199,12 @@ int b200_sv_run_inner2(b200_ctx *ctx, int dst_slot, int src_slot, const b200_gat
  * (adaptaqc/utils/cost_minimiser.py:267-316) is such a state: its tail is built on a small register and only the head gates
  * run at full size.  b200_sv_run_embedded_inner2: the same followed by the transfer pass of b200_sv_run_inner2, in one pass
  * (read `other`, write dst: 32 * 2^n bytes against 16 + 32 + 32). */
+/* b200_sv_run followed by b200_sv_gather without storing the swept state: compact_dst[c] = (gates applied to src)[deposit(c,
+ * qmap)], i.e. the swept state projected onto |0> of every qubit outside qmap -- the input of the "projected tail"
+ * (DESIGN 2.3).  The last sweep stores only the 2^K surviving amplitudes (16 * 2^n + 16 * 2^K bytes instead of 32 * 2^n plus
+ * the gather).  A program of several sweeps uses `scratch_slot` for its intermediate states (*scratch_used = 1). */
+int b200_sv_run_project(b200_ctx *ctx, int scratch_slot, int src_slot, const b200_gate *gates, int n_gates, const double *mats,
+                        int n_mats, int inverse, void *compact_dst, int K, const int32_t *qmap, int *scratch_used);
 int b200_sv_run_embedded(b200_ctx *ctx, int dst_slot, const void *compact_state, int K, const int32_t *qmap,
                          const b200_gate *gates, int n_gates, const double *mats, int n_mats, int inverse);
 int b200_sv_run_embedded_inner2(b200_ctx *ctx, int dst_slot, const void *compact_state, int K, const int32_t *qmap,

@@ -55,6 +55,8 @@ def emu():
                                ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int32)]
     lib.emu_sv_run_inner2.argtypes = [ctypes.c_int, dp, dp, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, ctypes.POINTER(ctypes.c_int32)]
+    lib.emu_sv_run_project.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int32)]
     lib.emu_sv_run_embedded.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp,
                                         ctypes.POINTER(ctypes.c_int32)]

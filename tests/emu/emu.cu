@@ -26,7 +26,8 @@ extern "C" void emu_set_variant(int v) { g_variant = v; }
 // sv_sweep_inner2_kernel against `other`; T (32 doubles, bit0 = lower qubit) comes back in t_out.
 static int emu_run_impl(int nq, double* state_ri, int src_is_zero, const b200_gate* gates, int n_gates,
                         const double* mats, int n_mats, int inverse, int32_t stats[4], int qa, int qb,
-                        const double* other_ri, int write_back, double* t_out, const EmbedSrc* es = nullptr) {
+                        const double* other_ri, int write_back, double* t_out, const EmbedSrc* es = nullptr,
+                        ProjectDst* pd = nullptr) {
     const bool fused = qa >= 0;
     std::vector<COp> ops;
     g_err = canonicalize(nq, gates, n_gates, mats, n_mats, inverse != 0, ops);
@@ -34,7 +35,8 @@ static int emu_run_impl(int nq, double* state_ri, int src_is_zero, const b200_ga
     fuse_single_qubit_runs(ops);
     fuse_diagonals(ops);
     Plan plan;
-    build_plan(nq, ops, plan, /*fold_perm=*/g_variant == 0 || fused, fused ? qa : -1, fused ? qb : -1);
+    build_plan(nq, ops, plan, /*fold_perm=*/g_variant == 0 || fused, fused ? qa : (pd ? -2 : -1), fused ? qb : (pd ? -2 : -1));
+    if (pd != nullptr && (plan.small || plan.sweeps.empty() || g_variant != 0)) { g_err = "projected store: tiled direct kernel only"; return -1; }
     if (fused && (plan.small || g_variant != 0)) { g_err = "fused path: tiled direct kernel only"; return -1; }
     if (es != nullptr && (plan.small || plan.sweeps.empty() || g_variant != 0)) { g_err = "embedded source: needs a tiled sweep to ride on"; return -1; }
     double2* psi = reinterpret_cast<double2*>(state_ri);
@@ -94,6 +96,8 @@ static int emu_run_impl(int nq, double* state_ri, int src_is_zero, const b200_ga
         const bool tail = fused && si + 1 == plan.sweeps.size();
         EmbedSrc e1;
         if (es != nullptr && si == 0) { e1 = *es; embed_prepare(e1, sp); }
+        const bool proj = pd != nullptr && si + 1 == plan.sweeps.size();
+        if (proj) project_prepare(*pd, sp);
         const int nr = sp.nrounds;
         // the direct kernel takes |0..0> as an IMPLICIT source (src == nullptr) in its first sweep
         const double2* hbm_src = (first_sweep && src_is_zero && g_variant == 0) ? nullptr : psi;
@@ -142,7 +146,7 @@ static int emu_run_impl(int nq, double* state_ri, int src_is_zero, const b200_ga
                 for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid) {
                     if (rd.has_pend) apply_pend<REG_BITS>(regs[tid].a, pend[tid]);
                     if (r == nr - 1 && g_variant == 1) round_store_lin<REG_BITS>(regs[tid].a, smem.data(), rd, tlin[tid]);
-                    else if (r == nr - 1 && !tail) round_store_hbm<REG_BITS>(regs[tid].a, psi, sp, rd, gidx[tid]);
+                    else if (r == nr - 1 && !tail) round_store_hbm<REG_BITS>(regs[tid].a, psi, sp, rd, gidx[tid], proj ? pd : nullptr);
                     else round_store_smem<REG_BITS>(regs[tid].a, smem.data(), rd, tls[tid], gidx[tid]);
                 }
             }
@@ -207,6 +211,26 @@ extern "C" int emu_sv_run_embedded(int nq, double* state_ri, const double* phi_r
     const int saved = g_variant;
     g_variant = 0;
     const int rc = emu_run_impl(nq, state_ri, 0, gates, n_gates, mats, n_mats, inverse, stats, qa, qb, other_ri, 1, t_out, &es);
+    g_variant = saved;
+    return rc;
+}
+
+
+// phi (2^K amplitudes) <- projection of (gates applied to state) onto |0> of every qubit outside qmap, through the
+// projected-store sweep; `state` holds intermediate sweeps of longer programs (the product's scratch slot) and is NOT the
+// swept state afterwards.  stats[0] = number of sweeps.
+extern "C" int emu_sv_run_project(int nq, double* state_ri, double* phi_ri, int K, const int32_t* qmap, const b200_gate* gates,
+                                  int n_gates, const double* mats, int n_mats, int inverse, int32_t stats[4]) {
+    ProjectDst pd;
+    std::memset(&pd, 0, sizeof pd);
+    uint64_t inside = 0;
+    for (int b = 0; b < K; ++b) { pd.q[b] = qmap[b]; inside |= 1ull << qmap[b]; }
+    pd.phi = reinterpret_cast<double2*>(phi_ri);
+    pd.K = K;
+    pd.outside = ~inside & ((1ull << nq) - 1ull);
+    const int saved = g_variant;
+    g_variant = 0;
+    const int rc = emu_run_impl(nq, state_ri, 0, gates, n_gates, mats, n_mats, inverse, stats, -1, -1, nullptr, 0, nullptr, nullptr, &pd);
     g_variant = saved;
     return rc;
 }

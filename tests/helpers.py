@@ -139,6 +139,20 @@ def emu_run_embedded(emu, n, gates, phi, qmap, inverse=False, fuse=None, other=N
     return st, T.copy()
 
 
+def emu_run_project(emu, n, gates, psi0, qmap, inverse=False):
+    """CPU execution of the projected-store sweep: (phi, number of sweeps)."""
+    gs = gates if isinstance(gates, GateStream) else GateStream.from_gates(gates)
+    qm = np.ascontiguousarray(np.asarray(qmap, dtype=np.int32))
+    st = np.array(psi0, dtype=np.complex128)
+    phi = np.full(1 << len(qm), np.nan + 0j, dtype=np.complex128)        # every entry must be written
+    stats = (ctypes.c_int32 * 4)()
+    dp = ctypes.POINTER(ctypes.c_double)
+    rc = emu.emu_sv_run_project(n, st.view(np.float64).ctypes.data_as(dp), phi.view(np.float64).ctypes.data_as(dp), len(qm),
+                                qm.ctypes.data, gs.rec_ptr(), len(gs), gs.mats_ptr(), len(gs.mats), int(inverse), stats)
+    assert rc == 0, emu.emu_last_error()
+    return phi, int(stats[0])
+
+
 class FakeEngine:
     """CPU stand-in for SVEngine used by the `not gpu` host-logic tests: gate application goes
     through the product planner + kernel thread bodies (tests/emu), read-outs through the oracle.
@@ -174,6 +188,14 @@ class FakeEngine:
                                          inverse=inverse, write_back=False)
             assert np.array_equal(keep, self.slots[src]) and np.array_equal(T2, T)
         return T if store else (T, stored)
+
+    def run_project(self, scratch, src, stream, qmap, dst_engine, dst_slot, inverse=False):
+        phi, sweeps = emu_run_project(self.emu, self.num_qubits, stream, self.slots[src], qmap, inverse=inverse)
+        dst_engine.slots[dst_slot][...] = phi
+        self.runs += 1
+        if sweeps > 1:
+            self.slots[scratch][...] = np.nan      # the product leaves an intermediate state there: nobody may rely on it
+        return sweeps > 1
 
     def run_embedded(self, dst, qmap, src_engine, src_slot, stream, inverse=False, fuse=None):
         other = self.slots[fuse[0]] if fuse is not None else None

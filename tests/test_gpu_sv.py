@@ -269,6 +269,37 @@ def test_embedded_source_sweep_equals_scatter_then_run(n):
     eng.close()
 
 
+@pytest.mark.parametrize("n", [12, 15, 22])
+def test_projected_store_sweep_equals_run_then_gather(n):
+    """b200_sv_run_project = b200_sv_run + b200_sv_gather without storing the swept state: same 2^K amplitudes, the source
+    untouched, the scratch slot untouched unless the program needs several sweeps."""
+    rng = np.random.default_rng(9000 + n)
+    dim = 1 << n
+    eng = SVEngine(n, n_slots=3)
+    for trial in range(7):
+        K = [2, 5, n - 1, n, 7, 9, 8][trial]
+        qmap = [int(q) for q in (rng.permutation(n)[:K] if trial % 2 else np.sort(rng.permutation(n)[:K]))]
+        small = SVEngine(K, n_slots=2)
+        psi0 = rng.normal(size=dim) + 1j * rng.normal(size=dim); psi0 /= np.linalg.norm(psi0)
+        marker = rng.normal(size=dim) + 1j * rng.normal(size=dim)
+        gates = [] if trial == 0 else random_gates(n, int(rng.integers(1, 100 if trial < 6 else 400)), rng)
+        gs = GateStream.from_gates(gates)
+        inverse = bool(trial % 2)
+        eng.upload(0, psi0); eng.upload(1, marker)
+        eng.run(2, 0, gs, inverse=inverse)
+        eng.gather(2, qmap, small, 0)
+        ref = small.download(0)
+        used = eng.run_project(1, 0, gs, qmap, small, 1, inverse=inverse)
+        np.testing.assert_allclose(small.download(1), ref, rtol=0, atol=1e-14)
+        np.testing.assert_array_equal(eng.download(0), psi0)
+        if not used:
+            np.testing.assert_array_equal(eng.download(1), marker)
+        if not gates:
+            assert not used
+        small.close()
+    eng.close()
+
+
 # ---- error behaviour ----------------------------------------------------------------------------
 def test_errors_are_raised_not_swallowed():
     eng = SVEngine(4, n_slots=2)
@@ -370,7 +401,7 @@ def test_evaluator_tracks_rotosolve_edits(n):
             replace_1q_gate(c.full_circuit, idx, name, theta)
         assert abs(comp.evaluate_cost() - oracle_comp.evaluate_cost()) < COST_TOL
     st = backend._evaluator.stats
-    assert st["moves_R"] + st.get("front_blocks", 0) > 0 and st["t_passes"] + st["t_gathers"] < st["evals"]
+    assert st["moves_R"] + st.get("front_blocks", 0) + st.get("direct_projections", 0) > 0 and st["t_passes"] + st["t_gathers"] < st["evals"]
 
 
 def test_shift_costs_equal_individual_evaluations(backend):

@@ -106,7 +106,7 @@ def test_incremental_evaluator_equals_full_resimulation(fake_backend, n, front, 
                 replace_1q_gate(c.full_circuit, idx, name, theta)
             assert abs(comp.evaluate_cost() - ocomp.evaluate_cost()) < 1e-10
     st = fake_backend._evaluator.stats
-    assert st["moves_R"] + st["rebuild_R"] + st.get("front_blocks", 0) > 0 and st["t_passes"] + st["t_gathers"] < st["evals"]
+    assert st["moves_R"] + st["rebuild_R"] + st.get("front_blocks", 0) + st.get("direct_projections", 0) > 0 and st["t_passes"] + st["t_gathers"] < st["evals"]
     if front and not fake_backend._evaluator.projected:
         assert st.get("front_blocks", 0) > 0
         if n >= 12:      # the bra's move and the transfer matrix came out of ONE pass (b200_sv_run_inner2)
@@ -117,6 +117,8 @@ def test_incremental_evaluator_equals_full_resimulation(fake_backend, n, front, 
         assert st["projected_evals"] > 0 and st["projections"] > 0
         if n >= 12:      # bras whose tail was built on a smaller engine entered the register through an embedded-source sweep
             assert st.get("embedded_L", 0) == st.get("scattered_L", 0)
+            if front:    # ... and prefix|base> was never stored: the sweep kept the projected amplitudes only
+                assert st.get("direct_projections", 0) > 0 and st["rebuild_R"] == 0
 
 
 @pytest.mark.parametrize("fake_backend", [None, 5], indirect=True)
@@ -333,3 +335,46 @@ def test_resimulation_then_tail_edit_does_not_reuse_a_stale_projection(emu):
         window[idx] = canonical_window(ansatz, idx, idx + 1)[0]
         check(window, [idx])
     assert ev.stats.get("resimulations", 0) >= 2 and ev.stats["projected_evals"] >= 3
+
+
+@pytest.mark.parametrize("direct", [True, False])
+def test_front_mode_head_edit_then_tail_edit_reprojects(emu, direct, monkeypatch):
+    """Front mode serves head blocks from the base state and never touches slot R, so nothing on the ket side records
+    that a head gate changed: the projection must be tied to the CONTENT of the prefix it was taken from.  Order: tail
+    edit, head edit (evaluated, so the edit is no longer pending), tail edit -> the last one needs a fresh phi."""
+    from adapt_aqc_b200.gates import GateStream, canonical_window
+    from oracle import sv_oracle as orc
+    from oracle.oracle_backends import circuit_to_gates
+    monkeypatch.setattr(SVCostEvaluator, "project_direct", direct)
+    n = 12
+    target, trng = brickwork(n, 3, seed=5)
+    ansatz = Circuit(n)
+    pairs = [(0, 1), (2, 3), (8, 9), (10, 11), (4, 5), (6, 7), (5, 6), (4, 5), (6, 7), (9, 10)]     # tail: qubits 4..11
+    for a, b in pairs:
+        th = trng.uniform(-np.pi, np.pi, 4)
+        ansatz.rz(th[0], a, label="rz"); ansatz.rz(th[1], b, label="rz"); ansatz.cx(a, b)
+        ansatz.rz(th[2], a, label="rz"); ansatz.rz(th[3], b, label="rz")
+    eng = FakeEngine(emu, n)
+    ev = SVCostEvaluator(eng, None, [FakeEngine(emu, 8, n_slots=4)])
+    ev.set_base("t", GateStream.from_circuit(target))
+    base_gates = circuit_to_gates(target)
+
+    def check(window, changed):
+        got = ev.amp0(list(window), changed=changed)
+        c = Circuit(n)
+        c.data = list(ansatz.data)
+        ref = orc.evaluate_circuit(n, base_gates + circuit_to_gates(c))[0]
+        assert abs(got - ref) < 1e-10, (got, ref)
+
+    window = canonical_window(ansatz)
+    check(window, None)
+    tail_idx, head_idx = len(window) - 1, 0
+    order = [tail_idx, head_idx, tail_idx, head_idx + 6, tail_idx - 7, head_idx + 3, head_idx + 3, tail_idx, tail_idx]
+    for step, idx in enumerate(order):
+        replace_1q_gate(ansatz, idx, "rz", 0.41 * (step + 1))
+        window[idx] = canonical_window(ansatz, idx, idx + 1)[0]
+        check(window, [idx])
+    st = ev.stats
+    assert st.get("front_blocks", 0) >= 1 and st["projected_evals"] >= 4 and st["projections"] >= 3, st
+    if direct:
+        assert st.get("direct_projections", 0) >= 2 and st["rebuild_R"] == 0, st

@@ -276,3 +276,25 @@ def test_embedded_source_sweep_matches_scatter_then_run(emu, n):
         ref2 = ref if trial else psi
         np.testing.assert_allclose(got2, ref2, atol=1e-13)
         np.testing.assert_allclose(T, _transfer(ref2, other, n, qa, qb), atol=1e-12)
+
+
+@pytest.mark.parametrize("n", [12, 14])
+def test_projected_store_sweep_matches_run_then_gather(emu, n):
+    """The last round keeps only the amplitudes with |0> on every qubit outside qmap (b200_sv_run_project): same 2^K numbers
+    as sweeping the whole state and gathering them afterwards, every entry of phi written exactly once."""
+    from helpers import emu_run_project
+    rng = np.random.default_rng(4400 + n)
+    dim = 1 << n
+    for trial in range(7):
+        K = [2, 5, n - 1, n, 7, 9, 8][trial]
+        qmap = [int(q) for q in (rng.permutation(n)[:K] if trial % 2 else np.sort(rng.permutation(n)[:K]))]
+        psi0 = rng.normal(size=dim) + 1j * rng.normal(size=dim); psi0 /= np.linalg.norm(psi0)
+        gates = [] if trial == 0 else random_gates(n, int(rng.integers(1, 100 if trial < 6 else 400)), rng)
+        inverse = bool(trial % 2)
+        ref, _ = emu_run(emu, n, gates, psi0=psi0, inverse=inverse)
+        c = np.arange(1 << K)
+        x = np.zeros_like(c)
+        for b, q in enumerate(qmap):
+            x |= ((c >> b) & 1) << q
+        phi, sweeps = emu_run_project(emu, n, gates, psi0, qmap, inverse=inverse)
+        np.testing.assert_allclose(phi, ref[x], atol=1e-13)
