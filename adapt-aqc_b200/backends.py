@@ -371,7 +371,15 @@ class B200SVBackend(_SVBase):
         cur = data[lhs:] if lhs else list(data)
         insts, params = wc_lists = self._wlists
         flags = list(map(_is, cur, insts))
-        suspects = [] if all(flags) else [i for i, f in enumerate(flags) if not f]
+        suspects = []
+        if not all(flags):                             # (C-level search: usually ONE instruction was replaced)
+            i = -1
+            try:
+                while True:
+                    i = flags.index(False, i + 1)
+                    suspects.append(i)
+            except ValueError:
+                pass
         if len(suspects) * 4 > m:                      # fresh objects everywhere (qiskit): value comparison of every entry
             suspects = range(m)
         else:
@@ -384,18 +392,32 @@ class B200SVBackend(_SVBase):
             except ValueError:                         # array-valued parameters
                 suspects = range(m)
         changed = []
+        keys = {}
         for i in suspects:
             inst = cur[i]
-            if not _same_instruction(inst, fps[i], qmap):
-                changed.append(i)
-            insts[i] = fps[i][0]                       # (refreshed by _same_instruction on a value match)
+            fp = fps[i]
+            if inst is fp[0]:                          # same object: unchanged unless its params were edited in place
+                try:
+                    if inst.operation.params == fp[1]:
+                        continue
+                except ValueError:                     # array-valued parameters compared element-wise
+                    pass
+                key = G.instruction_key(inst, qmap)
+            else:
+                key = G.instruction_key(inst, qmap)
+                if key is not None and key == fp[2]:   # a fresh object carrying the same gate
+                    fp[0] = insts[i] = inst            # the next call may hit the identity shortcut
+                    continue
+            changed.append(i)
+            keys[i] = key
         for i in changed:
             ent = G.canonical_window(circuit, lhs + i, lhs + i + 1, qmap)
             if len(ent) != 1:
                 self._wcache = None
                 return G.canonical_window(circuit, lhs, None), None
             window[i] = ent[0]
-            fps[i] = _fingerprint(cur[i], qmap)
+            inst = cur[i]
+            fps[i] = [inst, list(inst.operation.params), keys[i]]      # (= _fingerprint, with the key computed above)
             insts[i], params[i] = fps[i][0], fps[i][1]
         return window, changed
 
