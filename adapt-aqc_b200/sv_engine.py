@@ -469,6 +469,20 @@ class SVCostEvaluator:
             self._part_key, self._part = key, partition_blocks(window)
         return self._part
 
+    _prev_k = None      # index of the gate whose value the previous amp0 call served (hot path), else None
+
+    def _current_gate(self, changed):
+        """The gate the optimiser is working on, out of the pending edits.  One scalar per call, the reference's optimiser
+        leaves TWO edits pending when it moves on (cost_minimiser.py:344-368): the final angle of the gate it has just
+        finished -- whose shifted values the previous calls served -- and the first shift of the next gate.  The next gate
+        is usually the later one, but not when a cycle wraps around (last gate of the window -> first gate): opening the
+        block of the finished gate there costs a projection and a bra rebuild for a single value."""
+        if not changed:
+            return None
+        if len(changed) == 2 and self._prev_k is not None and self._prev_k in changed:
+            return changed[0] if changed[1] == self._prev_k else changed[1]
+        return max(changed)
+
     def _select_block(self, window, focus, changed=None):
         blocks = self._blocks(window)
         old, target = self.window, None
@@ -482,7 +496,7 @@ class SVCostEvaluator:
                         return b
             target = outside[-1] if outside else (diff[-1] if diff else None)
         if target is None and changed:
-            target = max(changed)       # no previous window to diff against (e.g. after a projected phase)
+            target = self._current_gate(changed)       # no previous window to diff against (e.g. after a projected phase)
         if target is None:
             target = len(window) - 1 if focus is None else min(max(focus, 0), len(window) - 1)
         for b in blocks:
@@ -955,6 +969,7 @@ class SVCostEvaluator:
         # complex multiplications -- no block bookkeeping, no descent through the projection levels.  The levels below
         # have then not seen the latest entry of that gate: it is added to `changed` when the hot path is left.
         hot = self._hot
+        self._prev_k = hot[0] if hot is not None else None
         if hot is not None:
             if (changed is not None and len(changed) == 1 and changed[0] == hot[0] and len(window) == hot[2]
                     and window[hot[0]][2] < 0 and window[hot[0]][1] == hot[3]):
@@ -970,7 +985,9 @@ class SVCostEvaluator:
             self.invalidate()
             return self.eng.amp(SLOT_BASE, 0)
         if self.projected:
-            target = max(changed) if changed else (len(window) - 1 if focus is None else min(max(focus, 0), len(window) - 1))
+            target = self._current_gate(changed)
+            if target is None:
+                target = len(window) - 1 if focus is None else min(max(focus, 0), len(window) - 1)
             pj = self._projected(window, target, changed)
             if pj is not None:
                 sub, tail, sub_changed, m = pj
