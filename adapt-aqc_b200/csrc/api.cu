@@ -865,7 +865,8 @@ static int run_inner2_impl(b200_ctx* ctx, int dst_slot, int src_slot, const Embe
     ctx->counters[6] += 2;
     const uint64_t dim = 1ull << n;
     const uint32_t ntiles = (uint32_t)(dim >> TILE_BITS);
-    const double2* src = es != nullptr ? nullptr : (const double2*)ctx->slots[src_slot];
+    const double2* src = (es != nullptr || src_slot < 0) ? nullptr : (const double2*)ctx->slots[src_slot];
+    const bool from_zero = es == nullptr && src_slot < 0;
     double2* dst = (double2*)ctx->slots[dst_slot];
     // *stored == 0 on entry: the caller only wants T -- the swept state is not written when ONE sweep does the whole
     // program (32 bytes per amplitude instead of 48); a longer program needs dst for its intermediate state anyway
@@ -883,22 +884,24 @@ static int run_inner2_impl(b200_ctx* ctx, int dst_slot, int src_slot, const Embe
             const size_t smem = sw.nrounds > 1 ? tile_bytes : 0;
             const int per_sm = sw.nrounds > 1 ? ctx->sweep_occ_smem : ctx->sweep_occ_nosmem;
             const uint32_t g = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * per_sm * ctx->grid_mult);
-            KScope ks(ctx, embed ? B200_PROF_FILL : B200_PROF_SWEEP);
+            const bool no_read = embed || (from_zero && k == 0);
+            KScope ks(ctx, no_read ? B200_PROF_FILL : B200_PROF_SWEEP);
             if (embed) sv_sweep_kernel<REG_BITS, true><<<g, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles, e1);
             else sv_sweep_kernel<REG_BITS><<<g, SWEEP_THREADS, smem, ctx->stream>>>(src, dst, sw, ntiles, kNoEmbed);
-            ctx->counters[3] += (embed ? 16 : 32) * dim;
+            ctx->counters[3] += (no_read ? 16 : 32) * dim;
         } else {
             grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * ctx->fused_occ);
             // from an embedded source the pass reads `other` and writes dst only (32 B per amplitude): its own class, so
             // that the FUSED class holds 48-byte passes only (roofline accounting, bench.py)
-            KScope ks(ctx, embed ? B200_PROF_FUSED_EMBED : (keep ? B200_PROF_FUSED_READ : B200_PROF_FUSED));
+            const bool no_read = embed || (from_zero && k == 0);
+            KScope ks(ctx, no_read ? B200_PROF_FUSED_EMBED : (keep ? B200_PROF_FUSED_READ : B200_PROF_FUSED));
             if (embed)
                 sv_sweep_inner2_kernel<REG_BITS, true><<<grid, SWEEP_THREADS, FUSED_SMEM_BYTES, ctx->stream>>>(
                     src, dst, (const double2*)ctx->slots[other_slot], sw, ep, ntiles, ctx->d_partial, e1);
             else
                 sv_sweep_inner2_kernel<REG_BITS><<<grid, SWEEP_THREADS, FUSED_SMEM_BYTES, ctx->stream>>>(
                     src, keep ? nullptr : dst, (const double2*)ctx->slots[other_slot], sw, ep, ntiles, ctx->d_partial, kNoEmbed);
-            ctx->counters[3] += ((embed || keep) ? 32 : 48) * dim;
+            ctx->counters[3] += ((no_read || keep) ? 32 : 48) * dim;
         }
         CUDA_TRY(cudaGetLastError());
         ctx->counters[1] += 1;
@@ -929,7 +932,9 @@ static int run_inner2_impl(b200_ctx* ctx, int dst_slot, int src_slot, const Embe
 
 int b200_sv_run_inner2(b200_ctx* ctx, int dst_slot, int src_slot, const b200_gate* gates, int n_gates, const double* mats,
                        int n_mats, int inverse, int other_slot, int qa, int qb, double out[32], int* stored) {
-    if (check_slot(ctx, dst_slot) || check_slot(ctx, src_slot) || check_slot(ctx, other_slot)) return -1;
+    if (check_slot(ctx, dst_slot) || check_slot(ctx, other_slot)) return -1;
+    if (src_slot >= 0 && check_slot(ctx, src_slot)) return -1;      // src_slot = -1: the source is |0..0> (as in b200_sv_run)
+    if (src_slot < 0 && stored) *stored = 1;                        // (nothing to keep: the state exists only once swept)
     return run_inner2_impl(ctx, dst_slot, src_slot, nullptr, gates, n_gates, mats, n_mats, inverse, other_slot, qa, qb, out, stored);
 }
 

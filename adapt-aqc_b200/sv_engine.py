@@ -494,7 +494,7 @@ class SVCostEvaluator:
                 for b in blocks:
                     if b[0] == a0 and b[1] == a1:
                         return b
-            target = outside[-1] if outside else (diff[-1] if diff else None)
+            target = self._current_gate(outside if outside else diff)
         if target is None and changed:
             target = self._current_gate(changed)       # no previous window to diff against (e.g. after a projected phase)
         if target is None:
@@ -585,6 +585,9 @@ class SVCostEvaluator:
                 if m > 0:
                     eng.run(slot, slot, stream(window[:m]), inverse=True)
                 return None
+        if fuse is not None and self.fused_passes and eng.num_qubits >= getattr(eng, "FUSED_MIN_QUBITS", 1 << 30):
+            self.stats["fused_T"] = self.stats.get("fused_T", 0) + 1
+            return eng.run_inner2(slot, -1, stream(window), fuse[0], fuse[1], fuse[2], inverse=True)
         eng.run(slot, -1, stream(window), inverse=True)
         return None
 
@@ -706,9 +709,10 @@ class SVCostEvaluator:
         eng.run(SLOT_L, SLOT_L, gate_stream, inverse=inverse)
         return True
 
-    def _update_L_to(self, sfx, fuse=None):
+    def _update_L_to(self, sfx, fuse=None, next_gates=0):
         """Make slot L hold sfx^+ |0..0> (sfx: gate list applied in order to a ket).  Returns True if the slot changed.
-        fuse: see _move_L (self._fused_T is None afterwards unless the update was one fused sweep)."""
+        fuse: see _move_L (self._fused_T is None afterwards unless the update was one fused sweep).  next_gates: size of the
+        block the optimiser will open next from this bra (0: none at this level), see the lazy-bra rule below."""
         eng, stream = self.eng, G.GateStream.from_window
         old = self.lwin
         self._fused_T = None
@@ -742,7 +746,10 @@ class SVCostEvaluator:
                     # a short replacement whose T is all that is wanted leaves slot L where it is: the next block is
                     # then reached from the same stored bra with a (longer) replacement of its own, and each block costs
                     # two reads of the register instead of two reads and a write
-                    lazy = fuse is not None and self.lazy_bra and len(X) + len(Y) <= self.LAZY_MAX_GATES
+                    # ... unless the NEXT block's replacement from that stored bra would no longer fit (it would fall back to a
+                    # rebuild from |0..0> plus a separate transfer pass): then this pass stores and the chain starts afresh
+                    lazy = (fuse is not None and self.lazy_bra and len(X) + len(Y) <= self.LAZY_MAX_GATES
+                            and not (next_gates and len(X) + len(Y) + 2 * next_gates > self.MIDDLE_MAX_GATES))
                     stored = self._move_L(stream(list(X) + G.invert_window(Y)), False, fuse, store=not lazy)
                     self.stats["middle_L"] = self.stats.get("middle_L", 0) + 1
                     if stored:
@@ -854,7 +861,14 @@ class SVCostEvaluator:
                 self.window = list(window)
                 self._gw = None
                 return
-            self._update_L_to(sfx, fuse=(SLOT_BASE, pair[0], pair[1]))
+            # (the block that follows, if the optimiser will meet it at this level in front mode too)
+            nxt = next((b for b in self._blocks(window) if b[0] == b1), None)
+            next_gates = 0
+            if nxt is not None and len(nxt[2]) == 2 and self._front_ok(window, nxt[0], tuple(nxt[2])):
+                split = self._tail_split(window) if self.projected else None
+                if split is None or nxt[0] < split[0]:
+                    next_gates = nxt[1] - nxt[0]
+            self._update_L_to(sfx, fuse=(SLOT_BASE, pair[0], pair[1]), next_gates=next_gates)
             self.T = self._fused_T if self._fused_T is not None else eng.inner2(SLOT_L, SLOT_BASE, *pair)
             self._fused_T = None
             self.stats["t_passes"] += 1
@@ -957,7 +971,7 @@ class SVCostEvaluator:
         return op
 
     # ---- evaluation ----
-    def amp0(self, window, focus=None, changed=None):
+    def amp0(self, window, focus=None, changed=None, prev_k=None):
         """<0| W |base> for the canonical window `window` (one scalar, as the reference asks).
         `focus`: index of the gate the optimiser is most likely to edit next (block choice when the
         structure changed).  `changed`: indices at which `window` differs from the previous call's
@@ -969,7 +983,7 @@ class SVCostEvaluator:
         # complex multiplications -- no block bookkeeping, no descent through the projection levels.  The levels below
         # have then not seen the latest entry of that gate: it is added to `changed` when the hot path is left.
         hot = self._hot
-        self._prev_k = hot[0] if hot is not None else None
+        self._prev_k = hot[0] if hot is not None else prev_k       # (prev_k: the same hint from the level above)
         if hot is not None:
             if (changed is not None and len(changed) == 1 and changed[0] == hot[0] and len(window) == hot[2]
                     and window[hot[0]][2] < 0 and window[hot[0]][1] == hot[3]):
@@ -992,7 +1006,12 @@ class SVCostEvaluator:
             if pj is not None:
                 sub, tail, sub_changed, m = pj
                 self.stats["projected_evals"] += 1
-                out = sub.amp0(tail, focus=None if focus is None else max(focus - m, 0), changed=sub_changed)
+                pk = self._prev_k
+                # (the nested level may have nothing to diff against -- it was re-based by the projection: its block
+                # choice then follows `focus`, which is the gate the optimiser is working on whenever that is known)
+                sub_focus = target - m if changed else (None if focus is None else max(focus - m, 0))
+                out = sub.amp0(tail, focus=sub_focus, changed=sub_changed,
+                               prev_k=pk - m if pk is not None and pk >= m else None)
                 sh = sub._hot
                 if sh is not None and not sub._hot_dirty:
                     e = window[sh[0] + m]

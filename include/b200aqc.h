@@ -185,8 +185,8 @@ int b200_sv_inner2(b200_ctx *ctx, int l_slot, int r_slot, int qa, int qb, double
  * program keeps each tile in shared memory and contracts it with `other` before storing it, so the pair costs
  * 48 * 2^n bytes of HBM traffic instead of 64 * 2^n.  The optimiser's walk from one ansatz block to the next
  * (adaptaqc/utils/cost_minimiser.py:267-316: one small edit of the bra, then a fresh transfer matrix) is exactly this
- * pair.  dst may equal src; `other` must differ from dst.  Registers of fewer than 12 qubits: error (call the two
- * functions).  `stored` (may be NULL = always store): *stored = 0 on entry asks for T only -- when one sweep carries the
+ * pair.  dst may equal src; src_slot = -1: the source is |0..0> as in b200_sv_run (no read pass); `other` must differ from
+ * dst.  Registers of fewer than 12 qubits: error (call the two functions).  `stored` (may be NULL = always store): *stored = 0 on entry asks for T only -- when one sweep carries the
  * whole program the swept state is then NOT written (32 * 2^n bytes: the two reads) and dst keeps its contents; on return
  * *stored says whether dst was written (a program of several sweeps needs dst for its intermediate states). */
 int b200_sv_run_inner2(b200_ctx *ctx, int dst_slot, int src_slot, const b200_gate *gates, int n_gates, const double *mats,

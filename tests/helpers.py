@@ -177,6 +177,13 @@ class FakeEngine:
     FUSED_MIN_QUBITS = 12
 
     def run_inner2(self, dst, src, stream, other, qa, qb, inverse=False, store=True):
+        if src < 0:                                # |0..0> source: always stored
+            zero = np.zeros(1 << self.num_qubits, dtype=np.complex128); zero[0] = 1
+            out, T, _ = emu_run_inner2(self.emu, self.num_qubits, stream, zero, self.slots[other], qa, qb, inverse=inverse)
+            self.slots[dst][...] = out
+            self.runs += 1
+            self.inners += 1
+            return T if store else (T, True)
         out, T, stats = emu_run_inner2(self.emu, self.num_qubits, stream, self.slots[src], self.slots[other], qa, qb, inverse=inverse)
         self.runs += 1
         self.inners += 1

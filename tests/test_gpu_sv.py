@@ -228,6 +228,14 @@ def test_fused_sweep_and_transfer_pass_equals_the_two_calls(n):
             assert not stored                      # short programs are one sweep
         if len(plan_detail(n, gs)) > 1:
             assert stored                          # (keeping the pair in every tile can only add sweeps)
+    # |0..0> as the source (src = -1), as in b200_sv_run
+    gs = GateStream.from_gates(random_gates(n, 60, rng))
+    eng.upload(1, other)
+    eng.run(2, -1, gs, inverse=True)
+    ref_T = eng.inner2(2, 1, 3, n - 2)
+    T = eng.run_inner2(0, -1, gs, 1, 3, n - 2, inverse=True)
+    np.testing.assert_allclose(eng.download(0), eng.download(2), rtol=0, atol=1e-14)
+    np.testing.assert_allclose(T, ref_T, rtol=0, atol=1e-13)
     with pytest.raises(blib.B200Error, match="destination"):
         eng.run_inner2(1, 0, GateStream.from_gates([]), 1, 0, 1)
     eng.close()
