@@ -870,7 +870,7 @@ static int run_inner2_impl(b200_ctx* ctx, int dst_slot, int src_slot, const Embe
     double2* dst = (double2*)ctx->slots[dst_slot];
     // *stored == 0 on entry: the caller only wants T -- the swept state is not written when ONE sweep does the whole
     // program (32 bytes per amplitude instead of 48); a longer program needs dst for its intermediate state anyway
-    const bool keep = stored != nullptr && *stored == 0 && plan.sweeps.size() == 1 && es == nullptr;
+    const bool keep = stored != nullptr && *stored == 0 && plan.sweeps.size() == 1;
     if (stored != nullptr) *stored = keep ? 0 : 1;
     const size_t tile_bytes = ((size_t)1 << TILE_BITS) * sizeof(double2);
     Timer tm(ctx);
@@ -894,14 +894,15 @@ static int run_inner2_impl(b200_ctx* ctx, int dst_slot, int src_slot, const Embe
             // from an embedded source the pass reads `other` and writes dst only (32 B per amplitude): its own class, so
             // that the FUSED class holds 48-byte passes only (roofline accounting, bench.py)
             const bool no_read = embed || (from_zero && k == 0);
-            KScope ks(ctx, no_read ? B200_PROF_FUSED_EMBED : (keep ? B200_PROF_FUSED_READ : B200_PROF_FUSED));
+            KScope ks(ctx, no_read ? (keep ? B200_PROF_FUSED_EMBED_READ : B200_PROF_FUSED_EMBED)
+                                   : (keep ? B200_PROF_FUSED_READ : B200_PROF_FUSED));
             if (embed)
                 sv_sweep_inner2_kernel<REG_BITS, true><<<grid, SWEEP_THREADS, FUSED_SMEM_BYTES, ctx->stream>>>(
-                    src, dst, (const double2*)ctx->slots[other_slot], sw, ep, ntiles, ctx->d_partial, e1);
+                    src, keep ? nullptr : dst, (const double2*)ctx->slots[other_slot], sw, ep, ntiles, ctx->d_partial, e1);
             else
                 sv_sweep_inner2_kernel<REG_BITS><<<grid, SWEEP_THREADS, FUSED_SMEM_BYTES, ctx->stream>>>(
                     src, keep ? nullptr : dst, (const double2*)ctx->slots[other_slot], sw, ep, ntiles, ctx->d_partial, kNoEmbed);
-            ctx->counters[3] += ((no_read || keep) ? 32 : 48) * dim;
+            ctx->counters[3] += ((no_read && keep) ? 16 : ((no_read || keep) ? 32 : 48)) * dim;
         }
         CUDA_TRY(cudaGetLastError());
         ctx->counters[1] += 1;
@@ -1032,11 +1033,11 @@ int b200_sv_run_project(b200_ctx* ctx, int scratch_slot, int src_slot, const b20
 
 int b200_sv_run_embedded_inner2(b200_ctx* ctx, int dst_slot, const void* compact_state, int K, const int32_t* qmap,
                                 const b200_gate* gates, int n_gates, const double* mats, int n_mats, int inverse,
-                                int other_slot, int qa, int qb, double out[32]) {
+                                int other_slot, int qa, int qb, double out[32], int* stored) {
     if (check_slot(ctx, dst_slot) || check_slot(ctx, other_slot)) return -1;
     EmbedSrc es;
     if (make_embed(ctx, compact_state, K, qmap, es)) return -1;
-    return run_inner2_impl(ctx, dst_slot, -1, &es, gates, n_gates, mats, n_mats, inverse, other_slot, qa, qb, out);
+    return run_inner2_impl(ctx, dst_slot, -1, &es, gates, n_gates, mats, n_mats, inverse, other_slot, qa, qb, out, stored);
 }
 
 int b200_sv_inner2_gather(b200_ctx* ctx, int r_slot, const void* compact_state, int K, const int32_t* qmap, int qa,

@@ -88,7 +88,7 @@ def load():
     L.b200_sv_run_inner2.argtypes = [vp, ci, ci, vp, ci, vp, ci, ci, ci, ci, ci, dp, ctypes.POINTER(ctypes.c_int)]
     L.b200_sv_run_project.argtypes = [vp, ci, ci, vp, ci, vp, ci, ci, vp, ci, vp, ctypes.POINTER(ctypes.c_int)]
     L.b200_sv_run_embedded.argtypes = [vp, ci, vp, ci, vp, vp, ci, vp, ci, ci]
-    L.b200_sv_run_embedded_inner2.argtypes = [vp, ci, vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, ci, dp]
+    L.b200_sv_run_embedded_inner2.argtypes = [vp, ci, vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, ci, dp, ctypes.POINTER(ctypes.c_int)]
     L.b200_sv_inner2_gather.argtypes = [vp, ci, vp, ci, vp, ci, ci, dp]
     L.b200_sv_download.argtypes = [vp, ci, cu64, cu64, vp]
     L.b200_sv_upload.argtypes = [vp, ci, cu64, cu64, vp]

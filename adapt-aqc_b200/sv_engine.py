@@ -169,10 +169,11 @@ class SVEngine:
         self.sync()
         return bool(used.value)
 
-    def run_embedded(self, dst, qmap, src_engine, src_slot, stream, inverse=False, fuse=None):
+    def run_embedded(self, dst, qmap, src_engine, src_slot, stream, inverse=False, fuse=None, store=True):
         """dst <- stream applied to the embedded state (slot `src_slot` of `src_engine` on the qubits qmap, |0> elsewhere):
         scatter + run without the zero fill and the read pass.  fuse = (other slot, qa, qb): also returns the transfer
-        matrix of (dst, other) from the same pass (b200_sv_run_embedded_inner2)."""
+        matrix of (dst, other) from the same pass (b200_sv_run_embedded_inner2); store=False (with fuse): T is all that is
+        wanted -- returns (T, stored), dst is left alone when one sweep carries the program."""
         qm = np.ascontiguousarray(np.asarray(qmap, dtype=np.int32))
         src_engine.sync()
         ptr = ctypes.c_void_p(src_engine.device_ptr(src_slot))
@@ -181,10 +182,12 @@ class SVEngine:
                                                  stream.mats_ptr(), len(stream.mats), 1 if inverse else 0))
             return None
         out = np.zeros(32)
+        stored = ctypes.c_int(1 if store else 0)
         check(self._lib.b200_sv_run_embedded_inner2(self._ctx, int(dst), ptr, len(qm), qm.ctypes.data, stream.rec_ptr(),
                                                     len(stream.rec), stream.mats_ptr(), len(stream.mats), 1 if inverse else 0,
-                                                    int(fuse[0]), int(fuse[1]), int(fuse[2]), dptr(out)))
-        return out.view(np.complex128).reshape(4, 4).copy()
+                                                    int(fuse[0]), int(fuse[1]), int(fuse[2]), dptr(out), ctypes.byref(stored)))
+        T = out.view(np.complex128).reshape(4, 4).copy()
+        return T if store else (T, bool(stored.value))
 
     def inner2_gather(self, r_slot, compact_engine, compact_slot, qmap, qa, qb):
         """Same T with the bra given compactly: slot `compact_slot` of `compact_engine` (K qubits,
@@ -255,7 +258,7 @@ class SVEngine:
         check(self._lib.b200_ctx_elapsed_ms(self._ctx, ctypes.byref(ms)))
         return ms.value
 
-    PROF_CLASSES = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps", "svd", "gemm", "fused", "fused_embed", "fused_read", "project")
+    PROF_CLASSES = ("sweep", "small", "expz", "rdm", "inner", "fill", "reduce", "mps", "svd", "gemm", "fused", "fused_embed", "fused_read", "project", "fused_embed_read")
 
     def profile(self, enable=True):
         check(self._lib.b200_ctx_profile(self._ctx, 1 if enable else 0))
@@ -550,46 +553,69 @@ class SVCostEvaluator:
             sub = SVCostEvaluator(peng, None, nested, registry=self._registry)
         return sub
 
-    def _bra_into(self, slot, window, fuse=None):
+    def _bra_into(self, slot, window, fuse=None, store=True):
         """slot <- window^+ |0..0> on this engine.  The longest tail of `window` that fits a smaller engine is built THERE
-        (recursively); the head gates run at this size in a sweep that reads its tiles straight from the small engine's
-        slot (b200_sv_run_embedded: no zero fill, no scatter pass, no read pass).  fuse = (other slot, qa, qb): the
-        transfer matrix of (slot, other) comes out of that same sweep and is returned (else None)."""
+        (recursively, and kept: the optimiser asks for several bras with the same tail in a row); the head gates run at
+        this size in a sweep that reads its tiles straight from the small engine's slot (b200_sv_run_embedded: no zero
+        fill, no scatter pass, no read pass).  fuse = (other slot, qa, qb): the transfer matrix of (slot, other) comes out
+        of that same sweep and is returned (else None).  store=False (with fuse): T is all that is wanted -- returns
+        (T | None, stored): when one sweep carries the head gates the bra is never written to the register at all."""
         eng, stream = self.eng, G.GateStream.from_window
-        if self.projected and hasattr(eng, "scatter") and len(window):
-            kmax = max((e.num_qubits for e in self.projected if e.num_qubits + self.min_saving() <= eng.num_qubits), default=0)
-            supp, m = set(), len(window)
-            for (s0, _, sp) in reversed(partition_blocks(window)):
-                new = supp | set(sp)
-                if len(new) > kmax:
-                    break
-                supp, m = new, s0
-            if m < len(window):
-                peng = [e for e in self.projected if e.num_qubits >= len(supp)][0]
-                supp = sorted(supp)
-                used = set(supp)
-                qmap = supp + [q for q in range(eng.num_qubits) if q not in used][:peng.num_qubits - len(supp)]
-                pos = {q: c for c, q in enumerate(qmap)}
-                tail = [(e[0], pos[e[1]], pos[e[2]] if e[2] >= 0 else -1) + tuple(e[3:]) for e in window[m:]]
-                self._sub_for(peng)._bra_into(SLOT_WORK, tail)
+        T = None
+        split = self._embed_split(window)
+        if split is not None:
+            m, peng, qmap, tail = split
+            sub = self._sub_for(peng)
+            if sub._work_tail != tail:                  # slot WORK of that engine still holds this tail's bra otherwise
+                sub._work_tail = None
+                sub._bra_into(SLOT_WORK, tail)
+                sub._work_tail = tail
                 self.stats["scattered_L"] = self.stats.get("scattered_L", 0) + 1
-                T = None
-                if self.fused_passes and hasattr(eng, "run_embedded") and eng.num_qubits >= getattr(eng, "FUSED_MIN_QUBITS", 1 << 30) \
-                        and (m > 0 or fuse is not None):
-                    T = eng.run_embedded(slot, list(qmap), peng, SLOT_WORK, stream(window[:m]), inverse=True, fuse=fuse)
-                    self.stats["embedded_L"] = self.stats.get("embedded_L", 0) + 1
-                    if T is not None:
-                        self.stats["fused_T"] = self.stats.get("fused_T", 0) + 1
-                    return T
-                eng.scatter(slot, list(qmap), peng, SLOT_WORK)
-                if m > 0:
-                    eng.run(slot, slot, stream(window[:m]), inverse=True)
-                return None
+            if self.fused_passes and hasattr(eng, "run_embedded") and eng.num_qubits >= getattr(eng, "FUSED_MIN_QUBITS", 1 << 30) \
+                    and (m > 0 or fuse is not None):
+                self.stats["embedded_L"] = self.stats.get("embedded_L", 0) + 1
+                if fuse is not None:
+                    self.stats["fused_T"] = self.stats.get("fused_T", 0) + 1
+                if fuse is not None and not store:
+                    return eng.run_embedded(slot, list(qmap), peng, SLOT_WORK, stream(window[:m]), inverse=True, fuse=fuse,
+                                            store=False)
+                T = eng.run_embedded(slot, list(qmap), peng, SLOT_WORK, stream(window[:m]), inverse=True, fuse=fuse)
+                return T if store else (T, True)
+            eng.scatter(slot, list(qmap), peng, SLOT_WORK)
+            if m > 0:
+                eng.run(slot, slot, stream(window[:m]), inverse=True)
+            return None if store else (None, True)
         if fuse is not None and self.fused_passes and eng.num_qubits >= getattr(eng, "FUSED_MIN_QUBITS", 1 << 30):
             self.stats["fused_T"] = self.stats.get("fused_T", 0) + 1
-            return eng.run_inner2(slot, -1, stream(window), fuse[0], fuse[1], fuse[2], inverse=True)
+            T = eng.run_inner2(slot, -1, stream(window), fuse[0], fuse[1], fuse[2], inverse=True)
+            return T if store else (T, True)
         eng.run(slot, -1, stream(window), inverse=True)
-        return None
+        return None if store else (None, True)
+
+    _work_tail = None       # the gate list whose bra slot WORK of this engine holds for the level above (see _bra_into)
+
+    def _embed_split(self, window):
+        """(m, engine, qmap, tail in that engine's numbering): window[m:] is the longest block-aligned tail whose support
+        fits a smaller engine (its bra is built there and embedded); None if there is none."""
+        eng = self.eng
+        if not (self.projected and hasattr(eng, "scatter") and len(window)):
+            return None
+        kmax = max((e.num_qubits for e in self.projected if e.num_qubits + self.min_saving() <= eng.num_qubits), default=0)
+        supp, m = set(), len(window)
+        for (s0, _, sp) in reversed(partition_blocks(window)):
+            new = supp | set(sp)
+            if len(new) > kmax:
+                break
+            supp, m = new, s0
+        if m >= len(window):
+            return None
+        peng = [e for e in self.projected if e.num_qubits >= len(supp)][0]
+        supp = sorted(supp)
+        used = set(supp)
+        qmap = supp + [q for q in range(eng.num_qubits) if q not in used][:peng.num_qubits - len(supp)]
+        pos = {q: c for c, q in enumerate(qmap)}
+        tail = [(e[0], pos[e[1]], pos[e[2]] if e[2] >= 0 else -1) + tuple(e[3:]) for e in window[m:]]
+        return m, peng, qmap, tail
 
     def _projected(self, window, target, changed):
         """If window[target] lies in the projected tail: (nested evaluator, tail window in the engine's qubit
@@ -718,6 +744,24 @@ class SVCostEvaluator:
         self._fused_T = None
         if old is not None and old == sfx:
             return False
+        if (fuse is not None and self.lazy_bra and self.fused_passes and self.dense_blocks and hasattr(eng, "run_embedded")
+                and eng.num_qubits >= getattr(eng, "FUSED_MIN_QUBITS", 1 << 30) and self._embed_split(sfx) is not None):
+            # T is all that is wanted and the tail of this bra lives on a smaller engine: ONE read of the ket, the bra is
+            # formed tile by tile in shared memory from that engine's slot and never written (cheaper than any move of
+            # the stored bra, which costs a second read of the register)
+            T, stored = self._bra_into(SLOT_L, sfx, fuse=fuse, store=False)
+            if T is not None:
+                self._fused_T = T
+                if stored:
+                    self.lwin = list(sfx); self.l_moves = 0
+                    self.stats["rebuild_L"] += 1
+                else:
+                    self.stats["virtual_L"] = self.stats.get("virtual_L", 0) + 1
+                return True
+            if stored:                      # (the bra was built without a transfer matrix: the caller takes it)
+                self.lwin = list(sfx); self.l_moves = 0
+                self.stats["rebuild_L"] += 1
+                return True
         if old is not None and self.l_moves < self.REFRESH_MOVES:
             so, sn = len(old), len(sfx)
             if sn <= so and so - sn <= sn and old[so - sn:] == sfx:
@@ -1026,6 +1070,7 @@ class SVCostEvaluator:
             # slot R / phi were NOT advanced to this window: a later tail-only edit must not take the
             # "only tail gates changed since phi was gathered" shortcut of _projected
             self._proj_state = None
+            self._work_tail = None
             self.eng.run(SLOT_WORK, SLOT_BASE, G.GateStream.from_window(window))
             return self.eng.amp(SLOT_WORK, 0)
         if (changed is not None and self.T is not None and self.window is not None and len(self.window) == len(window)

@@ -890,20 +890,21 @@ def main():
 
     # the register-sized kernels of the step: the gate sweep (read + write: 32 B per amplitude) and the fused sweep +
     # transfer pass in its three forms (read two states, write one: 48 B; T only: two reads, 32 B; from an embedded source:
-    # one read, one write, 32 B) and the sweep that keeps only the projected amplitudes (one read, 16 B).  The one with the
-    # most device time leads, the others follow under `also`.
+    # one read, one write, 32 B; from an embedded source and T only: ONE read, 16 B) and the sweep that keeps only the projected
+    # amplitudes (one read, 16 B).  The one with the most device time leads, the others follow under `also`.
     cands = [hbm_roofline("sweep", "sv_sweep_kernel", 32),
              hbm_roofline("fused", "sv_sweep_inner2_kernel (store)", 48),
              hbm_roofline("fused_read", "sv_sweep_inner2_kernel (T only)", 32),
              hbm_roofline("fused_embed", "sv_sweep_inner2_kernel (embedded source)", 32),
-             hbm_roofline("project", "sv_sweep_project_kernel", 16)]
+             hbm_roofline("project", "sv_sweep_project_kernel", 16),
+             hbm_roofline("fused_embed_read", "sv_sweep_inner2_kernel (embedded source, T only)", 16)]
     cands = [c for c in cands if c["launches"]] or cands[:1]
     cands.sort(key=lambda c: -(c["avg_launch_ms"] * c["launches"]))
     roofline = dict(cands[0])
     if len(cands) > 1:
         roofline["also"] = cands[1:]
     roofline["other_kernels_ms"] = {k: round(v[0], 3) for k, v in prof.items()
-                                    if k not in ("sweep", "fused", "fused_read", "fused_embed", "project") and v[1]}
+                                    if k not in ("sweep", "fused", "fused_read", "fused_embed", "project", "fused_embed_read") and v[1]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,

@@ -77,7 +77,7 @@ int b200_ctx_elapsed_ms(b200_ctx *ctx, double *ms);
 /* Per-kernel-class device times: while enabled, every kernel launch is bracketed by its own CUDA
  * event pair on the context's stream.  enable != 0 also resets the accumulators.  profile_read
  * synchronises the stream and returns, per class, the summed milliseconds and launch count. */
-#define B200_PROF_CLASSES 14
+#define B200_PROF_CLASSES 15
 enum {
     B200_PROF_SWEEP = 0,  /* sv_sweep_kernel (fused gate sweep, tiled path)  */
     B200_PROF_SMALL = 1,  /* sv_small_kernel (n <= 11, one CTA)              */
@@ -92,7 +92,8 @@ enum {
     B200_PROF_FUSED = 10, /* sv_sweep_inner2_kernel (sweep + transfer pass)  */
     B200_PROF_FUSED_EMBED = 11, /* the same from an embedded source: read `other`, write dst (32 bytes per amplitude) */
     B200_PROF_FUSED_READ = 12,  /* the same, T only: read src and `other`, no write (32 bytes per amplitude) */
-    B200_PROF_PROJECT = 13      /* sv_sweep_project_kernel: sweep that keeps only the projected amplitudes (16 bytes per amplitude) */
+    B200_PROF_PROJECT = 13,     /* sv_sweep_project_kernel: sweep that keeps only the projected amplitudes (16 bytes per amplitude) */
+    B200_PROF_FUSED_EMBED_READ = 14 /* fused pass from an embedded source, T only: read `other` (16 bytes per amplitude) */
 };
 int b200_ctx_profile(b200_ctx *ctx, int enable);
 int b200_ctx_profile_read(b200_ctx *ctx, double ms[B200_PROF_CLASSES], uint64_t launches[B200_PROF_CLASSES]);
@@ -198,7 +199,9 @@ int b200_sv_run_inner2(b200_ctx *ctx, int dst_slot, int src_slot, const b200_gat
  * from the compact array (16 * 2^n bytes instead of 16 + 32).  The bra (suffix)^+ |0..0> of the optimiser's walk
  * (adaptaqc/utils/cost_minimiser.py:267-316) is such a state: its tail is built on a small register and only the head gates
  * run at full size.  b200_sv_run_embedded_inner2: the same followed by the transfer pass of b200_sv_run_inner2, in one pass
- * (read `other`, write dst: 32 * 2^n bytes against 16 + 32 + 32). */
+ * (read `other`, write dst: 32 * 2^n bytes against 16 + 32 + 32); `stored` as in b200_sv_run_inner2: with *stored = 0 a
+ * one-sweep program does not write dst either -- the whole bra exists only tile by tile in shared memory and the pass is
+ * ONE read of `other` (16 * 2^n bytes) for a transfer matrix that the reference obtains from 3-7 full re-simulations. */
 /* b200_sv_run followed by b200_sv_gather without storing the swept state: compact_dst[c] = (gates applied to src)[deposit(c,
  * qmap)], i.e. the swept state projected onto |0> of every qubit outside qmap -- the input of the "projected tail"
  * (DESIGN 2.3).  The last sweep stores only the 2^K surviving amplitudes (16 * 2^n + 16 * 2^K bytes instead of 32 * 2^n plus
@@ -209,7 +212,7 @@ int b200_sv_run_embedded(b200_ctx *ctx, int dst_slot, const void *compact_state,
                          const b200_gate *gates, int n_gates, const double *mats, int n_mats, int inverse);
 int b200_sv_run_embedded_inner2(b200_ctx *ctx, int dst_slot, const void *compact_state, int K, const int32_t *qmap,
                                 const b200_gate *gates, int n_gates, const double *mats, int n_mats, int inverse,
-                                int other_slot, int qa, int qb, double out[32]);
+                                int other_slot, int qa, int qb, double out[32], int *stored);
 
 /* Same T as b200_sv_inner2, for a bra that is given COMPACTLY: <L| = (suffix)^+ <0..0| is supported
  * only on the K qubits the suffix touches, so it is stored as a 2^K-amplitude device array

@@ -130,6 +130,7 @@ def emu_run_embedded(emu, n, gates, phi, qmap, inverse=False, fuse=None, other=N
                                  qm.ctypes.data, gs.rec_ptr(), len(gs), gs.mats_ptr(), len(gs.mats), int(inverse), qa, qb,
                                  oth.view(np.float64).ctypes.data_as(dp), t.ctypes.data_as(dp), stats)
     assert rc == 0, emu.emu_last_error()
+    emu_run_embedded.last_sweeps = int(stats[0])
     if fuse is None:
         return st, None
     T = t.view(np.complex128).reshape(4, 4)
@@ -204,13 +205,15 @@ class FakeEngine:
             self.slots[scratch][...] = np.nan      # the product leaves an intermediate state there: nobody may rely on it
         return sweeps > 1
 
-    def run_embedded(self, dst, qmap, src_engine, src_slot, stream, inverse=False, fuse=None):
+    def run_embedded(self, dst, qmap, src_engine, src_slot, stream, inverse=False, fuse=None, store=True):
         other = self.slots[fuse[0]] if fuse is not None else None
         out, T = emu_run_embedded(self.emu, self.num_qubits, stream, src_engine.slots[src_slot], qmap, inverse=inverse,
                                   fuse=None if fuse is None else (fuse[1], fuse[2]), other=other)
-        self.slots[dst][...] = out
         self.runs += 1
-        return T
+        stored = store or fuse is None or emu_run_embedded.last_sweeps != 1     # b200_sv_run_embedded_inner2's `stored`
+        if stored:
+            self.slots[dst][...] = out
+        return T if store else (T, stored)
 
     def copy(self, dst, src):
         self.slots[dst][...] = self.slots[src]

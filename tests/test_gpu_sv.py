@@ -273,6 +273,17 @@ def test_embedded_source_sweep_equals_scatter_then_run(n):
         T = eng.run_embedded(0, qmap, small, 0, gs, inverse=inverse, fuse=(1, qa, qb))
         np.testing.assert_allclose(eng.download(0), ref, rtol=0, atol=1e-14)
         np.testing.assert_allclose(T, ref_T, rtol=0, atol=1e-13)
+        # T only: the bra is never written when one sweep carries the program (one read of `other` is the whole pass)
+        marker = rng.normal(size=dim) + 1j * rng.normal(size=dim)
+        eng.upload(0, marker)
+        T2, stored = eng.run_embedded(0, qmap, small, 0, gs, inverse=inverse, fuse=(1, qa, qb), store=False)
+        np.testing.assert_allclose(T2, ref_T, rtol=0, atol=1e-13)
+        if stored:
+            np.testing.assert_allclose(eng.download(0), ref, rtol=0, atol=1e-14)
+        else:
+            np.testing.assert_array_equal(eng.download(0), marker)
+        if not gates:
+            assert not stored
         small.close()
     eng.close()
 

@@ -116,7 +116,7 @@ def test_incremental_evaluator_equals_full_resimulation(fake_backend, n, front, 
     if fake_backend._evaluator.projected:
         assert st["projected_evals"] > 0 and st["projections"] > 0
         if n >= 12:      # bras whose tail was built on a smaller engine entered the register through an embedded-source sweep
-            assert st.get("embedded_L", 0) == st.get("scattered_L", 0)
+            assert st.get("embedded_L", 0) >= st.get("scattered_L", 0) > 0      # (the tail's bra is kept between blocks)
             if front:    # ... and prefix|base> was never stored: the sweep kept the projected amplitudes only
                 assert st.get("direct_projections", 0) > 0 and st["rebuild_R"] == 0
 
@@ -376,5 +376,6 @@ def test_front_mode_head_edit_then_tail_edit_reprojects(emu, direct, monkeypatch
         check(window, [idx])
     st = ev.stats
     assert st.get("front_blocks", 0) >= 1 and st["projected_evals"] >= 4 and st["projections"] >= 3, st
+    assert st.get("virtual_L", 0) >= 1, st         # head blocks: T from ONE read of the ket, the bra never written
     if direct:
         assert st.get("direct_projections", 0) >= 2 and st["rebuild_R"] == 0, st
