@@ -857,7 +857,7 @@ static int run_inner2_impl(b200_ctx* ctx, int dst_slot, int src_slot, const Embe
         if (!err.empty()) return set_error(err);
         fuse_single_qubit_runs(ops);
         fuse_diagonals(ops);
-        build_plan(n, ops, plan, true, qa, qb);
+        build_plan(n, ops, plan, true, qa, qb, es != nullptr ? es->outside : 0);
         plan.n_gates_in = n_gates;
     }
     EpiProg ep;

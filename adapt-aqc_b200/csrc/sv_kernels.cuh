@@ -273,6 +273,7 @@ struct EmbedSrc {
     // extract(thread index) ^ coff[j]: ONE bit-gather loop per thread and tile instead of 16 (embed_prepare)
     uint64_t coff[1 << REG_BITS];
     uint64_t regspan;     // OR of the first round's register offsets
+    uint64_t outside_nontile;   // bits of `outside` that are not tile qubits: a tile whose base has one set is all zero
 };
 // The mirror image on the STORE side: only the amplitudes with no bit outside q[0..K) are kept, phi[extract(x)] = value --
 // the projection of the swept state onto |0> of every other qubit (sv_gather_kernel) without writing the swept state.
@@ -291,6 +292,9 @@ B200_HD uint64_t embed_extract(const EmbedSrc& es, const uint64_t x) {
 }
 // host: tables of the sweep's first round
 inline void embed_prepare(EmbedSrc& es, const SweepProg& sp) {
+    uint64_t tilemask = 0;
+    for (int i = 0; i < TILE_BITS; ++i) tilemask |= 1ull << sp.tileq[i];
+    es.outside_nontile = es.outside & ~tilemask;
     es.regspan = 0;
     for (int j = 0; j < (1 << REG_BITS); ++j) {
         es.coff[j] = embed_extract(es, sp.rounds[0].goff_ld[j]);
@@ -594,6 +598,14 @@ B200_HD void epi_tile(const double2* tile_smem, const double2* __restrict__ othe
     }
 }
 
+// zeros for the thread's 16 amplitudes of a tile (tiles of an embedded source that are zero as a whole)
+template <int R>
+B200_HD void epi_zero_tile(double2* __restrict__ dst, const EpiProg& ep, const EpiIdx& ix, const uint64_t tile_base) {
+    const uint64_t G = tile_base | ix.g0;
+#pragma unroll
+    for (int m = 0; m < (1 << R); ++m) dst[G | ep.moff_g[m]] = make_double2(0.0, 0.0);
+}
+
 #ifdef __CUDACC__
 // The whole program of the sweep is a kernel parameter: op decode is uniform constant-bank loads and
 // uniform branches.  One CTA owns one tile at a time (persistent grid-stride over tiles).
@@ -668,6 +680,11 @@ sv_sweep_inner2_kernel(const double2* __restrict__ src, double2* __restrict__ ds
     for (int i = 0; i < 4; ++i) acc[i * SWEEP_THREADS + tid] = make_double2(0.0, 0.0);
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t tile_base = sweep_tile_base(sp, tile);
+        if (EMBED && (tile_base & es.outside_nontile)) {
+            // the whole source tile is zero and the gates keep it zero: nothing for T, nothing to read (uniform per CTA)
+            if (dst != nullptr) epi_zero_tile<R>(dst, ep, epi_index(sp, ep, tid), tile_base);
+            continue;
+        }
         for (int r = 0; r < nr; ++r) {
             const PRound& rd = sp.rounds[r];
             uint32_t tl; uint64_t g;

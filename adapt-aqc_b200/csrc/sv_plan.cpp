@@ -471,7 +471,7 @@ bool make_epilogue(const SweepProg& sp, int qa, int qb, EpiProg& ep) {
     return true;
 }
 
-void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm, int pair_a, int pair_b) {
+void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm, int pair_a, int pair_b, uint64_t pad_avoid) {
     plan = Plan();
     plan.num_qubits = nq;
     if (nq <= SMALL_MAX_QUBITS) {
@@ -511,6 +511,10 @@ void build_plan(int nq, const std::vector<COp>& ops, Plan& plan, bool fold_perm,
 
         // ---- tile qubit list: lanes, H, padding with the lowest unused qubits ----
         uint64_t tile = low_mask | H;
+        // (pad_avoid: qubits better left OUT of the tile -- an embedded source is zero wherever one of them is set, and a
+        // tile whose base index has such a bit is skipped whole, sv_sweep_inner2_kernel)
+        for (int q = LANE_BITS; q < nq && __builtin_popcountll(tile) < TILE_BITS; ++q)
+            if (!(pad_avoid >> q & 1)) tile |= 1ull << q;
         for (int q = LANE_BITS; q < nq && __builtin_popcountll(tile) < TILE_BITS; ++q) tile |= 1ull << q;
         plan.sweeps.emplace_back();
         SweepProg& sp = plan.sweeps.back();

@@ -199,7 +199,7 @@ void fuse_diagonals(std::vector<COp>& ops);
 // last one), there is at least one sweep, and the last round of the last sweep stores to shared memory (no lane-qubit
 // folds on its store side).
 void build_plan(int num_qubits, const std::vector<COp>& ops, Plan& plan, bool fold_perm = true, int pair_a = -1,
-                int pair_b = -1);
+                int pair_b = -1, uint64_t pad_avoid = 0);
 // Epilogue tables for the pair (qa, qb) on the tile of `sp`; false if one of them is not a tile qubit.
 bool make_epilogue(const SweepProg& sp, int qa, int qb, EpiProg& ep);
 

@@ -35,7 +35,8 @@ static int emu_run_impl(int nq, double* state_ri, int src_is_zero, const b200_ga
     fuse_single_qubit_runs(ops);
     fuse_diagonals(ops);
     Plan plan;
-    build_plan(nq, ops, plan, /*fold_perm=*/g_variant == 0 || fused, fused ? qa : (pd ? -2 : -1), fused ? qb : (pd ? -2 : -1));
+    build_plan(nq, ops, plan, /*fold_perm=*/g_variant == 0 || fused, fused ? qa : (pd ? -2 : -1), fused ? qb : (pd ? -2 : -1),
+               (fused && es != nullptr) ? es->outside : 0);
     if (pd != nullptr && (plan.small || plan.sweeps.empty() || g_variant != 0)) { g_err = "projected store: tiled direct kernel only"; return -1; }
     if (fused && (plan.small || g_variant != 0)) { g_err = "fused path: tiled direct kernel only"; return -1; }
     if (es != nullptr && (plan.small || plan.sweeps.empty() || g_variant != 0)) { g_err = "embedded source: needs a tiled sweep to ride on"; return -1; }
@@ -104,6 +105,12 @@ static int emu_run_impl(int nq, double* state_ri, int src_is_zero, const b200_ga
         first_sweep = false;
         for (uint32_t tile = 0; tile < ntiles; ++tile) {
             const uint64_t base = sweep_tile_base(sp, tile);
+            if (tail && es != nullptr && si == 0 && (base & e1.outside_nontile)) {     // the kernel's zero-tile shortcut
+                if (write_back)
+                    for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid)
+                        epi_zero_tile<REG_BITS>(psi, ep, epi_index(sp, ep, tid), base);
+                continue;
+            }
             const uint32_t rows = 1u << (TILE_BITS - sp.c), row_len = 1u << sp.c;
             if (g_variant == 1)   // the producer warp's bulk copies: tile rows -> linear buffer
                 for (uint32_t row = 0; row < rows; ++row)

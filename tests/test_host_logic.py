@@ -379,3 +379,34 @@ def test_front_mode_head_edit_then_tail_edit_reprojects(emu, direct, monkeypatch
     assert st.get("virtual_L", 0) >= 1, st         # head blocks: T from ONE read of the ket, the bra never written
     if direct:
         assert st.get("direct_projections", 0) >= 2 and st["rebuild_R"] == 0, st
+
+
+@pytest.mark.parametrize("fake_backend", [(None, 8)], indirect=True)
+def test_both_front_ends_issue_the_same_device_calls_per_step(fake_backend):
+    """Registers large enough for the fused / embedded / projected-store passes (n = 12, tail engine of 8 qubits): the
+    one-scalar-per-call interface must cost the device exactly what the batched front end costs -- the optimiser leaves two
+    edits pending when it moves on, and opening the block of the WRONG one (cycle wrap-around, re-based nested level)
+    once cost a projection and a bra rebuild per step."""
+    import bench
+    n = 12
+    target, ansatz = bench.build_workload(n, 2, 16)
+    per_mode = []
+    for batched in (True, False):
+        fake_backend.reset_cache()
+        comp = bench.make_compiler(target, ansatz, fake_backend, batched)
+        comp.evaluate_cost()
+        for _ in range(2):
+            bench.one_step(comp)                  # reach the steady state
+        ev = fake_backend._evaluator
+        engines = [ev.eng] + list(ev.projected)
+        s0 = dict(ev.stats)
+        c0 = [(e.runs, e.inners) for e in engines]
+        bench.one_step(comp)
+        d = {k: ev.stats.get(k, 0) - s0.get(k, 0) for k in ev.stats}
+        calls = [(e.runs - r, e.inners - i) for e, (r, i) in zip(engines, c0)]
+        per_mode.append((d, calls))
+        assert d["projections"] == 1 and d.get("direct_projections", 0) == 1, d      # ONE projection per step
+        assert d.get("virtual_L", 0) >= 1, d
+    assert per_mode[0][1] == per_mode[1][1], per_mode
+    for k in ("projections", "t_passes", "rebuild_L", "rebuild_R", "fused_T"):
+        assert per_mode[0][0].get(k, 0) == per_mode[1][0].get(k, 0), (k, per_mode)
