@@ -953,6 +953,7 @@ static int make_embed(b200_ctx* ctx, const void* compact_state, int K, const int
     }
     es.phi = (const double2*)compact_state;
     es.K = K;
+    es.nq = n;
     es.outside = ~inside & ((1ull << n) - 1ull);
     return 0;
 }

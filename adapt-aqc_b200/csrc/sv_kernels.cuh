@@ -274,7 +274,17 @@ struct EmbedSrc {
     uint64_t coff[1 << REG_BITS];
     uint64_t regspan;     // OR of the first round's register offsets
     uint64_t outside_nontile;   // bits of `outside` that are not tile qubits: a tile whose base has one set is all zero
+    uint64_t skipmask;          // tile qubits | outside_nontile: the index bits a NON-ZERO tile's number does not cover
+    int32_t nq, n_skip;         // register size; popcount(outside_nontile)
 };
+// number t of a non-zero tile -> its base index: the bits of t go to the positions outside `skipmask`, ascending
+B200_HD uint64_t embed_tile_base(const EmbedSrc& es, const uint32_t t) {
+    uint64_t out = 0;
+    int k = 0;
+    for (int b = 0; b < es.nq; ++b)
+        if (!((es.skipmask >> b) & 1ull)) { out |= (uint64_t)((t >> k) & 1u) << b; ++k; }
+    return out;
+}
 // The mirror image on the STORE side: only the amplitudes with no bit outside q[0..K) are kept, phi[extract(x)] = value --
 // the projection of the swept state onto |0> of every other qubit (sv_gather_kernel) without writing the swept state.
 struct ProjectDst {
@@ -295,6 +305,9 @@ inline void embed_prepare(EmbedSrc& es, const SweepProg& sp) {
     uint64_t tilemask = 0;
     for (int i = 0; i < TILE_BITS; ++i) tilemask |= 1ull << sp.tileq[i];
     es.outside_nontile = es.outside & ~tilemask;
+    es.skipmask = tilemask | es.outside_nontile;
+    es.n_skip = 0;
+    for (uint64_t m = es.outside_nontile; m; m &= m - 1) ++es.n_skip;
     es.regspan = 0;
     for (int j = 0; j < (1 << REG_BITS); ++j) {
         es.coff[j] = embed_extract(es, sp.rounds[0].goff_ld[j]);
@@ -678,8 +691,12 @@ sv_sweep_inner2_kernel(const double2* __restrict__ src, double2* __restrict__ ds
     double2* acc = tile_smem + ((size_t)1 << TILE_BITS);
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[i * SWEEP_THREADS + tid] = make_double2(0.0, 0.0);
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t tile_base = sweep_tile_base(sp, tile);
+    // T only from an embedded source: the tiles that are zero as a whole are not even enumerated (skipping them inside a
+    // round-robin loop left the CTAs that drew them idle: the lowest zero qubit is the lowest bit of the tile number)
+    const bool compact = EMBED && dst == nullptr && es.n_skip > 0;
+    const uint32_t nt = compact ? (ntiles >> es.n_skip) : ntiles;
+    for (uint32_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+        const uint64_t tile_base = compact ? embed_tile_base(es, tile) : sweep_tile_base(sp, tile);
         if (EMBED && (tile_base & es.outside_nontile)) {
             // the whole source tile is zero and the gates keep it zero: nothing for T, nothing to read (uniform per CTA)
             if (dst != nullptr) epi_zero_tile<R>(dst, ep, epi_index(sp, ep, tid), tile_base);

@@ -105,6 +105,13 @@ static int emu_run_impl(int nq, double* state_ri, int src_is_zero, const b200_ga
         first_sweep = false;
         for (uint32_t tile = 0; tile < ntiles; ++tile) {
             const uint64_t base = sweep_tile_base(sp, tile);
+            if (tail && es != nullptr && si == 0 && !(base & e1.outside_nontile) && e1.n_skip > 0) {
+                // the kernel's compact enumeration (T only) must reach this tile: its number without the skipped bits
+                uint32_t t = 0; int k = 0;
+                for (int b = 0; b < e1.nq; ++b)
+                    if (!((e1.skipmask >> b) & 1ull)) { t |= (uint32_t)((base >> b) & 1ull) << k; ++k; }
+                if (embed_tile_base(e1, t) != base || t >= (ntiles >> e1.n_skip)) { g_err = "compact tile enumeration is off"; return -1; }
+            }
             if (tail && es != nullptr && si == 0 && (base & e1.outside_nontile)) {     // the kernel's zero-tile shortcut
                 if (write_back)
                     for (uint32_t tid = 0; tid < (uint32_t)SWEEP_THREADS; ++tid)
@@ -214,6 +221,7 @@ extern "C" int emu_sv_run_embedded(int nq, double* state_ri, const double* phi_r
     for (int b = 0; b < K; ++b) { es.q[b] = qmap[b]; inside |= 1ull << qmap[b]; }
     es.phi = reinterpret_cast<const double2*>(phi_ri);
     es.K = K;
+    es.nq = nq;
     es.outside = ~inside & ((1ull << nq) - 1ull);
     const int saved = g_variant;
     g_variant = 0;
