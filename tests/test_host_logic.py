@@ -410,3 +410,37 @@ def test_both_front_ends_issue_the_same_device_calls_per_step(fake_backend):
     assert per_mode[0][1] == per_mode[1][1], per_mode
     for k in ("projections", "t_passes", "rebuild_L", "rebuild_R", "fused_T"):
         assert per_mode[0][0].get(k, 0) == per_mode[1][0].get(k, 0), (k, per_mode)
+
+
+@pytest.mark.parametrize("switch", ["fused_passes", "lazy_bra", "front_mode", "project_direct"])
+def test_every_evaluator_switch_off_gives_the_same_numbers(emu, switch, monkeypatch):
+    """Each A/B switch of the evaluator selects a different sequence of device passes for the same
+    amplitudes: with any one of them off, head / tail edits in every order still equal a full re-simulation."""
+    from adapt_aqc_b200.gates import GateStream, canonical_window
+    from oracle import sv_oracle as orc
+    from oracle.oracle_backends import circuit_to_gates
+    monkeypatch.setattr(SVCostEvaluator, switch, False)
+    n = 12
+    target, trng = brickwork(n, 3, seed=9)
+    ansatz = Circuit(n)
+    pairs = [(0, 1), (2, 3), (8, 9), (10, 11), (4, 5), (6, 7), (5, 6), (4, 5), (6, 7), (9, 10)]     # tail: qubits 4..11
+    for a, b in pairs:
+        th = trng.uniform(-np.pi, np.pi, 4)
+        ansatz.rz(th[0], a, label="rz"); ansatz.rz(th[1], b, label="rz"); ansatz.cx(a, b)
+        ansatz.rz(th[2], a, label="rz"); ansatz.rz(th[3], b, label="rz")
+    ev = SVCostEvaluator(FakeEngine(emu, n), None, [FakeEngine(emu, 8, n_slots=4)])
+    ev.set_base("t", GateStream.from_circuit(target))
+    base_gates = circuit_to_gates(target)
+    window = canonical_window(ansatz)
+    rng = np.random.default_rng(17)
+    rot = [i for i, e in enumerate(window) if e[2] < 0]
+    order = [None] + [rot[int(rng.integers(len(rot)))] for _ in range(24)] + rot[:8] + rot[-8:]
+    for step, idx in enumerate(order):
+        if idx is not None:
+            replace_1q_gate(ansatz, idx, ["rx", "ry", "rz"][step % 3], float(rng.uniform(-np.pi, np.pi)))
+            window[idx] = canonical_window(ansatz, idx, idx + 1)[0]
+        got = ev.amp0(list(window), changed=None if idx is None else [idx])
+        c = Circuit(n)
+        c.data = list(ansatz.data)
+        ref = orc.evaluate_circuit(n, base_gates + circuit_to_gates(c))[0]
+        assert abs(got - ref) < 1e-10, (switch, step, idx, got, ref)
