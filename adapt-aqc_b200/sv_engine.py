@@ -553,7 +553,7 @@ class SVCostEvaluator:
             sub = SVCostEvaluator(peng, None, nested, registry=self._registry)
         return sub
 
-    def _bra_into(self, slot, window, fuse=None, store=True):
+    def _bra_into(self, slot, window, fuse=None, store=True, split=False):
         """slot <- window^+ |0..0> on this engine.  The longest tail of `window` that fits a smaller engine is built THERE
         (recursively, and kept: the optimiser asks for several bras with the same tail in a row); the head gates run at
         this size in a sweep that reads its tiles straight from the small engine's slot (b200_sv_run_embedded: no zero
@@ -562,7 +562,8 @@ class SVCostEvaluator:
         (T | None, stored): when one sweep carries the head gates the bra is never written to the register at all."""
         eng, stream = self.eng, G.GateStream.from_window
         T = None
-        split = self._embed_split(window)
+        if split is False:                              # (the caller may already have it)
+            split = self._embed_split(window)
         if split is not None:
             m, peng, qmap, tail = split
             sub = self._sub_for(peng)
@@ -594,27 +595,46 @@ class SVCostEvaluator:
 
     _work_tail = None       # the gate list whose bra slot WORK of this engine holds for the level above (see _bra_into)
 
+    _es_struct = None       # cache of _embed_split: (structure key, m, engine, qmap, pos)
+    _es_tail = None         # ... and (the tail's entries, their translation): unchanged entries are the same objects
+
     def _embed_split(self, window):
         """(m, engine, qmap, tail in that engine's numbering): window[m:] is the longest block-aligned tail whose support
-        fits a smaller engine (its bra is built there and embedded); None if there is none."""
+        fits a smaller engine (its bra is built there and embedded); None if there is none.  The split depends only on
+        which qubits the gates act on and the translated tail only on the tail's entries: both are remembered, the
+        optimiser asks for the same ones several times in a row."""
         eng = self.eng
         if not (self.projected and hasattr(eng, "scatter") and len(window)):
             return None
-        kmax = max((e.num_qubits for e in self.projected if e.num_qubits + self.min_saving() <= eng.num_qubits), default=0)
-        supp, m = set(), len(window)
-        for (s0, _, sp) in reversed(partition_blocks(window)):
-            new = supp | set(sp)
-            if len(new) > kmax:
-                break
-            supp, m = new, s0
-        if m >= len(window):
+        key = [(e[1], e[2]) for e in window]
+        st = self._es_struct
+        if st is None or st[0] != key:
+            kmax = max((e.num_qubits for e in self.projected if e.num_qubits + self.min_saving() <= eng.num_qubits), default=0)
+            supp, m = set(), len(window)
+            for (s0, _, sp) in reversed(partition_blocks(window)):
+                new = supp | set(sp)
+                if len(new) > kmax:
+                    break
+                supp, m = new, s0
+            if m >= len(window):
+                st = self._es_struct = (key, None, None, None, None)
+            else:
+                peng = [e for e in self.projected if e.num_qubits >= len(supp)][0]
+                supp = sorted(supp)
+                used = set(supp)
+                qmap = supp + [q for q in range(eng.num_qubits) if q not in used][:peng.num_qubits - len(supp)]
+                st = self._es_struct = (key, m, peng, qmap, {q: c for c, q in enumerate(qmap)})
+            self._es_tail = None
+        _, m, peng, qmap, pos = st
+        if m is None:
             return None
-        peng = [e for e in self.projected if e.num_qubits >= len(supp)][0]
-        supp = sorted(supp)
-        used = set(supp)
-        qmap = supp + [q for q in range(eng.num_qubits) if q not in used][:peng.num_qubits - len(supp)]
-        pos = {q: c for c, q in enumerate(qmap)}
-        tail = [(e[0], pos[e[1]], pos[e[2]] if e[2] >= 0 else -1) + tuple(e[3:]) for e in window[m:]]
+        src = window[m:]
+        tc = self._es_tail
+        if tc is not None and tc[0] == src:
+            tail = tc[1]
+        else:
+            tail = [(e[0], pos[e[1]], pos[e[2]] if e[2] >= 0 else -1) + tuple(e[3:]) for e in src]
+            self._es_tail = (src, tail)
         return m, peng, qmap, tail
 
     def _projected(self, window, target, changed):
@@ -744,12 +764,15 @@ class SVCostEvaluator:
         self._fused_T = None
         if old is not None and old == sfx:
             return False
+        split = False
         if (fuse is not None and self.lazy_bra and self.fused_passes and self.dense_blocks and hasattr(eng, "run_embedded")
-                and eng.num_qubits >= getattr(eng, "FUSED_MIN_QUBITS", 1 << 30) and self._embed_split(sfx) is not None):
+                and eng.num_qubits >= getattr(eng, "FUSED_MIN_QUBITS", 1 << 30)):
+            split = self._embed_split(sfx)
+        if split:
             # T is all that is wanted and the tail of this bra lives on a smaller engine: ONE read of the ket, the bra is
             # formed tile by tile in shared memory from that engine's slot and never written (cheaper than any move of
             # the stored bra, which costs a second read of the register)
-            T, stored = self._bra_into(SLOT_L, sfx, fuse=fuse, store=False)
+            T, stored = self._bra_into(SLOT_L, sfx, fuse=fuse, store=False, split=split)
             if T is not None:
                 self._fused_T = T
                 if stored:
@@ -804,7 +827,7 @@ class SVCostEvaluator:
         # rebuild: suffix^+ |0> is supported on the qubits the suffix touches -- built on the smaller engines as far as it
         # fits them (cheap sweeps), embedded level by level, only the remaining head gates are applied at this size
         if self.dense_blocks:
-            self._fused_T = self._bra_into(SLOT_L, sfx, fuse=fuse)
+            self._fused_T = self._bra_into(SLOT_L, sfx, fuse=fuse, split=split)
         else:
             eng.run(SLOT_L, -1, stream(sfx), inverse=True)
         self.lwin = list(sfx)
