@@ -9,6 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 import adapt_aqc_b200  # noqa: E402,F401
+from adapt_aqc_b200 import gates as G  # noqa: E402
 from adapt_aqc_b200.gates import GateStream, canonical_window  # noqa: E402
 from adapt_aqc_b200.sv_engine import SVCostEvaluator  # noqa: E402
 from harness.circuit import Circuit  # noqa: E402
@@ -54,12 +55,23 @@ for seed in range(seeds):
             replace_1q_gate(ansatz, idx, ["rx", "ry", "rz"][int(rng.integers(3))], float(rng.uniform(-np.pi, np.pi)))
             window[idx] = canonical_window(ansatz, idx, idx + 1)[0]
         changed = idxs if rng.random() < 0.85 else None
-        got = ev.amp0(list(window), changed=changed)
-        c = Circuit(n); c.data = list(ansatz.data)
-        ref = orc.evaluate_circuit(n, base_gates + circuit_to_gates(c))[0]
-        if abs(got - ref) > 1e-10:
+        if step % 3 == 1:       # the batched front end: every shift value of ONE gate from the same call
+            k = idxs[-1]
+            cands = [G.one_qubit_matrix(["rx", "ry", "rz"][int(rng.integers(3))], float(t)) for t in (0.0, np.pi / 2, -np.pi / 2)]
+            gots = ev.shift_amplitudes(list(window), k, cands, changed=changed)
+            refs = []
+            for cm in cands:
+                w2 = circuit_to_gates(ansatz)
+                w2[k] = ("mat1", w2[k][1], cm)
+                refs.append(orc.evaluate_circuit(n, base_gates + w2)[0])
+            err = max(abs(a - b) for a, b in zip(gots, refs))
+        else:
+            got = ev.amp0(list(window), changed=changed)
+            c = Circuit(n); c.data = list(ansatz.data)
+            err = abs(got - orc.evaluate_circuit(n, base_gates + circuit_to_gates(c))[0])
+        if err > 1e-10:
             bad += 1
-            print("MISMATCH seed", seed, "cfg", cfg, "step", step, idxs, changed, abs(got - ref))
+            print("MISMATCH seed", seed, "cfg", cfg, "step", step, idxs, changed, err)
             break
 print("soak done:", seeds, "seeds x", steps, "edits, mismatches:", bad)
 sys.exit(1 if bad else 0)
